@@ -1,0 +1,130 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (through oracle/shims).
+
+TEST INFRASTRUCTURE ONLY; runs in the build container (needs /root/reference):
+    python oracle/gen_golden.py
+Weights are the seeded "sensitised" recipe of lvae_oracle.sensitised_state_dict (regenerated
+identically on any machine from key names), inputs are seeded, so fixtures hold only outputs.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE))
+import ref_loader          # noqa: E402
+import lvae_oracle as O    # noqa: E402
+
+OUT = HERE.parent / 'tests' / 'golden'
+
+
+def synth_image(nB, H, W, seed):
+    """Seeded smooth-ish RGB in [0,1]: random low-frequency waves + noise (more image-like than iid)."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing='ij')
+    im = torch.zeros(nB, 3, H, W)
+    for b in range(nB):
+        for c in range(3):
+            acc = torch.zeros(H, W)
+            for _ in range(6):
+                fx, fy, ph, amp = (torch.rand(4, generator=g) * torch.tensor([9.0, 9.0, 6.283, 0.5])).tolist()
+                acc += amp * torch.sin(6.283 * (fx * xx + fy * yy) + ph)
+            im[b, c] = acc
+    im = im * 0.25 + 0.5 + 0.08 * torch.randn(nB, 3, H, W, generator=g)
+    return im.clamp_(0, 1).contiguous()
+
+
+CASES = {
+    # name: (kind, nB, H, W, lambdas, seed)
+    'qarv_rand_1x64x64': ('rand', 1, 64, 64, [2048.0], 0),          # BASELINE config 1
+    'qarv_rand_2x128x192': ('rand', 2, 128, 192, [2048.0, 64.0], 1),
+    'qarv_synth_1x256x256': ('synth', 1, 256, 256, [256.0], 2),
+    'qarv_synth_3x64x128': ('synth', 3, 64, 128, [16.0, 700.0, 2048.0], 3),
+}
+
+
+def make_input(kind, nB, H, W, seed):
+    if kind == 'rand':
+        return torch.rand(nB, 3, H, W, generator=torch.Generator().manual_seed(seed))
+    return synth_image(nB, H, W, seed)
+
+
+def main():
+    ref = ref_loader.load_reference()
+    torch.manual_seed(0)
+    model = ref.get_model('qarv_base').eval()
+    sd = O.sensitised_state_dict(O.qarv_param_shapes(), seed=0)
+    model.load_state_dict(sd, strict=False)
+    model.compress_mode()
+    OUT.mkdir(parents=True, exist_ok=True)
+    for name, (kind, nB, H, W, lmbs, seed) in CASES.items():
+        im = make_input(kind, nB, H, W, seed)
+        lmb = torch.tensor(lmbs)
+        with torch.no_grad():
+            stats = model(im, lmb=lmb, return_rec=True)
+            x_hat, lat = model.forward_end2end(im, lmb, get_latent=True)
+            blobs, dec = [], []
+            for b in range(nB):
+                s = model.compress(im[b:b + 1], lmb=float(lmbs[b]))
+                blobs.append(np.frombuffer(s, dtype=np.uint8))
+                dec.append(model.decompress(s))
+        rec = dict(
+            lmb=np.array(lmbs, dtype=np.float32),
+            loss=np.float32(stats['loss'].item()), bppix=np.float64(stats['bppix']),
+            mse=np.float64(stats['mse']), psnr=np.float64(stats['psnr']),
+            im_hat=stats['im_hat'].numpy(),
+            dec_im_hat=torch.cat(dec, 0).numpy(),
+            kl_per_image=np.stack([st['kl'].sum(dim=(1, 2, 3)).numpy() for st in lat]),  # [L, B]
+        )
+        for li, (st, blk) in enumerate(zip(lat, [b for b in model.dec_blocks if getattr(b, 'is_latent_block', False)])):
+            z = st['z']
+            # recover pm from z and qm is not exposed; store symbols via the block arithmetic
+            rec[f'z{li}'] = z.numpy()
+        # symbols / indexes from the reference's own compress path pieces
+        with torch.no_grad():
+            emb = model._get_lmb_embedding(lmb, n=nB)
+            x = model.preprocess_input(im)
+            _, feats = model.encoder(x, emb)
+            feature = model.get_bias(bhw_repeat=(nB, H // 64, W // 64))
+            li = 0
+            for blk in model.dec_blocks:
+                if getattr(blk, 'is_latent_block', False):
+                    f2, pm, pv = blk.transform_prior(feature, emb)
+                    qm = blk.transform_posterior(f2, feats[blk.enc_key], emb)
+                    rec[f'sym{li}'] = blk.discrete_gaussian.quantize(qm, 'symbols', pm).numpy().astype(np.int16)
+                    rec[f'idx{li}'] = blk.discrete_gaussian.build_indexes(pv).numpy().astype(np.uint8)
+                    feature, _ = blk(feature, emb, enc_feature=feats[blk.enc_key])
+                    li += 1
+                elif getattr(blk, 'requires_embedding', False):
+                    feature = blk(feature, emb)
+                else:
+                    feature = blk(feature)
+        for b, blob in enumerate(blobs):
+            rec[f'bytes{b}'] = blob
+        np.savez_compressed(OUT / f'{name}.npz', **rec)
+        print(name, 'loss', float(rec['loss']), 'bppix', float(rec['bppix']), 'psnr', float(rec['psnr']),
+              'bytes', [len(b) for b in blobs])
+    # CDF tables + entropy KATs straight from the reference class
+    dg = [b for b in model.dec_blocks if getattr(b, 'is_latent_block', False)][0].discrete_gaussian
+    qm = torch.tensor([0.3, 0.5, 1.5, 2.5, -0.5, -1.5, 3.7, -7.2, 0.49999997, 12.0, 0.0, 40.0])
+    pm = torch.tensor([0, 0, 0, 0, 0, 0, 0.25, 0.4, 0, 0.1, 0, 0.0])
+    pv = torch.tensor([1.0, 1.0, 1.0, 0.2, 0.1003, 0.5, 2.0, 0.11, 0.3, 0.15, 20.0, 25.0])
+    z, P = dg(qm, scales=pv, means=pm)
+    ent = ref_loader  # noqa
+    import lvae.models.entropy_coding as ec
+    x_t = torch.tensor([0.2, 3.0, 6.0, -9.0, 0.0])
+    s_t = torch.tensor([1.0, 1.0, 1.0, 1.0, 0.1003])
+    np.savez_compressed(
+        OUT / 'entropy_kat.npz',
+        qm=qm.numpy(), pm=pm.numpy(), pv=pv.numpy(), z=z.numpy(), P=P.numpy(),
+        kl=(-torch.log(P)).numpy(), sym=dg.quantize(qm, 'symbols', pm).numpy(),
+        idx=dg.build_indexes(pv).numpy(), scale_table=dg.scale_table.numpy(),
+        cdf=dg._quantized_cdf.numpy(), cdf_length=dg._cdf_length.numpy(), offset=dg._offset.numpy(),
+        train_x=x_t.numpy(), train_scale=s_t.numpy(),
+        train_logp=ec.gaussian_log_prob_mass(torch.zeros(5), s_t, x_t).numpy())
+    print('entropy_kat written')
+
+
+if __name__ == '__main__':
+    main()
