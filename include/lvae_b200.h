@@ -1,0 +1,175 @@
+/*
+ * lvae_b200.h -- C ABI of the B200-native hierarchical-VAE rate-distortion path.
+ *
+ * The reference (duanzhiihao/lossy-vae) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md F1, section 8(b)); the drop-in boundary its callers see is the Python `lvae` package.
+ * This header is the C boundary *underneath* that package: every entry point below replaces a
+ * group of ATen/cuDNN/cuBLAS/CompressAI call sites of the reference, cited per function as
+ * (reference file:line, relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; device pointers are raw CUDA device addresses, `stream` is a
+ *     cudaStream_t passed as void*; the caller owns every buffer; kernels never allocate.
+ *   - activations are NHWC fp32: a feature map [B,H,W,C] is the row-major matrix [M=B*H*W, C].
+ *   - every function returns 0 on success, a positive cudaError_t, or a negative LVAE_E_* code;
+ *     lvae_last_error() returns a thread-local message.
+ *   - no global mutable state besides one-time cudaFuncSetAttribute calls and the tensor-map
+ *     driver entry point lookup.
+ */
+#ifndef LVAE_B200_H
+#define LVAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LVAE_E_BADARG   (-1)
+#define LVAE_E_UNSUPPORTED (-2)
+#define LVAE_E_CORRUPT  (-3)
+
+int lvae_version(void);
+const char* lvae_last_error(void);
+
+/* ---- GEMM-shaped operators -------------------------------------------------------------------
+ * One descriptor covers every dense contraction of the path:
+ *   nn.Linear fc1/fc2 of the ConvNeXt MLP          lvae/models/common.py:131-132,154
+ *   patch_downsample (k = s = 2 | 4 conv)          common.py:29-30
+ *   patch_upsample (1x1 conv + PixelShuffle)       common.py:33-38
+ *   post_merge 1x1 on cat([feature, enc_feature])  lvae/models/qarv/model.py:36,66-67
+ *   posterior 3x3 conv, prior / z_proj 1x1 convs   qarv/model.py:37-39,51,69,74
+ * out[m, n] = epilogue( sum_k A[m, k] * Wp[n, k] + bias[n] )
+ *   A[m, k]: m = (b, ho, wo) output pixel; k = (ky, kx, c) over segment 0 (NHWC a0 with C0 channels,
+ *   square kernel `ksize`, `stride`, zero `pad`), followed for 1x1 ops by the C1 channels of
+ *   segment 1 (a1) -- the K-concat that replaces torch.cat for post_merge.
+ *   Wp is the packed weight [N, K] (K contiguous), produced by the host from the reference layout.
+ */
+enum lvae_epilogue {
+  LVAE_EPI_BIAS = 0,          /* out = acc + bias                                   */
+  LVAE_EPI_BIAS_GELU = 1,     /* out = gelu_erf(acc + bias)            (Mlp.act)     */
+  LVAE_EPI_SCALE_RES = 2,     /* out = (acc + bias) * gamma[n] + res[m,n] (common.py:157-160) */
+  LVAE_EPI_BIAS_RES = 3,      /* out = res[m,n] + (acc + bias)         (qarv/model.py:74) */
+  LVAE_EPI_SHUFFLE_NHWC = 4,  /* PixelShuffle(r) into NHWC [B,H*r,W*r,N/r^2]; packed n = (i*r+j)*Co + c */
+  LVAE_EPI_SHUFFLE_NCHW = 5   /* PixelShuffle(r) into NCHW [B,N/r^2,H*r,W*r] (final image)  */
+};
+
+enum lvae_precision {
+  LVAE_PREC_FP32 = 0,         /* fp32 FFMA on CUDA cores: closest to the CPU fp32 reference   */
+  LVAE_PREC_BF16X3 = 1,       /* tcgen05 kind::f16, hi/lo bf16 operand split, 3 MMAs, fp32 TMEM accumulate */
+  LVAE_PREC_BF16 = 2          /* tcgen05 single pass bf16 (non-parity fast mode)              */
+};
+
+typedef struct lvae_gemm_desc {
+  const float* a0;     /* segment 0 activations, NHWC [B,H,W,C0] */
+  const float* a1;     /* segment 1 activations, NHWC [B,H,W,C1] or NULL */
+  int32_t B, H, W;     /* input spatial dims */
+  int32_t C0, C1;
+  int32_t ksize, stride, pad;
+  const float* w;      /* packed [N, K], K = ksize*ksize*C0 + C1 */
+  const float* bias;   /* [N] or NULL */
+  int32_t N;
+  int32_t epilogue;    /* enum lvae_epilogue */
+  const float* gamma;  /* [N]   (SCALE_RES) */
+  const float* res;    /* [M,N] (SCALE_RES, BIAS_RES) */
+  float* out;
+  int32_t shuffle_r;   /* r for the SHUFFLE epilogues */
+  int32_t precision;   /* enum lvae_precision */
+  /* operand caches for the tensor-core path (device pointers, may be NULL in fp32 mode) */
+  const void* w_hi;    /* bf16 [N,K] high part of w */
+  const void* w_lo;    /* bf16 [N,K] low part  of w */
+  void* workspace;     /* device scratch, >= lvae_gemm_workspace_bytes() */
+  int64_t workspace_bytes;
+} lvae_gemm_desc;
+
+int lvae_gemm(const lvae_gemm_desc* d, void* stream);
+int64_t lvae_gemm_workspace_bytes(const lvae_gemm_desc* d);
+/* split fp32 -> (hi, lo) bf16 pair, hi = rn(x), lo = rn(x - hi) (weights, once per weight version) */
+int lvae_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
+
+/* ---- depthwise conv + LayerNorm + AdaLN (common.py:145-152) ------------------------------------
+ * y[m, c] = LN_c( dwconv_kxk(x)[m, c] + dw_bias[c] ) * (1 + scale[b, c]) + shift[b, c]
+ * x NHWC [B,H,W,C]; dw_w packed [k*k, C]; ada = [B, ada_stride] with shift at ada[b, ada_off + c]
+ * and scale at ada[b, ada_off + C + c]; y row-major [M, C]. C % 64 == 0, k in {1,3,5,7}.
+ * If ln_w != NULL the affine LayerNorm of qresvae's block is applied instead of AdaLN
+ * (lvae/models/qresvae/model.py:163-182). */
+int lvae_dwconv_ln_adaln(const float* x, const float* dw_w, const float* dw_b,
+                         const float* ada, int64_t ada_stride, int64_t ada_off,
+                         const float* ln_w, const float* ln_b,
+                         float* y, int B, int H, int W, int C, int k, void* stream);
+
+/* ---- fused latent-layer kernels (qarv/model.py:51-53,90-96,104-113; CompressAI GaussianConditional) --
+ * prior [M, 2*zdim] (pm | plogv_raw) and qm [M, zdim] are NHWC matrices; hw = h*w positions per image.
+ * Eval (K11+K12+K15): z = rint(qm-pm)+pm; kl = -ln max(Phi((.5-|z-pm|)/s) - Phi((-.5-|z-pm|)/s), 1e-9),
+ * s = max(exp(softplus(plogv+2.3)-2.3), 0.11).  kl_partial[b * kl_stride + blk] gets a deterministic
+ * partial sum (blk < lvae_latent_num_partials() <= kl_stride), so the layers of a model can share one
+ * [B, kl_stride] matrix, each at its own column offset.  Optional outputs (NULL to skip): kl_elem [M,zdim];
+ * sym (int32) and idx (int32) in NCHW order [B,zdim,h,w] for the host coder (K14). */
+int lvae_latent_num_partials(int hw, int zdim);
+int lvae_latent_eval(const float* qm, const float* prior, const float* scale_table, int n_scales,
+                     float* z, float* kl_partial, int kl_stride, float* kl_elem, int32_t* sym, int32_t* idx,
+                     int B, int hw, int zdim, void* stream);
+/* Training (K13): z = qm + noise; kl = -gaussian_log_prob_mass(pm, pv, z) (entropy_coding.py:17-49) */
+int lvae_latent_train(const float* qm, const float* prior, const float* noise,
+                      float* z, float* kl_partial, int kl_stride, float* kl_elem,
+                      int B, int hw, int zdim, void* stream);
+/* Decompress side: idx from the prior only (NCHW int32), then z = float(sym) + pm from decoded symbols */
+int lvae_latent_prior_index(const float* prior, const float* scale_table, int n_scales,
+                            int32_t* idx, int B, int hw, int zdim, void* stream);
+int lvae_latent_dequant(const int32_t* sym, const float* prior, float* z,
+                        int B, int hw, int zdim, void* stream);
+/* Sampling (qarv/model.py:98-103): z = pm + pv*randn*t + uniform*t with caller-supplied noise */
+int lvae_latent_sample(const float* prior, const float* randn, const float* unif, float t,
+                       float* z, int B, int hw, int zdim, void* stream);
+
+/* ---- small host-side-M operators ----------------------------------------------------------------
+ * lmb -> sinusoidal embedding (common.py:101-107, qarv/model.py:275-287): emb0[b, :] =
+ * [cos(a*f) | sin(a*f)], a = log(lmb[b]) * period / log(max_lmb), f = host-supplied [dim/2] table. */
+int lvae_lmb_sinusoid(const float* lmb, const float* freqs, float* emb0, int B, int dim,
+                      float period, float max_lmb, void* stream);
+/* out[b, n] = act_out( sum_k act_in(x[b,k]) * w[n,k] + bias[n] ); act flags: 0 none, 1 gelu_erf.
+ * Used for the lambda-embedding MLP and for ALL AdaLN projections of a model in one launch
+ * (common.py:150: embedding_layer = GELU -> Linear(256, 2C)). */
+int lvae_small_linear(const float* x, const float* w, const float* bias, float* out,
+                      int B, int K, int N, int act_in, int act_out, void* stream);
+
+/* ---- image side (qarv/model.py:213-242,338-346) ---------------------------------------------------
+ * im NCHW [B,3,H,W] in [0,1] -> space-to-depth operand [B*H/4*W/4, 48], k = (i*4+j)*3 + c,
+ * value (im + shift) * scale */
+int lvae_image_to_patches(const float* im, float* a, int B, int H, int W, int r,
+                          float shift, float scale, void* stream);
+/* per-image partial sums: sq_target[b] = sum (x_hat - (im-.5)*2)^2, sq_im[b] = sum (clamp(x_hat)*.5+.5 - im)^2;
+ * also writes im_hat if non-NULL. partial arrays are [B, lvae_image_num_partials()] */
+int lvae_image_num_partials(int chw);
+int lvae_image_distortion(const float* x_hat, const float* im, float* im_hat,
+                          float* sq_target_partial, float* sq_im_partial, int B, int chw, void* stream);
+/* loss assembly (qarv/model.py:338-358): stats = [loss, mean_b kl/ndims (nats), mean_b mse, image-domain mse,
+ * kl_img[B] (nats per dimension), mse_img[B], sqerr_img[B]]; kl_partial is [B, kl_stride] with kl_cols
+ * valid columns; ndims = C*H*W of the image; lmb [B]. stats must hold 4 + 3*B floats. */
+int lvae_rd_finalize(const float* kl_partial, int kl_stride, int kl_cols,
+                     const float* sq_target_partial, const float* sq_im_partial, int np,
+                     const float* lmb, int B, int64_t ndims, float* stats, void* stream);
+/* feature[b,h,w,c] = bias[c] (qarv/model.py:289-292) */
+int lvae_broadcast_bias(const float* bias, float* out, int64_t M, int C, void* stream);
+/* out[i] = sum_j partial[i, j] in fixed order (double accumulation), n rows of `cols` */
+int lvae_sum_partials(const float* partial, float* out, int n, int cols, void* stream);
+
+/* ---- host entropy coder (CompressAI: entropy_models.py update()/compress()/decompress(),
+ *      cpp_exts/ops/ops.cpp pmf_to_quantized_cdf, cpp_exts/rans/rans_interface.cpp; call sites
+ *      qarv/model.py:106-113,123-124) -- host pointers only --------------------------------------- */
+/* pmf (fp32, length n) -> quantized cdf (length n+1, last = 1<<precision) */
+int lvae_pmf_to_quantized_cdf(const float* pmf, int n, int precision, int32_t* cdf_out);
+/* worst-case encoded size in bytes for n symbols */
+int64_t lvae_rans_bound(int64_t n);
+/* encode n symbols; cdf is [n_cdf, cdf_stride] int32; returns bytes written in *out_len */
+int lvae_rans_encode(const int32_t* sym, const int32_t* idx, int64_t n,
+                     const int32_t* cdf, int cdf_stride, const int32_t* cdf_len, const int32_t* offset,
+                     int n_cdf, uint8_t* out, int64_t out_cap, int64_t* out_len);
+int lvae_rans_decode(const uint8_t* in, int64_t in_len, const int32_t* idx, int64_t n,
+                     const int32_t* cdf, int cdf_stride, const int32_t* cdf_len, const int32_t* offset,
+                     int n_cdf, int32_t* sym_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVAE_B200_H */

@@ -1,0 +1,37 @@
+// extern "C" entry for the GEMM-shaped operators: argument validation and dispatch between the
+// fp32 CUDA-core kernel (gemm_f32.cu) and the tcgen05 tensor-core kernel (gemm_tc.cu).
+#include "common.cuh"
+
+namespace lvae {
+int gemm_f32_launch(const lvae_gemm_desc* d, cudaStream_t stream);
+int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream);
+int64_t gemm_tc_workspace_bytes(const lvae_gemm_desc* d);
+}
+
+extern "C" int64_t lvae_gemm_workspace_bytes(const lvae_gemm_desc* d) {
+  if (!d || d->precision == LVAE_PREC_FP32) return 0;
+  return lvae::gemm_tc_workspace_bytes(d);
+}
+
+extern "C" int lvae_gemm(const lvae_gemm_desc* d, void* stream) {
+  using namespace lvae;
+  LVAE_CHECK_ARG(d != nullptr);
+  LVAE_CHECK_ARG(d->a0 && d->w && d->out);
+  LVAE_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->N > 0);
+  LVAE_CHECK_ARG(d->C0 > 0 && d->C0 % 4 == 0);
+  LVAE_CHECK_ARG(d->a1 == nullptr || (d->C1 > 0 && d->C1 % 4 == 0 && d->ksize == 1 && d->stride == 1 && d->pad == 0));
+  LVAE_CHECK_ARG(d->ksize >= 1 && d->stride >= 1 && d->pad >= 0);
+  LVAE_CHECK_ARG(d->H + 2 * d->pad >= d->ksize && d->W + 2 * d->pad >= d->ksize);
+  LVAE_CHECK_ARG(d->epilogue >= LVAE_EPI_BIAS && d->epilogue <= LVAE_EPI_SHUFFLE_NCHW);
+  if (d->epilogue == LVAE_EPI_SCALE_RES) LVAE_CHECK_ARG(d->gamma && d->res);
+  if (d->epilogue == LVAE_EPI_BIAS_RES) LVAE_CHECK_ARG(d->res != nullptr);
+  if (d->epilogue == LVAE_EPI_SHUFFLE_NHWC || d->epilogue == LVAE_EPI_SHUFFLE_NCHW)
+    LVAE_CHECK_ARG(d->shuffle_r >= 1 && d->N % (d->shuffle_r * d->shuffle_r) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d->precision) {
+    case LVAE_PREC_FP32: return gemm_f32_launch(d, st);
+    case LVAE_PREC_BF16X3:
+    case LVAE_PREC_BF16: return gemm_tc_launch(d, st);
+    default: set_error("unknown precision mode %d", d->precision); return LVAE_E_BADARG;
+  }
+}

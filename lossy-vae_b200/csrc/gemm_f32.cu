@@ -1,0 +1,208 @@
+// fp32 conv-as-GEMM on CUDA cores (LVAE_PREC_FP32): the arithmetic closest to the CPU fp32
+// reference (true fp32 products, fp32 accumulation).  One kernel covers 1x1 / 3x3 / patch (k=s)
+// convolutions over NHWC activations with an optional second K segment (the post_merge concat),
+// and the fused epilogues of lvae_b200.h.  The tensor-core path lives in gemm_tc.cu.
+//
+// Tiling: BM=128 x BN in {128,64,32} x BK=16, 256 threads, each thread a (2x4) x (TNx) register
+// tile split in two 4-wide groups so that shared-memory reads are conflict-free 128-bit loads.
+// K order is fixed and there is no split-K: results are bit-reproducible and batch-invariant
+// (SURVEY F12).
+#include "common.cuh"
+
+namespace lvae {
+
+struct GemmParams {
+  const float* a0; const float* a1;
+  int B, H, W, Ho, Wo, C0, C1, ks, stride, pad;
+  const float* w; const float* bias; int N, K, M;
+  int epi; const float* gamma; const float* res; float* out; int r;
+};
+
+constexpr int BM = 128, BK = 16, NT = 256;
+
+__device__ __forceinline__ void store_out(const GemmParams& p, int m, int n, float v) {
+  if (p.epi == LVAE_EPI_SHUFFLE_NHWC || p.epi == LVAE_EPI_SHUFFLE_NCHW) {
+    const int r = p.r, Co = p.N / (r * r);
+    const int q = n / Co, c = n - q * Co, i = q / r, j = q - i * r;
+    const int wo = m % p.Wo; const int t = m / p.Wo; const int ho = t % p.Ho; const int b = t / p.Ho;
+    const int Hr = p.Ho * r, Wr = p.Wo * r;
+    if (p.epi == LVAE_EPI_SHUFFLE_NHWC)
+      p.out[(((int64_t)b * Hr + ho * r + i) * Wr + wo * r + j) * Co + c] = v;
+    else
+      p.out[(((int64_t)b * Co + c) * Hr + ho * r + i) * Wr + wo * r + j] = v;
+  } else {
+    p.out[(int64_t)m * p.N + n] = v;
+  }
+}
+
+__device__ __forceinline__ float apply_epi(const GemmParams& p, int m, int n, float acc) {
+  float v = acc;
+  if (p.bias) v = __fadd_rn(v, p.bias[n]);
+  switch (p.epi) {
+    case LVAE_EPI_BIAS_GELU: v = gelu_erf(v); break;
+    case LVAE_EPI_SCALE_RES: v = __fadd_rn(__fmul_rn(v, p.gamma[n]), p.res[(int64_t)m * p.N + n]); break;
+    case LVAE_EPI_BIAS_RES:  v = __fadd_rn(p.res[(int64_t)m * p.N + n], v); break;
+    default: break;
+  }
+  return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NT) gemm_f32_kernel(const GemmParams p) {
+  constexpr int TN = BN / 16;          // columns per thread (8, 4, 2)
+  constexpr int TNH = TN / 2;          // per 2 groups
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  // ---- A loader: thread loads 2 float4: rows (tid>>2) and (tid>>2)+64, k quad (tid&3) ----
+  const int a_kq = tid & 3;
+  int a_row[2]; int a_b[2], a_h0[2], a_w0[2]; bool a_ok[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    a_row[i] = (tid >> 2) + 64 * i;
+    const int m = m0 + a_row[i];
+    a_ok[i] = m < p.M;
+    const int mm = a_ok[i] ? m : 0;
+    const int wo = mm % p.Wo; const int t = mm / p.Wo; const int ho = t % p.Ho;
+    a_b[i] = t / p.Ho; a_h0[i] = ho * p.stride - p.pad; a_w0[i] = wo * p.stride - p.pad;
+  }
+  // ---- B loader: BN rows x 16 k = BN*4 float4; thread loads BN/64 of them ----
+  constexpr int BLD = BN * 4 / NT > 0 ? BN * 4 / NT : 1;
+  const int K0 = p.ks * p.ks * p.C0;
+
+  float4 ra[2]; float4 rb[BLD];
+  auto load_tiles = [&](int k0) {
+    const int k = k0 + a_kq * 4;
+    // decode k -> (segment, tap, c)
+    const float* base = nullptr; int C = 0, c = 0, ky = 0, kx = 0; bool kvalid = k < p.K;
+    if (kvalid) {
+      if (k < K0) { const int tap = k / p.C0; c = k - tap * p.C0; ky = tap / p.ks; kx = tap - ky * p.ks; base = p.a0; C = p.C0; }
+      else { c = k - K0; base = p.a1; C = p.C1; }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kvalid && a_ok[i]) {
+        const int hh = a_h0[i] + ky, ww = a_w0[i] + kx;
+        if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W)
+          v = __ldg(reinterpret_cast<const float4*>(base + (((int64_t)a_b[i] * p.H + hh) * p.W + ww) * C + c));
+      }
+      ra[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < BLD; ++i) {
+      const int f = tid + i * NT;            // float4 index within the tile
+      const int row = f >> 2, kq = f & 3;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (BN * 4 >= NT || f < BN * 4) {
+        const int n = n0 + row, kk = k0 + kq * 4;
+        if (n < p.N && kk < p.K) v = __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)n * p.K + kk));
+      }
+      rb[i] = v;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      As[buf][a_kq * 4 + 0][a_row[i]] = ra[i].x; As[buf][a_kq * 4 + 1][a_row[i]] = ra[i].y;
+      As[buf][a_kq * 4 + 2][a_row[i]] = ra[i].z; As[buf][a_kq * 4 + 3][a_row[i]] = ra[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < BLD; ++i) {
+      const int f = tid + i * NT;
+      if (BN * 4 >= NT || f < BN * 4) {
+        const int row = f >> 2, kq = f & 3;
+        Bs[buf][kq * 4 + 0][row] = rb[i].x; Bs[buf][kq * 4 + 1][row] = rb[i].y;
+        Bs[buf][kq * 4 + 2][row] = rb[i].z; Bs[buf][kq * 4 + 3][row] = rb[i].w;
+      }
+    }
+  };
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nk = (p.K + BK - 1) / BK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[8], b[TN];
+      *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      if constexpr (TNH == 4) {
+        *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(&Bs[buf][k][BN / 2 + tx * 4]);
+      } else if constexpr (TNH == 2) {
+        *reinterpret_cast<float2*>(&b[0]) = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 2]);
+        *reinterpret_cast<float2*>(&b[2]) = *reinterpret_cast<const float2*>(&Bs[buf][k][BN / 2 + tx * 2]);
+      } else {
+        b[0] = Bs[buf][k][tx]; b[1] = Bs[buf][k][BN / 2 + tx];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) { store_tiles(buf ^ 1); }
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+  const bool plain = !(p.epi == LVAE_EPI_SHUFFLE_NHWC || p.epi == LVAE_EPI_SHUFFLE_NCHW);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int nb = n0 + g * (BN / 2) + tx * TNH;
+      float v[TNH];
+#pragma unroll
+      for (int j = 0; j < TNH; ++j) v[j] = (nb + j < p.N) ? apply_epi(p, m, nb + j, acc[i][g * TNH + j]) : 0.f;
+      if (plain && TNH == 4 && (p.N & 3) == 0 && nb + 3 < p.N) {
+        *reinterpret_cast<float4*>(p.out + (int64_t)m * p.N + nb) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < TNH; ++j) if (nb + j < p.N) store_out(p, m, nb + j, v[j]);
+      }
+    }
+  }
+}
+
+int gemm_f32_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
+  GemmParams p;
+  p.a0 = d->a0; p.a1 = d->a1; p.B = d->B; p.H = d->H; p.W = d->W;
+  p.C0 = d->C0; p.C1 = d->a1 ? d->C1 : 0; p.ks = d->ksize; p.stride = d->stride; p.pad = d->pad;
+  p.Ho = (d->H + 2 * d->pad - d->ksize) / d->stride + 1;
+  p.Wo = (d->W + 2 * d->pad - d->ksize) / d->stride + 1;
+  p.w = d->w; p.bias = d->bias; p.N = d->N; p.K = d->ksize * d->ksize * d->C0 + p.C1;
+  p.M = d->B * p.Ho * p.Wo;
+  p.epi = d->epilogue; p.gamma = d->gamma; p.res = d->res; p.out = d->out; p.r = d->shuffle_r;
+  if (p.M == 0) return 0;
+  dim3 block(NT);
+  if (p.N > 64) {
+    dim3 grid((p.M + BM - 1) / BM, (p.N + 127) / 128);
+    gemm_f32_kernel<128><<<grid, block, 0, stream>>>(p);
+  } else if (p.N > 32) {
+    dim3 grid((p.M + BM - 1) / BM, 1);
+    gemm_f32_kernel<64><<<grid, block, 0, stream>>>(p);
+  } else {
+    dim3 grid((p.M + BM - 1) / BM, 1);
+    gemm_f32_kernel<32><<<grid, block, 0, stream>>>(p);
+  }
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace lvae

@@ -1,0 +1,219 @@
+// Fused latent-layer kernels: prior transform + quantise + discretised-Gaussian likelihood +
+// per-image rate partial sums, one bandwidth-bound pass per latent layer.
+//
+// Reference arithmetic (fp32, this exact op order -- SURVEY Appendix A):
+//   VRLVBlockBase.transform_prior   lvae/models/qarv/model.py:51-53   plogv = softplus(x+2.3)-2.3; pv = exp(plogv)
+//   eval branch                     qarv/model.py:95-96 -> CompressAI GaussianConditional.forward:
+//       z = rint(qm - pm) + pm ; v = |z - pm| ; s = max(pv, 0.11)
+//       P = Phi((.5 - v)/s) - Phi((-.5 - v)/s), Phi(t) = 0.5*(1 + erf(t * 1/sqrt(2))) [td.Normal(0,1).cdf,
+//       lvae/models/entropy_coding.py:81-82]; P = max(P, 1e-9); kl = -ln P
+//   compress branch                 qarv/model.py:106-108: sym = int(rint(qm-pm)), idx = build_indexes(pv)
+//   train branch                    qarv/model.py:91-93 + entropy_coding.py:17-49
+//
+// Layout: qm / z are [M, zdim] (NHWC), prior is [M, 2*zdim] = (pm | plogv_raw) per position, so one
+// thread handles one (position, channel) element with fully coalesced 128 B-per-warp accesses.
+// Algorithmic bytes per element: read qm, pm, plogv (12 B) + write z (4 B) = 16 B with the rate
+// reduced in-kernel (20 B when kl_elem is requested; +8 B for sym/idx).
+// The per-image reduction is deterministic: fixed grid, in-block tree, one partial per block.
+#include "common.cuh"
+
+namespace lvae {
+
+constexpr int LT = 256;            // threads per block
+constexpr int LE = 4;              // elements per thread
+
+__device__ __forceinline__ float softplus_torch(float x) {   // beta=1, threshold=20
+  return x > 20.0f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float prior_scale(float plogv_raw) {
+  const float plogv = __fsub_rn(softplus_torch(__fadd_rn(plogv_raw, 2.3f)), 2.3f);
+  return expf(plogv);
+}
+// td.Normal(0,1).cdf(t) = 0.5 * (1 + erf((t - 0) * (1/1) / sqrt(2)))
+__device__ __forceinline__ float std_normal_cdf(float t) {
+  const float a = __fdiv_rn(t, 1.4142135623730951f);
+  return __fmul_rn(0.5f, __fadd_rn(1.0f, erff(a)));
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (wid == 0) {
+    t = lane < (LT / 32) ? red[lane] : 0.f;
+    t = warp_sum(t);
+  }
+  return t;   // valid in warp 0
+}
+
+// mode 0: eval, 1: train
+template <int MODE>
+__global__ void __launch_bounds__(LT) latent_kernel(
+    const float* __restrict__ qm, const float* __restrict__ prior, const float* __restrict__ noise,
+    const float* __restrict__ table, int n_scales,
+    float* __restrict__ z, float* __restrict__ kl_partial, float* __restrict__ kl_elem,
+    int32_t* __restrict__ sym, int32_t* __restrict__ idx, int hw, int zdim, int kl_stride) {
+  __shared__ float red[LT / 32];
+  __shared__ float stab[64];
+  if (MODE == 0 && idx != nullptr) {
+    for (int i = threadIdx.x; i < n_scales && i < 64; i += LT) stab[i] = table[i];
+    __syncthreads();
+  }
+  const int b = blockIdx.y;
+  const int per_img = hw * zdim;
+  float local = 0.f;
+#pragma unroll
+  for (int e = 0; e < LE; ++e) {
+    const int i = (blockIdx.x * LE + e) * LT + threadIdx.x;     // element within the image, (pos, c)
+    if (i < per_img) {
+      const int pos = i / zdim, c = i - pos * zdim;
+      const int64_t m = (int64_t)b * hw + pos;
+      const float q = qm[m * zdim + c];
+      const float pm = prior[m * 2 * zdim + c];
+      const float pv = prior_scale(prior[m * 2 * zdim + zdim + c]);
+      float kl, zz;
+      if (MODE == 0) {
+        const float r = rintf(__fsub_rn(q, pm));             // torch.round: half to even
+        zz = __fadd_rn(r, pm);
+        const float v = fabsf(__fsub_rn(zz, pm));
+        const float s = fmaxf(pv, 0.11f);
+        const float up = std_normal_cdf(__fdiv_rn(__fsub_rn(0.5f, v), s));
+        const float lo = std_normal_cdf(__fdiv_rn(__fsub_rn(-0.5f, v), s));
+        const float P = fmaxf(__fsub_rn(up, lo), 1e-9f);
+        kl = -logf(P);
+        if (sym != nullptr) {
+          const int64_t o = ((int64_t)b * zdim + c) * hw + pos;     // NCHW order for the coder
+          sym[o] = (int32_t)r;
+          int k = n_scales - 1;
+          for (int t = 0; t < n_scales - 1; ++t) k -= (s <= stab[t]) ? 1 : 0;
+          idx[o] = k;
+        }
+      } else {
+        zz = __fadd_rn(q, noise[m * zdim + c]);
+        // td.Normal(pm, pv).cdf(x) = 0.5*(1+erf((x-pm)*(1/pv)/sqrt(2)))
+        const float rcp = __frcp_rn(pv);
+        const float cu = __fmul_rn(0.5f, __fadd_rn(1.0f, erff(__fdiv_rn(__fmul_rn(__fsub_rn(__fadd_rn(zz, 0.5f), pm), rcp), 1.4142135623730951f))));
+        const float cl = __fmul_rn(0.5f, __fadd_rn(1.0f, erff(__fdiv_rn(__fmul_rn(__fsub_rn(__fsub_rn(zz, 0.5f), pm), rcp), 1.4142135623730951f))));
+        const float mass = __fsub_rn(cu, cl);
+        float lp;
+        if (mass > 1e-6f) {
+          lp = logf(fmaxf(mass, 1e-8f));
+        } else {
+          // Normal.log_prob: -((x-mu)^2)/(2 var) - log(scale) - log(sqrt(2 pi));  + log(bin_size=1) = 0
+          const float d = __fsub_rn(zz, pm);
+          const float var = __fmul_rn(pv, pv);
+          lp = __fsub_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.0f, var)), logf(pv)), 0.9189385332046727f);
+          lp = __fadd_rn(lp, 0.0f);
+        }
+        kl = -lp;
+      }
+      z[m * zdim + c] = zz;
+      if (kl_elem != nullptr) kl_elem[m * zdim + c] = kl;
+      local += kl;
+    }
+  }
+  const float t = block_sum(local, red);
+  if (threadIdx.x == 0) kl_partial[(int64_t)b * kl_stride + blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(LT) prior_index_kernel(
+    const float* __restrict__ prior, const float* __restrict__ table, int n_scales,
+    int32_t* __restrict__ idx, int hw, int zdim) {
+  __shared__ float stab[64];
+  for (int i = threadIdx.x; i < n_scales && i < 64; i += LT) stab[i] = table[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * LT + threadIdx.x;
+  if (i >= hw * zdim) return;
+  const int pos = i / zdim, c = i - pos * zdim;
+  const int64_t m = (int64_t)b * hw + pos;
+  const float s = fmaxf(prior_scale(prior[m * 2 * zdim + zdim + c]), 0.11f);
+  int k = n_scales - 1;
+  for (int t = 0; t < n_scales - 1; ++t) k -= (s <= stab[t]) ? 1 : 0;
+  idx[((int64_t)b * zdim + c) * hw + pos] = k;
+}
+
+__global__ void __launch_bounds__(LT) dequant_kernel(
+    const int32_t* __restrict__ sym, const float* __restrict__ prior, float* __restrict__ z, int hw, int zdim) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * LT + threadIdx.x;
+  if (i >= hw * zdim) return;
+  const int pos = i / zdim, c = i - pos * zdim;
+  const int64_t m = (int64_t)b * hw + pos;
+  const float pm = prior[m * 2 * zdim + c];
+  z[m * zdim + c] = __fadd_rn((float)sym[((int64_t)b * zdim + c) * hw + pos], pm);
+}
+
+__global__ void __launch_bounds__(LT) sample_kernel(
+    const float* __restrict__ prior, const float* __restrict__ randn, const float* __restrict__ unif, float t,
+    float* __restrict__ z, int64_t M, int zdim) {
+  const int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x;
+  if (i >= M * zdim) return;
+  const int64_t m = i / zdim; const int c = (int)(i - m * zdim);
+  const float pm = prior[m * 2 * zdim + c];
+  const float pv = prior_scale(prior[m * 2 * zdim + zdim + c]);
+  // z = pm + pv * randn * t + unif * t       (qarv/model.py:100)
+  z[i] = __fadd_rn(__fadd_rn(pm, __fmul_rn(__fmul_rn(pv, randn[i]), t)), __fmul_rn(unif[i], t));
+}
+
+}  // namespace lvae
+
+using namespace lvae;
+
+extern "C" int lvae_latent_num_partials(int hw, int zdim) {
+  const int per = LT * LE;
+  return (hw * zdim + per - 1) / per;
+}
+
+extern "C" int lvae_latent_eval(const float* qm, const float* prior, const float* scale_table, int n_scales,
+                                float* z, float* kl_partial, int kl_stride, float* kl_elem,
+                                int32_t* sym, int32_t* idx, int B, int hw, int zdim, void* stream) {
+  LVAE_CHECK_ARG(qm && prior && z && kl_partial && B > 0 && hw > 0 && zdim > 0);
+  LVAE_CHECK_ARG((sym == nullptr) == (idx == nullptr));
+  LVAE_CHECK_ARG(sym == nullptr || (scale_table != nullptr && n_scales >= 1 && n_scales <= 64));
+  const int np = lvae_latent_num_partials(hw, zdim);
+  LVAE_CHECK_ARG(kl_stride >= np);
+  latent_kernel<0><<<dim3(np, B), LT, 0, (cudaStream_t)stream>>>(qm, prior, nullptr, scale_table, n_scales,
+                                                                  z, kl_partial, kl_elem, sym, idx, hw, zdim, kl_stride);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lvae_latent_train(const float* qm, const float* prior, const float* noise,
+                                 float* z, float* kl_partial, int kl_stride, float* kl_elem,
+                                 int B, int hw, int zdim, void* stream) {
+  LVAE_CHECK_ARG(qm && prior && noise && z && kl_partial && B > 0 && hw > 0 && zdim > 0);
+  const int np = lvae_latent_num_partials(hw, zdim);
+  LVAE_CHECK_ARG(kl_stride >= np);
+  latent_kernel<1><<<dim3(np, B), LT, 0, (cudaStream_t)stream>>>(qm, prior, noise, nullptr, 0,
+                                                                  z, kl_partial, kl_elem, nullptr, nullptr, hw, zdim, kl_stride);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lvae_latent_prior_index(const float* prior, const float* scale_table, int n_scales,
+                                       int32_t* idx, int B, int hw, int zdim, void* stream) {
+  LVAE_CHECK_ARG(prior && scale_table && idx && n_scales >= 1 && n_scales <= 64 && B > 0 && hw > 0 && zdim > 0);
+  prior_index_kernel<<<dim3((hw * zdim + LT - 1) / LT, B), LT, 0, (cudaStream_t)stream>>>(prior, scale_table, n_scales, idx, hw, zdim);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lvae_latent_dequant(const int32_t* sym, const float* prior, float* z,
+                                   int B, int hw, int zdim, void* stream) {
+  LVAE_CHECK_ARG(sym && prior && z && B > 0 && hw > 0 && zdim > 0);
+  dequant_kernel<<<dim3((hw * zdim + LT - 1) / LT, B), LT, 0, (cudaStream_t)stream>>>(sym, prior, z, hw, zdim);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lvae_latent_sample(const float* prior, const float* randn, const float* unif, float t,
+                                  float* z, int B, int hw, int zdim, void* stream) {
+  LVAE_CHECK_ARG(prior && randn && unif && z && B > 0 && hw > 0 && zdim > 0);
+  const int64_t M = (int64_t)B * hw;
+  sample_kernel<<<(unsigned)((M * zdim + LT - 1) / LT), LT, 0, (cudaStream_t)stream>>>(prior, randn, unif, t, z, M, zdim);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,93 @@
+"""ctypes binding of liblvae_b200.so (the C ABI declared in include/lvae_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent.parent / 'lib' / 'liblvae_b200.so'
+_lib = None
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_SCALE_RES, EPI_BIAS_RES, EPI_SHUFFLE_NHWC, EPI_SHUFFLE_NCHW = range(6)
+PREC_FP32, PREC_BF16X3, PREC_BF16 = range(3)
+PRECISIONS = {'fp32': PREC_FP32, 'bf16x3': PREC_BF16X3, 'bf16': PREC_BF16}
+
+_fp = C.c_void_p   # device / host pointers are passed as integers
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ('a0', _fp), ('a1', _fp),
+        ('B', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
+        ('C0', C.c_int32), ('C1', C.c_int32),
+        ('ksize', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32),
+        ('w', _fp), ('bias', _fp),
+        ('N', C.c_int32), ('epilogue', C.c_int32),
+        ('gamma', _fp), ('res', _fp), ('out', _fp),
+        ('shuffle_r', C.c_int32), ('precision', C.c_int32),
+        ('w_hi', _fp), ('w_lo', _fp),
+        ('workspace', _fp), ('workspace_bytes', C.c_int64),
+    ]
+
+
+_PROTOS = {
+    'lvae_version': (C.c_int, []),
+    'lvae_last_error': (C.c_char_p, []),
+    'lvae_gemm': (C.c_int, [C.POINTER(GemmDesc), _fp]),
+    'lvae_gemm_workspace_bytes': (C.c_int64, [C.POINTER(GemmDesc)]),
+    'lvae_split_bf16': (C.c_int, [_fp, _fp, _fp, C.c_int64, _fp]),
+    'lvae_dwconv_ln_adaln': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_latent_num_partials': (C.c_int, [C.c_int, C.c_int]),
+    'lvae_latent_eval': (C.c_int, [_fp, _fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp, _fp,
+                                   C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_latent_train': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_latent_prior_index': (C.c_int, [_fp, _fp, C.c_int, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_latent_dequant': (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_latent_sample': (C.c_int, [_fp, _fp, _fp, C.c_float, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_lmb_sinusoid': (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_float, C.c_float, _fp]),
+    'lvae_small_linear': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_image_to_patches': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp]),
+    'lvae_image_num_partials': (C.c_int, [C.c_int]),
+    'lvae_image_distortion': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp]),
+    'lvae_rd_finalize': (C.c_int, [_fp, C.c_int, C.c_int, _fp, _fp, C.c_int, _fp, C.c_int, C.c_int64, _fp, _fp]),
+    'lvae_broadcast_bias': (C.c_int, [_fp, _fp, C.c_int64, C.c_int, _fp]),
+    'lvae_sum_partials': (C.c_int, [_fp, _fp, C.c_int, C.c_int, _fp]),
+    'lvae_pmf_to_quantized_cdf': (C.c_int, [_fp, C.c_int, C.c_int, _fp]),
+    'lvae_rans_bound': (C.c_int64, [C.c_int64]),
+    'lvae_rans_encode': (C.c_int, [_fp, _fp, C.c_int64, _fp, C.c_int, _fp, _fp, C.c_int, _fp, C.c_int64,
+                                   C.POINTER(C.c_int64)]),
+    'lvae_rans_decode': (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, _fp, C.c_int, _fp, _fp, C.c_int, _fp]),
+}
+
+EXPORTS = tuple(_PROTOS)
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.is_file():
+            raise RuntimeError(
+                f'{_LIB_PATH} not found: the sm_100a CUDA library has not been built. '
+                f'Run `python lossy-vae_b200/build.py` (or __graft_entry__.build()). There is no CPU fallback.')
+        L = C.CDLL(str(_LIB_PATH))
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code, what=''):
+    if code != 0:
+        msg = lib().lvae_last_error().decode(errors='replace')
+        raise RuntimeError(f'liblvae_b200 {what} failed with code {code}: {msg}')
+
+
+launch_count = 0   # number of kernel-launching C calls issued (bench.py reports it)

@@ -1,0 +1,553 @@
+"""QarvEngine: compiles a qarv model into a static sequence of liblvae_b200 kernel launches.
+
+The reference runs the model as ~2000 ATen ops per forward with NCHW<->NHWC permutes around every
+block (lvae/models/common.py:142-161, lvae/models/qarv/model.py:294-363).  Here a *plan* is built
+once per (batch, height, width, mode): activations stay resident in HBM as NHWC fp32 matrices
+[M = B*h*w, C]; every ConvNeXt block is three launches
+
+    dwconv+LayerNorm+AdaLN  ->  fc1 GEMM + GELU  ->  fc2 GEMM * gamma + residual
+
+the AdaLN projections of all 90 blocks are one launch, each latent layer's prior transform +
+quantise + likelihood + per-image rate partial sums are one launch, and the loss assembly is one
+launch.  The plan is replayed through a CUDA graph.  torch is used for device memory, streams and
+graphs only.
+
+Dense contractions run in one of three precisions (model.precision):
+    'bf16x3'  tcgen05 tensor cores, operands split into bf16 (hi, lo) pairs, 3 MMAs per product,
+              fp32 accumulation in TMEM -- the parity mode
+    'bf16'    tcgen05, single bf16 pass -- fast, non-parity
+    'fp32'    fp32 FFMA on CUDA cores
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .models import common
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class _Op:
+    __slots__ = ('fn', 'args', 'keep', 'name')
+
+    def __init__(self, name, fn, args, keep=None):
+        self.name, self.fn, self.args, self.keep = name, fn, args, keep
+
+
+class Plan:
+    """A static launch list + its device buffers for one (B, H, W, mode)."""
+
+    def __init__(self, engine, B, H, W, mode, want_elem):
+        self.eng, self.B, self.H, self.W, self.mode, self.want_elem = engine, B, H, W, mode, want_elem
+        self.dev = engine.device
+        self.segments = [[]]      # op lists split at host interaction points
+        self.bufs = {}
+        self.retired = []
+        self.graphs = None
+        self.n_launch = 0
+
+    # ---- buffers
+    def f32(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.dev)
+
+    def i32(self, *shape):
+        return torch.empty(shape, dtype=torch.int32, device=self.dev)
+
+    def named(self, name, numel, dtype=torch.float32):
+        t = self.bufs.get(name)
+        if t is None or t.numel() < numel:
+            if t is not None:
+                self.retired.append(t)     # earlier ops hold raw pointers into it
+            t = torch.empty(numel, dtype=dtype, device=self.dev)
+            self.bufs[name] = t
+        return t
+
+    # ---- op emission
+    def op(self, name, fn, *args, keep=None):
+        self.segments[-1].append(_Op(name, fn, args, keep))
+        self.n_launch += 1
+
+    def cut(self):
+        self.segments.append([])
+
+    def run_segment(self, i, stream):
+        for o in self.segments[i]:
+            rc = o.fn(*o.args, stream)
+            if rc != 0:
+                N.check(rc, o.name)
+
+
+class QarvEngine:
+    def __init__(self, model):
+        self.model = model
+        self.lib = N.lib()
+        self.device = None
+        self._wver = None
+        self._plans = {}
+        self.use_graphs = True
+        self.blocks = [m for m in model.modules() if isinstance(m, common.ConvNeXtBlockAdaLN)]
+        self.ada_off = {}
+        off = 0
+        for b in self.blocks:
+            self.ada_off[id(b)] = off
+            off += 2 * b.dim
+        self.ada_total = off
+        self.w = {}
+
+    # ------------------------------------------------------------------ weights
+    def _weights_version(self):
+        return (self.model._dummy.device, self.model.precision,
+                sum(p._version for p in self.model.parameters()),
+                tuple(p.data_ptr() for p in (self.model.bias, self.blocks[0].gamma)))
+
+    def _dev_f32(self, t):
+        return t.detach().to(self.device, torch.float32).contiguous()
+
+    def _pack_gemm_weight(self, w2d, bias):
+        """w2d: [N, K] fp32 on device -> dict(w, bias[, hi, lo])"""
+        ent = dict(w=w2d.contiguous(), bias=None if bias is None else self._dev_f32(bias),
+                   N=w2d.shape[0], K=w2d.shape[1])
+        if self.tc:
+            n = ent['w'].numel()
+            hi = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+            lo = torch.empty(n, dtype=torch.bfloat16, device=self.device) if self.prec == N.PREC_BF16X3 else None
+            N.check(self.lib.lvae_split_bf16(_ptr(ent['w']), _ptr(hi), _ptr(lo), n, self._stream()), 'split_bf16')
+            ent['hi'], ent['lo'] = hi, lo
+        return ent
+
+    def _conv_weight(self, conv):
+        w = self._dev_f32(conv.weight)                    # [N, C, kh, kw]
+        n, c, kh, kw = w.shape
+        return self._pack_gemm_weight(w.permute(0, 2, 3, 1).reshape(n, kh * kw * c), conv.bias)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def refresh_weights(self, force=False):
+        m = self.model
+        dev = m._dummy.device
+        if dev.type != 'cuda':
+            raise RuntimeError('lvae (B200 build) has no CPU path: move the model to a CUDA device first '
+                               '(model.to("cuda")); the arithmetic lives in liblvae_b200.so')
+        ver = self._weights_version()
+        if not force and ver == self._wver:
+            return
+        if self.device != dev or self.__dict__.get('prec') != N.PRECISIONS[m.precision]:
+            self._plans.clear()
+        self.device = dev
+        self.prec = N.PRECISIONS[m.precision]
+        self.tc = self.prec != N.PREC_FP32
+        w = {}
+        with torch.cuda.device(dev):
+            for b in self.blocks:
+                C_, k = b.dim, b.kernel_size
+                w[id(b)] = dict(
+                    dw_w=self._dev_f32(b.conv_dw.weight).reshape(C_, k * k).t().contiguous(),
+                    dw_b=self._dev_f32(b.conv_dw.bias),
+                    fc1=self._pack_gemm_weight(self._dev_f32(b.mlp.fc1.weight), b.mlp.fc1.bias),
+                    fc2=self._pack_gemm_weight(self._dev_f32(b.mlp.fc2.weight), b.mlp.fc2.bias),
+                    gamma=self._dev_f32(b.gamma).reshape(C_),
+                )
+            w['ada_w'] = torch.cat([self._dev_f32(b.embedding_layer[1].weight) for b in self.blocks], 0).contiguous()
+            w['ada_b'] = torch.cat([self._dev_f32(b.embedding_layer[1].bias) for b in self.blocks], 0).contiguous()
+            for j in (0, 2):
+                w[f'emb{j}_w'] = self._dev_f32(m.lmb_embedding[j].weight)
+                w[f'emb{j}_b'] = self._dev_f32(m.lmb_embedding[j].bias)
+            w['freqs'] = common.sinusoidal_frequencies(m.lmb_embed_dim[0], m._sin_period).to(dev)
+            w['bias'] = self._dev_f32(m.bias).reshape(-1)
+            mods = list(m.encoder.enc_blocks) + list(m.dec_blocks)
+            for mod in mods:
+                kind = getattr(mod, 'op_kind', None)
+                if kind == 'down':
+                    w[id(mod)] = self._conv_weight(mod)
+                elif kind == 'up':
+                    conv, r = mod[0], mod.rate
+                    wt = self._dev_f32(conv.weight).reshape(conv.out_channels, conv.in_channels)
+                    co = conv.out_channels // (r * r)
+                    # packed row (i*r+j)*Co + c  <-  reference row c*r*r + i*r + j  (PixelShuffle, common.py:33-38)
+                    perm = torch.arange(conv.out_channels, device=dev).reshape(co, r * r).t().reshape(-1)
+                    w[id(mod)] = self._pack_gemm_weight(wt[perm], self._dev_f32(conv.bias)[perm])
+                elif getattr(mod, 'is_latent_block', False):
+                    w[id(mod)] = dict(post_merge=self._conv_weight(mod.post_merge),
+                                      posterior=self._conv_weight(mod.posterior),
+                                      z_proj=self._conv_weight(mod.z_proj),
+                                      prior=self._conv_weight(mod.prior),
+                                      table=mod.discrete_gaussian.scale_table.detach().to(dev, torch.float32).contiguous())
+        self.w = w
+        self._wver = ver
+        # plans hold raw weight pointers -> rebuild them
+        self._plans.clear()
+
+    # ------------------------------------------------------------------ plan construction helpers
+    def _gemm(self, P, name, a0, geom, went, out, epi=N.EPI_BIAS, a1=None, C1=0, gamma=None, res=None, r=0):
+        """geom = (B, H, W, C0, ksize, stride, pad) of the NHWC input a0."""
+        B, H, W, C0, ks, st, pad = geom
+        d = N.GemmDesc()
+        d.a0, d.a1 = _ptr(a0), _ptr(a1)
+        d.B, d.H, d.W, d.C0, d.C1 = B, H, W, C0, C1
+        d.ksize, d.stride, d.pad = ks, st, pad
+        d.w, d.bias, d.N = _ptr(went['w']), _ptr(went['bias']), went['N']
+        d.epilogue, d.gamma, d.res, d.out = epi, _ptr(gamma), _ptr(res), _ptr(out)
+        d.shuffle_r, d.precision = r, N.PREC_FP32
+        assert went['K'] == ks * ks * C0 + C1, (name, went['K'], ks, C0, C1)
+        P.op(name, self.lib.lvae_gemm, C.byref(d), keep=(d, a0, a1, went, out, gamma, res))
+
+    def _block(self, P, blk, x, B, Hs, Ws, out=None):
+        """x: [M, C] fp32 NHWC; returns the output buffer (x itself when out is None: in place)."""
+        wb = self.w[id(blk)]
+        C_, hid, k = blk.dim, blk.hidden, blk.kernel_size
+        M = B * Hs * Ws
+        A = P.named('scratch_a', M * C_)
+        Hd = P.named('scratch_h', M * hid)
+        out = x if out is None else out
+        P.op('dwln', self.lib.lvae_dwconv_ln_adaln, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']),
+             _ptr(P.ada), self.ada_total, self.ada_off[id(blk)], 0, 0, _ptr(A), B, Hs, Ws, C_, k,
+             keep=(x, A))
+        self._gemm(P, 'fc1', A, (1, 1, M, C_, 1, 1, 0), wb['fc1'], Hd, epi=N.EPI_BIAS_GELU)
+        self._gemm(P, 'fc2', Hd, (1, 1, M, hid, 1, 1, 0), wb['fc2'], out, epi=N.EPI_SCALE_RES,
+                   gamma=wb['gamma'], res=x)
+        return out
+
+    def _embedding(self, P, lmb):
+        m, w, B = self.model, self.w, P.B
+        E0, E1 = m.lmb_embed_dim
+        emb0, e1, emb = P.f32(B, E0), P.f32(B, E1), P.f32(B, E1)
+        P.ada = P.f32(B, self.ada_total)
+        P.op('sinusoid', self.lib.lvae_lmb_sinusoid, _ptr(lmb), _ptr(w['freqs']), _ptr(emb0), B, E0,
+             float(m._sin_period), float(m.MAX_LMB), keep=(lmb, emb0))
+        P.op('emb0', self.lib.lvae_small_linear, _ptr(emb0), _ptr(w['emb0_w']), _ptr(w['emb0_b']), _ptr(e1),
+             B, E0, E1, 0, 1, keep=(e1,))
+        P.op('emb2', self.lib.lvae_small_linear, _ptr(e1), _ptr(w['emb2_w']), _ptr(w['emb2_b']), _ptr(emb),
+             B, E1, E1, 0, 0, keep=(emb,))
+        P.op('adaln_all', self.lib.lvae_small_linear, _ptr(emb), _ptr(w['ada_w']), _ptr(w['ada_b']), _ptr(P.ada),
+             B, E1, self.ada_total, 1, 0)
+
+    def _encoder(self, P, im):
+        m, B, H, W = self.model, P.B, P.H, P.W
+        feats = {}
+        x, Cc, s = None, 3, 1
+        pinned = False
+        for mod in m.encoder.enc_blocks:
+            kind = getattr(mod, 'op_kind', None)
+            if kind == 'down':
+                r = mod.rate
+                s *= r
+                Hs, Ws = H // s, W // s
+                out = P.f32(B * Hs * Ws, mod.out_channels)
+                if x is None:
+                    patches = P.f32(B * Hs * Ws, Cc * r * r)
+                    P.op('im2patch', self.lib.lvae_image_to_patches, _ptr(im), _ptr(patches), B, H, W, r,
+                         float(m.im_shift), float(m.im_scale), keep=(im, patches))
+                    self._gemm(P, 'down0', patches, (1, 1, B * Hs * Ws, Cc * r * r, 1, 1, 0), self.w[id(mod)], out)
+                else:
+                    self._gemm(P, 'down', x, (B, Hs * r, Ws * r, Cc, r, r, 0), self.w[id(mod)], out)
+                x, Cc, pinned = out, mod.out_channels, False
+            elif isinstance(mod, common.ConvNeXtBlockAdaLN):
+                Hs, Ws = H // s, W // s
+                x = self._block(P, mod, x, B, Hs, Ws, out=P.f32(B * Hs * Ws, Cc) if pinned else None)
+                pinned = False
+            elif isinstance(mod, common.SetKey):
+                feats[mod.key] = x
+                pinned = True
+            else:
+                raise TypeError(f'unsupported encoder module {type(mod)}')
+        return feats
+
+    def _top_down(self, P, feats, nH, nW, latent_fn, stop_at_flag=False):
+        """Walks dec_blocks.  latent_fn(P, blk, li, feature, prior, geom) emits the ops that produce z
+        [M, zdim] for latent layer li and returns the z buffer."""
+        m, B = self.model, P.B
+        Hs, Ws = nH, nW
+        Cc = m.dec_blocks[0].in_channels
+        x = P.f32(B * Hs * Ws, Cc)
+        P.op('bias', self.lib.lvae_broadcast_bias, _ptr(self.w['bias']), _ptr(x), B * Hs * Ws, Cc, keep=(x,))
+        li = 0
+        for mod in m.dec_blocks:
+            kind = getattr(mod, 'op_kind', None)
+            M = B * Hs * Ws
+            if getattr(mod, 'is_latent_block', False):
+                wl = self.w[id(mod)]
+                zd = mod.zdim
+                x = self._block(P, mod.resnet_front, x, B, Hs, Ws)
+                prior = P.f32(M, 2 * zd)
+                self._gemm(P, 'prior', x, (B, Hs, Ws, Cc, 1, 1, 0), wl['prior'], prior)
+                z = latent_fn(P, mod, li, x, prior, (B, Hs, Ws, Cc))
+                li += 1
+                self._gemm(P, 'z_proj', z, (B, Hs, Ws, zd, 1, 1, 0), wl['z_proj'], x, epi=N.EPI_BIAS_RES, res=x)
+                x = self._block(P, mod.resnet_end, x, B, Hs, Ws)
+            elif isinstance(mod, common.ConvNeXtBlockAdaLN):
+                x = self._block(P, mod, x, B, Hs, Ws)
+            elif kind == 'up':
+                r = mod.rate
+                co = mod[0].out_channels // (r * r)
+                last = co == 3
+                out = P.f32(B, 3, Hs * r, Ws * r) if last else P.f32(M * r * r, co)
+                self._gemm(P, 'up', x, (B, Hs, Ws, Cc, 1, 1, 0), self.w[id(mod)], out,
+                           epi=N.EPI_SHUFFLE_NCHW if last else N.EPI_SHUFFLE_NHWC, r=r)
+                x, Cc, Hs, Ws = out, co, Hs * r, Ws * r
+            elif isinstance(mod, common.CompresionStopFlag):
+                if stop_at_flag:
+                    return None
+            else:
+                raise TypeError(f'unsupported decoder module {type(mod)}')
+        return x
+
+    def _posterior(self, P, blk, x, enc_feat, geom):
+        """transform_posterior (qarv/model.py:56-70) -> qm [M, zdim]"""
+        B, Hs, Ws, Cc = geom
+        M = B * Hs * Ws
+        wl = self.w[id(blk)]
+        We = blk.enc_width
+        e = self._block(P, blk.posterior0, enc_feat, B, Hs, Ws, out=P.named('post_e', M * We)[:M * We])
+        f = self._block(P, blk.posterior1, x, B, Hs, Ws, out=P.named('post_f', M * Cc)[:M * Cc])
+        mg = P.named('post_m', M * Cc)[:M * Cc]
+        self._gemm(P, 'post_merge', f, (B, Hs, Ws, Cc, 1, 1, 0), wl['post_merge'], mg, a1=e, C1=We)
+        mg = self._block(P, blk.posterior2, mg, B, Hs, Ws)
+        qm = P.f32(M, blk.zdim)
+        self._gemm(P, 'posterior', mg, (B, Hs, Ws, Cc, 3, 1, 1), wl['posterior'], qm)
+        return qm
+
+    # ------------------------------------------------------------------ plans
+    def _latent_layout(self, B, nH, nW):
+        """per latent layer: (hw, zdim, n_partials, column offset)"""
+        lay, off = [], 0
+        Hs, Ws = nH, nW
+        for mod in self.model.dec_blocks:
+            if getattr(mod, 'is_latent_block', False):
+                hw = Hs * Ws
+                np_ = self.lib.lvae_latent_num_partials(hw, mod.zdim)
+                lay.append((hw, mod.zdim, np_, off, Hs, Ws))
+                off += np_
+            elif getattr(mod, 'op_kind', None) == 'up':
+                Hs, Ws = Hs * mod.rate, Ws * mod.rate
+        return lay, off
+
+    def _build_forward_plan(self, B, H, W, mode, want_elem):
+        """mode: 'eval' | 'train' | 'compress'"""
+        m = self.model
+        P = Plan(self, B, H, W, mode, want_elem)
+        nH, nW = H // m.max_stride, W // m.max_stride
+        P.im = P.f32(B, 3, H, W)
+        P.lmb = P.f32(B)
+        lay, kl_cols = self._latent_layout(B, nH, nW)
+        P.layout = lay
+        P.kl_partial = torch.zeros(B, kl_cols, dtype=torch.float32, device=self.device)
+        P.z, P.kl_elem, P.sym, P.idx, P.noise = [], [], [], [], []
+        self._embedding(P, P.lmb)
+        feats = self._encoder(P, P.im)
+
+        def latent_fn(P, blk, li, x, prior, geom):
+            hw, zd, np_, off, Hs, Ws = lay[li]
+            qm = self._posterior(P, blk, x, feats[blk.enc_key], geom)
+            z = P.f32(B * hw, zd)
+            kle = P.f32(B * hw, zd) if want_elem else None
+            P.z.append(z)
+            P.kl_elem.append(kle)
+            klp = P.kl_partial[:, off:]
+            if mode == 'train':
+                noise = P.f32(B * hw, zd)
+                P.noise.append(noise)
+                P.op('latent_train', self.lib.lvae_latent_train, _ptr(qm), _ptr(prior), _ptr(noise), _ptr(z),
+                     klp.data_ptr(), kl_cols, _ptr(kle), B, hw, zd, keep=(qm, prior, z, kle))
+            else:
+                sym = idx = None
+                if mode == 'compress':
+                    sym, idx = P.i32(B, zd, Hs, Ws), P.i32(B, zd, Hs, Ws)
+                    P.sym.append(sym)
+                    P.idx.append(idx)
+                tab = self.w[id(blk)]['table']
+                P.op('latent_eval', self.lib.lvae_latent_eval, _ptr(qm), _ptr(prior), _ptr(tab), tab.numel(), _ptr(z),
+                     klp.data_ptr(), kl_cols, _ptr(kle), _ptr(sym), _ptr(idx), B, hw, zd, keep=(qm, prior, z, kle))
+            return z
+
+        x_hat = self._top_down(P, feats, nH, nW, latent_fn, stop_at_flag=(mode == 'compress'))
+        if mode != 'compress':
+            P.x_hat = x_hat
+            chw = 3 * H * W
+            npi = self.lib.lvae_image_num_partials(chw)
+            P.im_hat = P.f32(B, 3, H, W)
+            pt, pi = P.f32(B, npi), P.f32(B, npi)
+            P.stats = P.f32(4 + 3 * B)
+            P.op('distortion', self.lib.lvae_image_distortion, _ptr(x_hat), _ptr(P.im), _ptr(P.im_hat), _ptr(pt), _ptr(pi),
+                 B, chw, keep=(pt, pi))
+            P.op('finalize', self.lib.lvae_rd_finalize, _ptr(P.kl_partial), kl_cols, kl_cols, _ptr(pt), _ptr(pi), npi,
+                 _ptr(P.lmb), B, chw, _ptr(P.stats))
+            P.stats_host = torch.empty(4 + 3 * B, dtype=torch.float32, pin_memory=True)
+        return P
+
+    def _get_plan(self, key, builder):
+        P = self._plans.get(key)
+        if P is None:
+            with torch.cuda.device(self.device):
+                P = builder()
+            self._plans[key] = P
+        return P
+
+    def _launch(self, P, seg=0):
+        """Replay one plan segment on the current stream (through a CUDA graph once warmed up)."""
+        N.launch_count += len(P.segments[seg])
+        if not self.use_graphs:
+            P.run_segment(seg, self._stream())
+            return
+        if P.graphs is None:
+            P.graphs = [None] * len(P.segments)
+            P.warm = [0] * len(P.segments)
+        g = P.graphs[seg]
+        if g is None:
+            if P.warm[seg] < 1:           # first call runs eagerly (lazy module loading, error surfacing)
+                P.warm[seg] += 1
+                P.run_segment(seg, self._stream())
+                return
+            g = torch.cuda.CUDAGraph()
+            cur = torch.cuda.current_stream(self.device)
+            cur.synchronize()
+            with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                P.run_segment(seg, self._stream())
+            P.graphs[seg] = g
+        g.replay()
+
+    # ------------------------------------------------------------------ public entry points
+    @torch.no_grad()
+    def run(self, im, lmb, mode='eval', want_elem=False, want_im_hat=False):
+        self.refresh_weights()
+        B, _, H, W = im.shape
+        with torch.cuda.device(self.device):
+            P = self._get_plan((B, H, W, mode, want_elem), lambda: self._build_forward_plan(B, H, W, mode, want_elem))
+            P.im.copy_(im, non_blocking=True)
+            P.lmb.copy_(lmb.to(torch.float32), non_blocking=True)
+            if mode == 'train':
+                for nz in P.noise:         # same generator order as the reference: one uniform_ per layer
+                    nz.uniform_(-0.5, 0.5)
+            self._launch(P)
+            if mode == 'compress':
+                return dict(strings=self._encode_strings(P))
+            P.stats_host.copy_(P.stats, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            res = dict(stats=P.stats.clone(), stats_host=P.stats_host.numpy().copy(), x_hat=P.x_hat)
+            if want_im_hat:
+                res['im_hat'] = P.im_hat.clone()
+            if want_elem:
+                res['x_hat'] = P.x_hat.clone()
+                res['kl_elem'] = [self._nchw(k, B, l) for k, l in zip(P.kl_elem, P.layout)]
+                res['z'] = [self._nchw(z, B, l) for z, l in zip(P.z, P.layout)]
+            return res
+
+    @staticmethod
+    def _nchw(t, B, lay):
+        hw, zd, _, _, Hs, Ws = lay
+        return t.view(B, Hs, Ws, zd).permute(0, 3, 1, 2).contiguous()
+
+    # ---- host entropy coding
+    def _tables(self, blk):
+        return blk.discrete_gaussian.host_tables()
+
+    def _encode_strings(self, P):
+        """per latent layer: list (over the batch) of rANS byte strings.  Symbols / indexes arrive in NCHW
+        order, the order CompressAI flattens them in (qarv/model.py:106-108)."""
+        blocks = [b for b in self.model.dec_blocks if getattr(b, 'is_latent_block', False)]
+        host = []
+        for sym, idx in zip(P.sym, P.idx):
+            host.append((sym.to('cpu', non_blocking=True), idx.to('cpu', non_blocking=True)))
+        torch.cuda.current_stream(self.device).synchronize()
+        out = []
+        for blk, (sym, idx) in zip(blocks, host):
+            cdf, clen, coff = self._tables(blk)
+            sym, idx = sym.numpy(), idx.numpy()
+            per_image = sym[0].size
+            cap = int(self.lib.lvae_rans_bound(per_image))
+            buf = np.empty(cap, dtype=np.uint8)
+            strings = []
+            for b in range(P.B):
+                n = C.c_int64(0)
+                s_b, i_b = np.ascontiguousarray(sym[b]).reshape(-1), np.ascontiguousarray(idx[b]).reshape(-1)
+                N.check(self.lib.lvae_rans_encode(s_b.ctypes.data, i_b.ctypes.data, per_image, cdf.ctypes.data,
+                                                  cdf.shape[1], clen.ctypes.data, coff.ctypes.data, cdf.shape[0],
+                                                  buf.ctypes.data, cap, C.byref(n)), 'rans_encode')
+                strings.append(buf[:n.value].tobytes())
+            out.append(strings)
+        return out
+
+    def _build_decode_plan(self, B, nH, nW, sampling=False):
+        m = self.model
+        H, W = nH * m.max_stride, nW * m.max_stride
+        P = Plan(self, B, H, W, 'sample' if sampling else 'decompress', False)
+        P.lmb = P.f32(B)
+        lay, _ = self._latent_layout(B, nH, nW)
+        P.layout = lay
+        P.z, P.idx, P.sym, P.prior = [], [], [], []
+        self._embedding(P, P.lmb)
+
+        def latent_fn(P, blk, li, x, prior, geom):
+            hw, zd, np_, off, Hs, Ws = lay[li]
+            z = P.f32(B * hw, zd)
+            P.z.append(z)
+            P.prior.append(prior)
+            if sampling:
+                P.cut()          # host decides per layer: given latent (copied into z) or prior sample
+                return z
+            idx, sym = P.i32(B, zd, Hs, Ws), P.i32(B, zd, Hs, Ws)
+            P.idx.append(idx)
+            P.sym.append(sym)
+            tab = self.w[id(blk)]['table']
+            P.op('prior_index', self.lib.lvae_latent_prior_index, _ptr(prior), _ptr(tab), tab.numel(), _ptr(idx),
+                 B, hw, zd, keep=(prior, idx))
+            P.cut()              # host: D2H idx -> rANS decode -> H2D sym
+            P.op('dequant', self.lib.lvae_latent_dequant, _ptr(sym), _ptr(prior), _ptr(z), B, hw, zd, keep=(sym, z))
+            return z
+
+        x_hat = self._top_down(P, None, nH, nW, latent_fn)
+        P.x_hat = x_hat
+        return P
+
+    @torch.no_grad()
+    def decompress(self, lmb, strings, bhw):
+        """strings: one byte string per latent layer (batch 1, as the reference container holds)."""
+        self.refresh_weights()
+        B, nH, nW = bhw
+        assert B == 1, 'the container format carries one image (qarv/model.py:521)'
+        blocks = [b for b in self.model.dec_blocks if getattr(b, 'is_latent_block', False)]
+        with torch.cuda.device(self.device):
+            P = self._get_plan(('dec', B, nH, nW), lambda: self._build_decode_plan(B, nH, nW))
+            P.lmb.copy_(lmb.to(torch.float32), non_blocking=True)
+            stream = torch.cuda.current_stream(self.device)
+            for li, blk in enumerate(blocks):
+                self._launch(P, li)
+                idx = P.idx[li].to('cpu', non_blocking=True)
+                stream.synchronize()
+                cdf, clen, coff = self._tables(blk)
+                idx_np = idx.numpy().reshape(-1)
+                sym_np = np.empty(idx_np.size, dtype=np.int32)
+                data = np.frombuffer(strings[li], dtype=np.uint8)
+                N.check(self.lib.lvae_rans_decode(data.ctypes.data, data.size, idx_np.ctypes.data, idx_np.size,
+                                                  cdf.ctypes.data, cdf.shape[1], clen.ctypes.data, coff.ctypes.data,
+                                                  cdf.shape[0], sym_np.ctypes.data), 'rans_decode')
+                P.sym[li].copy_(torch.from_numpy(sym_np).view_as(P.sym[li]), non_blocking=False)
+            self._launch(P, len(blocks))
+            return P.x_hat.clone().clamp_(min=-1.0, max=1.0).mul_(0.5).add_(0.5)
+
+    @torch.no_grad()
+    def sample(self, lmb, latents, bhw, t):
+        self.refresh_weights()
+        B, nH, nW = bhw
+        with torch.cuda.device(self.device):
+            P = self._get_plan(('smp', B, nH, nW), lambda: self._build_decode_plan(B, nH, nW, sampling=True))
+            P.lmb.copy_(lmb.to(torch.float32), non_blocking=True)
+            for li in range(len(P.z)):
+                self._launch(P, li)
+                hw, zd, _, _, Hs, Ws = P.layout[li]
+                if latents[li] is None:
+                    rn = torch.randn(B * hw, zd, device=self.device)
+                    un = torch.empty(B * hw, zd, device=self.device).uniform_(-0.5, 0.5)
+                    N.check(self.lib.lvae_latent_sample(_ptr(P.prior[li]), _ptr(rn), _ptr(un), t, _ptr(P.z[li]),
+                                                        B, hw, zd, self._stream()), 'latent_sample')
+                    N.launch_count += 1
+                else:
+                    assert tuple(latents[li].shape) == (B, zd, Hs, Ws)
+                    P.z[li].view(B, Hs, Ws, zd).copy_(latents[li].to(self.device).permute(0, 2, 3, 1))
+            self._launch(P, len(P.z))
+            return P.x_hat.clone().clamp_(min=-1.0, max=1.0).mul_(0.5).add_(0.5)
