@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- 512x768 images/s of the qarv_base rate-distortion forward (encoder + decoder networks,
+per-layer quantise + likelihood, loss assembly) on N B200s, next to the reference's CPU path.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--batch 8] [--precision fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One JSON line on stdout (rank 0).  A "step" is one eval `forward()` of BASELINE.json configs[1]:
+qarv_base, synthetic 512x768 RGB, batch 8 per GPU (weak scaling: every rank runs its own batch, no
+data-path collective -- SURVEY 8(e)).  `value` = images/s with the batch resident in HBM (CUDA-graph
+replay of the launch plan), `e2e` = images/s through `model.forward(batch_on_pinned_host, lmb)` with the
+H2D image copy and the D2H stats read inside the timed region.  `roofline` is the dominant kernel
+class (the dense contractions) measured per launch with CUDA events; `roofline_entropy` the fused
+latent kernel against HBM bandwidth; `cpu_baseline` the oracle (torch-CPU restatement of the
+reference, oracle/lvae_oracle.py) timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT / 'lossy-vae_b200', ROOT / 'oracle'):
+    sys.path.insert(0, str(p))
+
+H, W = 512, 768
+METRIC = '512x768 images/sec (enc+dec)'
+DENSE_GFLOP_PER_IMAGE = 287.61       # qarv_base eval forward, Linear + non-depthwise conv, 2*MAC
+
+
+def peaks():
+    f = ROOT / 'MEASURED_PEAKS.json'
+    if f.is_file():
+        d = json.loads(f.read_text())
+        return dict(hbm=d['hbm_gbs'], tensor_burst=d['bf16_tflops'], tensor_sustained=d['bf16_tflops_sustained'],
+                    src='measured')
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, src='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
+
+
+def cpu_reference_images_per_s(n_timed, threads=None):
+    """The oracle's eval forward on the host CPU: B=1, 512x768, seeded sensitised weights.  Returns (img/s, cores, sample)."""
+    import torch
+    import lvae_oracle as O
+    from oracle_inputs import make_input
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.sensitised_state_dict(O.qarv_param_shapes(), seed=0)
+    im = make_input('rand', 1, H, W, 0)
+    lmb = torch.tensor([2048.0])
+    O.qarv_forward(sd, im, lmb)                         # warm-up (thread pools, oneDNN primitive caches)
+    t0 = time.perf_counter()
+    for _ in range(n_timed):
+        O.qarv_forward(sd, im, lmb)
+    dt = time.perf_counter() - t0
+    return n_timed / dt, cores, f'{n_timed} x (1 image 512x768, eval forward) after 1 warm-up, torch CPU fp32, {cores} threads'
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    # every "step" is a bounded sample: one 512x768 image through the oracle
+    import torch
+    import lvae_oracle as O
+    from oracle_inputs import make_input
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.sensitised_state_dict(O.qarv_param_shapes(), seed=0)
+    im = make_input('rand', 1, H, W, 0)
+    lmb = torch.tensor([2048.0])
+    steps, warm = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    for _ in range(warm):
+        O.qarv_forward(sd, im, lmb)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.qarv_forward(sd, im, lmb)
+    dt = time.perf_counter() - t0
+    v = steps / dt
+    sample = f'{steps} steps x 1 image 512x768 eval forward (bounded sample of the batch-8 workload), {cores} host threads'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': warm, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'qarv_base eval forward, synthetic 512x768 RGB, 1 image per step on host CPU '
+                               '(torch-CPU restatement of the reference: oracle/lvae_oracle.py)'},
+        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=8, help='images per GPU per step (BASELINE configs[1]: 8)')
+    ap.add_argument('--precision', default=None, help="fp32 | bf16x3 | bf16 (default: the model's default)")
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-samples', type=int, default=5)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import lvae
+    from lvae import _native as N
+    import lvae_oracle as O
+    from oracle_inputs import make_input
+
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (there is no CPU path; use --impl reference for the CPU baseline)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    warmup = max(args.warmup, 3)
+    B = args.batch
+
+    torch.manual_seed(0)
+    model = lvae.get_model('qarv_base')
+    model.load_state_dict(O.sensitised_state_dict(O.qarv_param_shapes(), seed=0), strict=False)
+    if args.precision:
+        model.precision = args.precision
+    model = model.to(dev).eval()
+    eng = model.engine
+
+    # each rank gets its own seeded batch (weak scaling)
+    im_host = make_input('rand', B, H, W, 1000 + rank).pin_memory()
+    lmb_host = torch.full((B,), 2048.0).pin_memory()
+    lmb_dev = lmb_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: CUDA-graph replay of the launch plan
+    P = eng.forward_plan(B, H, W, 'eval')
+    P.im.copy_(im_host); P.lmb.copy_(lmb_host)
+    for _ in range(warmup + 2):                       # +2: first call is eager, second captures the graph
+        eng.replay(P)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = N.launch_count
+    st = torch.cuda.current_stream()
+    barrier()
+    e0.record(st)
+    for _ in range(args.steps):
+        eng.replay(P)
+    e1.record(st)
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    launches = N.launch_count - launches0
+    stats = P.stats.cpu()
+
+    # ---- end to end through the public API: pinned host batch in, stats out, every step
+    for _ in range(warmup):
+        out = model(im_host, lmb=lmb_dev)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e2.record(st)
+    for _ in range(args.steps):
+        out = model(im_host, lmb=lmb_dev)
+    e3.record(st)
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+
+    if rank == 0:
+        pk = peaks()
+        # ---- per-launch roofline (rank 0, after the timed region; CUDA events around each eager launch)
+        prof = eng.profile_ops(P, reps=3)
+        tot_ms = sum(ms for _, _, ms in prof)
+        by_kind = {}
+        for name, meta, ms in prof:
+            k = by_kind.setdefault(meta.get('kind', 'misc'), dict(ms=0.0, flops=0, bytes=0, n=0))
+            k['ms'] += ms; k['flops'] += meta.get('flops', 0); k['bytes'] += meta.get('bytes', 0); k['n'] += 1
+        gm, lt, dw = by_kind['gemm'], by_kind['latent'], by_kind['dwln']
+        issued = {'fp32': 1, 'bf16': 1, 'bf16x3': 3}[model.precision]
+        roof = dict(bound='tensor', kernel=f'lvae_gemm ({model.precision})', achieved=gm['flops'] / gm['ms'] / 1e9,
+                    peak=pk['tensor_sustained'], unit='TFLOP/s', traffic=None, peak_source=pk['src'] + ' (sustained bf16 cuBLAS)',
+                    launches=gm['n'], share_of_step=gm['ms'] / tot_ms, issued_mma_multiplier=issued,
+                    note='achieved = sum over the GEMM launches of 2*M*N*K / sum of their CUDA-event durations')
+        roof['frac'] = roof['achieved'] / roof['peak']
+        # biggest latent layer alone (the only ones large enough to be bandwidth- rather than latency-bound)
+        big = max((p for p in prof if p[1].get('kind') == 'latent'), key=lambda p: p[1]['bytes'])
+        roof_e = dict(bound='hbm', kernel='latent_kernel<eval>', achieved=big[1]['bytes'] / big[2] / 1e6, peak=pk['hbm'],
+                      unit='GB/s', traffic=None, peak_source=pk['src'], elems=big[1]['elems'],
+                      all_layers_gbs=lt['bytes'] / lt['ms'] / 1e6, share_of_step=lt['ms'] / tot_ms)
+        roof_e['frac'] = roof_e['achieved'] / roof_e['peak']
+        roof_d = dict(bound='hbm', kernel='dwln_kernel', achieved=dw['bytes'] / dw['ms'] / 1e6, peak=pk['hbm'], unit='GB/s',
+                      frac=dw['bytes'] / dw['ms'] / 1e6 / pk['hbm'], share_of_step=dw['ms'] / tot_ms, traffic=None)
+
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, cores, sample = cpu_reference_images_per_s(args.cpu_samples)
+            cpu = dict(value=v, unit='images/s', cores=cores, kind='port', sample=sample)
+
+        n_img = B * world * args.steps
+        line = {
+            'metric': METRIC, 'value': n_img / (ms_dev / 1e3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': {'fp32': 'f32', 'bf16x3': 'bf16x3 (split-bf16 products, f32 accumulate)', 'bf16': 'bf16'}[model.precision],
+            'data': 'synthetic',
+            'config': {'workload': f'qarv_base eval forward (rate + MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 2048 '
+                                   f'(BASELINE configs[1])', 'batch_per_gpu': B, 'global_batch': B * world, 'precision': model.precision,
+                       'parallelism': f'batch-shard x{world}, no data-path collective', 'weights': 'seeded sensitised init (no checkpoint offline)',
+                       'l2': 'no flush: per-step working set (weights 374 MB + activations > 1 GB) exceeds the 126 MB L2',
+                       'dense_gflop_per_image': DENSE_GFLOP_PER_IMAGE},
+            'e2e': {'value': n_img / (ms_e2e / 1e3), 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,
+                    'h2d_bytes_per_step': im_host.numel() * 4, 'd2h_bytes_per_step': P.stats_host.numel() * 4 + 8},
+            'gpu_launches': launches, 'launches_per_step': launches // max(1, args.steps),
+            'clocks': clocks, 'roofline': roof, 'roofline_entropy': roof_e, 'roofline_dwln': roof_d,
+            'tensor_frac_of_step': DENSE_GFLOP_PER_IMAGE * B / (ms_dev / args.steps) / pk['tensor_sustained'],
+            'cpu_baseline': cpu,
+            'result': {'bppix': float(stats[1]) * 1.4426950408889634 * 3, 'loss': float(stats[0]), 'e2e_bppix': out['bppix'], 'e2e_psnr': out['psnr']},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -33,10 +33,10 @@ def _ptr(t):
 
 
 class _Op:
-    __slots__ = ('fn', 'args', 'keep', 'name')
+    __slots__ = ('fn', 'args', 'keep', 'name', 'meta')
 
-    def __init__(self, name, fn, args, keep=None):
-        self.name, self.fn, self.args, self.keep = name, fn, args, keep
+    def __init__(self, name, fn, args, keep=None, meta=None):
+        self.name, self.fn, self.args, self.keep, self.meta = name, fn, args, keep, meta or {}
 
 
 class Plan:
@@ -68,8 +68,10 @@ class Plan:
         return t
 
     # ---- op emission
-    def op(self, name, fn, *args, keep=None):
-        self.segments[-1].append(_Op(name, fn, args, keep))
+    def op(self, name, fn, *args, keep=None, meta=None):
+        """meta: dict(kind='gemm'|'dwln'|'latent'|'misc', flops=..., bytes=...) -- ALGORITHMIC work of the launch,
+        used by bench.py for the roofline figures."""
+        self.segments[-1].append(_Op(name, fn, args, keep, meta))
         self.n_launch += 1
 
     def cut(self):
@@ -195,7 +197,10 @@ class QarvEngine:
         d.epilogue, d.gamma, d.res, d.out = epi, _ptr(gamma), _ptr(res), _ptr(out)
         d.shuffle_r, d.precision = r, N.PREC_FP32
         assert went['K'] == ks * ks * C0 + C1, (name, went['K'], ks, C0, C1)
-        P.op(name, self.lib.lvae_gemm, C.byref(d), keep=(d, a0, a1, went, out, gamma, res))
+        Mo = B * ((H + 2 * pad - ks) // st + 1) * ((W + 2 * pad - ks) // st + 1)
+        meta = dict(kind='gemm', flops=2 * Mo * went['N'] * went['K'], M=Mo, N=went['N'], K=went['K'],
+                    bytes=4 * (B * H * W * (C0 + C1) + went['N'] * went['K'] + Mo * went['N'] * (2 if res is not None else 1)))
+        P.op(name, self.lib.lvae_gemm, C.byref(d), keep=(d, a0, a1, went, out, gamma, res), meta=meta)
 
     def _block(self, P, blk, x, B, Hs, Ws, out=None):
         """x: [M, C] fp32 NHWC; returns the output buffer (x itself when out is None: in place)."""
@@ -207,7 +212,7 @@ class QarvEngine:
         out = x if out is None else out
         P.op('dwln', self.lib.lvae_dwconv_ln_adaln, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']),
              _ptr(P.ada), self.ada_total, self.ada_off[id(blk)], 0, 0, _ptr(A), B, Hs, Ws, C_, k,
-             keep=(x, A))
+             keep=(x, A), meta=dict(kind='dwln', bytes=8 * M * C_, flops=2 * M * C_ * k * k))
         self._gemm(P, 'fc1', A, (1, 1, M, C_, 1, 1, 0), wb['fc1'], Hd, epi=N.EPI_BIAS_GELU)
         self._gemm(P, 'fc2', Hd, (1, 1, M, hid, 1, 1, 0), wb['fc2'], out, epi=N.EPI_SCALE_RES,
                    gamma=wb['gamma'], res=x)
@@ -353,7 +358,8 @@ class QarvEngine:
                 noise = P.f32(B * hw, zd)
                 P.noise.append(noise)
                 P.op('latent_train', self.lib.lvae_latent_train, _ptr(qm), _ptr(prior), _ptr(noise), _ptr(z),
-                     klp.data_ptr(), kl_cols, _ptr(kle), B, hw, zd, keep=(qm, prior, z, kle))
+                     klp.data_ptr(), kl_cols, _ptr(kle), B, hw, zd, keep=(qm, prior, z, kle),
+                     meta=dict(kind='latent', elems=B * hw * zd, bytes=B * hw * zd * (20 + (4 if want_elem else 0))))
             else:
                 sym = idx = None
                 if mode == 'compress':
@@ -362,7 +368,9 @@ class QarvEngine:
                     P.idx.append(idx)
                 tab = self.w[id(blk)]['table']
                 P.op('latent_eval', self.lib.lvae_latent_eval, _ptr(qm), _ptr(prior), _ptr(tab), tab.numel(), _ptr(z),
-                     klp.data_ptr(), kl_cols, _ptr(kle), _ptr(sym), _ptr(idx), B, hw, zd, keep=(qm, prior, z, kle))
+                     klp.data_ptr(), kl_cols, _ptr(kle), _ptr(sym), _ptr(idx), B, hw, zd, keep=(qm, prior, z, kle),
+                     meta=dict(kind='latent', elems=B * hw * zd,
+                               bytes=B * hw * zd * (16 + (4 if want_elem else 0) + (8 if mode == 'compress' else 0))))
             return z
 
         x_hat = self._top_down(P, feats, nH, nW, latent_fn, stop_at_flag=(mode == 'compress'))
@@ -411,23 +419,60 @@ class QarvEngine:
             P.graphs[seg] = g
         g.replay()
 
+    # ------------------------------------------------------------------ measurement hooks (bench.py)
+    def forward_plan(self, B, H, W, mode='eval', want_elem=False):
+        """The resident launch plan for one batch shape; fill P.im / P.lmb, then replay(P)."""
+        self.refresh_weights()
+        return self._get_plan((B, H, W, mode, want_elem), lambda: self._build_forward_plan(B, H, W, mode, want_elem))
+
+    def replay(self, P, seg=0):
+        with torch.cuda.device(self.device):
+            self._launch(P, seg)
+
+    def profile_ops(self, P, reps=3, seg=0):
+        """Per-launch device time (CUDA events on the launching stream, eager launches, mean of `reps`)
+        for every op of a plan segment -> list of (name, meta, ms)."""
+        ops = P.segments[seg]
+        out = []
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device)
+            ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops]
+                  for _ in range(reps)]
+            for r in range(reps):
+                for o, (e0, e1) in zip(ops, ev[r]):
+                    e0.record(st)
+                    rc = o.fn(*o.args, st.cuda_stream)
+                    e1.record(st)
+                    if rc != 0:
+                        N.check(rc, o.name)
+            st.synchronize()
+            for i, o in enumerate(ops):
+                ms = sum(ev[r][i][0].elapsed_time(ev[r][i][1]) for r in range(reps)) / reps
+                out.append((o.name, o.meta, ms))
+        return out
+
     # ------------------------------------------------------------------ public entry points
     @torch.no_grad()
-    def run(self, im, lmb, mode='eval', want_elem=False, want_im_hat=False):
+    def run(self, im, lmb, mode='eval', want_elem=False, want_im_hat=False, check_range=True):
+        """im: [B,3,H,W] fp32 in [0,1], on the host (pinned for an async copy) or on the device; lmb: [B]."""
         self.refresh_weights()
         B, _, H, W = im.shape
         with torch.cuda.device(self.device):
             P = self._get_plan((B, H, W, mode, want_elem), lambda: self._build_forward_plan(B, H, W, mode, want_elem))
             P.im.copy_(im, non_blocking=True)
             P.lmb.copy_(lmb.to(torch.float32), non_blocking=True)
+            rng = torch.aminmax(P.im) if check_range else None        # read back with the results: one sync
             if mode == 'train':
                 for nz in P.noise:         # same generator order as the reference: one uniform_ per layer
                     nz.uniform_(-0.5, 0.5)
             self._launch(P)
             if mode == 'compress':
-                return dict(strings=self._encode_strings(P))
+                strings = self._encode_strings(P)
+                self._assert_range(rng)
+                return dict(strings=strings)
             P.stats_host.copy_(P.stats, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
+            self._assert_range(rng)
             res = dict(stats=P.stats.clone(), stats_host=P.stats_host.numpy().copy(), x_hat=P.x_hat)
             if want_im_hat:
                 res['im_hat'] = P.im_hat.clone()
@@ -436,6 +481,13 @@ class QarvEngine:
                 res['kl_elem'] = [self._nchw(k, B, l) for k, l in zip(P.kl_elem, P.layout)]
                 res['z'] = [self._nchw(z, B, l) for z, l in zip(P.z, P.layout)]
             return res
+
+    @staticmethod
+    def _assert_range(rng):
+        # reference: assert 0 <= im.min() <= im.max() <= 1 (lvae/models/qarv/model.py:220)
+        if rng is not None:
+            lo, hi = float(rng[0]), float(rng[1])
+            assert 0 <= lo <= hi <= 1, f'image values must lie in [0, 1], got [{lo}, {hi}]'
 
     @staticmethod
     def _nchw(t, B, lay):

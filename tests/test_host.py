@@ -1,0 +1,184 @@
+"""Host-side logic (no GPU): C rANS coder + CDF builder against the oracle and the reference-made
+fixtures, bit-stream container, model surface / state-dict contract, error conventions."""
+import copy
+import ctypes as C
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+import lvae_oracle as O
+
+
+def _enc(lib, sym, idx, tables):
+    cdf, clen, off = (np.ascontiguousarray(t.numpy()) for t in tables)
+    sym = np.ascontiguousarray(sym, dtype=np.int32)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    cap = int(lib.lvae_rans_bound(sym.size))
+    buf = np.empty(cap, dtype=np.uint8)
+    n = C.c_int64(0)
+    rc = lib.lvae_rans_encode(sym.ctypes.data, idx.ctypes.data, sym.size, cdf.ctypes.data, cdf.shape[1],
+                              clen.ctypes.data, off.ctypes.data, cdf.shape[0], buf.ctypes.data, cap, C.byref(n))
+    assert rc == 0
+    return buf[:n.value].tobytes()
+
+
+def _dec(lib, data, idx, tables):
+    cdf, clen, off = (np.ascontiguousarray(t.numpy()) for t in tables)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    out = np.empty(idx.size, dtype=np.int32)
+    d = np.frombuffer(data, dtype=np.uint8)
+    rc = lib.lvae_rans_decode(d.ctypes.data, d.size, idx.ctypes.data, idx.size, cdf.ctypes.data, cdf.shape[1],
+                              clen.ctypes.data, off.ctypes.data, cdf.shape[0], out.ctypes.data)
+    return rc, out
+
+
+@pytest.fixture(scope='module')
+def tables():
+    return O.build_cdf_tables()
+
+
+def test_c_cdf_builder_equals_reference_tables(native_lib, golden):
+    from lvae.models import entropy_coding as ec
+    k = golden('entropy_kat')
+    cdf, length, offset = ec.build_cdf_tables(ec.default_scale_table())
+    assert np.array_equal(cdf.numpy(), k['cdf'])
+    assert np.array_equal(length.numpy(), k['cdf_length'])
+    assert np.array_equal(offset.numpy(), k['offset'])
+    assert np.array_equal(ec.default_scale_table().numpy(), k['scale_table'])
+
+
+def test_c_pmf_to_quantized_cdf_steals_for_zero_bins(native_lib):
+    pmf = np.array([0.5, 1e-9, 0.25, 0.25 - 1e-9, 0.0], dtype=np.float32)
+    out = np.zeros(6, dtype=np.int32)
+    assert native_lib.lvae_pmf_to_quantized_cdf(pmf.ctypes.data, 5, 16, out.ctypes.data) == 0
+    assert out.tolist() == O.pmf_to_quantized_cdf(pmf.tolist(), 16)
+    assert out[-1] == 65536 and np.all(np.diff(out) >= 1)
+    bad = np.array([0.5, float('nan')], dtype=np.float32)
+    assert native_lib.lvae_pmf_to_quantized_cdf(bad.ctypes.data, 2, 16, out.ctypes.data) == -1
+
+
+def test_c_rans_equals_python_oracle_and_roundtrips(native_lib, tables):
+    g = torch.Generator().manual_seed(3)
+    n = 6000
+    idx = torch.randint(0, 64, (n,), generator=g).int().numpy()
+    sym = torch.round(torch.randn(n, generator=g) * 4).int().numpy()
+    sym[[5, 900, n - 1]] = [400, -300, 70000]           # bypass path: 4-bit nibbles
+    data = _enc(native_lib, sym, idx, tables)
+    assert data == O.rans_encode(sym.tolist(), idx.tolist(), *tables)
+    rc, out = _dec(native_lib, data, idx, tables)
+    assert rc == 0 and np.array_equal(out, sym)
+    assert O.rans_decode(data, idx.tolist(), *tables) == sym.tolist()
+
+
+def test_c_rans_golden_stream(native_lib, tables, golden):
+    """The byte stream the reference produced for config 1 is reproduced from its symbols/indexes."""
+    g = golden('qarv_rand_1x64x64')
+    blob = g['bytes0'].tobytes()
+    from lvae.utils import coding
+    strings = coding.unpack_byte_string(blob[10:])
+    assert len(strings) == 9
+    for li, s in enumerate(strings):
+        sym = g[f'sym{li}'][0].astype(np.int32).reshape(-1)
+        idx = g[f'idx{li}'][0].astype(np.int32).reshape(-1)
+        assert _enc(native_lib, sym, idx, tables) == s
+        rc, out = _dec(native_lib, s, idx, tables)
+        assert rc == 0 and np.array_equal(out, sym)
+
+
+def test_c_rans_edge_cases(native_lib, tables):
+    empty = np.zeros(0, dtype=np.int32)
+    data = _enc(native_lib, empty, empty, tables)
+    assert len(data) == 8                                 # just the flushed 64-bit state
+    rc, out = _dec(native_lib, data, empty, tables)
+    assert rc == 0 and out.size == 0
+    sym = np.array([0, 1, -1, 2], dtype=np.int32)
+    idx = np.array([0, 10, 63, 30], dtype=np.int32)
+    data = _enc(native_lib, sym, idx, tables)
+    rc, _ = _dec(native_lib, data[:4], idx, tables)       # truncated
+    assert rc == -3
+    rc, _ = _dec(native_lib, data, np.array([0, 10, 64, 30], dtype=np.int32), tables)   # index out of table
+    assert rc == -1
+
+
+def test_container_roundtrip_and_layout():
+    from lvae.utils import coding
+    strings = [b'', b'abc', bytes(range(256)) * 3, b'\x00']
+    blob = coding.pack_byte_strings(strings)
+    assert blob == O.pack_byte_strings(strings)
+    assert blob[0] == 4 and struct.unpack('4I', blob[1:17]) == (0, 3, 768, 1)
+    assert coding.unpack_byte_string(blob) == strings
+    with pytest.raises(AssertionError):
+        coding.unpack_byte_string(blob + b'x')
+
+
+def test_bd_rate_identity_and_shift():
+    from lvae.utils.coding import bd_rate
+    r = [0.2, 0.4, 0.8, 1.6]
+    p = [30.0, 33.0, 36.0, 39.0]
+    assert abs(bd_rate(r, p, r, p)) < 1e-9
+    assert abs(bd_rate(r, p, [x * 0.9 for x in r], p) + 10.0) < 1e-6
+
+
+def test_model_surface_and_state_dict_contract(native_lib, sensitised_sd):
+    import lvae
+    torch.manual_seed(0)
+    m = lvae.get_model('qarv_base')
+    names = [k for k, _ in m.named_parameters()]
+    want = dict(O.qarv_param_shapes())
+    assert sorted(names) == sorted(want)
+    for k, p in m.named_parameters():
+        assert tuple(p.shape) == tuple(want[k]), k
+    assert sum(p.numel() for p in m.parameters()) == 93_433_104 or round(sum(p.numel() for p in m.parameters()) / 1e6, 3) == 93.433
+    sd = m.state_dict()
+    assert len(sd) == 952                                   # 907 params + 45 buffers
+    assert 'dec_blocks.0.discrete_gaussian._quantized_cdf' in sd
+    assert 'dec_blocks.0.discrete_gaussian.likelihood_lower_bound.bound' in sd
+    assert not any(k.endswith('scale_table') or k == '_dummy' for k in sd)
+    missing, unexpected = m.load_state_dict(sensitised_sd, strict=False)
+    assert not unexpected and all('discrete_gaussian' in k for k in missing)
+    for attr in ('forward', 'forward_end2end', 'compress_mode', 'compress', 'decompress', 'compress_file',
+                 'decompress_file', 'self_evaluate', 'conditional_sample', 'unconditional_sample', 'study',
+                 'sample_lmb', 'expand_to_tensor'):
+        assert callable(getattr(m, attr))
+    assert m.num_latents == 9 and m.max_stride == 64 and m.lmb_range == (16.0, 2048.0) and m.default_lmb == 2048.0
+    # optimizer param groups key on these substrings (lvae/trainer.py:182-194)
+    assert all(('.weight' in k) or ('.bias' in k) or k.endswith('gamma') or k == 'bias' for k in names)
+    m2 = copy.deepcopy(m)                                   # EMA (trainer.py:311)
+    assert m2.__dict__['_engine'] is None and torch.equal(m2.bias, m.bias)
+    str(m)
+
+
+def test_default_init_matches_reference_conventions(native_lib):
+    import lvae
+    torch.manual_seed(0)
+    m = lvae.get_model('qarv_base')
+    sd = m.state_dict()
+    assert float(sd['encoder.enc_blocks.1.gamma'].flatten()[0]) == pytest.approx(1e-6)
+    assert torch.count_nonzero(sd['encoder.enc_blocks.0.bias']) == 0
+    assert torch.count_nonzero(sd['dec_blocks.0.prior.bias']) == 0
+    assert torch.count_nonzero(sd['bias']) == 0
+    assert torch.count_nonzero(sd['encoder.enc_blocks.1.mlp.fc1.bias']) > 0      # Linear keeps torch default init
+
+
+def test_no_cpu_fallback_and_error_conventions(native_lib):
+    import lvae
+    m = lvae.get_model('qarv_base').eval()
+    im = torch.rand(1, 3, 64, 64)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        m(im, lmb=torch.tensor([64.0]))
+    with pytest.raises(AssertionError):
+        m(torch.rand(1, 3, 65, 64), lmb=torch.tensor([64.0]))
+    with pytest.raises(ValueError):
+        m.forward_end2end(im, 64.0, mode='bogus')
+    with pytest.raises(AssertionError):
+        m.compress(torch.rand(2, 3, 64, 64))
+    with pytest.raises(KeyError):
+        lvae.get_model('no_such_model')
+    blk = m.dec_blocks[0]
+    with pytest.raises(ValueError, match='Uninitialized CDFs'):
+        blk.discrete_gaussian.host_tables()
+    m.compress_mode()
+    cdf, clen, off = blk.discrete_gaussian.host_tables()
+    assert cdf.shape == (64, 249) and clen.max() == 249 and off.min() == -123

@@ -1,0 +1,123 @@
+"""Pins oracle/lvae_oracle.py: (1) against the committed golden fixtures (made by the UNMODIFIED
+reference through oracle/shims, see oracle/gen_golden.py) -- runs everywhere; (2) against the
+reference itself when /root/reference is present (build container only); (3) against the
+known answers of SURVEY.md Appendix A.  CPU only."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import lvae_oracle as O
+import ref_loader
+from oracle_inputs import CASES, make_input
+
+
+@pytest.fixture(scope='module')
+def sd(sensitised_sd):
+    return sensitised_sd
+
+
+def test_param_shapes_count_matches_readme():
+    # lvae/models/qarv/README.md:18 -- 93.4 M parameters (93.433 M, 907 tensors)
+    shapes = O.qarv_param_shapes()
+    n = sum(int(np.prod(s)) for _, s in shapes)
+    assert len(shapes) == 907
+    assert round(n / 1e6, 3) == 93.433
+
+
+def test_entropy_kat_appendix_a(golden):
+    k = golden('entropy_kat')
+    qm, pm, pv = (torch.from_numpy(k[n]) for n in ('qm', 'pm', 'pv'))
+    z, P = O.eval_quantize_likelihood(qm, pm, pv)
+    assert torch.equal(z, torch.from_numpy(k['z']))
+    assert torch.equal(P, torch.from_numpy(k['P']))
+    assert torch.equal(O.symbols(qm, pm), torch.from_numpy(k['sym']))
+    assert torch.equal(O.build_indexes(pv), torch.from_numpy(k['idx']))
+    # hand-checked rows of SURVEY Appendix A (half-to-even, floors, index mapping)
+    assert O.symbols(qm, pm).tolist() == [0, 0, 2, 2, 0, -2, 3, -8, 0, 12, 0, 40]
+    assert O.build_indexes(pv).tolist() == [27, 27, 27, 8, 0, 19, 36, 0, 13, 4, 63, 63]
+    kl = -torch.log(P)
+    assert abs(kl[0].item() - 0.9599164) < 1e-6 and abs(kl[3].item() - 20.7232666) < 1e-5
+    lp = O.gaussian_log_prob_mass(torch.zeros(5), torch.from_numpy(k['train_scale']), torch.from_numpy(k['train_x']))
+    assert torch.equal(lp, torch.from_numpy(k['train_logp']))
+    assert abs(lp[1].item() + 5.1198306) < 1e-6 and abs(lp[3].item() + 41.4189377) < 1e-5
+
+
+def test_prior_floor():
+    pm, pv = O.prior_transform(torch.tensor([0.0, -1e9, 0.0, 0.0]).view(1, 4, 1, 1))
+    assert abs(pv.flatten()[0].item() - 1.10025895) < 1e-6      # plogv_raw = 0
+    pm, pv = O.prior_transform(torch.tensor([0.0, -1e9]).view(1, 2, 1, 1))
+    assert abs(pv.item() - 0.100258850) < 1e-7                  # floor e^-2.3
+
+
+def test_cdf_tables_match_reference_fixture(golden):
+    k = golden('entropy_kat')
+    cdf, length, offset = O.build_cdf_tables()
+    assert torch.equal(cdf, torch.from_numpy(k['cdf']))
+    assert torch.equal(length, torch.from_numpy(k['cdf_length']))
+    assert torch.equal(offset, torch.from_numpy(k['offset']))
+    assert cdf[0, :5].tolist() == [0, 1, 65534, 65535, 65536] and offset[0].item() == -1
+    assert torch.equal(torch.from_numpy(k['scale_table']), O.default_scale_table())
+
+
+@pytest.mark.parametrize('name', ['qarv_rand_1x64x64', 'qarv_synth_3x64x128', 'qarv_rand_2x128x192'])
+def test_oracle_forward_matches_golden(name, golden, sd):
+    g = golden(name)
+    kind, nB, H, W, lmbs, seed = CASES[name]
+    im = make_input(kind, nB, H, W, seed)
+    out = O.qarv_forward(sd, im, torch.tensor(lmbs))
+    assert np.float32(out['loss'].item()) == g['loss']
+    assert out['bppix'] == float(g['bppix']) and out['mse'] == float(g['mse']) and out['psnr'] == float(g['psnr'])
+    assert torch.equal(out['im_hat'], torch.from_numpy(g['im_hat']))
+    for li, r in enumerate(out['records']):
+        assert torch.equal(r['z'], torch.from_numpy(g[f'z{li}']))
+        assert torch.equal(r['sym'], torch.from_numpy(g[f'sym{li}'].astype(np.int32)))
+        assert torch.equal(r['idx'], torch.from_numpy(g[f'idx{li}'].astype(np.int32)))
+        assert torch.equal(r['kl'].sum(dim=(1, 2, 3)), torch.from_numpy(g['kl_per_image'][li]))
+
+
+def test_oracle_compress_decompress_matches_golden(golden, sd):
+    name = 'qarv_rand_1x64x64'
+    g = golden(name)
+    kind, nB, H, W, lmbs, seed = CASES[name]
+    im = make_input(kind, nB, H, W, seed)
+    blob = O.qarv_compress(sd, im, lmbs[0])
+    assert blob == g['bytes0'].tobytes()
+    rec = O.qarv_decompress(sd, blob)
+    assert torch.equal(rec, torch.from_numpy(g['dec_im_hat']))
+
+
+def test_rans_python_roundtrip_with_bypass():
+    tables = O.build_cdf_tables()
+    g = torch.Generator().manual_seed(5)
+    idx = torch.randint(0, 64, (4000,), generator=g).tolist()
+    sym = torch.round(torch.randn(4000, generator=g) * 3).int().tolist()
+    sym[7], sym[100], sym[3999] = 400, -300, 70000
+    data = O.rans_encode(sym, idx, *tables)
+    assert O.rans_decode(data, idx, *tables) == sym
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not on this machine')
+def test_oracle_equals_live_reference(sd):
+    """Bit-exact agreement with the reference's own Python run in this process."""
+    ref = ref_loader.load_reference()
+    try:
+        torch.manual_seed(0)
+        model = ref.get_model('qarv_base').eval()
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not unexpected
+        ref_keys = [k for k, _ in model.named_parameters()]
+        assert sorted(ref_keys) == sorted(k for k, _ in O.qarv_param_shapes())
+        for k, s in O.qarv_param_shapes():
+            assert tuple(model.state_dict()[k].shape) == tuple(s), k
+        im = torch.rand(2, 3, 64, 128, generator=torch.Generator().manual_seed(11))
+        lmb = torch.tensor([100.0, 1500.0])
+        with torch.no_grad():
+            st = model(im, lmb=lmb, return_rec=True)
+        out = O.qarv_forward(sd, im, lmb)
+        assert st['loss'].item() == out['loss'].item()
+        assert st['bppix'] == out['bppix'] and st['psnr'] == out['psnr'] and st['mse'] == out['mse']
+        assert torch.equal(st['im_hat'], out['im_hat'])
+    finally:
+        ref_loader.unload_reference()
