@@ -36,9 +36,39 @@ void set_error(const char* fmt, ...);
     }                                                                               \
   } while (0)
 
-// torch.nn.GELU() (erf form): 0.5 * x * (1 + erf(x / sqrt(2)))  -- ATen: x * 0.5 * (1 + erf(x * M_SQRT1_2))
+// erf as ATen's CPU GELU kernel evaluates it (the parity oracle is the reference on the CPU): at::vec::Vectorized
+// <float>::erf(), i.e. Abramowitz-Stegun 7.1.26 in fp32 with FMAs (torch/include/ATen/cpu/vec/vec512/
+// vec512_float.h:269-299; |error| <= 1.5e-7 -- larger than an fp32 ulp, so matching the formula, not the true
+// erf, is what keeps hidden activations within rounding noise of the oracle).
+__device__ __forceinline__ float erf_aten_vec(float x) {
+  const float a = fabsf(x);
+  const float t = __fdiv_rn(1.0f, fmaf(0.3275911f, a, 1.0f));
+  float r = fmaf(1.061405429f, t, -1.453152027f);
+  r = fmaf(r, t, 1.421413741f);
+  r = fmaf(r, t, -0.284496736f);
+  r = fmaf(r, t, 0.254829592f);
+  const float e = expf(-__fmul_rn(x, x));
+  const float res = fmaf(__fmul_rn(-e, t), r, 1.0f);
+  return copysignf(res, x);
+}
+
+// torch.nn.GELU() (erf form) on CPU: x * 0.5 * (1 + erf(x * M_SQRT1_2))  (ATen native/cpu/Activation.cpp GeluKernelImpl)
 __device__ __forceinline__ float gelu_erf(float x) {
-  return __fmul_rn(__fmul_rn(x, 0.5f), __fadd_rn(1.0f, erff(__fmul_rn(x, 0.70710678118654752440f))));
+  return __fmul_rn(__fmul_rn(x, 0.5f), __fadd_rn(1.0f, erf_aten_vec(__fmul_rn(x, 0.70710678118654752440f))));
+}
+
+// torch.erf on CPU float tensors (what td.Normal.cdf calls): a <= 0.55-ulp erf that saturates to +-1 from
+// |x| >= 3.8325069 (measured against this image's torch 2.11 / MKL build over every float in [1e-3, 4.5]:
+// 97 % of results equal the correctly rounded value, the rest are off by one ulp only where the true value is
+// within 0.05 ulp of a rounding midpoint).  CUDA's erff (2 ulp) saturates only from 3.919, which moves tail
+// likelihoods by whole quanta of 2^-25; 1 - erfcf(|x|) is correctly rounded except near midpoints.
+__device__ __forceinline__ float erf_torch_cpu(float x) {
+  const float a = fabsf(x);
+  float r;
+  if (a >= 3.8325069f) r = 1.0f;
+  else if (a > 1.5f) r = __fsub_rn(1.0f, erfcf(a));   // erfcf: 4 ulp relative -> < 0.3 ulp of erf here
+  else r = erff(a);
+  return copysignf(r, x);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -32,7 +32,7 @@ __device__ __forceinline__ float prior_scale(float plogv_raw) {
 // td.Normal(0,1).cdf(t) = 0.5 * (1 + erf((t - 0) * (1/1) / sqrt(2)))
 __device__ __forceinline__ float std_normal_cdf(float t) {
   const float a = __fdiv_rn(t, 1.4142135623730951f);
-  return __fmul_rn(0.5f, __fadd_rn(1.0f, erff(a)));
+  return __fmul_rn(0.5f, __fadd_rn(1.0f, erf_torch_cpu(a)));
 }
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -94,8 +94,8 @@ __global__ void __launch_bounds__(LT) latent_kernel(
         zz = __fadd_rn(q, noise[m * zdim + c]);
         // td.Normal(pm, pv).cdf(x) = 0.5*(1+erf((x-pm)*(1/pv)/sqrt(2)))
         const float rcp = __frcp_rn(pv);
-        const float cu = __fmul_rn(0.5f, __fadd_rn(1.0f, erff(__fdiv_rn(__fmul_rn(__fsub_rn(__fadd_rn(zz, 0.5f), pm), rcp), 1.4142135623730951f))));
-        const float cl = __fmul_rn(0.5f, __fadd_rn(1.0f, erff(__fdiv_rn(__fmul_rn(__fsub_rn(__fsub_rn(zz, 0.5f), pm), rcp), 1.4142135623730951f))));
+        const float cu = __fmul_rn(0.5f, __fadd_rn(1.0f, erf_torch_cpu(__fdiv_rn(__fmul_rn(__fsub_rn(__fadd_rn(zz, 0.5f), pm), rcp), 1.4142135623730951f))));
+        const float cl = __fmul_rn(0.5f, __fadd_rn(1.0f, erf_torch_cpu(__fdiv_rn(__fmul_rn(__fsub_rn(__fsub_rn(zz, 0.5f), pm), rcp), 1.4142135623730951f))));
         const float mass = __fsub_rn(cu, cl);
         float lp;
         if (mass > 1e-6f) {
