@@ -191,9 +191,17 @@ def test_train_mode_forward_uses_noise_and_matches_oracle(gpu_model, sensitised_
 
 
 def test_sampling_paths_run(gpu_model):
-    out = gpu_model.unconditional_sample(lmb=256.0, bhw_repeat=(2, 1, 2))
-    assert out.shape == (2, 3, 64, 128) and float(out.min()) >= 0 and float(out.max()) <= 1
+    """conditional_sample with the encoder's own latents reproduces forward()'s reconstruction (the decode-side
+    plan with host-supplied z); unconditional sampling is exercised at t = 0 (z = prior mean) because with seeded
+    random weights -- no trained checkpoint exists offline -- ancestral sampling at t = 1 diverges to inf in the
+    reference arithmetic as well."""
     im = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(1)).to(DEV)
     x_hat, lat = gpu_model.forward_end2end(im, 256.0, get_latent=True)
     rec = gpu_model.conditional_sample(256.0, [s['z'] for s in lat])
     assert (rec - gpu_model.process_output(x_hat)).abs().max().item() < 1e-5
+    out = gpu_model.unconditional_sample(lmb=256.0, bhw_repeat=(2, 1, 2), t=0.0)
+    assert out.shape == (2, 3, 64, 128)
+    assert bool(torch.isfinite(out).all()) and float(out.min()) >= 0 and float(out.max()) <= 1
+    # mixed: first latents given, the rest drawn at t = 0
+    mixed = gpu_model.conditional_sample(256.0, [lat[0]['z'], lat[1]['z']] + [None] * 7, t=0.0)
+    assert mixed.shape == (1, 3, 64, 64) and bool(torch.isfinite(mixed).all())
