@@ -1,9 +1,424 @@
-// tcgen05 tensor-core GEMM (placeholder until the TMA/UMMA kernel lands in this file).
+// tcgen05 tensor-core GEMM for the dense contractions of the path (LVAE_PREC_BF16X3 / LVAE_PREC_BF16).
+//
+//   out[m, n] = epilogue( sum_k A[m, k] * W[n, k] + bias[n] ),   A: [M, K], W: [N, K], both K-contiguous
+//
+// Operands are bf16 PLANES: every fp32 value x is carried as hi = rn_bf16(x), lo = rn_bf16(x - hi).
+// BF16X3 issues three MMAs per logical product (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM), which
+// restores ~2^-17 relative accuracy per product -- the mode in which the quantised latent symbols match
+// the fp32 CPU oracle; BF16 issues hi*hi only.
+//
+// Kernel structure (one persistent CTA per SM, 6 warps, no clusters):
+//   warp 0   TMA producer: cp.async.bulk.tensor.2d of the [128 x 64] A tile(s) and [BN x 64] W tile(s) of a
+//            k-block into a SWIZZLE_128B ring of shared-memory stages, completion on an mbarrier
+//   warp 1   allocates TMEM, then one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BN,
+//            K = 16 per instruction) from shared-memory descriptors; tcgen05.commit releases the stage and,
+//            after the last k-block, publishes the accumulator
+//   warps 2-5  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (32 lanes per warp), transpose 32 x 32
+//            chunks through padded shared memory so that global traffic is 128-byte coalesced, apply
+//            bias / GELU / layer-scale + residual / pixel-shuffle, write fp32 and/or bf16 hi-lo planes
+// Two accumulator buffers in TMEM (2 x BN <= 512 columns) let the epilogue of tile i overlap the MMAs of
+// tile i+1.  K order is fixed, there is no split-K and BN depends on N only, so results are bit-reproducible
+// and do not depend on the batch an image travels in.
 #include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+
 namespace lvae {
-int64_t gemm_tc_workspace_bytes(const lvae_gemm_desc*) { return 0; }
-int gemm_tc_launch(const lvae_gemm_desc*, cudaStream_t) {
-  set_error("tensor-core GEMM not built into this library yet");
-  return LVAE_E_UNSUPPORTED;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;            // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_TILE = TC_BM * TC_BK * 2;     // 16 KB
+constexpr int TC_EPI_STAGE = 4 * 32 * 33 * 4;    // per-warp 32 x 33 fp32 transpose buffers
+
+struct TcParams {
+  int M, N, K;
+  int BN, n_tiles, num_tiles, stages, tmem_cols;
+  const float* bias; const float* gamma; const float* res;
+  float* out; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  int epi, r, Ho, Wo;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, 128-byte rows, SWIZZLE_128B (what the TMA box writes): descriptor
+// fields per cute/arch/mma_sm100_desc.hpp SmemDescriptor -- start address >> 4, LBO (unused for swizzled
+// K-major, 1), SBO = 8 rows * 128 B = 1024 B >> 4, version 1 (sm_100), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ float epi_value(const TcParams& p, int m, int n, float acc) {
+  float v = acc;
+  if (p.bias) v = __fadd_rn(v, __ldg(p.bias + n));
+  switch (p.epi) {
+    case LVAE_EPI_BIAS_GELU: v = gelu_erf(v); break;
+    case LVAE_EPI_SCALE_RES: v = __fadd_rn(__fmul_rn(v, __ldg(p.gamma + n)), p.res[(int64_t)m * p.N + n]); break;
+    case LVAE_EPI_BIAS_RES:  v = __fadd_rn(p.res[(int64_t)m * p.N + n], v); break;
+    default: break;
+  }
+  return v;
+}
+
+__device__ __forceinline__ void epi_store(const TcParams& p, int m, int n, float v) {
+  if (p.epi == LVAE_EPI_SHUFFLE_NHWC || p.epi == LVAE_EPI_SHUFFLE_NCHW) {
+    const int r = p.r, Co = p.N / (r * r);
+    const int q = n / Co, c = n - q * Co, i = q / r, j = q - i * r;
+    const int wo = m % p.Wo; const int t = m / p.Wo; const int ho = t % p.Ho; const int b = t / p.Ho;
+    const int Hr = p.Ho * r, Wr = p.Wo * r;
+    if (p.epi == LVAE_EPI_SHUFFLE_NHWC) p.out[(((int64_t)b * Hr + ho * r + i) * Wr + wo * r + j) * Co + c] = v;
+    else p.out[(((int64_t)b * Co + c) * Hr + ho * r + i) * Wr + wo * r + j] = v;
+    return;
+  }
+  const int64_t o = (int64_t)m * p.N + n;
+  if (p.out) p.out[o] = v;
+  if (p.out_hi) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    p.out_hi[o] = h;
+    if (p.out_lo) p.out_lo[o] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(h)));
+  }
+}
+
+template <int TERMS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+               const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment of the swizzled tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int NPL = (TERMS == 3) ? 2 : 1;                 // planes per operand
+  const int b_tile = p.BN * TC_BK * 2;
+  const int stage_bytes = NPL * (TC_A_TILE + b_tile);
+  uint8_t* epi_smem = smem + (size_t)p.stages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + TC_EPI_STAGE);
+  uint64_t* full_bar = bars;                                // [stages]
+  uint64_t* empty_bar = bars + p.stages;                    // [stages]
+  uint64_t* tfull_bar = bars + 2 * p.stages;                // [2]
+  uint64_t* tempty_bar = bars + 2 * p.stages + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (p.K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(tfull_bar + a), 1); mbar_init(smem_u32(tempty_bar + a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_hi) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int m0 = (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(smem_u32(empty_bar + s), ph ^ 1);
+          const uint32_t fb = smem_u32(full_bar + s);
+          mbar_expect_tx(fb, (uint32_t)stage_bytes);
+          const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+          tma_load_2d(base, &tm_a_hi, fb, kb * TC_BK, m0);
+          if (NPL == 2) tma_load_2d(base + TC_A_TILE, &tm_a_lo, fb, kb * TC_BK, m0);
+          tma_load_2d(base + NPL * TC_A_TILE, &tm_b_hi, fb, kb * TC_BK, n0);
+          if (NPL == 2) tma_load_2d(base + NPL * TC_A_TILE + b_tile, &tm_b_lo, fb, kb * TC_BK, n0);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D fp32, A/B bf16, both K-major
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    int s = 0; uint32_t ph = 0; int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(smem_u32(tempty_bar + acc), (((uint32_t)it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(smem_u32(full_bar + s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint64_t a_hi = make_desc(base), a_lo = make_desc(base + TC_A_TILE);
+          const uint64_t b_hi = make_desc(base + NPL * TC_A_TILE), b_lo = make_desc(base + NPL * TC_A_TILE + b_tile);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t ko = (uint64_t)(k * 2);           // 16 bf16 = 32 bytes = 2 x 16-byte units along K
+            tc_mma(d_tmem, a_hi + ko, b_hi + ko, idesc, (kb | k) ? 1u : 0u);
+            if (TERMS == 3) {
+              tc_mma(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              tc_mma(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
+            }
+          }
+          tc_commit(smem_u32(empty_bar + s));               // frees the stage once these MMAs have read it
+          if (kb == nkb - 1) tc_commit(smem_u32(tfull_bar + acc));
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ============================ epilogue (warps 2..5) ============================
+    const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+    float* stg = reinterpret_cast<float*>(epi_smem) + (warp - 2) * (32 * 33);
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int m0 = (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.BN;
+      mbar_wait(smem_u32(tfull_bar + acc), ((uint32_t)it >> 1) & 1);
+      tc_fence_after();
+      const int row0 = m0 + q * 32;
+      const int nchunks = p.BN / 32 + ((p.BN & 31) ? 1 : 0);
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c * 32);
+        tc_ld32(taddr, v);
+        tc_wait_ld();
+        if (c == nchunks - 1) {                              // accumulator fully read: hand the buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int n = n0 + c * 32 + lane;
+        const bool n_ok = (c * 32 + lane < p.BN) && (n < p.N);
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const int m = row0 + r;
+          if (m < p.M && n_ok) epi_store(p, m, n, epi_value(p, m, n, stg[r * 33 + lane]));
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- fp32 -> planes
+// im2col + hi/lo split of an NHWC fp32 activation (same K order as the packed weights: (ky, kx, c) then segment 1)
+__global__ void __launch_bounds__(256) split_im2col_kernel(
+    const float* __restrict__ a0, const float* __restrict__ a1, int B, int H, int W, int Ho, int Wo,
+    int C0, int C1, int ks, int stride, int pad, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+    int64_t total4, int K) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int K4 = K >> 2;
+  const int64_t m = i / K4; const int k = (int)(i - m * K4) * 4;
+  const int K0 = ks * ks * C0;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k < K0) {
+    const int tap = k / C0, c = k - tap * C0, ky = tap / ks, kx = tap - ky * ks;
+    const int wo = (int)(m % Wo); const int64_t t = m / Wo; const int ho = (int)(t % Ho); const int b = (int)(t / Ho);
+    const int hh = ho * stride - pad + ky, ww = wo * stride - pad + kx;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+      v = __ldg(reinterpret_cast<const float4*>(a0 + (((int64_t)b * H + hh) * W + ww) * C0 + c));
+  } else {
+    v = __ldg(reinterpret_cast<const float4*>(a1 + m * C1 + (k - K0)));
+  }
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2bfloat16_rn(f[j]);
+    l[j] = __float2bfloat16_rn(__fsub_rn(f[j], __bfloat162float(h[j])));
+  }
+  *reinterpret_cast<uint2*>(hi + m * K + k) = *reinterpret_cast<const uint2*>(h);
+  if (lo) *reinterpret_cast<uint2*>(lo + m * K + k) = *reinterpret_cast<const uint2*>(l);
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// [rows, K] bf16 row-major, box = [box_rows x 64], SWIZZLE_128B, zero fill outside the tensor
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LVAE_E_UNSUPPORTED; }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld box=%d", (int)r, (long long)rows, (long long)K, box_rows); return LVAE_E_BADARG; }
+  return 0;
+}
+
+static void tc_geometry(const lvae_gemm_desc* d, int* Ho, int* Wo, int64_t* M, int* K) {
+  *Ho = (d->H + 2 * d->pad - d->ksize) / d->stride + 1;
+  *Wo = (d->W + 2 * d->pad - d->ksize) / d->stride + 1;
+  *M = (int64_t)d->B * *Ho * *Wo;
+  *K = d->ksize * d->ksize * d->C0 + (d->a1 ? d->C1 : 0);
+}
+
+int64_t gemm_tc_workspace_bytes(const lvae_gemm_desc* d) {
+  if (d->a_hi) return 0;
+  int Ho, Wo, K; int64_t M;
+  tc_geometry(d, &Ho, &Wo, &M, &K);
+  return M * K * 2 * (d->precision == LVAE_PREC_BF16X3 ? 2 : 1);
+}
+
+static int pick_bn(int N) {
+  const int nt = (N + 255) / 256;
+  int bn = (N + nt - 1) / nt;
+  return (bn + 15) & ~15;
+}
+
+int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
+  const bool x3 = d->precision == LVAE_PREC_BF16X3;
+  int Ho, Wo, K; int64_t M64;
+  tc_geometry(d, &Ho, &Wo, &M64, &K);
+  LVAE_CHECK_ARG(M64 > 0 && M64 < (1ll << 31));
+  LVAE_CHECK_ARG(K % 8 == 0);                                  // 16-byte row pitch for the tensor maps
+  LVAE_CHECK_ARG(d->w_hi != nullptr && (!x3 || d->w_lo != nullptr));
+  const int M = (int)M64;
+  const __nv_bfloat16* a_hi = (const __nv_bfloat16*)d->a_hi;
+  const __nv_bfloat16* a_lo = (const __nv_bfloat16*)d->a_lo;
+  if (!a_hi) {
+    const int64_t need = gemm_tc_workspace_bytes(d);
+    if (!d->workspace || d->workspace_bytes < need) {
+      set_error("tensor-core GEMM from fp32 activations needs %lld workspace bytes, got %lld", (long long)need, (long long)d->workspace_bytes);
+      return LVAE_E_BADARG;
+    }
+    __nv_bfloat16* hi = (__nv_bfloat16*)d->workspace;
+    __nv_bfloat16* lo = x3 ? hi + (int64_t)M * K : nullptr;
+    const int64_t total4 = (int64_t)M * (K / 4);
+    split_im2col_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, stream>>>(
+        d->a0, d->a1, d->B, d->H, d->W, Ho, Wo, d->C0, d->a1 ? d->C1 : 0, d->ksize, d->stride, d->pad, hi, lo, total4, K);
+    LVAE_CUDA_LAUNCH_CHECK();
+    a_hi = hi; a_lo = lo;
+  } else {
+    LVAE_CHECK_ARG(!x3 || a_lo != nullptr);
+  }
+
+  TcParams p;
+  p.M = M; p.N = d->N; p.K = K;
+  p.BN = pick_bn(d->N);
+  p.n_tiles = (d->N + p.BN - 1) / p.BN;
+  p.num_tiles = ((M + TC_BM - 1) / TC_BM) * p.n_tiles;
+  int cols = 32; while (cols < 2 * p.BN) cols <<= 1;
+  p.tmem_cols = cols;
+  const int npl = x3 ? 2 : 1;
+  const int stage_bytes = npl * (TC_A_TILE + p.BN * TC_BK * 2);
+  const int fixed = 1024 + TC_EPI_STAGE + 256;                 // alignment slack + transpose buffers + barriers
+  int stages = (227 * 1024 - fixed) / stage_bytes;
+  if (stages > 6) stages = 6;
+  const int nkb = (K + TC_BK - 1) / TC_BK;
+  if (stages > nkb + 1) stages = nkb + 1 > 2 ? nkb + 1 : 2;
+  LVAE_CHECK_ARG(stages >= 2);
+  p.stages = stages;
+  p.bias = d->bias; p.gamma = d->gamma; p.res = d->res;
+  p.out = d->out; p.out_hi = (__nv_bfloat16*)d->out_hi; p.out_lo = (__nv_bfloat16*)d->out_lo;
+  p.epi = d->epilogue; p.r = d->shuffle_r; p.Ho = Ho; p.Wo = Wo;
+  LVAE_CHECK_ARG(p.out != nullptr || p.out_hi != nullptr);
+
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, a_hi, M, K, TC_BM))) return rc;
+  if ((rc = make_map(&mb_hi, d->w_hi, d->N, K, p.BN))) return rc;
+  if (x3) {
+    if ((rc = make_map(&ma_lo, a_lo, M, K, TC_BM))) return rc;
+    if ((rc = make_map(&mb_lo, d->w_lo, d->N, K, p.BN))) return rc;
+  } else { ma_lo = ma_hi; mb_lo = mb_hi; }
+
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    LVAE_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LVAE_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  const int smem = fixed + stages * stage_bytes;
+  const int grid = p.num_tiles < n_sm ? p.num_tiles : n_sm;
+  if (x3) gemm_tc_kernel<3><<<grid, TC_THREADS, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  else gemm_tc_kernel<1><<<grid, TC_THREADS, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace lvae
