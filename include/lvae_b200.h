@@ -75,10 +75,15 @@ typedef struct lvae_gemm_desc {
   float* out;
   int32_t shuffle_r;   /* r for the SHUFFLE epilogues */
   int32_t precision;   /* enum lvae_precision */
-  /* operand caches for the tensor-core path (device pointers, may be NULL in fp32 mode) */
-  const void* w_hi;    /* bf16 [N,K] high part of w */
+  /* operand planes for the tensor-core path (device pointers; unused in fp32 mode).  A value x travels as
+   * hi = rn_bf16(x), lo = rn_bf16(x - hi); BF16X3 uses both planes, BF16 only hi. */
+  const void* w_hi;    /* bf16 [N,K] high part of w (lvae_split_bf16) */
   const void* w_lo;    /* bf16 [N,K] low part  of w */
-  void* workspace;     /* device scratch, >= lvae_gemm_workspace_bytes() */
+  const void* a_hi;    /* optional pre-split A planes, plain [M,K] bf16 (written by lvae_dwconv_ln_adaln or by a */
+  const void* a_lo;    /*   previous lvae_gemm through out_hi/out_lo); when set, a0/a1 are not read              */
+  void* out_hi;        /* optional bf16 [M,N] planes of the epilogue result (non-shuffle epilogues); `out` may  */
+  void* out_lo;        /*   then be NULL                                                                         */
+  void* workspace;     /* device scratch >= lvae_gemm_workspace_bytes(): im2col + split of a0/a1 when a_hi == NULL */
   int64_t workspace_bytes;
 } lvae_gemm_desc;
 
@@ -97,6 +102,12 @@ int lvae_dwconv_ln_adaln(const float* x, const float* dw_w, const float* dw_b,
                          const float* ada, int64_t ada_stride, int64_t ada_off,
                          const float* ln_w, const float* ln_b,
                          float* y, int B, int H, int W, int C, int k, void* stream);
+/* Same operator writing the result as bf16 (hi, lo) planes [M, C] -- the A operand of the tensor-core fc1 GEMM
+ * (y_lo may be NULL for single-pass bf16). */
+int lvae_dwconv_ln_adaln_planes(const float* x, const float* dw_w, const float* dw_b,
+                                const float* ada, int64_t ada_stride, int64_t ada_off,
+                                const float* ln_w, const float* ln_b,
+                                void* y_hi, void* y_lo, int B, int H, int W, int C, int k, void* stream);
 
 /* ---- fused latent-layer kernels (qarv/model.py:51-53,90-96,104-113; CompressAI GaussianConditional) --
  * prior [M, 2*zdim] (pm | plogv_raw) and qm [M, zdim] are NHWC matrices; hw = h*w positions per image.

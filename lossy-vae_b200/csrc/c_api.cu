@@ -16,17 +16,19 @@ extern "C" int64_t lvae_gemm_workspace_bytes(const lvae_gemm_desc* d) {
 extern "C" int lvae_gemm(const lvae_gemm_desc* d, void* stream) {
   using namespace lvae;
   LVAE_CHECK_ARG(d != nullptr);
-  LVAE_CHECK_ARG(d->a0 && d->w && d->out);
+  LVAE_CHECK_ARG(d->w != nullptr);
+  LVAE_CHECK_ARG(d->a0 != nullptr || (d->a_hi != nullptr && d->precision != LVAE_PREC_FP32));
+  LVAE_CHECK_ARG(d->out != nullptr || (d->out_hi != nullptr && d->precision != LVAE_PREC_FP32));
   LVAE_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->N > 0);
   LVAE_CHECK_ARG(d->C0 > 0 && d->C0 % 4 == 0);
-  LVAE_CHECK_ARG(d->a1 == nullptr || (d->C1 > 0 && d->C1 % 4 == 0 && d->ksize == 1 && d->stride == 1 && d->pad == 0));
+  LVAE_CHECK_ARG(d->a1 == nullptr || d->a_hi != nullptr || (d->C1 > 0 && d->C1 % 4 == 0 && d->ksize == 1 && d->stride == 1 && d->pad == 0));
   LVAE_CHECK_ARG(d->ksize >= 1 && d->stride >= 1 && d->pad >= 0);
   LVAE_CHECK_ARG(d->H + 2 * d->pad >= d->ksize && d->W + 2 * d->pad >= d->ksize);
   LVAE_CHECK_ARG(d->epilogue >= LVAE_EPI_BIAS && d->epilogue <= LVAE_EPI_SHUFFLE_NCHW);
   if (d->epilogue == LVAE_EPI_SCALE_RES) LVAE_CHECK_ARG(d->gamma && d->res);
   if (d->epilogue == LVAE_EPI_BIAS_RES) LVAE_CHECK_ARG(d->res != nullptr);
   if (d->epilogue == LVAE_EPI_SHUFFLE_NHWC || d->epilogue == LVAE_EPI_SHUFFLE_NCHW)
-    LVAE_CHECK_ARG(d->shuffle_r >= 1 && d->N % (d->shuffle_r * d->shuffle_r) == 0);
+    LVAE_CHECK_ARG(d->shuffle_r >= 1 && d->N % (d->shuffle_r * d->shuffle_r) == 0 && d->out != nullptr);
   cudaStream_t st = (cudaStream_t)stream;
   switch (d->precision) {
     case LVAE_PREC_FP32: return gemm_f32_launch(d, st);

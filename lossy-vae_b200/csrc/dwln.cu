@@ -8,6 +8,7 @@
 // line.  The strip re-uses each loaded input pixel for up to k outputs (sliding window in registers).
 // LayerNorm is a two-pass (mean, then centred second moment) warp-shuffle reduction in fp32.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace lvae {
 
@@ -16,7 +17,8 @@ __global__ void __launch_bounds__(256) dwln_kernel(
     const float* __restrict__ x, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
     const float* __restrict__ ada, int64_t ada_stride, int64_t ada_off,
     const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-    float* __restrict__ y, int B, int H, int W, int strips_per_row, int64_t total_strips) {
+    float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
+    int B, int H, int W, int strips_per_row, int64_t total_strips) {
   constexpr int C = NJ * 64, PAD = (KS - 1) / 2, NX = S + KS - 1;
   const int lane = threadIdx.x & 31;
   const int64_t strip = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(256) dwln_kernel(
     }
     const float var = warp_sum(sq) * (1.0f / C);
     const float rstd = 1.0f / sqrtf(var + 1e-6f);
-    float* yrow = y + (((int64_t)b * H + h) * W + w) * C;
+    const int64_t yoff = (((int64_t)b * H + h) * W + w) * C;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int c = j * 64 + lane * 2;
@@ -96,7 +98,16 @@ __global__ void __launch_bounds__(256) dwln_kernel(
         v.x = __fadd_rn(__fmul_rn(v.x, __fadd_rn(1.0f, scale.x)), shift.x);
         v.y = __fadd_rn(__fmul_rn(v.y, __fadd_rn(1.0f, scale.y)), shift.y);
       }
-      *reinterpret_cast<float2*>(yrow + c) = v;
+      if (y != nullptr) *reinterpret_cast<float2*>(y + yoff + c) = v;
+      if (y_hi != nullptr) {
+        // A operand of the tensor-core fc1 GEMM: hi = rn_bf16(v), lo = rn_bf16(v - hi)
+        const __nv_bfloat162 hv = __floats2bfloat162_rn(v.x, v.y);
+        *reinterpret_cast<__nv_bfloat162*>(y_hi + yoff + c) = hv;
+        if (y_lo != nullptr) {
+          const float2 hf = __bfloat1622float2(hv);
+          *reinterpret_cast<__nv_bfloat162*>(y_lo + yoff + c) = __floats2bfloat162_rn(__fsub_rn(v.x, hf.x), __fsub_rn(v.y, hf.y));
+        }
+      }
     }
   }
 }
@@ -104,14 +115,14 @@ __global__ void __launch_bounds__(256) dwln_kernel(
 template <int NJ, int KS>
 static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, const float* ada,
                        int64_t ada_stride, int64_t ada_off, const float* ln_w, const float* ln_b,
-                       float* y, int B, int H, int W, cudaStream_t stream) {
+                       float* y, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, int B, int H, int W, cudaStream_t stream) {
   constexpr int S = (NJ >= 6) ? 4 : 4;
   const int spr = (W + S - 1) / S;
   const int64_t total = (int64_t)B * H * spr;
   const int warps = 8;
   const int64_t blocks = (total + warps - 1) / warps;
   dwln_kernel<NJ, KS, S><<<(unsigned)blocks, warps * 32, 0, stream>>>(
-      x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, B, H, W, spr, total);
+      x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, B, H, W, spr, total);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -119,31 +130,48 @@ static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, con
 template <int NJ>
 static int dispatch_k(int k, const float* x, const float* dw_w, const float* dw_b, const float* ada,
                       int64_t ada_stride, int64_t ada_off, const float* ln_w, const float* ln_b,
-                      float* y, int B, int H, int W, cudaStream_t stream) {
+                      float* y, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, int B, int H, int W, cudaStream_t stream) {
   switch (k) {
-    case 1: return launch_dwln<NJ, 1>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, B, H, W, stream);
-    case 3: return launch_dwln<NJ, 3>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, B, H, W, stream);
-    case 5: return launch_dwln<NJ, 5>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, B, H, W, stream);
-    case 7: return launch_dwln<NJ, 7>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, B, H, W, stream);
+    case 1: return launch_dwln<NJ, 1>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, B, H, W, stream);
+    case 3: return launch_dwln<NJ, 3>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, B, H, W, stream);
+    case 5: return launch_dwln<NJ, 5>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, B, H, W, stream);
+    case 7: return launch_dwln<NJ, 7>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, B, H, W, stream);
     default: set_error("dwconv kernel size %d unsupported", k); return LVAE_E_UNSUPPORTED;
   }
 }
 
 }  // namespace lvae
 
-extern "C" int lvae_dwconv_ln_adaln(const float* x, const float* dw_w, const float* dw_b,
-                                    const float* ada, int64_t ada_stride, int64_t ada_off,
-                                    const float* ln_w, const float* ln_b,
-                                    float* y, int B, int H, int W, int C, int k, void* stream) {
+static int dwln_dispatch(const float* x, const float* dw_w, const float* dw_b,
+                         const float* ada, int64_t ada_stride, int64_t ada_off,
+                         const float* ln_w, const float* ln_b, float* y, void* y_hi, void* y_lo,
+                         int B, int H, int W, int C, int k, void* stream) {
   using namespace lvae;
-  LVAE_CHECK_ARG(x && dw_w && dw_b && y && (ada || ln_w));
+  LVAE_CHECK_ARG(x && dw_w && dw_b && (y || y_hi) && (ada || ln_w));
   LVAE_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 64 == 0);
   cudaStream_t st = (cudaStream_t)stream;
-#define LVAE_DWLN_CASE(nj) case nj: return dispatch_k<nj>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, B, H, W, st);
+  __nv_bfloat16* h = (__nv_bfloat16*)y_hi; __nv_bfloat16* l = (__nv_bfloat16*)y_lo;
+#define LVAE_DWLN_CASE(nj) case nj: return dispatch_k<nj>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, h, l, B, H, W, st);
   switch (C / 64) {
     LVAE_DWLN_CASE(1) LVAE_DWLN_CASE(2) LVAE_DWLN_CASE(3) LVAE_DWLN_CASE(4)
     LVAE_DWLN_CASE(6) LVAE_DWLN_CASE(8)
     default: set_error("dwconv channel count %d unsupported (need C/64 in {1,2,3,4,6,8})", C); return LVAE_E_UNSUPPORTED;
   }
 #undef LVAE_DWLN_CASE
+}
+
+extern "C" int lvae_dwconv_ln_adaln(const float* x, const float* dw_w, const float* dw_b,
+                                    const float* ada, int64_t ada_stride, int64_t ada_off,
+                                    const float* ln_w, const float* ln_b,
+                                    float* y, int B, int H, int W, int C, int k, void* stream) {
+  LVAE_CHECK_ARG(y != nullptr);
+  return dwln_dispatch(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, nullptr, nullptr, B, H, W, C, k, stream);
+}
+
+extern "C" int lvae_dwconv_ln_adaln_planes(const float* x, const float* dw_w, const float* dw_b,
+                                           const float* ada, int64_t ada_stride, int64_t ada_off,
+                                           const float* ln_w, const float* ln_b,
+                                           void* y_hi, void* y_lo, int B, int H, int W, int C, int k, void* stream) {
+  LVAE_CHECK_ARG(y_hi != nullptr);
+  return dwln_dispatch(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, nullptr, y_hi, y_lo, B, H, W, C, k, stream);
 }

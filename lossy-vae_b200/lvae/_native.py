@@ -25,7 +25,7 @@ class GemmDesc(C.Structure):
         ('N', C.c_int32), ('epilogue', C.c_int32),
         ('gamma', _fp), ('res', _fp), ('out', _fp),
         ('shuffle_r', C.c_int32), ('precision', C.c_int32),
-        ('w_hi', _fp), ('w_lo', _fp),
+        ('w_hi', _fp), ('w_lo', _fp), ('a_hi', _fp), ('a_lo', _fp), ('out_hi', _fp), ('out_lo', _fp),
         ('workspace', _fp), ('workspace_bytes', C.c_int64),
     ]
 
@@ -38,6 +38,8 @@ _PROTOS = {
     'lvae_split_bf16': (C.c_int, [_fp, _fp, _fp, C.c_int64, _fp]),
     'lvae_dwconv_ln_adaln': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_dwconv_ln_adaln_planes': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp, _fp,
+                                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_latent_num_partials': (C.c_int, [C.c_int, C.c_int]),
     'lvae_latent_eval': (C.c_int, [_fp, _fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp, _fp,
                                    C.c_int, C.c_int, C.c_int, _fp]),
