@@ -55,10 +55,14 @@ enum lvae_epilogue {
 };
 
 enum lvae_precision {
-  LVAE_PREC_FP32 = 0,         /* fp32 FFMA on CUDA cores: closest to the CPU fp32 reference   */
-  LVAE_PREC_BF16X3 = 1,       /* tcgen05 kind::f16, hi/lo bf16 operand split, 3 MMAs, fp32 TMEM accumulate */
-  LVAE_PREC_BF16 = 2          /* tcgen05 single pass bf16 (non-parity fast mode)              */
+  LVAE_PREC_FP32 = 0,         /* fp32 FFMA on CUDA cores                                                      */
+  LVAE_PREC_BF16X3 = 1,       /* tcgen05 kind::f16, 2 bf16 planes per operand, 3 MMAs (hh + hm + mh): ~2^-17  */
+  LVAE_PREC_BF16 = 2,         /* tcgen05, 1 plane, 1 MMA: ~2^-8 (non-parity fast mode)                        */
+  LVAE_PREC_BF16X6 = 3        /* tcgen05, 3 bf16 planes, 6 MMAs (hh + hm + mh + mm + hl + lh): ~2^-23, the    */
+                              /* fp32-class mode in which quantised symbols match the fp32 CPU reference      */
 };
+/* planes per operand for a precision mode: fp32 0, bf16 1, bf16x3 2, bf16x6 3 */
+#define LVAE_MAX_PLANES 3
 
 typedef struct lvae_gemm_desc {
   const float* a0;     /* segment 0 activations, NHWC [B,H,W,C0] */
@@ -75,22 +79,23 @@ typedef struct lvae_gemm_desc {
   float* out;
   int32_t shuffle_r;   /* r for the SHUFFLE epilogues */
   int32_t precision;   /* enum lvae_precision */
-  /* operand planes for the tensor-core path (device pointers; unused in fp32 mode).  A value x travels as
-   * hi = rn_bf16(x), lo = rn_bf16(x - hi); BF16X3 uses both planes, BF16 only hi. */
-  const void* w_hi;    /* bf16 [N,K] high part of w (lvae_split_bf16) */
-  const void* w_lo;    /* bf16 [N,K] low part  of w */
-  const void* a_hi;    /* optional pre-split A planes, plain [M,K] bf16 (written by lvae_dwconv_ln_adaln or by a */
-  const void* a_lo;    /*   previous lvae_gemm through out_hi/out_lo); when set, a0/a1 are not read              */
-  void* out_hi;        /* optional bf16 [M,N] planes of the epilogue result (non-shuffle epilogues); `out` may  */
-  void* out_lo;        /*   then be NULL                                                                         */
-  void* workspace;     /* device scratch >= lvae_gemm_workspace_bytes(): im2col + split of a0/a1 when a_hi == NULL */
+  /* operand planes for the tensor-core path (device pointers; unused in fp32 mode).  A value x travels as the
+   * bf16 planes p0 = rn(x), p1 = rn(x - p0), p2 = rn(x - p0 - p1) (lvae_split_bf16); a mode reads its first
+   * 1 / 2 / 3 planes. */
+  const void* w_planes[3];    /* bf16 [N,K] planes of w */
+  const void* a_planes[3];    /* optional pre-split A planes, plain [M,K] bf16 (written by lvae_dwconv_ln_adaln_planes
+                               * or by a previous lvae_gemm through out_planes); when [0] is set, a0/a1 are not read */
+  void* out_planes[3];        /* optional bf16 [M,N] planes of the epilogue result (non-shuffle epilogues); `out`
+                               * may then be NULL */
+  void* workspace;            /* device scratch >= lvae_gemm_workspace_bytes(): im2col + split of a0/a1 when
+                               * a_planes[0] == NULL */
   int64_t workspace_bytes;
 } lvae_gemm_desc;
 
 int lvae_gemm(const lvae_gemm_desc* d, void* stream);
 int64_t lvae_gemm_workspace_bytes(const lvae_gemm_desc* d);
-/* split fp32 -> (hi, lo) bf16 pair, hi = rn(x), lo = rn(x - hi) (weights, once per weight version) */
-int lvae_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
+/* split fp32 -> bf16 planes p0 = rn(x), p1 = rn(x - p0), p2 = rn(x - p0 - p1); p1 / p2 may be NULL */
+int lvae_split_bf16(const float* x, void* p0, void* p1, void* p2, int64_t n, void* stream);
 
 /* ---- depthwise conv + LayerNorm + AdaLN (common.py:145-152) ------------------------------------
  * y[m, c] = LN_c( dwconv_kxk(x)[m, c] + dw_bias[c] ) * (1 + scale[b, c]) + shift[b, c]
@@ -102,12 +107,12 @@ int lvae_dwconv_ln_adaln(const float* x, const float* dw_w, const float* dw_b,
                          const float* ada, int64_t ada_stride, int64_t ada_off,
                          const float* ln_w, const float* ln_b,
                          float* y, int B, int H, int W, int C, int k, void* stream);
-/* Same operator writing the result as bf16 (hi, lo) planes [M, C] -- the A operand of the tensor-core fc1 GEMM
- * (y_lo may be NULL for single-pass bf16). */
+/* Same operator writing the result as bf16 planes [M, C] -- the A operand of the tensor-core fc1 GEMM
+ * (y1 / y2 may be NULL when the precision mode reads fewer planes). */
 int lvae_dwconv_ln_adaln_planes(const float* x, const float* dw_w, const float* dw_b,
                                 const float* ada, int64_t ada_stride, int64_t ada_off,
                                 const float* ln_w, const float* ln_b,
-                                void* y_hi, void* y_lo, int B, int H, int W, int C, int k, void* stream);
+                                void* y0, void* y1, void* y2, int B, int H, int W, int C, int k, void* stream);
 
 /* ---- fused latent-layer kernels (qarv/model.py:51-53,90-96,104-113; CompressAI GaussianConditional) --
  * prior [M, 2*zdim] (pm | plogv_raw) and qm [M, zdim] are NHWC matrices; hw = h*w positions per image.

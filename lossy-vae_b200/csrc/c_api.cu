@@ -17,11 +17,11 @@ extern "C" int lvae_gemm(const lvae_gemm_desc* d, void* stream) {
   using namespace lvae;
   LVAE_CHECK_ARG(d != nullptr);
   LVAE_CHECK_ARG(d->w != nullptr);
-  LVAE_CHECK_ARG(d->a0 != nullptr || (d->a_hi != nullptr && d->precision != LVAE_PREC_FP32));
-  LVAE_CHECK_ARG(d->out != nullptr || (d->out_hi != nullptr && d->precision != LVAE_PREC_FP32));
+  LVAE_CHECK_ARG(d->a0 != nullptr || (d->a_planes[0] != nullptr && d->precision != LVAE_PREC_FP32));
+  LVAE_CHECK_ARG(d->out != nullptr || (d->out_planes[0] != nullptr && d->precision != LVAE_PREC_FP32));
   LVAE_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->N > 0);
   LVAE_CHECK_ARG(d->C0 > 0 && d->C0 % 4 == 0);
-  LVAE_CHECK_ARG(d->a1 == nullptr || d->a_hi != nullptr || (d->C1 > 0 && d->C1 % 4 == 0 && d->ksize == 1 && d->stride == 1 && d->pad == 0));
+  LVAE_CHECK_ARG(d->a1 == nullptr || d->a_planes[0] != nullptr || (d->C1 > 0 && d->C1 % 4 == 0 && d->ksize == 1 && d->stride == 1 && d->pad == 0));
   LVAE_CHECK_ARG(d->ksize >= 1 && d->stride >= 1 && d->pad >= 0);
   LVAE_CHECK_ARG(d->H + 2 * d->pad >= d->ksize && d->W + 2 * d->pad >= d->ksize);
   LVAE_CHECK_ARG(d->epilogue >= LVAE_EPI_BIAS && d->epilogue <= LVAE_EPI_SHUFFLE_NCHW);
@@ -33,7 +33,8 @@ extern "C" int lvae_gemm(const lvae_gemm_desc* d, void* stream) {
   switch (d->precision) {
     case LVAE_PREC_FP32: return gemm_f32_launch(d, st);
     case LVAE_PREC_BF16X3:
-    case LVAE_PREC_BF16: return gemm_tc_launch(d, st);
+    case LVAE_PREC_BF16:
+    case LVAE_PREC_BF16X6: return gemm_tc_launch(d, st);
     default: set_error("unknown precision mode %d", d->precision); return LVAE_E_BADARG;
   }
 }

@@ -42,7 +42,7 @@ void set_error(const char* fmt, ...);
 // erf, is what keeps hidden activations within rounding noise of the oracle).
 __device__ __forceinline__ float erf_aten_vec(float x) {
   const float a = fabsf(x);
-  const float t = __fdiv_rn(1.0f, fmaf(0.3275911f, a, 1.0f));
+  const float t = __frcp_rn(fmaf(0.3275911f, a, 1.0f));        // IEEE reciprocal == _mm512_div_ps(1, .)
   float r = fmaf(1.061405429f, t, -1.453152027f);
   r = fmaf(r, t, 1.421413741f);
   r = fmaf(r, t, -0.284496736f);

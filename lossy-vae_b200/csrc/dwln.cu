@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) dwln_kernel(
     const float* __restrict__ x, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
     const float* __restrict__ ada, int64_t ada_stride, int64_t ada_off,
     const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-    float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
+    float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, __nv_bfloat16* __restrict__ y_l2,
     int B, int H, int W, int strips_per_row, int64_t total_strips) {
   constexpr int C = NJ * 64, PAD = (KS - 1) / 2, NX = S + KS - 1;
   const int lane = threadIdx.x & 31;
@@ -105,7 +105,13 @@ __global__ void __launch_bounds__(256) dwln_kernel(
         *reinterpret_cast<__nv_bfloat162*>(y_hi + yoff + c) = hv;
         if (y_lo != nullptr) {
           const float2 hf = __bfloat1622float2(hv);
-          *reinterpret_cast<__nv_bfloat162*>(y_lo + yoff + c) = __floats2bfloat162_rn(__fsub_rn(v.x, hf.x), __fsub_rn(v.y, hf.y));
+          const float2 r1 = make_float2(__fsub_rn(v.x, hf.x), __fsub_rn(v.y, hf.y));
+          const __nv_bfloat162 mv = __floats2bfloat162_rn(r1.x, r1.y);
+          *reinterpret_cast<__nv_bfloat162*>(y_lo + yoff + c) = mv;
+          if (y_l2 != nullptr) {
+            const float2 mf = __bfloat1622float2(mv);
+            *reinterpret_cast<__nv_bfloat162*>(y_l2 + yoff + c) = __floats2bfloat162_rn(__fsub_rn(r1.x, mf.x), __fsub_rn(r1.y, mf.y));
+          }
         }
       }
     }
@@ -115,14 +121,14 @@ __global__ void __launch_bounds__(256) dwln_kernel(
 template <int NJ, int KS>
 static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, const float* ada,
                        int64_t ada_stride, int64_t ada_off, const float* ln_w, const float* ln_b,
-                       float* y, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, int B, int H, int W, cudaStream_t stream) {
+                       float* y, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, __nv_bfloat16* y_l2, int B, int H, int W, cudaStream_t stream) {
   constexpr int S = (NJ >= 6) ? 4 : 4;
   const int spr = (W + S - 1) / S;
   const int64_t total = (int64_t)B * H * spr;
   const int warps = 8;
   const int64_t blocks = (total + warps - 1) / warps;
   dwln_kernel<NJ, KS, S><<<(unsigned)blocks, warps * 32, 0, stream>>>(
-      x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, B, H, W, spr, total);
+      x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, y_l2, B, H, W, spr, total);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -130,12 +136,12 @@ static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, con
 template <int NJ>
 static int dispatch_k(int k, const float* x, const float* dw_w, const float* dw_b, const float* ada,
                       int64_t ada_stride, int64_t ada_off, const float* ln_w, const float* ln_b,
-                      float* y, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, int B, int H, int W, cudaStream_t stream) {
+                      float* y, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, __nv_bfloat16* y_l2, int B, int H, int W, cudaStream_t stream) {
   switch (k) {
-    case 1: return launch_dwln<NJ, 1>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, B, H, W, stream);
-    case 3: return launch_dwln<NJ, 3>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, B, H, W, stream);
-    case 5: return launch_dwln<NJ, 5>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, B, H, W, stream);
-    case 7: return launch_dwln<NJ, 7>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, B, H, W, stream);
+    case 1: return launch_dwln<NJ, 1>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, y_l2, B, H, W, stream);
+    case 3: return launch_dwln<NJ, 3>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, y_l2, B, H, W, stream);
+    case 5: return launch_dwln<NJ, 5>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, y_l2, B, H, W, stream);
+    case 7: return launch_dwln<NJ, 7>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y_hi, y_lo, y_l2, B, H, W, stream);
     default: set_error("dwconv kernel size %d unsupported", k); return LVAE_E_UNSUPPORTED;
   }
 }
@@ -144,14 +150,14 @@ static int dispatch_k(int k, const float* x, const float* dw_w, const float* dw_
 
 static int dwln_dispatch(const float* x, const float* dw_w, const float* dw_b,
                          const float* ada, int64_t ada_stride, int64_t ada_off,
-                         const float* ln_w, const float* ln_b, float* y, void* y_hi, void* y_lo,
+                         const float* ln_w, const float* ln_b, float* y, void* y_hi, void* y_lo, void* y_l2,
                          int B, int H, int W, int C, int k, void* stream) {
   using namespace lvae;
   LVAE_CHECK_ARG(x && dw_w && dw_b && (y || y_hi) && (ada || ln_w));
   LVAE_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 64 == 0);
   cudaStream_t st = (cudaStream_t)stream;
-  __nv_bfloat16* h = (__nv_bfloat16*)y_hi; __nv_bfloat16* l = (__nv_bfloat16*)y_lo;
-#define LVAE_DWLN_CASE(nj) case nj: return dispatch_k<nj>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, h, l, B, H, W, st);
+  __nv_bfloat16* h = (__nv_bfloat16*)y_hi; __nv_bfloat16* l = (__nv_bfloat16*)y_lo; __nv_bfloat16* l2 = (__nv_bfloat16*)y_l2;
+#define LVAE_DWLN_CASE(nj) case nj: return dispatch_k<nj>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, h, l, l2, B, H, W, st);
   switch (C / 64) {
     LVAE_DWLN_CASE(1) LVAE_DWLN_CASE(2) LVAE_DWLN_CASE(3) LVAE_DWLN_CASE(4)
     LVAE_DWLN_CASE(6) LVAE_DWLN_CASE(8)
@@ -165,13 +171,13 @@ extern "C" int lvae_dwconv_ln_adaln(const float* x, const float* dw_w, const flo
                                     const float* ln_w, const float* ln_b,
                                     float* y, int B, int H, int W, int C, int k, void* stream) {
   LVAE_CHECK_ARG(y != nullptr);
-  return dwln_dispatch(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, nullptr, nullptr, B, H, W, C, k, stream);
+  return dwln_dispatch(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, nullptr, nullptr, nullptr, B, H, W, C, k, stream);
 }
 
 extern "C" int lvae_dwconv_ln_adaln_planes(const float* x, const float* dw_w, const float* dw_b,
                                            const float* ada, int64_t ada_stride, int64_t ada_off,
                                            const float* ln_w, const float* ln_b,
-                                           void* y_hi, void* y_lo, int B, int H, int W, int C, int k, void* stream) {
-  LVAE_CHECK_ARG(y_hi != nullptr);
-  return dwln_dispatch(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, nullptr, y_hi, y_lo, B, H, W, C, k, stream);
+                                           void* y0, void* y1, void* y2, int B, int H, int W, int C, int k, void* stream) {
+  LVAE_CHECK_ARG(y0 != nullptr && (y2 == nullptr || y1 != nullptr));
+  return dwln_dispatch(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, nullptr, y0, y1, y2, B, H, W, C, k, stream);
 }

@@ -2,10 +2,12 @@
 //
 //   out[m, n] = epilogue( sum_k A[m, k] * W[n, k] + bias[n] ),   A: [M, K], W: [N, K], both K-contiguous
 //
-// Operands are bf16 PLANES: every fp32 value x is carried as hi = rn_bf16(x), lo = rn_bf16(x - hi).
-// BF16X3 issues three MMAs per logical product (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM), which
-// restores ~2^-17 relative accuracy per product -- the mode in which the quantised latent symbols match
-// the fp32 CPU oracle; BF16 issues hi*hi only.
+// Operands are bf16 PLANES: an fp32 value x is carried as p0 = rn(x), p1 = rn(x - p0), p2 = rn(x - p0 - p1)
+// (24 mantissa bits in three 8-bit pieces).  Per logical product, with fp32 accumulation in TMEM:
+//   BF16    1 plane,  1 MMA   p0*p0                                        ~2^-8
+//   BF16X3  2 planes, 3 MMAs  p0*p0 + p0*p1 + p1*p0                        ~2^-17
+//   BF16X6  3 planes, 6 MMAs  ... + p1*p1 + p0*p2 + p2*p0                  ~2^-23 (fp32-class: the mode in which
+//                                                                          the quantised symbols match the CPU oracle)
 //
 // Kernel structure (one persistent CTA per SM, 6 warps, no clusters):
 //   warp 0   TMA producer: cp.async.bulk.tensor.2d of the [128 x 64] A tile(s) and [BN x 64] W tile(s) of a
@@ -27,18 +29,19 @@
 namespace lvae {
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;            // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int TC_THREADS = 192;
-constexpr int TC_A_TILE = TC_BM * TC_BK * 2;     // 16 KB
-constexpr int TC_EPI_STAGE = 4 * 32 * 33 * 4;    // per-warp 32 x 33 fp32 transpose buffers
+constexpr int TC_EPI_WARPS = 8;                  // two per TMEM lane quarter, alternating 32-column chunks
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_EPI_STAGE = TC_EPI_WARPS * 32 * 33 * 4;    // per-warp 32 x 33 word transpose buffers
 
 struct TcParams {
   int M, N, K;
-  int BN, n_tiles, num_tiles, stages, tmem_cols;
+  int BN, BK, n_tiles, num_tiles, stages, tmem_cols;   // BK: bf16 elements per k-block = one swizzle row (64 -> 128 B, 32 -> 64 B)
   const float* bias; const float* gamma; const float* res;
-  float* out; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  float* out; __nv_bfloat16* out_pl[3];
   int epi, r, Ho, Wo;
 };
+
+struct TcMaps { CUtensorMap a[3]; CUtensorMap b[3]; };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,13 +93,23 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major operand tile in shared memory, 128-byte rows, SWIZZLE_128B (what the TMA box writes): descriptor
+// K-major operand tile in shared memory, one swizzle row per matrix row (what the TMA box writes): descriptor
 // fields per cute/arch/mma_sm100_desc.hpp SmemDescriptor -- start address >> 4, LBO (unused for swizzled
-// K-major, 1), SBO = 8 rows * 128 B = 1024 B >> 4, version 1 (sm_100), layout type 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+// K-major, 1), SBO = 8 rows * row bytes >> 4, version 1 (sm_100), layout type 2 (SWIZZLE_128B) / 4 (SWIZZLE_64B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int bk) {
+  const uint64_t sbo = (uint64_t)(8 * bk * 2) >> 4;
+  const uint64_t layout = bk == 64 ? 2ull : 4ull;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
 __device__ __forceinline__ float epi_value(const TcParams& p, int m, int n, float acc) {
@@ -123,24 +136,27 @@ __device__ __forceinline__ void epi_store(const TcParams& p, int m, int n, float
   }
   const int64_t o = (int64_t)m * p.N + n;
   if (p.out) p.out[o] = v;
-  if (p.out_hi) {
+  if (p.out_pl[0]) {
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    p.out_hi[o] = h;
-    if (p.out_lo) p.out_lo[o] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(h)));
+    p.out_pl[0][o] = h;
+    if (p.out_pl[1]) {
+      const float r1 = __fsub_rn(v, __bfloat162float(h));
+      const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+      p.out_pl[1][o] = m;
+      if (p.out_pl[2]) p.out_pl[2][o] = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(m)));
+    }
   }
 }
 
-template <int TERMS>
+template <int NPL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-               const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-               const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment of the swizzled tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int NPL = (TERMS == 3) ? 2 : 1;                 // planes per operand
-  const int b_tile = p.BN * TC_BK * 2;
-  const int stage_bytes = NPL * (TC_A_TILE + b_tile);
+  const int a_tile = TC_BM * p.BK * 2;
+  const int b_tile = p.BN * p.BK * 2;
+  const int stage_bytes = NPL * (a_tile + b_tile);          // [A planes | B planes]
   uint8_t* epi_smem = smem + (size_t)p.stages * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + TC_EPI_STAGE);
   uint64_t* full_bar = bars;                                // [stages]
@@ -150,14 +166,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (p.K + TC_BK - 1) / TC_BK;
+  const int nkb = (p.K + p.BK - 1) / p.BK;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(tfull_bar + a), 1); mbar_init(smem_u32(tempty_bar + a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(tfull_bar + a), 1); mbar_init(smem_u32(tempty_bar + a), TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[0]) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
@@ -179,10 +195,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           const uint32_t fb = smem_u32(full_bar + s);
           mbar_expect_tx(fb, (uint32_t)stage_bytes);
           const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
-          tma_load_2d(base, &tm_a_hi, fb, kb * TC_BK, m0);
-          if (NPL == 2) tma_load_2d(base + TC_A_TILE, &tm_a_lo, fb, kb * TC_BK, m0);
-          tma_load_2d(base + NPL * TC_A_TILE, &tm_b_hi, fb, kb * TC_BK, n0);
-          if (NPL == 2) tma_load_2d(base + NPL * TC_A_TILE + b_tile, &tm_b_lo, fb, kb * TC_BK, n0);
+#pragma unroll
+          for (int pl = 0; pl < NPL; ++pl) {
+            tma_load_2d(base + pl * a_tile, &maps.a[pl], fb, kb * p.BK, m0);
+            tma_load_2d(base + NPL * a_tile + pl * b_tile, &maps.b[pl], fb, kb * p.BK, n0);
+          }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -202,16 +219,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         tc_fence_after();
         if (lane == 0) {
           const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t a_hi = make_desc(base), a_lo = make_desc(base + TC_A_TILE);
-          const uint64_t b_hi = make_desc(base + NPL * TC_A_TILE), b_lo = make_desc(base + NPL * TC_A_TILE + b_tile);
+          uint64_t da[NPL], db[NPL];
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
+          for (int pl = 0; pl < NPL; ++pl) {
+            da[pl] = make_desc(base + pl * a_tile, p.BK);
+            db[pl] = make_desc(base + NPL * a_tile + pl * b_tile, p.BK);
+          }
+          const int ksteps = p.BK / 16;
+          for (int k = 0; k < ksteps; ++k) {
             const uint64_t ko = (uint64_t)(k * 2);           // 16 bf16 = 32 bytes = 2 x 16-byte units along K
-            tc_mma(d_tmem, a_hi + ko, b_hi + ko, idesc, (kb | k) ? 1u : 0u);
-            if (TERMS == 3) {
-              tc_mma(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-              tc_mma(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
+            // smallest cross terms first, the dominant p0*p0 last
+            if (NPL == 3) {
+              tc_mma(d_tmem, da[2] + ko, db[0] + ko, idesc, (kb | k) ? 1u : 0u);
+              tc_mma(d_tmem, da[0] + ko, db[2] + ko, idesc, 1u);
+              tc_mma(d_tmem, da[1] + ko, db[1] + ko, idesc, 1u);
             }
+            if (NPL >= 2) {
+              tc_mma(d_tmem, da[1] + ko, db[0] + ko, idesc, (NPL == 3 || (kb | k)) ? 1u : 0u);
+              tc_mma(d_tmem, da[0] + ko, db[1] + ko, idesc, 1u);
+            }
+            tc_mma(d_tmem, da[0] + ko, db[0] + ko, idesc, (NPL >= 2 || (kb | k)) ? 1u : 0u);
           }
           tc_commit(smem_u32(empty_bar + s));               // frees the stage once these MMAs have read it
           if (kb == nkb - 1) tc_commit(smem_u32(tfull_bar + acc));
@@ -221,9 +248,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       }
     }
   } else {
-    // ============================ epilogue (warps 2..5) ============================
+    // ============================ epilogue (warps 2 .. 2+TC_EPI_WARPS) ============================
+    const int ew = warp - 2;
     const int q = warp & 3;                                  // TMEM lane quarter this warp may access
-    float* stg = reinterpret_cast<float*>(epi_smem) + (warp - 2) * (32 * 33);
+    const int cpar = ew >> 2, cstep = TC_EPI_WARPS / 4;      // this warp takes chunks cpar, cpar + cstep, ...
+    uint32_t* stg = reinterpret_cast<uint32_t*>(epi_smem) + ew * (32 * 33);
+    const bool gelu_planes = (p.epi == LVAE_EPI_BIAS_GELU) && p.out_pl[0] != nullptr && p.out == nullptr && (p.N % 2 == 0);
+    const bool shuffle = (p.epi == LVAE_EPI_SHUFFLE_NHWC || p.epi == LVAE_EPI_SHUFFLE_NCHW);
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -231,28 +262,103 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       mbar_wait(smem_u32(tfull_bar + acc), ((uint32_t)it >> 1) & 1);
       tc_fence_after();
       const int row0 = m0 + q * 32;
-      const int nchunks = p.BN / 32 + ((p.BN & 31) ? 1 : 0);
-      for (int c = 0; c < nchunks; ++c) {
+      const int nchunks = (p.BN + 31) / 32;
+      int last_c = cpar; while (last_c + cstep < nchunks) last_c += cstep;
+      if (cpar >= nchunks) {                                 // narrow tile: nothing for this warp to read
+        if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+        continue;
+      }
+      for (int c = cpar; c < nchunks; c += cstep) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c * 32);
-        tc_ld32(taddr, v);
+        const int width = (p.BN - c * 32) >= 32 ? 32 : 16;   // BN is a multiple of 16
+        if (width == 32) tc_ld32(taddr, v);
+        else {
+          tc_ld16(taddr, v);
+#pragma unroll
+          for (int j = 16; j < 32; ++j) v[j] = 0u;
+        }
         tc_wait_ld();
-        if (c == nchunks - 1) {                              // accumulator fully read: hand the buffer back
+        if (c == last_c) {                                   // this warp has read its share of the accumulator
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
         }
+        const int nb = n0 + c * 32;                          // first column of the chunk
+        if (gelu_planes) {
+          // ---- fc1: bias + GELU in the row-owner layout (32 independent chains per thread), then per plane
+          //      pack bf16 pairs, transpose through shared memory, store 64-byte row segments
+          float g[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
-        __syncwarp();
-        const int n = n0 + c * 32 + lane;
-        const bool n_ok = (c * 32 + lane < p.BN) && (n < p.N);
+          for (int j = 0; j < 32; ++j) {
+            const int n = nb + j;
+            const float b = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
+            g[j] = gelu_erf(__fadd_rn(__uint_as_float(v[j]), b));
+          }
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) {
+            if (p.out_pl[pl] == nullptr) break;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(g[2 * jj], g[2 * jj + 1]);
+              stg[lane * 17 + jj] = *reinterpret_cast<const uint32_t*>(&h2);
+              const float2 hf = __bfloat1622float2(h2);
+              g[2 * jj] = __fsub_rn(g[2 * jj], hf.x);        // exact residual for the next plane
+              g[2 * jj + 1] = __fsub_rn(g[2 * jj + 1], hf.y);
+            }
+            __syncwarp();
+            const int half = lane >> 4, l16 = lane & 15;
+            const int n = nb + 2 * l16;
+            __nv_bfloat16* dst = p.out_pl[pl] + (int64_t)(row0 + half) * p.N + n;
+#pragma unroll 8
+            for (int r = 0; r < 32; r += 2) {
+              const uint32_t w = stg[(r + half) * 17 + l16];
+              if (row0 + r + half < p.M && n < p.N && 2 * l16 < width)
+                *reinterpret_cast<uint32_t*>(dst + (int64_t)r * p.N) = w;
+            }
+            __syncwarp();
+          }
+        } else {
+          // ---- generic: transpose first, then bias / layer-scale + residual / shuffle with lane = column
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+          __syncwarp();
+          const int n = nb + lane;
+          const bool n_ok = (lane < width) && (n < p.N);
+          if (n_ok) {
+            const float b = p.bias ? __ldg(p.bias + n) : 0.f;
+            if (!shuffle && p.out != nullptr && p.out_pl[0] == nullptr && p.epi != LVAE_EPI_BIAS_GELU) {
+              const float gm = (p.epi == LVAE_EPI_SCALE_RES) ? __ldg(p.gamma + n) : 1.f;
+              const bool has_res = (p.epi == LVAE_EPI_SCALE_RES || p.epi == LVAE_EPI_BIAS_RES);
+              const int rows = (p.M - row0) < 32 ? (p.M - row0) : 32;
+              float* dst = p.out + (int64_t)row0 * p.N + n;
+              const float* rsrc = has_res ? p.res + (int64_t)row0 * p.N + n : nullptr;
+              if (rows == 32) {
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                  float x = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
+                  if (p.epi == LVAE_EPI_SCALE_RES) x = __fadd_rn(__fmul_rn(x, gm), rsrc[(int64_t)r * p.N]);
+                  else if (p.epi == LVAE_EPI_BIAS_RES) x = __fadd_rn(rsrc[(int64_t)r * p.N], x);
+                  dst[(int64_t)r * p.N] = x;
+                }
+              } else {
+                for (int r = 0; r < rows; ++r) {
+                  float x = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
+                  if (p.epi == LVAE_EPI_SCALE_RES) x = __fadd_rn(__fmul_rn(x, gm), rsrc[(int64_t)r * p.N]);
+                  else if (p.epi == LVAE_EPI_BIAS_RES) x = __fadd_rn(rsrc[(int64_t)r * p.N], x);
+                  dst[(int64_t)r * p.N] = x;
+                }
+              }
+            } else {
 #pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const int m = row0 + r;
-          if (m < p.M && n_ok) epi_store(p, m, n, epi_value(p, m, n, stg[r * 33 + lane]));
+              for (int r = 0; r < 32; ++r) {
+                const int m = row0 + r;
+                if (m < p.M) epi_store(p, m, n, epi_value(p, m, n, __uint_as_float(stg[r * 33 + lane])));
+              }
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   }
@@ -270,7 +376,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 __global__ void __launch_bounds__(256) split_im2col_kernel(
     const float* __restrict__ a0, const float* __restrict__ a1, int B, int H, int W, int Ho, int Wo,
     int C0, int C1, int ks, int stride, int pad, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-    int64_t total4, int K) {
+    __nv_bfloat16* __restrict__ l2, int64_t total4, int K) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int K4 = K >> 2;
@@ -287,14 +393,17 @@ __global__ void __launch_bounds__(256) split_im2col_kernel(
     v = __ldg(reinterpret_cast<const float4*>(a1 + m * C1 + (k - K0)));
   }
   const float f[4] = {v.x, v.y, v.z, v.w};
-  __nv_bfloat16 h[4], l[4];
+  __align__(8) __nv_bfloat16 h[4], l[4], t[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     h[j] = __float2bfloat16_rn(f[j]);
-    l[j] = __float2bfloat16_rn(__fsub_rn(f[j], __bfloat162float(h[j])));
+    const float r1 = __fsub_rn(f[j], __bfloat162float(h[j]));
+    l[j] = __float2bfloat16_rn(r1);
+    t[j] = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(l[j])));
   }
   *reinterpret_cast<uint2*>(hi + m * K + k) = *reinterpret_cast<const uint2*>(h);
   if (lo) *reinterpret_cast<uint2*>(lo + m * K + k) = *reinterpret_cast<const uint2*>(l);
+  if (l2) *reinterpret_cast<uint2*>(l2 + m * K + k) = *reinterpret_cast<const uint2*>(t);
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -316,15 +425,16 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // [rows, K] bf16 row-major, box = [box_rows x 64], SWIZZLE_128B, zero fill outside the tensor
-static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box_rows) {
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box_rows, int bk) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LVAE_E_UNSUPPORTED; }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld box=%d", (int)r, (long long)rows, (long long)K, box_rows); return LVAE_E_BADARG; }
   return 0;
@@ -337,11 +447,15 @@ static void tc_geometry(const lvae_gemm_desc* d, int* Ho, int* Wo, int64_t* M, i
   *K = d->ksize * d->ksize * d->C0 + (d->a1 ? d->C1 : 0);
 }
 
+static int num_planes(int precision) {
+  return precision == LVAE_PREC_BF16X6 ? 3 : (precision == LVAE_PREC_BF16X3 ? 2 : 1);
+}
+
 int64_t gemm_tc_workspace_bytes(const lvae_gemm_desc* d) {
-  if (d->a_hi) return 0;
+  if (d->a_planes[0]) return 0;
   int Ho, Wo, K; int64_t M;
   tc_geometry(d, &Ho, &Wo, &M, &K);
-  return M * K * 2 * (d->precision == LVAE_PREC_BF16X3 ? 2 : 1);
+  return M * K * 2 * num_planes(d->precision);
 }
 
 static int pick_bn(int N) {
@@ -351,30 +465,31 @@ static int pick_bn(int N) {
 }
 
 int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
-  const bool x3 = d->precision == LVAE_PREC_BF16X3;
+  const int npl = num_planes(d->precision);
   int Ho, Wo, K; int64_t M64;
   tc_geometry(d, &Ho, &Wo, &M64, &K);
   LVAE_CHECK_ARG(M64 > 0 && M64 < (1ll << 31));
   LVAE_CHECK_ARG(K % 8 == 0);                                  // 16-byte row pitch for the tensor maps
-  LVAE_CHECK_ARG(d->w_hi != nullptr && (!x3 || d->w_lo != nullptr));
+  for (int i = 0; i < npl; ++i) LVAE_CHECK_ARG(d->w_planes[i] != nullptr);
   const int M = (int)M64;
-  const __nv_bfloat16* a_hi = (const __nv_bfloat16*)d->a_hi;
-  const __nv_bfloat16* a_lo = (const __nv_bfloat16*)d->a_lo;
-  if (!a_hi) {
+  const __nv_bfloat16* a_pl[3] = {(const __nv_bfloat16*)d->a_planes[0], (const __nv_bfloat16*)d->a_planes[1],
+                                  (const __nv_bfloat16*)d->a_planes[2]};
+  if (!a_pl[0]) {
     const int64_t need = gemm_tc_workspace_bytes(d);
     if (!d->workspace || d->workspace_bytes < need) {
       set_error("tensor-core GEMM from fp32 activations needs %lld workspace bytes, got %lld", (long long)need, (long long)d->workspace_bytes);
       return LVAE_E_BADARG;
     }
-    __nv_bfloat16* hi = (__nv_bfloat16*)d->workspace;
-    __nv_bfloat16* lo = x3 ? hi + (int64_t)M * K : nullptr;
+    __nv_bfloat16* ws = (__nv_bfloat16*)d->workspace;
+    __nv_bfloat16* pl[3] = {ws, npl > 1 ? ws + (int64_t)M * K : nullptr, npl > 2 ? ws + 2 * (int64_t)M * K : nullptr};
     const int64_t total4 = (int64_t)M * (K / 4);
     split_im2col_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, stream>>>(
-        d->a0, d->a1, d->B, d->H, d->W, Ho, Wo, d->C0, d->a1 ? d->C1 : 0, d->ksize, d->stride, d->pad, hi, lo, total4, K);
+        d->a0, d->a1, d->B, d->H, d->W, Ho, Wo, d->C0, d->a1 ? d->C1 : 0, d->ksize, d->stride, d->pad,
+        pl[0], pl[1], pl[2], total4, K);
     LVAE_CUDA_LAUNCH_CHECK();
-    a_hi = hi; a_lo = lo;
+    for (int i = 0; i < 3; ++i) a_pl[i] = pl[i];
   } else {
-    LVAE_CHECK_ARG(!x3 || a_lo != nullptr);
+    for (int i = 0; i < npl; ++i) LVAE_CHECK_ARG(a_pl[i] != nullptr);
   }
 
   TcParams p;
@@ -384,40 +499,47 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   p.num_tiles = ((M + TC_BM - 1) / TC_BM) * p.n_tiles;
   int cols = 32; while (cols < 2 * p.BN) cols <<= 1;
   p.tmem_cols = cols;
-  const int npl = x3 ? 2 : 1;
-  const int stage_bytes = npl * (TC_A_TILE + p.BN * TC_BK * 2);
   const int fixed = 1024 + TC_EPI_STAGE + 256;                 // alignment slack + transpose buffers + barriers
-  int stages = (227 * 1024 - fixed) / stage_bytes;
+  const int budget = 227 * 1024 - fixed;
+  // k-block: a 128-byte swizzle row (64 bf16) unless two such stages do not fit (3 planes x wide N) -> 64-byte rows
+  p.BK = (2 * npl * (TC_BM + p.BN) * 64 * 2 <= budget) ? 64 : 32;
+  const int stage_bytes = npl * (TC_BM + p.BN) * p.BK * 2;
+  int stages = budget / stage_bytes;
   if (stages > 6) stages = 6;
-  const int nkb = (K + TC_BK - 1) / TC_BK;
-  if (stages > nkb + 1) stages = nkb + 1 > 2 ? nkb + 1 : 2;
-  LVAE_CHECK_ARG(stages >= 2);
+  const int nkb = (K + p.BK - 1) / p.BK;
+  if (stages > nkb + 1) stages = nkb + 1;
+  if (stages < 2) stages = 2;
+  LVAE_CHECK_ARG(stages * stage_bytes <= budget);
   p.stages = stages;
   p.bias = d->bias; p.gamma = d->gamma; p.res = d->res;
-  p.out = d->out; p.out_hi = (__nv_bfloat16*)d->out_hi; p.out_lo = (__nv_bfloat16*)d->out_lo;
+  p.out = d->out;
+  for (int i = 0; i < 3; ++i) p.out_pl[i] = (i < npl) ? (__nv_bfloat16*)d->out_planes[i] : nullptr;
+  if (p.out_pl[0] == nullptr) p.out_pl[1] = p.out_pl[2] = nullptr;
+  if (p.out_pl[1] == nullptr) p.out_pl[2] = nullptr;
   p.epi = d->epilogue; p.r = d->shuffle_r; p.Ho = Ho; p.Wo = Wo;
-  LVAE_CHECK_ARG(p.out != nullptr || p.out_hi != nullptr);
+  LVAE_CHECK_ARG(p.out != nullptr || p.out_pl[0] != nullptr);
 
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  TcMaps maps;
   int rc;
-  if ((rc = make_map(&ma_hi, a_hi, M, K, TC_BM))) return rc;
-  if ((rc = make_map(&mb_hi, d->w_hi, d->N, K, p.BN))) return rc;
-  if (x3) {
-    if ((rc = make_map(&ma_lo, a_lo, M, K, TC_BM))) return rc;
-    if ((rc = make_map(&mb_lo, d->w_lo, d->N, K, p.BN))) return rc;
-  } else { ma_lo = ma_hi; mb_lo = mb_hi; }
+  for (int i = 0; i < 3; ++i) {
+    const int j = i < npl ? i : 0;
+    if ((rc = make_map(&maps.a[i], a_pl[j], M, K, TC_BM, p.BK))) return rc;
+    if ((rc = make_map(&maps.b[i], d->w_planes[j], d->N, K, p.BN, p.BK))) return rc;
+  }
 
   static int n_sm = 0;
   if (n_sm == 0) {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    LVAE_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     LVAE_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LVAE_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LVAE_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   const int smem = fixed + stages * stage_bytes;
   const int grid = p.num_tiles < n_sm ? p.num_tiles : n_sm;
-  if (x3) gemm_tc_kernel<3><<<grid, TC_THREADS, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
-  else gemm_tc_kernel<1><<<grid, TC_THREADS, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  if (npl == 3) gemm_tc_kernel<3><<<grid, TC_THREADS, smem, stream>>>(maps, p);
+  else if (npl == 2) gemm_tc_kernel<2><<<grid, TC_THREADS, smem, stream>>>(maps, p);
+  else gemm_tc_kernel<1><<<grid, TC_THREADS, smem, stream>>>(maps, p);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

@@ -159,14 +159,19 @@ __global__ void __launch_bounds__(256) rd_finalize_kernel(
   }
 }
 
-__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, int64_t n) {
+__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ p0,
+                                  __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = x[i];
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  hi[i] = h;
-  if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  p0[i] = h;
+  if (p1) {
+    const float r1 = __fsub_rn(v, __bfloat162float(h));              // exact
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    p1[i] = m;
+    if (p2) p2[i] = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(m)));
+  }
 }
 
 }  // namespace lvae
@@ -230,9 +235,10 @@ extern "C" int lvae_sum_partials(const float* partial, float* out, int n, int co
   return 0;
 }
 
-extern "C" int lvae_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
-  LVAE_CHECK_ARG(x && hi && n > 0);
-  split_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+extern "C" int lvae_split_bf16(const float* x, void* p0, void* p1, void* p2, int64_t n, void* stream) {
+  LVAE_CHECK_ARG(x && p0 && n > 0 && (p2 == nullptr || p1 != nullptr));
+  split_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, (__nv_bfloat16*)p0, (__nv_bfloat16*)p1, (__nv_bfloat16*)p2, n);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

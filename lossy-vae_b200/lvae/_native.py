@@ -9,8 +9,10 @@ _LIB_PATH = Path(__file__).resolve().parent.parent / 'lib' / 'liblvae_b200.so'
 _lib = None
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_SCALE_RES, EPI_BIAS_RES, EPI_SHUFFLE_NHWC, EPI_SHUFFLE_NCHW = range(6)
-PREC_FP32, PREC_BF16X3, PREC_BF16 = range(3)
-PRECISIONS = {'fp32': PREC_FP32, 'bf16x3': PREC_BF16X3, 'bf16': PREC_BF16}
+PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_BF16X6 = range(4)
+PRECISIONS = {'fp32': PREC_FP32, 'bf16x3': PREC_BF16X3, 'bf16': PREC_BF16, 'bf16x6': PREC_BF16X6}
+NUM_PLANES = {PREC_FP32: 0, PREC_BF16: 1, PREC_BF16X3: 2, PREC_BF16X6: 3}
+MMA_TERMS = {PREC_FP32: 1, PREC_BF16: 1, PREC_BF16X3: 3, PREC_BF16X6: 6}
 
 _fp = C.c_void_p   # device / host pointers are passed as integers
 
@@ -25,7 +27,7 @@ class GemmDesc(C.Structure):
         ('N', C.c_int32), ('epilogue', C.c_int32),
         ('gamma', _fp), ('res', _fp), ('out', _fp),
         ('shuffle_r', C.c_int32), ('precision', C.c_int32),
-        ('w_hi', _fp), ('w_lo', _fp), ('a_hi', _fp), ('a_lo', _fp), ('out_hi', _fp), ('out_lo', _fp),
+        ('w_planes', _fp * 3), ('a_planes', _fp * 3), ('out_planes', _fp * 3),
         ('workspace', _fp), ('workspace_bytes', C.c_int64),
     ]
 
@@ -35,10 +37,10 @@ _PROTOS = {
     'lvae_last_error': (C.c_char_p, []),
     'lvae_gemm': (C.c_int, [C.POINTER(GemmDesc), _fp]),
     'lvae_gemm_workspace_bytes': (C.c_int64, [C.POINTER(GemmDesc)]),
-    'lvae_split_bf16': (C.c_int, [_fp, _fp, _fp, C.c_int64, _fp]),
+    'lvae_split_bf16': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp]),
     'lvae_dwconv_ln_adaln': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
-    'lvae_dwconv_ln_adaln_planes': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp, _fp,
+    'lvae_dwconv_ln_adaln_planes': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp, _fp, _fp,
                                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_latent_num_partials': (C.c_int, [C.c_int, C.c_int]),
     'lvae_latent_eval': (C.c_int, [_fp, _fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp, _fp,
@@ -90,6 +92,13 @@ def check(code, what=''):
     if code != 0:
         msg = lib().lvae_last_error().decode(errors='replace')
         raise RuntimeError(f'liblvae_b200 {what} failed with code {code}: {msg}')
+
+
+def set_planes(desc, which, tensors):
+    """desc.<which>_planes[i] = tensors[i].data_ptr() (which in 'w', 'a', 'out'); missing planes are NULL."""
+    arr = getattr(desc, which + '_planes')
+    for i in range(3):
+        arr[i] = tensors[i].data_ptr() if tensors is not None and i < len(tensors) and tensors[i] is not None else None
 
 
 launch_count = 0   # number of kernel-launching C calls issued (bench.py reports it)

@@ -111,15 +111,15 @@ class QarvEngine:
         return t.detach().to(self.device, torch.float32).contiguous()
 
     def _pack_gemm_weight(self, w2d, bias):
-        """w2d: [N, K] fp32 on device -> dict(w, bias[, hi, lo])"""
+        """w2d: [N, K] fp32 on device -> dict(w, bias, planes=[bf16 [N,K]] * npl)"""
         ent = dict(w=w2d.contiguous(), bias=None if bias is None else self._dev_f32(bias),
-                   N=w2d.shape[0], K=w2d.shape[1])
-        if self.tc:
+                   N=w2d.shape[0], K=w2d.shape[1], planes=[])
+        if self.npl:
             n = ent['w'].numel()
-            hi = torch.empty(n, dtype=torch.bfloat16, device=self.device)
-            lo = torch.empty(n, dtype=torch.bfloat16, device=self.device) if self.prec == N.PREC_BF16X3 else None
-            N.check(self.lib.lvae_split_bf16(_ptr(ent['w']), _ptr(hi), _ptr(lo), n, self._stream()), 'split_bf16')
-            ent['hi'], ent['lo'] = hi, lo
+            pl = [torch.empty(n, dtype=torch.bfloat16, device=self.device) for _ in range(self.npl)]
+            ptrs = [_ptr(t) for t in pl] + [0] * (3 - self.npl)
+            N.check(self.lib.lvae_split_bf16(_ptr(ent['w']), ptrs[0], ptrs[1], ptrs[2], n, self._stream()), 'split_bf16')
+            ent['planes'] = pl
         return ent
 
     def _conv_weight(self, conv):
@@ -143,7 +143,7 @@ class QarvEngine:
             self._plans.clear()
         self.device = dev
         self.prec = N.PRECISIONS[m.precision]
-        self.tc = self.prec != N.PREC_FP32
+        self.npl = N.NUM_PLANES[self.prec]        # bf16 planes per tensor-core operand (0: fp32 CUDA-core path)
         w = {}
         with torch.cuda.device(dev):
             for b in self.blocks:
@@ -186,8 +186,11 @@ class QarvEngine:
         self._plans.clear()
 
     # ------------------------------------------------------------------ plan construction helpers
-    def _gemm(self, P, name, a0, geom, went, out, epi=N.EPI_BIAS, a1=None, C1=0, gamma=None, res=None, r=0):
-        """geom = (B, H, W, C0, ksize, stride, pad) of the NHWC input a0."""
+    def _gemm(self, P, name, a0, geom, went, out, epi=N.EPI_BIAS, a1=None, C1=0, gamma=None, res=None, r=0,
+              a_planes=None, out_planes=None):
+        """geom = (B, H, W, C0, ksize, stride, pad) of the NHWC input a0.  In a tensor-core mode the A operand is
+        either `a_planes` (bf16 planes written by the producing kernel) or a0/a1, which the library im2col-splits
+        into the plan's workspace first."""
         B, H, W, C0, ks, st, pad = geom
         d = N.GemmDesc()
         d.a0, d.a1 = _ptr(a0), _ptr(a1)
@@ -195,24 +198,48 @@ class QarvEngine:
         d.ksize, d.stride, d.pad = ks, st, pad
         d.w, d.bias, d.N = _ptr(went['w']), _ptr(went['bias']), went['N']
         d.epilogue, d.gamma, d.res, d.out = epi, _ptr(gamma), _ptr(res), _ptr(out)
-        d.shuffle_r, d.precision = r, N.PREC_FP32
+        d.shuffle_r, d.precision = r, self.prec
         assert went['K'] == ks * ks * C0 + C1, (name, went['K'], ks, C0, C1)
         Mo = B * ((H + 2 * pad - ks) // st + 1) * ((W + 2 * pad - ks) // st + 1)
+        ws = None
+        if self.npl:
+            N.set_planes(d, 'w', went['planes'])
+            N.set_planes(d, 'a', a_planes)
+            N.set_planes(d, 'out', out_planes)
+            if a_planes is None:
+                ws = P.named('tc_ws', Mo * went['K'] * self.npl, dtype=torch.bfloat16)
+                d.workspace, d.workspace_bytes = _ptr(ws), ws.numel() * 2
+        else:
+            assert a_planes is None and out_planes is None
         meta = dict(kind='gemm', flops=2 * Mo * went['N'] * went['K'], M=Mo, N=went['N'], K=went['K'],
                     bytes=4 * (B * H * W * (C0 + C1) + went['N'] * went['K'] + Mo * went['N'] * (2 if res is not None else 1)))
-        P.op(name, self.lib.lvae_gemm, C.byref(d), keep=(d, a0, a1, went, out, gamma, res), meta=meta)
+        P.op(name, self.lib.lvae_gemm, C.byref(d), keep=(d, a0, a1, went, out, gamma, res, a_planes, out_planes, ws),
+             meta=meta)
 
     def _block(self, P, blk, x, B, Hs, Ws, out=None):
         """x: [M, C] fp32 NHWC; returns the output buffer (x itself when out is None: in place)."""
         wb = self.w[id(blk)]
         C_, hid, k = blk.dim, blk.hidden, blk.kernel_size
         M = B * Hs * Ws
+        out = x if out is None else out
+        dw_meta = dict(kind='dwln', bytes=8 * M * C_, flops=2 * M * C_ * k * k)
+        if self.npl:
+            # tensor-core modes: the A operand of each GEMM travels as bf16 planes written by its producer
+            A = [P.named(f'scratch_a{i}', M * C_, dtype=torch.bfloat16) for i in range(self.npl)]
+            Hd = [P.named(f'scratch_h{i}', M * hid, dtype=torch.bfloat16) for i in range(self.npl)]
+            ap = [_ptr(t) for t in A] + [0] * (3 - self.npl)
+            P.op('dwln', self.lib.lvae_dwconv_ln_adaln_planes, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']),
+                 _ptr(P.ada), self.ada_total, self.ada_off[id(blk)], 0, 0, ap[0], ap[1], ap[2], B, Hs, Ws, C_, k,
+                 keep=(x, A), meta=dw_meta)
+            self._gemm(P, 'fc1', None, (1, 1, M, C_, 1, 1, 0), wb['fc1'], None, epi=N.EPI_BIAS_GELU, a_planes=A, out_planes=Hd)
+            self._gemm(P, 'fc2', None, (1, 1, M, hid, 1, 1, 0), wb['fc2'], out, epi=N.EPI_SCALE_RES,
+                       gamma=wb['gamma'], res=x, a_planes=Hd)
+            return out
         A = P.named('scratch_a', M * C_)
         Hd = P.named('scratch_h', M * hid)
-        out = x if out is None else out
         P.op('dwln', self.lib.lvae_dwconv_ln_adaln, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']),
              _ptr(P.ada), self.ada_total, self.ada_off[id(blk)], 0, 0, _ptr(A), B, Hs, Ws, C_, k,
-             keep=(x, A), meta=dict(kind='dwln', bytes=8 * M * C_, flops=2 * M * C_ * k * k))
+             keep=(x, A), meta=dw_meta)
         self._gemm(P, 'fc1', A, (1, 1, M, C_, 1, 1, 0), wb['fc1'], Hd, epi=N.EPI_BIAS_GELU)
         self._gemm(P, 'fc2', Hd, (1, 1, M, hid, 1, 1, 0), wb['fc2'], out, epi=N.EPI_SCALE_RES,
                    gamma=wb['gamma'], res=x)
