@@ -147,7 +147,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='images per GPU per step (BASELINE configs[1]: 8)')
-    ap.add_argument('--precision', default=None, help="fp32 | bf16x3 | bf16 (default: the model's default)")
+    ap.add_argument('--precision', default=None, help="bf16x6 | bf16x3 | bf16 | fp32 (default: the model's default, bf16x6)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-samples', type=int, default=5)
     args = ap.parse_args()
@@ -243,12 +243,14 @@ def main():
             k = by_kind.setdefault(meta.get('kind', 'misc'), dict(ms=0.0, flops=0, bytes=0, n=0))
             k['ms'] += ms; k['flops'] += meta.get('flops', 0); k['bytes'] += meta.get('bytes', 0); k['n'] += 1
         gm, lt, dw = by_kind['gemm'], by_kind['latent'], by_kind['dwln']
-        issued = {'fp32': 1, 'bf16': 1, 'bf16x3': 3}[model.precision]
+        issued = {'fp32': 1, 'bf16': 1, 'bf16x3': 3, 'bf16x6': 6}[model.precision]
         roof = dict(bound='tensor', kernel=f'lvae_gemm ({model.precision})', achieved=gm['flops'] / gm['ms'] / 1e9,
                     peak=pk['tensor_sustained'], unit='TFLOP/s', traffic=None, peak_source=pk['src'] + ' (sustained bf16 cuBLAS)',
                     launches=gm['n'], share_of_step=gm['ms'] / tot_ms, issued_mma_multiplier=issued,
                     note='achieved = sum over the GEMM launches of 2*M*N*K / sum of their CUDA-event durations')
         roof['frac'] = roof['achieved'] / roof['peak']
+        roof['issued_tflops'] = roof['achieved'] * issued          # MMA FLOPs actually issued to the tensor pipe
+        roof['issued_frac'] = roof['issued_tflops'] / roof['peak']
         # biggest latent layer alone (the only ones large enough to be bandwidth- rather than latency-bound)
         big = max((p for p in prof if p[1].get('kind') == 'latent'), key=lambda p: p[1]['bytes'])
         roof_e = dict(bound='hbm', kernel='latent_kernel<eval>', achieved=big[1]['bytes'] / big[2] / 1e6, peak=pk['hbm'],
@@ -267,7 +269,8 @@ def main():
         line = {
             'metric': METRIC, 'value': n_img / (ms_dev / 1e3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': {'fp32': 'f32', 'bf16x3': 'bf16x3 (split-bf16 products, f32 accumulate)', 'bf16': 'bf16'}[model.precision],
+            'vs_baseline': None, 'dtype': {'fp32': 'f32', 'bf16x6': 'f32-class (3 bf16 planes per operand, 6 tcgen05 MMAs per product, f32 accumulate)',
+                      'bf16x3': 'bf16x3 (2 bf16 planes, 3 MMAs, f32 accumulate)', 'bf16': 'bf16'}[model.precision],
             'data': 'synthetic',
             'config': {'workload': f'qarv_base eval forward (rate + MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 2048 '
                                    f'(BASELINE configs[1])', 'batch_per_gpu': B, 'global_batch': B * world, 'precision': model.precision,

@@ -18,8 +18,13 @@
 //   warps 2-5  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (32 lanes per warp), transpose 32 x 32
 //            chunks through padded shared memory so that global traffic is 128-byte coalesced, apply
 //            bias / GELU / layer-scale + residual / pixel-shuffle, write fp32 and/or bf16 hi-lo planes
-// Two accumulator buffers in TMEM (2 x BN <= 512 columns) let the epilogue of tile i overlap the MMAs of
-// tile i+1.  K order is fixed, there is no split-K and BN depends on N only, so results are bit-reproducible
+// Accumulation: tcgen05.mma adds into the fp32 TMEM accumulator with truncation, one rounding per instruction,
+// so the error of an accumulator grows with the number of MMAs chained into it (measured: bf16x6 with all six
+// terms in one accumulator was no more accurate than bf16x3).  The multi-plane modes therefore keep TWO
+// accumulators per tile: `main` receives only the p0*p0 products (K/16 roundings), `cross` all correction
+// terms, whose magnitude -- and truncation error -- is 2^-8 of the main sum; the epilogue adds them once (RN).
+// Two such buffers in TMEM (2 x 2 x BN <= 512 columns, BN <= 128; 2 x BN with BN <= 256 for single-plane bf16)
+// let the epilogue of tile i overlap the MMAs of tile i+1.  K order is fixed, there is no split-K and BN depends on N only, so results are bit-reproducible
 // and do not depend on the batch an image travels in.
 #include "common.cuh"
 #include <cuda.h>
@@ -35,7 +40,7 @@ constexpr int TC_EPI_STAGE = TC_EPI_WARPS * 32 * 33 * 4;    // per-warp 32 x 33 
 
 struct TcParams {
   int M, N, K;
-  int BN, BK, n_tiles, num_tiles, stages, tmem_cols;   // BK: bf16 elements per k-block = one swizzle row (64 -> 128 B, 32 -> 64 B)
+  int BN, BK, n_tiles, num_tiles, stages, tmem_cols, acc_cols;   // acc_cols: TMEM columns per tile buffer (BN or 2*BN)   // BK: bf16 elements per k-block = one swizzle row (64 -> 128 B, 32 -> 64 B)
   const float* bias; const float* gamma; const float* res;
   float* out; __nv_bfloat16* out_pl[3];
   int epi, r, Ho, Wo;
@@ -213,7 +218,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const int acc = it & 1;
       mbar_wait(smem_u32(tempty_bar + acc), (((uint32_t)it >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);      // main accumulator
+      const uint32_t d_cross = d_tmem + (uint32_t)p.BN;                       // correction terms (NPL >= 2)
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(smem_u32(full_bar + s), ph);
         tc_fence_after();
@@ -228,17 +234,17 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           const int ksteps = p.BK / 16;
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t ko = (uint64_t)(k * 2);           // 16 bf16 = 32 bytes = 2 x 16-byte units along K
-            // smallest cross terms first, the dominant p0*p0 last
+            const uint32_t first = (kb | k) ? 1u : 0u;
             if (NPL == 3) {
-              tc_mma(d_tmem, da[2] + ko, db[0] + ko, idesc, (kb | k) ? 1u : 0u);
-              tc_mma(d_tmem, da[0] + ko, db[2] + ko, idesc, 1u);
-              tc_mma(d_tmem, da[1] + ko, db[1] + ko, idesc, 1u);
+              tc_mma(d_cross, da[2] + ko, db[0] + ko, idesc, first);
+              tc_mma(d_cross, da[0] + ko, db[2] + ko, idesc, 1u);
+              tc_mma(d_cross, da[1] + ko, db[1] + ko, idesc, 1u);
             }
             if (NPL >= 2) {
-              tc_mma(d_tmem, da[1] + ko, db[0] + ko, idesc, (NPL == 3 || (kb | k)) ? 1u : 0u);
-              tc_mma(d_tmem, da[0] + ko, db[1] + ko, idesc, 1u);
+              tc_mma(d_cross, da[1] + ko, db[0] + ko, idesc, NPL == 3 ? 1u : first);
+              tc_mma(d_cross, da[0] + ko, db[1] + ko, idesc, 1u);
             }
-            tc_mma(d_tmem, da[0] + ko, db[0] + ko, idesc, (NPL >= 2 || (kb | k)) ? 1u : 0u);
+            tc_mma(d_tmem, da[0] + ko, db[0] + ko, idesc, first);
           }
           tc_commit(smem_u32(empty_bar + s));               // frees the stage once these MMAs have read it
           if (kb == nkb - 1) tc_commit(smem_u32(tfull_bar + acc));
@@ -270,15 +276,25 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       }
       for (int c = cpar; c < nchunks; c += cstep) {
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c * 32);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols + c * 32);
         const int width = (p.BN - c * 32) >= 32 ? 32 : 16;   // BN is a multiple of 16
-        if (width == 32) tc_ld32(taddr, v);
-        else {
-          tc_ld16(taddr, v);
+        if (NPL >= 2) {
+          uint32_t u[32];
+          if (width == 32) { tc_ld32(taddr, v); tc_ld32(taddr + (uint32_t)p.BN, u); }
+          else { tc_ld16(taddr, v); tc_ld16(taddr + (uint32_t)p.BN, u); }
+          tc_wait_ld();
 #pragma unroll
-          for (int j = 16; j < 32; ++j) v[j] = 0u;
+          for (int j = 0; j < 32; ++j)
+            v[j] = (j < 16 || width == 32) ? __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(u[j]))) : 0u;
+        } else {
+          if (width == 32) tc_ld32(taddr, v);
+          else {
+            tc_ld16(taddr, v);
+#pragma unroll
+            for (int j = 16; j < 32; ++j) v[j] = 0u;
+          }
+          tc_wait_ld();
         }
-        tc_wait_ld();
         if (c == last_c) {                                   // this warp has read its share of the accumulator
           tc_fence_before();
           __syncwarp();
@@ -458,8 +474,9 @@ int64_t gemm_tc_workspace_bytes(const lvae_gemm_desc* d) {
   return M * K * 2 * num_planes(d->precision);
 }
 
-static int pick_bn(int N) {
-  const int nt = (N + 255) / 256;
+static int pick_bn(int N, int npl) {
+  const int maxbn = npl >= 2 ? 128 : 256;                      // split accumulators need 2 x BN columns per buffer
+  const int nt = (N + maxbn - 1) / maxbn;
   int bn = (N + nt - 1) / nt;
   return (bn + 15) & ~15;
 }
@@ -494,10 +511,11 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
 
   TcParams p;
   p.M = M; p.N = d->N; p.K = K;
-  p.BN = pick_bn(d->N);
+  p.BN = pick_bn(d->N, npl);
   p.n_tiles = (d->N + p.BN - 1) / p.BN;
   p.num_tiles = ((M + TC_BM - 1) / TC_BM) * p.n_tiles;
-  int cols = 32; while (cols < 2 * p.BN) cols <<= 1;
+  p.acc_cols = (npl >= 2 ? 2 : 1) * p.BN;
+  int cols = 32; while (cols < 2 * p.acc_cols) cols <<= 1;
   p.tmem_cols = cols;
   const int fixed = 1024 + TC_EPI_STAGE + 256;                 // alignment slack + transpose buffers + barriers
   const int budget = 227 * 1024 - fixed;

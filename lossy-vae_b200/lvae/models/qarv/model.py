@@ -87,9 +87,12 @@ class VariableRateLossyVAE(nn.Module):
         self.compressing = False
         self._logging_images = config.get('log_images', [])
         self._flops_mode = False
-        # 'bf16x3' (parity mode: split-bf16 tensor-core products, fp32 accumulation), 'bf16' (fast,
-        # non-parity) or 'fp32' (CUDA-core FFMA).  See DESIGN.md.
-        self.precision = config.get('precision', 'fp32')
+        # arithmetic of the dense contractions (DESIGN.md "Precision modes"):
+        #   'bf16x6'  tcgen05, 3 bf16 planes per operand, 6 MMAs, split main/cross TMEM accumulators: fp32-class,
+        #             the parity mode (default)
+        #   'bf16x3'  tcgen05, 2 planes, 3 MMAs (~2^-17 per product)      'bf16'  tcgen05 single pass (fast, non-parity)
+        #   'fp32'    fp32 FFMA on CUDA cores
+        self.precision = config.get('precision', 'bf16x6')
         self.__dict__['_engine'] = None   # not a submodule / not deep-copied state
 
     # ------------------------------------------------------------------ engine plumbing

@@ -68,8 +68,18 @@ def _check_integer_parity(syms, idxs, ref_syms, ref_idxs, oracle_records):
     return flips
 
 
+@pytest.fixture(params=['bf16x6', 'fp32'])
+def model_in_precision(request, gpu_model):
+    """The parity modes: tensor-core bf16x6 (default) and the fp32 CUDA-core path."""
+    old = gpu_model.precision
+    gpu_model.precision = request.param
+    yield gpu_model
+    gpu_model.precision = old
+
+
 @pytest.mark.parametrize('name', list(CASES))
-def test_forward_matches_reference_fixture(name, gpu_model, golden, sensitised_sd):
+def test_forward_matches_reference_fixture(name, model_in_precision, golden, sensitised_sd):
+    gpu_model = model_in_precision
     g = golden(name)
     kind, nB, H, W, lmbs, seed = CASES[name]
     im_cpu = make_input(kind, nB, H, W, seed)
@@ -142,6 +152,29 @@ def test_compress_decompress_roundtrip_equals_forward_at_kodak_shape(gpu_model):
     bpp_coded = len(blob) * 8 / (H * W)
     assert 0.90 * st['bppix'] < bpp_coded < 1.02 * st['bppix'], (bpp_coded, st['bppix'])
     assert struct.unpack('f', blob[:4])[0] == lmb and struct.unpack('3H', blob[4:10]) == (1, H // 64, W // 64)
+
+
+def test_fast_modes_stay_within_rate_distortion_tolerance(gpu_model, golden):
+    """bf16x3 (2 planes, 3 MMAs) keeps bpp / PSNR inside the north-star tolerances but may flip a few symbols;
+    single-pass bf16 is the non-parity fast mode: only sanity-bounded here (reported in DESIGN.md)."""
+    name = 'qarv_rand_2x128x192'
+    g = golden(name)
+    kind, nB, H, W, lmbs, seed = CASES[name]
+    im = make_input(kind, nB, H, W, seed).to(DEV)
+    lmb = torch.tensor(lmbs, device=DEV)
+    old = gpu_model.precision
+    try:
+        gpu_model.precision = 'bf16x3'
+        st = gpu_model(im, lmb=lmb)
+        assert abs(st['bppix'] - float(g['bppix'])) <= bpp_tol(H, W) and abs(st['psnr'] - float(g['psnr'])) <= PSNR_TOL
+        syms, idxs = _symbols_from_model(gpu_model, im, lmb)
+        mism = sum(int((syms[li].numpy() != g[f'sym{li}']).sum()) for li in range(9))
+        assert mism <= 2
+        gpu_model.precision = 'bf16'
+        st = gpu_model(im, lmb=lmb)
+        assert abs(st['bppix'] - float(g['bppix'])) <= 0.05 and abs(st['psnr'] - float(g['psnr'])) <= 0.1
+    finally:
+        gpu_model.precision = old
 
 
 def test_batch_invariance_and_determinism_at_full_size(gpu_model):
