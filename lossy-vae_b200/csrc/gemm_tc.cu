@@ -68,6 +68,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done) __nanosleep(20);                              // free issue slots for the epilogue warps while waiting
   } while (!done);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment of the swizzled tiles
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // (pointer arithmetic keeps the shared address space)
   const int a_tile = TC_BM * p.BK * 2;
   const int b_tile = p.BN * p.BK * 2;
   const int stage_bytes = NPL * (a_tile + b_tile);          // [A planes | B planes]
@@ -303,7 +304,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int nb = n0 + c * 32;                          // first column of the chunk
         if (gelu_planes) {
           // ---- fc1: bias + GELU in the row-owner layout (32 independent chains per thread), then per plane
-          //      pack bf16 pairs, transpose through shared memory, store 64-byte row segments
+          //      pack bf16 pairs, transpose through shared memory (80-byte rows: conflict-free 128-bit stores),
+          //      and store 64-byte row segments with 64-bit accesses
           float g[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -311,26 +313,40 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             const float b = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
             g[j] = gelu_erf(__fadd_rn(__uint_as_float(v[j]), b));
           }
+          const int sub = lane >> 3, l8 = lane & 7;          // 4 rows per pass, 8 lanes x 4 columns per row
+          const int n = nb + 4 * l8;
+          const bool full = (row0 + 32 <= p.M) && (nb + 32 <= p.N) && (width == 32);
 #pragma unroll
           for (int pl = 0; pl < 3; ++pl) {
             if (p.out_pl[pl] == nullptr) break;
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const __nv_bfloat162 h2 = __floats2bfloat162_rn(g[2 * jj], g[2 * jj + 1]);
-              stg[lane * 17 + jj] = *reinterpret_cast<const uint32_t*>(&h2);
-              const float2 hf = __bfloat1622float2(h2);
-              g[2 * jj] = __fsub_rn(g[2 * jj], hf.x);        // exact residual for the next plane
-              g[2 * jj + 1] = __fsub_rn(g[2 * jj + 1], hf.y);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = j4 * 8 + e * 2;
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(g[j], g[j + 1]);
+                w[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                const float2 hf = __bfloat1622float2(h2);
+                g[j] = __fsub_rn(g[j], hf.x);                // exact residual for the next plane
+                g[j + 1] = __fsub_rn(g[j + 1], hf.y);
+              }
+              *reinterpret_cast<uint4*>(stg + lane * 20 + j4 * 4) = make_uint4(w[0], w[1], w[2], w[3]);
             }
             __syncwarp();
-            const int half = lane >> 4, l16 = lane & 15;
-            const int n = nb + 2 * l16;
-            __nv_bfloat16* dst = p.out_pl[pl] + (int64_t)(row0 + half) * p.N + n;
-#pragma unroll 8
-            for (int r = 0; r < 32; r += 2) {
-              const uint32_t w = stg[(r + half) * 17 + l16];
-              if (row0 + r + half < p.M && n < p.N && 2 * l16 < width)
-                *reinterpret_cast<uint32_t*>(dst + (int64_t)r * p.N) = w;
+            __nv_bfloat16* dst = p.out_pl[pl] + (int64_t)(row0 + sub) * p.N + n;
+            if (full) {
+#pragma unroll
+              for (int r = 0; r < 32; r += 4)
+                *reinterpret_cast<uint2*>(dst + (int64_t)r * p.N) = *reinterpret_cast<const uint2*>(stg + (r + sub) * 20 + l8 * 2);
+            } else {
+              for (int r = 0; r < 32; r += 4) {
+                const uint2 w2 = *reinterpret_cast<const uint2*>(stg + (r + sub) * 20 + l8 * 2);
+                if (row0 + r + sub < p.M && 4 * l8 < width) {
+                  if (n + 3 < p.N) *reinterpret_cast<uint2*>(dst + (int64_t)r * p.N) = w2;
+                  else if (n + 1 < p.N) *reinterpret_cast<uint32_t*>(dst + (int64_t)r * p.N) = w2.x;
+                }
+              }
             }
             __syncwarp();
           }
@@ -350,12 +366,19 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               float* dst = p.out + (int64_t)row0 * p.N + n;
               const float* rsrc = has_res ? p.res + (int64_t)row0 * p.N + n : nullptr;
               if (rows == 32) {
+                if (has_res) {
+                  float rr[32];                               // all 32 residual loads in flight before any is consumed
+#pragma unroll
+                  for (int r = 0; r < 32; ++r) rr[r] = rsrc[(int64_t)r * p.N];
+#pragma unroll
+                  for (int r = 0; r < 32; ++r) {
+                    float x = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
+                    x = (p.epi == LVAE_EPI_SCALE_RES) ? __fadd_rn(__fmul_rn(x, gm), rr[r]) : __fadd_rn(rr[r], x);
+                    dst[(int64_t)r * p.N] = x;
+                  }
+                } else {
 #pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
-                  float x = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
-                  if (p.epi == LVAE_EPI_SCALE_RES) x = __fadd_rn(__fmul_rn(x, gm), rsrc[(int64_t)r * p.N]);
-                  else if (p.epi == LVAE_EPI_BIAS_RES) x = __fadd_rn(rsrc[(int64_t)r * p.N], x);
-                  dst[(int64_t)r * p.N] = x;
+                  for (int r = 0; r < 32; ++r) dst[(int64_t)r * p.N] = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
                 }
               } else {
                 for (int r = 0; r < rows; ++r) {

@@ -10,6 +10,7 @@ lib = N.lib()
 NPL = {1: 2, 2: 1, 3: 3}
 TERMS = {0: 1, 1: 3, 2: 1, 3: 6}
 precs = [int(a) for a in sys.argv[1].split(',')] if len(sys.argv) > 1 else [1, 2]
+only = sys.argv[2].split(',') if len(sys.argv) > 2 else None
 SHAPES = [  # (name, M, K, N, epi)
     ('s4 enc fc1', 196608, 192, 384, 1), ('s4 enc fc2', 196608, 384, 192, 2),
     ('s8 enc fc1', 49152, 384, 768, 1), ('s8 enc fc2', 49152, 768, 384, 2),
@@ -25,6 +26,8 @@ def planes(x, n):
     return ps
 for prec in precs:
     for name, M, K, Nn, epi in SHAPES:
+        if only and not any(o in name for o in only):
+            continue
         nbuf = max(2, int(300e6 // (M * (K + Nn) * 4)) + 1)
         g = torch.Generator().manual_seed(0)
         w = (torch.randn(Nn, K, generator=g) / K ** 0.5).cuda(); b = torch.randn(Nn, generator=g).cuda()
