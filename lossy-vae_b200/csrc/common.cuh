@@ -42,7 +42,13 @@ void set_error(const char* fmt, ...);
 // erf, is what keeps hidden activations within rounding noise of the oracle).
 __device__ __forceinline__ float erf_aten_vec(float x) {
   const float a = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, a, 1.0f));        // IEEE reciprocal == _mm512_div_ps(1, .)
+  // t = 1 / (1 + p|x|): the argument is a normal number >= 1, so the correctly rounded reciprocal is the
+  // MUFU approximation plus one Newton step -- the fast path of __frcp_rn without its range checks
+  // (== _mm512_div_ps(1, .) on the host)
+  const float d = fmaf(0.3275911f, a, 1.0f);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(d));
+  t = fmaf(t, -fmaf(d, t, -1.0f), t);
   float r = fmaf(1.061405429f, t, -1.453152027f);
   r = fmaf(r, t, 1.421413741f);
   r = fmaf(r, t, -0.284496736f);

@@ -30,6 +30,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace lvae {
 
@@ -542,11 +543,14 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   p.tmem_cols = cols;
   const int fixed = 1024 + TC_EPI_STAGE + 256;                 // alignment slack + transpose buffers + barriers
   const int budget = 227 * 1024 - fixed;
-  // k-block: a 128-byte swizzle row (64 bf16) unless two such stages do not fit (3 planes x wide N) -> 64-byte rows
+  // k-block: a 128-byte swizzle row (64 bf16) whenever two such stages fit (measured: 2 x 64 beats 4 x 32 on every
+  // qarv shape), else 64-byte rows (32 bf16)
   p.BK = (2 * npl * (TC_BM + p.BN) * 64 * 2 <= budget) ? 64 : 32;
+  if (K <= 32) p.BK = 32;
+  { static const char* e = getenv("LVAE_TC_BK"); if (e) { const int v = atoi(e); if ((v == 64 || v == 32) && 2 * npl * (TC_BM + p.BN) * v * 2 <= budget) p.BK = v; } }   // tuning knob
   const int stage_bytes = npl * (TC_BM + p.BN) * p.BK * 2;
   int stages = budget / stage_bytes;
-  if (stages > 6) stages = 6;
+  if (stages > 8) stages = 8;
   const int nkb = (K + p.BK - 1) / p.BK;
   if (stages > nkb + 1) stages = nkb + 1;
   if (stages < 2) stages = 2;
