@@ -222,7 +222,8 @@ class QarvEngine:
         C_, hid, k = blk.dim, blk.hidden, blk.kernel_size
         M = B * Hs * Ws
         out = x if out is None else out
-        dw_meta = dict(kind='dwln', bytes=8 * M * C_, flops=2 * M * C_ * k * k)
+        # algorithmic bytes: read x fp32, write the GEMM operand (fp32, or npl bf16 planes)
+        dw_meta = dict(kind='dwln', bytes=M * C_ * (4 + (2 * self.npl if self.npl else 4)), flops=2 * M * C_ * k * k)
         if self.npl:
             # tensor-core modes: the A operand of each GEMM travels as bf16 planes written by its producer
             A = [P.named(f'scratch_a{i}', M * C_, dtype=torch.bfloat16) for i in range(self.npl)]
