@@ -4,27 +4,47 @@
 //
 // HBM-bound stage (algorithmic bytes per position: read 4C, write 4C fp32 or 2C per bf16 plane).  One CTA of
 // 8 warps owns an 8 x 8 tile of output pixels of one image, all C channels:
-//   * channels are processed in chunks of 64; the (8+k-1)^2 halo of a chunk is staged in shared memory with
-//     16-byte cp.async (zero-filled outside the image), double-buffered so chunk j+1 streams in while chunk j
-//     is convolved -- every input element is read from global memory once per tile, fully coalesced;
+//   * channels are processed in chunks of 64; the (8+k-1)^2 halo of a chunk is one TMA box load
+//     (cp.async.bulk.tensor.4d over the [C, W, H, B] view; coordinates outside the image are zero-filled by the
+//     hardware = the conv's zero padding), double-buffered on mbarriers so chunk j+1 streams in while chunk j is
+//     convolved -- no fill loop, no index arithmetic, every input element is read once per tile;
 //   * warp w convolves output row w: lane l owns channels {64 j + 2 l, 64 j + 2 l + 1}, a sliding window of the
 //     shared-memory row feeds the 8 pixels, results stay in registers (8 pixels x 2 channels x C/64 chunks);
 //   * LayerNorm is then warp-local: two-pass (mean, centred second moment) warp-shuffle reductions in fp32,
 //     followed by the modulation and the split into bf16 planes for the tensor-core GEMM that consumes it.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda.h>
+#include <mutex>
 
 namespace lvae {
 
 constexpr int DW_T = 8;                 // output tile edge
 constexpr int DW_CH = 64;               // channels per chunk
-constexpr int DW_NBUF = 1;              // halo buffers per CTA: 1 = rely on co-resident CTAs for overlap (more CTAs per SM)
+constexpr int DW_NBUF = 2;              // halo buffers per CTA (chunk j+1 streams in while chunk j is convolved)
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;        // src-size 0: the 16 destination bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+__device__ __forceinline__ uint32_t dw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dw_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void dw_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dw_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void dw_tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 // packed fp32x2 FMA (sm_100): both lanes are IEEE fma, i.e. bit-identical to two fmaf() at half the issue slots
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   uint64_t d;
@@ -33,53 +53,44 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
         "l"(*reinterpret_cast<const uint64_t*>(&c)));
   return *reinterpret_cast<float2*>(&d);
 }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int NJ, int KS>
 __global__ void __launch_bounds__(256) dwln_kernel(
-    const float* __restrict__ x, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+    const __grid_constant__ CUtensorMap x_map, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
     const float* __restrict__ ada, int64_t ada_stride, int64_t ada_off,
     const float* __restrict__ ln_w, const float* __restrict__ ln_b,
     float* __restrict__ y, __nv_bfloat16* __restrict__ y0, __nv_bfloat16* __restrict__ y1, __nv_bfloat16* __restrict__ y2,
     int H, int W, int tiles_x, int tiles_y) {
   constexpr int C = NJ * DW_CH, PAD = (KS - 1) / 2, HT = DW_T + KS - 1;     // halo tile edge
   constexpr int CHUNK_FLOATS = HT * HT * DW_CH;
-  extern __shared__ __align__(16) float dw_smem[];                           // [2][HT][HT][64]
+  extern __shared__ __align__(128) float dw_smem[];                          // [DW_NBUF][HT][HT][64]
+  __shared__ __align__(8) uint64_t dw_bar[2];
   const int tid = threadIdx.x, lane = tid & 31, wrow = tid >> 5;
   int t = blockIdx.x;
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y; const int b = t / tiles_y;
   const int h0 = ty * DW_T, w0 = tx * DW_T;
-  const float* xb = x + (int64_t)b * H * W * C;
 
-  auto load_chunk = [&](int j, int buf) {
-    // HT*HT pixels x 16 float4 per pixel
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(dw_smem + buf * CHUNK_FLOATS);
-    for (int i = tid; i < HT * HT * 16; i += 256) {
-      const int q = i & 15, pix = i >> 4;
-      const int px = pix % HT, py = pix / HT;
-      const int hh = h0 + py - PAD, ww = w0 + px - PAD;
-      const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
-      const float* src = ok ? xb + ((int64_t)hh * W + ww) * C + j * DW_CH + q * 4 : xb;
-      cp_async16(sbase + (uint32_t)(pix * DW_CH + q * 4) * 4u, src, ok);
-    }
-    cp_async_commit();
+  if (tid == 0) {
+    dw_mbar_init(dw_smem_u32(&dw_bar[0]), 1);
+    dw_mbar_init(dw_smem_u32(&dw_bar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto load_chunk = [&](int j, int buf) {                                    // one thread
+    const uint32_t bar = dw_smem_u32(&dw_bar[buf]);
+    dw_mbar_expect_tx(bar, (uint32_t)(CHUNK_FLOATS * 4));
+    dw_tma_load_4d(dw_smem_u32(dw_smem + buf * CHUNK_FLOATS), &x_map, bar, j * DW_CH, w0 - PAD, h0 - PAD, b);
   };
 
   float2 res[NJ][DW_T];
-  if (DW_NBUF == 2) load_chunk(0, 0);
+  if (tid == 0) load_chunk(0, 0);
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
-    if (DW_NBUF == 2) {
-      if (j + 1 < NJ) { load_chunk(j + 1, (j + 1) & 1); cp_async_wait<1>(); }
-      else cp_async_wait<0>();
-    } else {
-      load_chunk(j, 0);
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    const float* tile = dw_smem + (DW_NBUF == 2 ? (j & 1) : 0) * CHUNK_FLOATS;
+    // buffer (j+1)&1 was last read in iteration j-1, which ended with __syncthreads()
+    if (tid == 0 && j + 1 < NJ) load_chunk(j + 1, (j + 1) & 1);
+    dw_mbar_wait(dw_smem_u32(&dw_bar[j & 1]), (uint32_t)((j >> 1) & 1));
+    const float* tile = dw_smem + (j & 1) * CHUNK_FLOATS;
     const int c = j * DW_CH + lane * 2;
     const float2 bias = __ldg(reinterpret_cast<const float2*>(dw_b + c));
     float2 acc[DW_T];
@@ -161,22 +172,50 @@ __global__ void __launch_bounds__(256) dwln_kernel(
   }
 }
 
+typedef CUresult (*DwEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static DwEncodeTiledFn dw_encode_fn() {
+  static DwEncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<DwEncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
 template <int NJ, int KS>
 static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, const float* ada,
                        int64_t ada_stride, int64_t ada_off, const float* ln_w, const float* ln_b,
                        float* y, __nv_bfloat16* y0, __nv_bfloat16* y1, __nv_bfloat16* y2,
                        int B, int H, int W, cudaStream_t stream) {
-  constexpr int HT = DW_T + KS - 1;
+  constexpr int HT = DW_T + KS - 1, C = NJ * DW_CH;
   constexpr int smem = DW_NBUF * HT * HT * DW_CH * 4;
   static bool configured = false;
   if (!configured) {
     LVAE_CUDA_CALL(cudaFuncSetAttribute(dwln_kernel<NJ, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
+  DwEncodeTiledFn enc = dw_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LVAE_E_UNSUPPORTED; }
+  // NHWC fp32 viewed as a 4-D tensor (C, W, H, B); box = (64 channels, HT, HT, 1); out-of-image coordinates -> 0
+  CUtensorMap map;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {DW_CH, HT, HT, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (dwconv input) failed: %d", (int)r); return LVAE_E_BADARG; }
   const int tiles_x = (W + DW_T - 1) / DW_T, tiles_y = (H + DW_T - 1) / DW_T;
   const int64_t blocks = (int64_t)B * tiles_x * tiles_y;
   dwln_kernel<NJ, KS><<<(unsigned)blocks, 256, smem, stream>>>(
-      x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, H, W, tiles_x, tiles_y);
+      map, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, H, W, tiles_x, tiles_y);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
