@@ -5,6 +5,8 @@
 namespace lvae {
 int gemm_f32_launch(const lvae_gemm_desc* d, cudaStream_t stream);
 int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream);
+bool gemm_smallk_applicable(const lvae_gemm_desc* d);
+int gemm_smallk_launch(const lvae_gemm_desc* d, cudaStream_t stream);
 int64_t gemm_tc_workspace_bytes(const lvae_gemm_desc* d);
 }
 
@@ -30,6 +32,8 @@ extern "C" int lvae_gemm(const lvae_gemm_desc* d, void* stream) {
   if (d->epilogue == LVAE_EPI_SHUFFLE_NHWC || d->epilogue == LVAE_EPI_SHUFFLE_NCHW)
     LVAE_CHECK_ARG(d->shuffle_r >= 1 && d->N % (d->shuffle_r * d->shuffle_r) == 0 && d->out != nullptr);
   cudaStream_t st = (cudaStream_t)stream;
+  // rank-K updates with tiny K (z_proj) are pure bandwidth: exact fp32 FMAs on the CUDA cores in every mode
+  if (gemm_smallk_applicable(d)) return gemm_smallk_launch(d, st);
   switch (d->precision) {
     case LVAE_PREC_FP32: return gemm_f32_launch(d, st);
     case LVAE_PREC_BF16X3:

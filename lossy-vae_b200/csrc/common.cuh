@@ -63,6 +63,55 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return __fmul_rn(__fmul_rn(x, 0.5f), __fadd_rn(1.0f, erf_aten_vec(__fmul_rn(x, 0.70710678118654752440f))));
 }
 
+// ---- packed fp32x2 arithmetic (sm_100): each lane is an IEEE op, i.e. bit-identical to the scalar instruction, at
+// half the issue slots.  Used where the CUDA cores, not memory, bound a kernel (GELU epilogue, depthwise conv).
+__device__ __forceinline__ uint64_t f2_as_u64(float2 v) { return *reinterpret_cast<uint64_t*>(&v); }
+__device__ __forceinline__ float2 u64_as_f2(uint64_t v) { return *reinterpret_cast<float2*>(&v); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)), "l"(f2_as_u64(c)));
+  return u64_as_f2(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+  return u64_as_f2(d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+  return u64_as_f2(d);
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+// gelu_erf on two values: the same formula and the same roundings as gelu_erf(), except that e^{-x^2} comes from
+// an inlined range reduction + ex2.approx (<= 2 ulp, like expf) so that everything around the two MUFU ops packs.
+// Carries -t instead of t: every sign flip below is exact, so the polynomial matches erf_aten_vec bit for bit.
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 xk = mul2(x, splat2(0.70710678118654752440f));
+  const float2 a = make_float2(fabsf(xk.x), fabsf(xk.y));
+  const float2 d = fma2(splat2(0.3275911f), a, splat2(1.0f));                 // 1 + p|x|  (>= 1)
+  float2 tn;                                                                   // -1/d
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tn.x) : "f"(-d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tn.y) : "f"(-d.y));
+  tn = fma2(tn, fma2(d, tn, splat2(1.0f)), tn);                                // Newton step: correctly rounded -1/d
+  float2 r = fma2(splat2(1.061405429f), tn, splat2(1.453152027f));             // -(p5 t + p4)
+  r = fma2(r, tn, splat2(1.421413741f));                                       //  (..) t + p3
+  r = fma2(r, tn, splat2(0.284496736f));                                       // -((..) t + p2)
+  r = fma2(r, tn, splat2(0.254829592f));                                       //  (..) t + p1
+  // e = exp(-xk^2)
+  float2 y = mul2(xk, make_float2(-xk.x, -xk.y));
+  y.x = fmaxf(y.x, -87.0f); y.y = fmaxf(y.y, -87.0f);
+  const float2 z = fma2(y, splat2(1.4426950408889634f), splat2(12583039.0f)); // low mantissa bits: n + 127
+  const float2 nf = add2(z, splat2(-12583039.0f));
+  float2 u = fma2(y, splat2(1.4426950216293335f), make_float2(-nf.x, -nf.y));
+  u = fma2(y, splat2(1.925963033500011e-08f), u);
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(u.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(u.y));
+  e = mul2(e, make_float2(__uint_as_float(__float_as_uint(z.x) << 23), __uint_as_float(__float_as_uint(z.y) << 23)));
+  const float2 res = fma2(mul2(e, tn), r, splat2(1.0f));                       // 1 - e t r
+  const float2 erf = make_float2(copysignf(res.x, xk.x), copysignf(res.y, xk.y));
+  return mul2(mul2(x, splat2(0.5f)), add2(splat2(1.0f), erf));
+}
+
 // torch.erf on CPU float tensors (what td.Normal.cdf calls): a <= 0.55-ulp erf that saturates to +-1 from
 // |x| >= 3.8325069 (measured against this image's torch 2.11 / MKL build over every float in [1e-3, 4.5]:
 // 97 % of results equal the correctly rounded value, the rest are off by one ulp only where the true value is

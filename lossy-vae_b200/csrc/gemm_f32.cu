@@ -180,6 +180,80 @@ __global__ void __launch_bounds__(NT) gemm_f32_kernel(const GemmParams p) {
   }
 }
 
+// Rank-K update for tiny K (z_proj: feature += W z + b with K = zdim in {8, 32, 96}, qarv/model.py:72-75):
+// bandwidth-bound, so plain fp32 FMAs; the [N, K] weight tile of a CTA sits in shared memory, each thread owns
+// one output column for a strip of rows and streams the residual in and the result out with coalesced accesses.
+template <int KMAX>
+__global__ void __launch_bounds__(256) gemm_smallk_kernel(const GemmParams p) {
+  extern __shared__ float sk_smem[];                   // [256][K + 1] weights | [32][K] A rows
+  const int K = p.K, n0 = blockIdx.y * 256, tid = threadIdx.x;
+  float* ws = sk_smem; float* as = sk_smem + 256 * (K + 1);
+  for (int i = tid; i < 256 * K; i += 256) {
+    const int n = i / K, k = i - n * K;
+    ws[n * (K + 1) + k] = (n0 + n < p.N) ? __ldg(p.w + (int64_t)(n0 + n) * K + k) : 0.f;
+  }
+  const int n = n0 + tid;
+  const bool n_ok = n < p.N;
+  const float b = (n_ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+  const float g = (n_ok && p.epi == LVAE_EPI_SCALE_RES) ? __ldg(p.gamma + n) : 1.f;
+  const float* wrow = ws + tid * (K + 1);
+  for (int m0 = blockIdx.x * 32; m0 < p.M; m0 += gridDim.x * 32) {
+    __syncthreads();
+    const int rows = (p.M - m0) < 32 ? (p.M - m0) : 32;
+    for (int i = tid; i < rows * K; i += 256) as[i] = __ldg(p.a0 + (int64_t)m0 * K + i);
+    __syncthreads();
+    if (!n_ok) continue;
+    float rr[32];
+    const bool has_res = (p.epi == LVAE_EPI_SCALE_RES || p.epi == LVAE_EPI_BIAS_RES);
+    if (has_res) {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) rr[r] = (r < rows) ? p.res[(int64_t)(m0 + r) * p.N + n] : 0.f;
+    }
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      if (r >= rows) break;
+      float acc = 0.f;
+      const float* arow = as + r * K;
+#pragma unroll 8
+      for (int k = 0; k < K; ++k) acc = fmaf(arow[k], wrow[k], acc);
+      float v = __fadd_rn(acc, b);
+      if (p.epi == LVAE_EPI_BIAS_GELU) v = gelu_erf(v);
+      else if (p.epi == LVAE_EPI_SCALE_RES) v = __fadd_rn(__fmul_rn(v, g), rr[r]);
+      else if (p.epi == LVAE_EPI_BIAS_RES) v = __fadd_rn(rr[r], v);
+      p.out[(int64_t)(m0 + r) * p.N + n] = v;
+    }
+  }
+}
+
+bool gemm_smallk_applicable(const lvae_gemm_desc* d) {
+  const int K = d->ksize * d->ksize * d->C0 + (d->a1 ? d->C1 : 0);
+  return d->ksize == 1 && d->stride == 1 && d->pad == 0 && d->a1 == nullptr && d->a0 != nullptr && d->out != nullptr &&
+         K <= 32 && d->N >= 128 && d->out_planes[0] == nullptr &&
+         (d->epilogue == LVAE_EPI_BIAS || d->epilogue == LVAE_EPI_BIAS_RES || d->epilogue == LVAE_EPI_SCALE_RES);
+}
+
+int gemm_smallk_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
+  GemmParams p;
+  p.a0 = d->a0; p.a1 = nullptr; p.B = d->B; p.H = d->H; p.W = d->W; p.Ho = d->H; p.Wo = d->W;
+  p.C0 = d->C0; p.C1 = 0; p.ks = 1; p.stride = 1; p.pad = 0;
+  p.w = d->w; p.bias = d->bias; p.N = d->N; p.K = d->C0; p.M = d->B * d->H * d->W;
+  p.epi = d->epilogue; p.gamma = d->gamma; p.res = d->res; p.out = d->out; p.r = 0;
+  if (p.M == 0) return 0;
+  const int smem = (256 * (p.K + 1) + 32 * p.K) * 4;
+  static bool configured = false;
+  if (!configured) {
+    LVAE_CUDA_CALL(cudaFuncSetAttribute(gemm_smallk_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 97 + 32 * 96) * 4));
+    configured = true;
+  }
+  const int ny = (p.N + 255) / 256;
+  int nx = (p.M + 31) / 32;
+  const int cap = 148 * 4 / ny > 0 ? 148 * 4 / ny : 1;
+  if (nx > cap) nx = cap;
+  gemm_smallk_kernel<96><<<dim3(nx, ny), 256, smem, stream>>>(p);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
 int gemm_f32_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   GemmParams p;
   p.a0 = d->a0; p.a1 = d->a1; p.B = d->B; p.H = d->H; p.W = d->W;

@@ -308,11 +308,20 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           //      pack bf16 pairs, transpose through shared memory (80-byte rows: conflict-free 128-bit stores),
           //      and store 64-byte row segments with 64-bit accesses
           float g[32];
+          if (nb + 32 <= p.N && p.bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nb + j;
-            const float b = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
-            g[j] = gelu_erf(__fadd_rn(__uint_as_float(v[j]), b));
+            for (int j = 0; j < 32; j += 2) {
+              const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.bias + nb + j));
+              const float2 o = gelu_erf2(add2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), b2));
+              g[j] = o.x; g[j + 1] = o.y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = nb + j;
+              const float b = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
+              g[j] = gelu_erf(__fadd_rn(__uint_as_float(v[j]), b));
+            }
           }
           const int sub = lane >> 3, l8 = lane & 7;          // 4 rows per pass, 8 lanes x 4 columns per row
           const int n = nb + 4 * l8;
@@ -388,6 +397,23 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                   else if (p.epi == LVAE_EPI_BIAS_RES) x = __fadd_rn(rsrc[(int64_t)r * p.N], x);
                   dst[(int64_t)r * p.N] = x;
                 }
+              }
+            } else if (shuffle) {
+              // PixelShuffle(r) store: address = base(m) + offset(n), both separable (common.py:33-38)
+              const int rr = p.r, Co = p.N / (rr * rr);
+              const int qq = n / Co, cc = n - qq * Co, si = qq / rr, sj = qq - si * rr;
+              const int Hr = p.Ho * rr, Wr = p.Wo * rr;
+              const bool nhwc = p.epi == LVAE_EPI_SHUFFLE_NHWC;
+              const int64_t coff = nhwc ? ((int64_t)si * Wr + sj) * Co + cc : ((int64_t)cc * Hr + si) * Wr + sj;
+              int wo = row0 % p.Wo; int tq = row0 / p.Wo; int ho = tq % p.Ho; int bb = tq / p.Ho;
+#pragma unroll 4
+              for (int r = 0; r < 32; ++r) {
+                if (row0 + r < p.M) {
+                  const int64_t base = nhwc ? (((int64_t)bb * Hr + ho * rr) * Wr + wo * rr) * Co
+                                            : ((int64_t)bb * Co * Hr + ho * rr) * Wr + wo * rr;
+                  p.out[base + coff] = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
+                }
+                if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; ++bb; } }
               }
             } else {
 #pragma unroll 4
