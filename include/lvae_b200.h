@@ -138,6 +138,17 @@ int lvae_latent_dequant(const int32_t* sym, const float* prior, float* z,
 int lvae_latent_sample(const float* prior, const float* randn, const float* unif, float t,
                        float* z, int B, int hw, int zdim, void* stream);
 
+/* rd model (lvae/models/rd/model.py:27-49,162-227): continuous Gaussian posterior.  post / prior are [M, 2*zdim]
+ * (mean_raw | std_raw); mean = linear_sqrt(raw), std = softplus(raw, beta = ln 2, threshold = 12);
+ * kl = gaussian_kl(qm, qv, pm, pv); z = qm + qv * noise with caller-supplied N(0,1) noise [M, zdim].
+ * kl_partial as for lvae_latent_eval. */
+int lvae_rd_latent(const float* post, const float* prior, const float* noise,
+                   float* z, float* kl_partial, int kl_stride, float* kl_elem,
+                   int B, int hw, int zdim, void* stream);
+/* z = pm + pv * randn * t (rd/model.py:216) */
+int lvae_rd_sample(const float* prior, const float* randn, float t, float* z,
+                   int B, int hw, int zdim, void* stream);
+
 /* ---- small host-side-M operators ----------------------------------------------------------------
  * lmb -> sinusoidal embedding (common.py:101-107, qarv/model.py:275-287): emb0[b, :] =
  * [cos(a*f) | sin(a*f)], a = log(lmb[b]) * period / log(max_lmb), f = host-supplied [dim/2] table. */

@@ -11,10 +11,14 @@
 //   * warp w convolves output row w: lane l owns channels {64 j + 2 l, 64 j + 2 l + 1}, a sliding window of the
 //     shared-memory row feeds the 8 pixels, results stay in registers (8 pixels x 2 channels x C/64 chunks);
 //   * LayerNorm is then warp-local: two-pass (mean, centred second moment) warp-shuffle reductions in fp32,
-//     followed by the modulation and the split into bf16 planes for the tensor-core GEMM that consumes it.
+//     followed by the modulation and the split into bf16 planes for the tensor-core GEMM that consumes it;
+//   * wide layers (C > 512, the rd model's 640 / 768) run as a 2-CTA thread-block cluster: each CTA convolves half
+//     of the channels of the same pixel tile and the two exchange their per-pixel LayerNorm partial sums through
+//     distributed shared memory (always added in rank order, so both CTAs -- and every launch -- agree bit for bit).
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <cuda.h>
+#include <cooperative_groups.h>
 #include <mutex>
 
 namespace lvae {
@@ -54,19 +58,22 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return *reinterpret_cast<float2*>(&d);
 }
 
-template <int NJ, int KS>
+template <int NJ, int KS, int CL>
 __global__ void __launch_bounds__(256) dwln_kernel(
     const __grid_constant__ CUtensorMap x_map, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
     const float* __restrict__ ada, int64_t ada_stride, int64_t ada_off,
     const float* __restrict__ ln_w, const float* __restrict__ ln_b,
     float* __restrict__ y, __nv_bfloat16* __restrict__ y0, __nv_bfloat16* __restrict__ y1, __nv_bfloat16* __restrict__ y2,
     int H, int W, int tiles_x, int tiles_y) {
-  constexpr int C = NJ * DW_CH, PAD = (KS - 1) / 2, HT = DW_T + KS - 1;     // halo tile edge
+  constexpr int C = NJ * DW_CH * CL, PAD = (KS - 1) / 2, HT = DW_T + KS - 1;   // halo tile edge
   constexpr int CHUNK_FLOATS = HT * HT * DW_CH;
   extern __shared__ __align__(128) float dw_smem[];                          // [DW_NBUF][HT][HT][64]
   __shared__ __align__(8) uint64_t dw_bar[2];
+  __shared__ float ln_part[2][8][DW_T];                                      // [pass][warp][pixel] partial sums (CL > 1)
   const int tid = threadIdx.x, lane = tid & 31, wrow = tid >> 5;
-  int t = blockIdx.x;
+  const int crank = (CL > 1) ? (int)(blockIdx.x % CL) : 0;                   // cluster dims (CL,1,1): rank == blockIdx.x % CL
+  const int cbase = crank * NJ * DW_CH;                                      // first channel of this CTA
+  int t = blockIdx.x / CL;
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y; const int b = t / tiles_y;
   const int h0 = ty * DW_T, w0 = tx * DW_T;
@@ -80,7 +87,7 @@ __global__ void __launch_bounds__(256) dwln_kernel(
   auto load_chunk = [&](int j, int buf) {                                    // one thread
     const uint32_t bar = dw_smem_u32(&dw_bar[buf]);
     dw_mbar_expect_tx(bar, (uint32_t)(CHUNK_FLOATS * 4));
-    dw_tma_load_4d(dw_smem_u32(dw_smem + buf * CHUNK_FLOATS), &x_map, bar, j * DW_CH, w0 - PAD, h0 - PAD, b);
+    dw_tma_load_4d(dw_smem_u32(dw_smem + buf * CHUNK_FLOATS), &x_map, bar, cbase + j * DW_CH, w0 - PAD, h0 - PAD, b);
   };
 
   float2 res[NJ][DW_T];
@@ -91,7 +98,7 @@ __global__ void __launch_bounds__(256) dwln_kernel(
     if (tid == 0 && j + 1 < NJ) load_chunk(j + 1, (j + 1) & 1);
     dw_mbar_wait(dw_smem_u32(&dw_bar[j & 1]), (uint32_t)((j >> 1) & 1));
     const float* tile = dw_smem + (j & 1) * CHUNK_FLOATS;
-    const int c = j * DW_CH + lane * 2;
+    const int c = cbase + j * DW_CH + lane * 2;
     const float2 bias = __ldg(reinterpret_cast<const float2*>(dw_b + c));
     float2 acc[DW_T];
 #pragma unroll
@@ -115,25 +122,61 @@ __global__ void __launch_bounds__(256) dwln_kernel(
   }
 
   const int h = h0 + wrow;
-  if (h >= H) return;                      // warp-uniform
+  if (CL == 1 && h >= H) return;           // warp-uniform (cluster CTAs stay for the exchanges below)
+  namespace cg = cooperative_groups;
   float mean[DW_T], rstd[DW_T];
+  float part[DW_T];
 #pragma unroll
   for (int s = 0; s < DW_T; ++s) {
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) sum += res[j][s].x + res[j][s].y;
-    mean[s] = warp_sum(sum) * (1.0f / C);
+    part[s] = warp_sum(sum);
+  }
+  if (CL > 1) {
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < DW_T; ++s) ln_part[0][wrow][s] = part[s];
+    }
+    cg::this_cluster().sync();
+#pragma unroll
+    for (int s = 0; s < DW_T; ++s) {
+      float tot = 0.f;
+      for (int r = 0; r < CL; ++r) tot += cg::this_cluster().map_shared_rank(&ln_part[0][wrow][s], r)[0];
+      part[s] = tot;
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < DW_T; ++s) {
+    mean[s] = part[s] * (1.0f / C);
     float sq = 0.f;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const float dx = res[j][s].x - mean[s], dy = res[j][s].y - mean[s];
       sq = fmaf(dx, dx, sq); sq = fmaf(dy, dy, sq);
     }
-    rstd[s] = 1.0f / sqrtf(warp_sum(sq) * (1.0f / C) + 1e-6f);
+    part[s] = warp_sum(sq);
+  }
+  if (CL > 1) {
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < DW_T; ++s) ln_part[1][wrow][s] = part[s];
+    }
+    cg::this_cluster().sync();
+#pragma unroll
+    for (int s = 0; s < DW_T; ++s) {
+      float tot = 0.f;
+      for (int r = 0; r < CL; ++r) tot += cg::this_cluster().map_shared_rank(&ln_part[1][wrow][s], r)[0];
+      part[s] = tot;
+    }
+    cg::this_cluster().sync();               // nobody exits while a peer may still read its shared memory
+    if (h >= H) return;
   }
 #pragma unroll
+  for (int s = 0; s < DW_T; ++s) rstd[s] = 1.0f / sqrtf(part[s] * (1.0f / C) + 1e-6f);
+#pragma unroll
   for (int j = 0; j < NJ; ++j) {
-    const int c = j * DW_CH + lane * 2;
+    const int c = cbase + j * DW_CH + lane * 2;
     float2 mul, add;                       // v * mul + add with mul = (1 + scale) | gamma, add = shift | beta
     if (ln_w != nullptr) {
       mul = __ldg(reinterpret_cast<const float2*>(ln_w + c));
@@ -188,16 +231,16 @@ static DwEncodeTiledFn dw_encode_fn() {
   return fn;
 }
 
-template <int NJ, int KS>
+template <int NJ, int KS, int CL>
 static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, const float* ada,
                        int64_t ada_stride, int64_t ada_off, const float* ln_w, const float* ln_b,
                        float* y, __nv_bfloat16* y0, __nv_bfloat16* y1, __nv_bfloat16* y2,
                        int B, int H, int W, cudaStream_t stream) {
-  constexpr int HT = DW_T + KS - 1, C = NJ * DW_CH;
+  constexpr int HT = DW_T + KS - 1, C = NJ * DW_CH * CL;
   constexpr int smem = DW_NBUF * HT * HT * DW_CH * 4;
   static bool configured = false;
   if (!configured) {
-    LVAE_CUDA_CALL(cudaFuncSetAttribute(dwln_kernel<NJ, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LVAE_CUDA_CALL(cudaFuncSetAttribute(dwln_kernel<NJ, KS, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   DwEncodeTiledFn enc = dw_encode_fn();
@@ -214,22 +257,33 @@ static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, con
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (dwconv input) failed: %d", (int)r); return LVAE_E_BADARG; }
   const int tiles_x = (W + DW_T - 1) / DW_T, tiles_y = (H + DW_T - 1) / DW_T;
   const int64_t blocks = (int64_t)B * tiles_x * tiles_y;
-  dwln_kernel<NJ, KS><<<(unsigned)blocks, 256, smem, stream>>>(
-      map, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, H, W, tiles_x, tiles_y);
+  if (CL == 1) {
+    dwln_kernel<NJ, KS, CL><<<(unsigned)blocks, 256, smem, stream>>>(
+        map, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, H, W, tiles_x, tiles_y);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(blocks * CL)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    LVAE_CUDA_CALL(cudaLaunchKernelEx(&cfg, dwln_kernel<NJ, KS, CL>, map, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b,
+                                      y, y0, y1, y2, H, W, tiles_x, tiles_y));
+  }
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
 
-template <int NJ>
+template <int NJ, int CL>
 static int dispatch_k(int k, const float* x, const float* dw_w, const float* dw_b, const float* ada,
                       int64_t ada_stride, int64_t ada_off, const float* ln_w, const float* ln_b,
                       float* y, __nv_bfloat16* y0, __nv_bfloat16* y1, __nv_bfloat16* y2,
                       int B, int H, int W, cudaStream_t stream) {
   switch (k) {
-    case 1: return launch_dwln<NJ, 1>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, B, H, W, stream);
-    case 3: return launch_dwln<NJ, 3>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, B, H, W, stream);
-    case 5: return launch_dwln<NJ, 5>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, B, H, W, stream);
-    case 7: return launch_dwln<NJ, 7>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, B, H, W, stream);
+    case 1: return launch_dwln<NJ, 1, CL>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, B, H, W, stream);
+    case 3: return launch_dwln<NJ, 3, CL>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, B, H, W, stream);
+    case 5: return launch_dwln<NJ, 5, CL>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, B, H, W, stream);
+    case 7: return launch_dwln<NJ, 7, CL>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, B, H, W, stream);
     default: set_error("dwconv kernel size %d unsupported", k); return LVAE_E_UNSUPPORTED;
   }
 }
@@ -246,11 +300,13 @@ static int dwln_dispatch(const float* x, const float* dw_w, const float* dw_b,
   LVAE_CHECK_ARG(ln_w != nullptr || (ada_off % 2 == 0 && ada_stride % 2 == 0));      // float2 loads of shift / scale
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* p0 = (__nv_bfloat16*)y0; __nv_bfloat16* p1 = (__nv_bfloat16*)y1; __nv_bfloat16* p2 = (__nv_bfloat16*)y2;
-#define LVAE_DWLN_CASE(nj) case nj: return dispatch_k<nj>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, B, H, W, st);
+#define LVAE_DWLN_CASE(nj) case nj: return dispatch_k<nj, 1>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, B, H, W, st);
   switch (C / 64) {
     LVAE_DWLN_CASE(1) LVAE_DWLN_CASE(2) LVAE_DWLN_CASE(3) LVAE_DWLN_CASE(4)
     LVAE_DWLN_CASE(6) LVAE_DWLN_CASE(8)
-    default: set_error("dwconv channel count %d unsupported (need C/64 in {1,2,3,4,6,8})", C); return LVAE_E_UNSUPPORTED;
+    case 10: return dispatch_k<5, 2>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, B, H, W, st);
+    case 12: return dispatch_k<6, 2>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, B, H, W, st);
+    default: set_error("dwconv channel count %d unsupported (need C/64 in {1,2,3,4,6,8,10,12})", C); return LVAE_E_UNSUPPORTED;
   }
 #undef LVAE_DWLN_CASE
 }

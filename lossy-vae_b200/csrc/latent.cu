@@ -158,6 +158,65 @@ __global__ void __launch_bounds__(LT) sample_kernel(
   z[i] = __fadd_rn(__fadd_rn(pm, __fmul_rn(__fmul_rn(pv, randn[i]), t)), __fmul_rn(unif[i], t));
 }
 
+// ---- rd model (continuous Gaussian posterior; lvae/models/rd/model.py:27-49,162-227) ----------------------------
+// linear_sqrt (rd/model.py:27-39): sign(x) |x|^(1 - tanh(|x|)/2) for |x| <= 6, sign(x) sqrt(|x| + 1e-8) beyond
+__device__ __forceinline__ float rd_linear_sqrt(float x) {
+  const float a = fabsf(x);
+  if (a == 0.0f) return x;
+  float v;
+  if (a <= 6.0f) v = powf(a, __fsub_rn(1.0f, __fmul_rn(0.5f, tanhf(a))));
+  else v = sqrtf(__fadd_rn(a, 1e-8f));
+  return copysignf(v, x);
+}
+// F.softplus(v, beta = ln 2, threshold = 12) (rd/model.py:162-165)
+__device__ __forceinline__ float rd_std_smooth(float v) {
+  const float beta = 0.6931471805599453f;
+  const float vb = __fmul_rn(v, beta);
+  return vb > 12.0f ? v : __fdiv_rn(log1pf(expf(vb)), beta);
+}
+
+// post / prior: [M, 2*zdim] = (mean_raw | std_raw) per position; noise [M, zdim] ~ N(0,1) supplied by the caller
+__global__ void __launch_bounds__(LT) rd_latent_kernel(
+    const float* __restrict__ post, const float* __restrict__ prior, const float* __restrict__ noise,
+    float* __restrict__ z, float* __restrict__ kl_partial, float* __restrict__ kl_elem, int hw, int zdim, int kl_stride) {
+  __shared__ float red[LT / 32];
+  const int b = blockIdx.y;
+  const int per_img = hw * zdim;
+  float local = 0.f;
+#pragma unroll
+  for (int e = 0; e < LE; ++e) {
+    const int i = (blockIdx.x * LE + e) * LT + threadIdx.x;
+    if (i < per_img) {
+      const int pos = i / zdim, c = i - pos * zdim;
+      const int64_t m = (int64_t)b * hw + pos;
+      const float qm = rd_linear_sqrt(post[m * 2 * zdim + c]);
+      const float qv = rd_std_smooth(post[m * 2 * zdim + zdim + c]);
+      const float pm = rd_linear_sqrt(prior[m * 2 * zdim + c]);
+      const float pv = rd_std_smooth(prior[m * 2 * zdim + zdim + c]);
+      // gaussian_kl(qm, qv, pm, pv) = -0.5 + log(pv) - log(qv) + 0.5 * (qv^2 + (qm - pm)^2) / pv^2, left to right
+      const float d = __fsub_rn(qm, pm);
+      const float t2 = __fsub_rn(__fadd_rn(-0.5f, logf(pv)), logf(qv));
+      const float t5 = __fdiv_rn(__fmul_rn(0.5f, __fadd_rn(__fmul_rn(qv, qv), __fmul_rn(d, d))), __fmul_rn(pv, pv));
+      const float kl = __fadd_rn(t2, t5);
+      z[m * zdim + c] = __fadd_rn(qm, __fmul_rn(qv, noise[m * zdim + c]));      // rd/model.py:213
+      if (kl_elem != nullptr) kl_elem[m * zdim + c] = kl;
+      local += kl;
+    }
+  }
+  const float t = block_sum(local, red);
+  if (threadIdx.x == 0) kl_partial[(int64_t)b * kl_stride + blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(LT) rd_sample_kernel(
+    const float* __restrict__ prior, const float* __restrict__ randn, float t, float* __restrict__ z, int64_t M, int zdim) {
+  const int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x;
+  if (i >= M * zdim) return;
+  const int64_t m = i / zdim; const int c = (int)(i - m * zdim);
+  const float pm = rd_linear_sqrt(prior[m * 2 * zdim + c]);
+  const float pv = rd_std_smooth(prior[m * 2 * zdim + zdim + c]);
+  z[i] = __fadd_rn(pm, __fmul_rn(__fmul_rn(pv, randn[i]), t));                    // rd/model.py:216
+}
+
 }  // namespace lvae
 
 using namespace lvae;
@@ -214,6 +273,26 @@ extern "C" int lvae_latent_sample(const float* prior, const float* randn, const 
   LVAE_CHECK_ARG(prior && randn && unif && z && B > 0 && hw > 0 && zdim > 0);
   const int64_t M = (int64_t)B * hw;
   sample_kernel<<<(unsigned)((M * zdim + LT - 1) / LT), LT, 0, (cudaStream_t)stream>>>(prior, randn, unif, t, z, M, zdim);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lvae_rd_latent(const float* post, const float* prior, const float* noise,
+                              float* z, float* kl_partial, int kl_stride, float* kl_elem,
+                              int B, int hw, int zdim, void* stream) {
+  LVAE_CHECK_ARG(post && prior && noise && z && kl_partial && B > 0 && hw > 0 && zdim > 0);
+  const int np = lvae_latent_num_partials(hw, zdim);
+  LVAE_CHECK_ARG(kl_stride >= np);
+  rd_latent_kernel<<<dim3(np, B), LT, 0, (cudaStream_t)stream>>>(post, prior, noise, z, kl_partial, kl_elem, hw, zdim, kl_stride);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lvae_rd_sample(const float* prior, const float* randn, float t, float* z,
+                              int B, int hw, int zdim, void* stream) {
+  LVAE_CHECK_ARG(prior && randn && z && B > 0 && hw > 0 && zdim > 0);
+  const int64_t M = (int64_t)B * hw;
+  rd_sample_kernel<<<(unsigned)((M * zdim + LT - 1) / LT), LT, 0, (cudaStream_t)stream>>>(prior, randn, t, z, M, zdim);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

@@ -49,6 +49,8 @@ _PROTOS = {
     'lvae_latent_prior_index': (C.c_int, [_fp, _fp, C.c_int, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_latent_dequant': (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_latent_sample': (C.c_int, [_fp, _fp, _fp, C.c_float, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_rd_latent': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_rd_sample': (C.c_int, [_fp, _fp, C.c_float, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_lmb_sinusoid': (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_float, C.c_float, _fp]),
     'lvae_small_linear': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_image_to_patches': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp]),

@@ -87,6 +87,7 @@ class Plan:
 class QarvEngine:
     def __init__(self, model):
         self.model = model
+        self.family = getattr(model, 'family', 'qarv')      # 'qarv' (discretised-Gaussian latents) | 'rd' (continuous)
         self.lib = N.lib()
         self.device = None
         self._wver = None
@@ -165,6 +166,8 @@ class QarvEngine:
             mods = list(m.encoder.enc_blocks) + list(m.dec_blocks)
             for mod in mods:
                 kind = getattr(mod, 'op_kind', None)
+                if getattr(mod, 'downsapmle', None) is not None:        # rd: ConvNeXt block followed by a patch conv
+                    w[id(mod.downsapmle)] = self._conv_weight(mod.downsapmle)
                 if kind == 'down':
                     w[id(mod)] = self._conv_weight(mod)
                 elif kind == 'up':
@@ -178,8 +181,9 @@ class QarvEngine:
                     w[id(mod)] = dict(post_merge=self._conv_weight(mod.post_merge),
                                       posterior=self._conv_weight(mod.posterior),
                                       z_proj=self._conv_weight(mod.z_proj),
-                                      prior=self._conv_weight(mod.prior),
-                                      table=mod.discrete_gaussian.scale_table.detach().to(dev, torch.float32).contiguous())
+                                      prior=self._conv_weight(mod.prior))
+                    if self.family == 'qarv':
+                        w[id(mod)]['table'] = mod.discrete_gaussian.scale_table.detach().to(dev, torch.float32).contiguous()
         self.w = w
         self._wver = ver
         # plans hold raw weight pointers -> rebuild them
@@ -280,6 +284,17 @@ class QarvEngine:
                 else:
                     self._gemm(P, 'down', x, (B, Hs * r, Ws * r, Cc, r, r, 0), self.w[id(mod)], out)
                 x, Cc, pinned = out, mod.out_channels, False
+            elif getattr(mod, 'downsapmle', None) is not None:
+                # rd ConvNeXtAdaLNPatchDown (rd/model.py:16-24): the block's own output is not a tapped feature, the
+                # tapped one (last plain block at this resolution) must survive -> block out of place, then patch conv
+                Hs, Ws = H // s, W // s
+                y = self._block(P, mod, x, B, Hs, Ws, out=P.named('enc_tmp', B * Hs * Ws * Cc)[:B * Hs * Ws * Cc])
+                conv = mod.downsapmle
+                r = conv.rate
+                s *= r
+                out = P.f32(B * (Hs // r) * (Ws // r), conv.out_channels)
+                self._gemm(P, 'down', y, (B, Hs, Ws, Cc, r, r, 0), self.w[id(conv)], out)
+                x, Cc, pinned = out, conv.out_channels, False
             elif isinstance(mod, common.ConvNeXtBlockAdaLN):
                 Hs, Ws = H // s, W // s
                 x = self._block(P, mod, x, B, Hs, Ws, out=P.f32(B * Hs * Ws, Cc) if pinned else None)
@@ -289,6 +304,8 @@ class QarvEngine:
                 pinned = True
             else:
                 raise TypeError(f'unsupported encoder module {type(mod)}')
+            if self.family == 'rd':
+                feats[H // s] = x          # keyed by feature height, last writer wins (rd/model.py:236-244)
         return feats
 
     def _top_down(self, P, feats, nH, nW, latent_fn, stop_at_flag=False):
@@ -341,7 +358,7 @@ class QarvEngine:
         mg = P.named('post_m', M * Cc)[:M * Cc]
         self._gemm(P, 'post_merge', f, (B, Hs, Ws, Cc, 1, 1, 0), wl['post_merge'], mg, a1=e, C1=We)
         mg = self._block(P, blk.posterior2, mg, B, Hs, Ws)
-        qm = P.f32(M, blk.zdim)
+        qm = P.f32(M, wl['posterior']['N'])          # qarv: zdim means; rd: (mean_raw | std_raw) = 2 * zdim
         self._gemm(P, 'posterior', mg, (B, Hs, Ws, Cc, 3, 1, 1), wl['posterior'], qm)
         return qm
 
@@ -376,13 +393,20 @@ class QarvEngine:
 
         def latent_fn(P, blk, li, x, prior, geom):
             hw, zd, np_, off, Hs, Ws = lay[li]
-            qm = self._posterior(P, blk, x, feats[blk.enc_key], geom)
+            qm = self._posterior(P, blk, x, feats[blk.enc_key] if self.family == 'qarv' else feats[Hs], geom)
             z = P.f32(B * hw, zd)
             kle = P.f32(B * hw, zd) if want_elem else None
             P.z.append(z)
             P.kl_elem.append(kle)
             klp = P.kl_partial[:, off:]
-            if mode == 'train':
+            if self.family == 'rd':
+                # continuous posterior: z = qm + qv * eps with eps ~ N(0,1) also in eval (rd/model.py:206-213)
+                noise = P.f32(B * hw, zd)
+                P.noise.append(noise)
+                P.op('rd_latent', self.lib.lvae_rd_latent, _ptr(qm), _ptr(prior), _ptr(noise), _ptr(z),
+                     klp.data_ptr(), kl_cols, _ptr(kle), B, hw, zd, keep=(qm, prior, z, kle),
+                     meta=dict(kind='latent', elems=B * hw * zd, bytes=B * hw * zd * (28 - (0 if want_elem else 4))))
+            elif mode == 'train':
                 noise = P.f32(B * hw, zd)
                 P.noise.append(noise)
                 P.op('latent_train', self.lib.lvae_latent_train, _ptr(qm), _ptr(prior), _ptr(noise), _ptr(z),
@@ -481,8 +505,10 @@ class QarvEngine:
 
     # ------------------------------------------------------------------ public entry points
     @torch.no_grad()
-    def run(self, im, lmb, mode='eval', want_elem=False, want_im_hat=False, check_range=True):
-        """im: [B,3,H,W] fp32 in [0,1], on the host (pinned for an async copy) or on the device; lmb: [B]."""
+    def run(self, im, lmb, mode='eval', want_elem=False, want_im_hat=False, check_range=True, noise=None):
+        """im: [B,3,H,W] fp32 in [0,1], on the host (pinned for an async copy) or on the device; lmb: [B].
+        noise: optional per-layer [B,zdim,h,w] tensors replacing the generator draws (qarv train mode: U(-.5,.5);
+        rd: N(0,1)) -- how the tests feed the oracle's values."""
         self.refresh_weights()
         B, _, H, W = im.shape
         with torch.cuda.device(self.device):
@@ -490,8 +516,13 @@ class QarvEngine:
             P.im.copy_(im, non_blocking=True)
             P.lmb.copy_(lmb.to(torch.float32), non_blocking=True)
             rng = torch.aminmax(P.im) if check_range else None        # read back with the results: one sync
-            if mode == 'train':
-                for nz in P.noise:         # same generator order as the reference: one uniform_ per layer
+            for li, nz in enumerate(P.noise):      # same generator order as the reference: one draw per layer
+                if noise is not None:
+                    hw, zd, _, _, Hs, Ws = P.layout[li]
+                    nz.view(B, Hs, Ws, zd).copy_(noise[li].to(self.device).permute(0, 2, 3, 1))
+                elif self.family == 'rd':
+                    nz.normal_()
+                else:
                     nz.uniform_(-0.5, 0.5)
             self._launch(P)
             if mode == 'compress':
@@ -622,9 +653,13 @@ class QarvEngine:
                 hw, zd, _, _, Hs, Ws = P.layout[li]
                 if latents[li] is None:
                     rn = torch.randn(B * hw, zd, device=self.device)
-                    un = torch.empty(B * hw, zd, device=self.device).uniform_(-0.5, 0.5)
-                    N.check(self.lib.lvae_latent_sample(_ptr(P.prior[li]), _ptr(rn), _ptr(un), t, _ptr(P.z[li]),
-                                                        B, hw, zd, self._stream()), 'latent_sample')
+                    if self.family == 'rd':
+                        N.check(self.lib.lvae_rd_sample(_ptr(P.prior[li]), _ptr(rn), t, _ptr(P.z[li]),
+                                                        B, hw, zd, self._stream()), 'rd_sample')
+                    else:
+                        un = torch.empty(B * hw, zd, device=self.device).uniform_(-0.5, 0.5)
+                        N.check(self.lib.lvae_latent_sample(_ptr(P.prior[li]), _ptr(rn), _ptr(un), t, _ptr(P.z[li]),
+                                                            B, hw, zd, self._stream()), 'latent_sample')
                     N.launch_count += 1
                 else:
                     assert tuple(latents[li].shape) == (B, zd, Hs, Ws)

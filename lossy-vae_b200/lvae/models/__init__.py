@@ -1,1 +1,2 @@
 from . import qarv
+from . import rd

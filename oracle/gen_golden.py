@@ -19,7 +19,8 @@ import lvae_oracle as O    # noqa: E402
 OUT = HERE.parent / 'tests' / 'golden'
 
 
-from oracle_inputs import CASES, make_input, synth_image   # noqa: E402,F401
+from oracle_inputs import CASES, RD_CASES, make_input, synth_image   # noqa: E402,F401
+import rd_oracle as R      # noqa: E402
 
 
 def main():
@@ -98,5 +99,34 @@ def main():
     print('entropy_kat written')
 
 
+def main_rd():
+    """rd_model_base fixtures: the unmodified reference with torch.manual_seed(noise_seed) before the forward, so
+    its randn_like draws are reproducible as rd_oracle.draw_noise(shapes, noise_seed)."""
+    ref = ref_loader.load_reference()
+    torch.manual_seed(0)
+    model = ref.get_model('rd_model_base').eval()
+    sd = O.sensitised_state_dict(R.rd_param_shapes(), seed=0, wide_heads=False)
+    model.load_state_dict(sd, strict=True)
+    for name, (kind, nB, H, W, lmbs, seed, nseed) in RD_CASES.items():
+        im = make_input(kind, nB, H, W, seed)
+        lmb = torch.tensor(lmbs)
+        with torch.no_grad():
+            torch.manual_seed(nseed)
+            stats = model(im, lmb=lmb, return_rec=True)
+            torch.manual_seed(nseed)
+            x_hat, lat = model.forward_end2end(im, lmb, get_latents=True)
+        rec = dict(lmb=np.array(lmbs, dtype=np.float32), loss=np.float32(stats['loss'].item()),
+                   bppix=np.float64(stats['bppix']), mse=np.float64(stats['mse']), psnr=np.float64(stats['psnr']),
+                   im_hat=stats['im_hat'].numpy(),
+                   kl_per_image=np.stack([st['kl'].sum(dim=(1, 2, 3)).numpy() for st in lat]),
+                   z0=lat[0]['z'].numpy(), z14=lat[14]['z'].numpy())
+        np.savez_compressed(OUT / f'{name}.npz', **rec)
+        print(name, 'loss', float(rec['loss']), 'bppix', float(rec['bppix']), 'psnr', float(rec['psnr']))
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'rd':
+        main_rd()
+    else:
+        main()
+        main_rd()

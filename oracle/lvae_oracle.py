@@ -75,7 +75,9 @@ def _key_generator(seed, key):
     return g
 
 
-def sensitised_tensor(key, shape, seed=0):
+def sensitised_tensor(key, shape, seed=0, wide_heads=True):
+    """wide_heads: widen the posterior / prior head weights (qarv: symbols beyond {-1,0,1}); the rd fixtures use
+    False, which keeps its continuous KL in a sane range."""
     g = _key_generator(seed, key)
     shape = tuple(shape)
     if key.endswith('gamma'):
@@ -89,16 +91,16 @@ def sensitised_tensor(key, shape, seed=0):
     assert key.endswith('.weight'), key
     fan_in = int(np.prod(shape[1:]))
     bound = 1.0 / math.sqrt(fan_in)
-    if key.endswith('posterior.weight'):    # wider posterior means -> symbols beyond {-1,0,1}
+    if wide_heads and key.endswith('posterior.weight'):    # wider posterior means -> symbols beyond {-1,0,1}
         bound *= 3.0
-    if key.endswith('prior.weight'):
+    if wide_heads and key.endswith('prior.weight'):
         bound *= 2.0
     return (torch.rand(shape, generator=g) * 2 - 1) * bound
 
 
-def sensitised_state_dict(named_shapes, seed=0):
+def sensitised_state_dict(named_shapes, seed=0, wide_heads=True):
     """named_shapes: iterable of (key, shape) for the floating-point parameters."""
-    return OrderedDict((k, sensitised_tensor(k, s, seed)) for k, s in named_shapes)
+    return OrderedDict((k, sensitised_tensor(k, s, seed, wide_heads)) for k, s in named_shapes)
 
 
 def qarv_param_shapes(arch=None):

@@ -34,3 +34,10 @@ def make_input(kind, nB, H, W, seed):
     if kind == 'rand':
         return torch.rand(nB, 3, H, W, generator=torch.Generator().manual_seed(seed))
     return synth_image(nB, H, W, seed)
+
+
+# rd model fixtures: name -> (kind, nB, H, W, lambdas, image seed, noise seed)
+RD_CASES = {
+    'rd_rand_1x64x64': ('rand', 1, 64, 64, [256.0], 10, 5),
+    'rd_synth_2x128x128': ('synth', 2, 128, 128, [16.0, 1024.0], 11, 6),
+}

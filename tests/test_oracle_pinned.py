@@ -121,3 +121,41 @@ def test_oracle_equals_live_reference(sd):
         assert torch.equal(st['im_hat'], out['im_hat'])
     finally:
         ref_loader.unload_reference()
+
+
+# ----------------------------------------------------------------------------- rd model (continuous posterior)
+def test_rd_param_count_matches_readme():
+    import rd_oracle as R
+    shapes = R.rd_param_shapes()       # lvae/models/rd/README.md:23 -- 186.7 M parameters
+    assert round(sum(int(np.prod(s)) for _, s in shapes) / 1e6, 3) == 186.670
+
+
+@pytest.mark.parametrize('name', ['rd_rand_1x64x64', 'rd_synth_2x128x128'])
+def test_rd_oracle_matches_golden(name, golden):
+    import rd_oracle as R
+    from oracle_inputs import RD_CASES
+    g = golden(name)
+    kind, nB, H, W, lmbs, seed, nseed = RD_CASES[name]
+    sd = O.sensitised_state_dict(R.rd_param_shapes(), seed=0, wide_heads=False)
+    im = make_input(kind, nB, H, W, seed)
+    arch = R.rd_base_arch()
+    out = R.rd_forward(sd, im, torch.tensor(lmbs), R.draw_noise(R.latent_shapes(arch, nB, H, W), nseed))
+    assert np.float32(out['loss'].item()) == g['loss']
+    assert out['bppix'] == float(g['bppix']) and out['psnr'] == float(g['psnr']) and out['mse'] == float(g['mse'])
+    assert torch.equal(out['im_hat'], torch.from_numpy(g['im_hat']))
+    assert torch.equal(out['records'][0]['z'], torch.from_numpy(g['z0']))
+    assert torch.equal(out['records'][14]['z'], torch.from_numpy(g['z14']))
+    for li, r in enumerate(out['records']):
+        assert torch.equal(r['kl'].sum(dim=(1, 2, 3)), torch.from_numpy(g['kl_per_image'][li]))
+
+
+def test_rd_scalar_functions_known_answers():
+    import rd_oracle as R
+    x = torch.tensor([0.0, -0.0, 1.0, -2.0, 6.0, 6.5, -9.0])
+    y = R.linear_sqrt(x)
+    assert y[0] == 0 and y[2] == 1.0                                  # |x|^(1 - tanh/2) at 1 is 1
+    assert abs(y[3].item() + 2.0 ** (1 - 0.5 * math.tanh(2.0))) < 1e-6
+    assert abs(y[5].item() - math.sqrt(6.5 + 1e-8)) < 1e-6 and abs(y[6].item() + 3.0) < 1e-6
+    assert abs(R.std_smooth(torch.tensor([0.0])).item() - 1.0) < 1e-6  # softplus_beta=ln2 (0) = ln2 / ln2
+    kl = R.gaussian_kl(torch.tensor([0.3]), torch.tensor([0.5]), torch.tensor([0.1]), torch.tensor([2.0]))
+    assert abs(kl.item() - (-0.5 + math.log(2.0) - math.log(0.5) + 0.5 * (0.25 + 0.04) / 4.0)) < 1e-6
