@@ -148,6 +148,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='images per GPU per step (BASELINE configs[1]: 8)')
     ap.add_argument('--precision', default=None, help="bf16x6 | bf16x3 | bf16 | fp32 (default: the model's default, bf16x6)")
+    ap.add_argument('--workload', default='qarv', choices=['qarv', 'rd'],
+                    help='qarv: BASELINE configs[1] (headline, default); rd: configs[4] rd_model_base 256x256, batch 32 per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-samples', type=int, default=5)
     args = ap.parse_args()
@@ -173,10 +175,22 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     warmup = max(args.warmup, 3)
     B = args.batch
+    global H, W, DENSE_GFLOP_PER_IMAGE
+    rd = args.workload == 'rd'
+    if rd:
+        import rd_oracle as R
+        H = W = 256
+        DENSE_GFLOP_PER_IMAGE = 181.82 * 0.96      # 181.82 GFLOP total at 256^2, ~4 % of it depthwise
+        if B == 8:
+            B = 32                                   # configs[4]: batch 256 over 8 GPUs
 
     torch.manual_seed(0)
-    model = lvae.get_model('qarv_base')
-    model.load_state_dict(O.sensitised_state_dict(O.qarv_param_shapes(), seed=0), strict=False)
+    if rd:
+        model = lvae.get_model('rd_model_base')
+        model.load_state_dict(O.sensitised_state_dict(R.rd_param_shapes(), seed=0, wide_heads=False), strict=True)
+    else:
+        model = lvae.get_model('qarv_base')
+        model.load_state_dict(O.sensitised_state_dict(O.qarv_param_shapes(), seed=0), strict=False)
     if args.precision:
         model.precision = args.precision
     model = model.to(dev).eval()
@@ -184,7 +198,7 @@ def main():
 
     # each rank gets its own seeded batch (weak scaling)
     im_host = make_input('rand', B, H, W, 1000 + rank).pin_memory()
-    lmb_host = torch.full((B,), 2048.0).pin_memory()
+    lmb_host = torch.full((B,), 256.0 if rd else 2048.0).pin_memory()
     lmb_dev = lmb_host.to(dev)
 
     def barrier():
@@ -195,6 +209,8 @@ def main():
     # ---- device-resident throughput: CUDA-graph replay of the launch plan
     P = eng.forward_plan(B, H, W, 'eval')
     P.im.copy_(im_host); P.lmb.copy_(lmb_host)
+    for nz in P.noise:                                # rd: posterior-sampling noise (resident, like the batch)
+        nz.normal_()
     for _ in range(warmup + 2):                       # +2: first call is eager, second captures the graph
         eng.replay(P)
     barrier()
@@ -261,19 +277,21 @@ def main():
                       frac=dw['bytes'] / dw['ms'] / 1e6 / pk['hbm'], share_of_step=dw['ms'] / tot_ms, traffic=None)
 
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and not rd:
             v, cores, sample = cpu_reference_images_per_s(args.cpu_samples)
             cpu = dict(value=v, unit='images/s', cores=cores, kind='port', sample=sample)
 
         n_img = B * world * args.steps
         line = {
-            'metric': METRIC, 'value': n_img / (ms_dev / 1e3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+            'metric': METRIC if not rd else '256x256 images/sec (rd forward)', 'value': n_img / (ms_dev / 1e3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': {'fp32': 'f32', 'bf16x6': 'f32-class (3 bf16 planes per operand, 6 tcgen05 MMAs per product, f32 accumulate)',
                       'bf16x3': 'bf16x3 (2 bf16 planes, 3 MMAs, f32 accumulate)', 'bf16': 'bf16'}[model.precision],
             'data': 'synthetic',
-            'config': {'workload': f'qarv_base eval forward (rate + MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 2048 '
-                                   f'(BASELINE configs[1])', 'batch_per_gpu': B, 'global_batch': B * world, 'precision': model.precision,
+            'config': {'workload': (f'rd_model_base forward (KL + MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 256 (BASELINE configs[4])'
+                                    if rd else
+                                    f'qarv_base eval forward (rate + MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 2048 '
+                                    f'(BASELINE configs[1])'), 'batch_per_gpu': B, 'global_batch': B * world, 'precision': model.precision,
                        'parallelism': f'batch-shard x{world}, no data-path collective', 'weights': 'seeded sensitised init (no checkpoint offline)',
                        'l2': 'no flush: per-step working set (weights 374 MB + activations > 1 GB) exceeds the 126 MB L2',
                        'dense_gflop_per_image': DENSE_GFLOP_PER_IMAGE},
