@@ -45,7 +45,10 @@ struct TcParams {
   const float* bias; const float* gamma; const float* res;
   float* out; __nv_bfloat16* out_pl[3];
   int epi, r, Ho, Wo;
+  // implicit 3x3 conv (stride 1, pad 1) from NHWC planes: an M-tile is a CONV_TH x CONV_TW pixel patch of one image
+  int conv, cH, cW, cC, tiles_w, tiles_h;
 };
+constexpr int CONV_TW = 16, CONV_TH = 8;       // 128 output pixels per tile
 
 struct TcMaps { CUtensorMap a[3]; CUtensorMap b[3]; };
 
@@ -76,6 +79,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -129,6 +137,17 @@ __device__ __forceinline__ float epi_value(const TcParams& p, int m, int n, floa
     default: break;
   }
   return v;
+}
+
+__device__ __forceinline__ void store_planes(const TcParams& p, int64_t o, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  p.out_pl[0][o] = h;
+  if (p.out_pl[1]) {
+    const float r1 = __fsub_rn(v, __bfloat162float(h));
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    p.out_pl[1][o] = m;
+    if (p.out_pl[2]) p.out_pl[2][o] = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(m)));
+  }
 }
 
 __device__ __forceinline__ void epi_store(const TcParams& p, int m, int n, float v) {
@@ -196,16 +215,31 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const int m0 = (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.BN;
+        const int mt = t / p.n_tiles;
+        const int m0 = mt * TC_BM, n0 = (t % p.n_tiles) * p.BN;
+        // conv mode: tile -> (image, patch row, patch column)
+        const int ctx = mt % p.tiles_w, cty = (mt / p.tiles_w) % p.tiles_h, cb = mt / (p.tiles_w * p.tiles_h);
+        const int cpt = p.cC / p.BK;                             // k-blocks per filter tap
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(empty_bar + s), ph ^ 1);
           const uint32_t fb = smem_u32(full_bar + s);
           mbar_expect_tx(fb, (uint32_t)stage_bytes);
           const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+          if (p.conv) {
+            // the (dy, dx)-shifted patch of the input planes: out-of-image pixels are zero-filled by TMA (= padding)
+            const int tap = kb / cpt, c0 = (kb - tap * cpt) * p.BK;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
 #pragma unroll
-          for (int pl = 0; pl < NPL; ++pl) {
-            tma_load_2d(base + pl * a_tile, &maps.a[pl], fb, kb * p.BK, m0);
-            tma_load_2d(base + NPL * a_tile + pl * b_tile, &maps.b[pl], fb, kb * p.BK, n0);
+            for (int pl = 0; pl < NPL; ++pl) {
+              tma_load_4d(base + pl * a_tile, &maps.a[pl], fb, c0, ctx * CONV_TW + dx, cty * CONV_TH + dy, cb);
+              tma_load_2d(base + NPL * a_tile + pl * b_tile, &maps.b[pl], fb, kb * p.BK, n0);
+            }
+          } else {
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl) {
+              tma_load_2d(base + pl * a_tile, &maps.a[pl], fb, kb * p.BK, m0);
+              tma_load_2d(base + NPL * a_tile + pl * b_tile, &maps.b[pl], fb, kb * p.BK, n0);
+            }
           }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -303,7 +337,26 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
         }
         const int nb = n0 + c * 32;                          // first column of the chunk
-        if (gelu_planes) {
+        if (p.conv) {
+          // rows of the tile are the pixels of a CONV_TH x CONV_TW patch: row -> (h, w) -> m; N is small here
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+          __syncwarp();
+          const int mt = t / p.n_tiles;
+          const int ctx = mt % p.tiles_w, cty = (mt / p.tiles_w) % p.tiles_h, cb = mt / (p.tiles_w * p.tiles_h);
+          const int n = nb + lane;
+          if (lane < width && n < p.N) {
+            const float b = p.bias ? __ldg(p.bias + n) : 0.f;
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+              const int row = q * 32 + r;
+              const int hh = cty * CONV_TH + row / CONV_TW, ww = ctx * CONV_TW + row % CONV_TW;
+              if (hh < p.cH && ww < p.cW)
+                p.out[(((int64_t)cb * p.cH + hh) * p.cW + ww) * p.N + n] = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
+            }
+          }
+          __syncwarp();
+        } else if (gelu_planes) {
           // ---- fc1: bias + GELU in the row-owner layout (32 independent chains per thread), then per plane
           //      pack bf16 pairs, transpose through shared memory (80-byte rows: conflict-free 128-bit stores),
           //      and store 64-byte row segments with 64-bit accesses
@@ -369,7 +422,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           const bool n_ok = (lane < width) && (n < p.N);
           if (n_ok) {
             const float b = p.bias ? __ldg(p.bias + n) : 0.f;
-            if (!shuffle && p.out != nullptr && p.out_pl[0] == nullptr && p.epi != LVAE_EPI_BIAS_GELU) {
+            if (!shuffle && p.out != nullptr && p.epi != LVAE_EPI_BIAS_GELU) {
               const float gm = (p.epi == LVAE_EPI_SCALE_RES) ? __ldg(p.gamma + n) : 1.f;
               const bool has_res = (p.epi == LVAE_EPI_SCALE_RES || p.epi == LVAE_EPI_BIAS_RES);
               const int rows = (p.M - row0) < 32 ? (p.M - row0) : 32;
@@ -385,10 +438,15 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     float x = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
                     x = (p.epi == LVAE_EPI_SCALE_RES) ? __fadd_rn(__fmul_rn(x, gm), rr[r]) : __fadd_rn(rr[r], x);
                     dst[(int64_t)r * p.N] = x;
+                    if (p.out_pl[0] != nullptr) store_planes(p, (int64_t)(row0 + r) * p.N + n, x);
                   }
                 } else {
 #pragma unroll 8
-                  for (int r = 0; r < 32; ++r) dst[(int64_t)r * p.N] = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
+                  for (int r = 0; r < 32; ++r) {
+                    const float x = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
+                    dst[(int64_t)r * p.N] = x;
+                    if (p.out_pl[0] != nullptr) store_planes(p, (int64_t)(row0 + r) * p.N + n, x);
+                  }
                 }
               } else {
                 for (int r = 0; r < rows; ++r) {
@@ -396,6 +454,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                   if (p.epi == LVAE_EPI_SCALE_RES) x = __fadd_rn(__fmul_rn(x, gm), rsrc[(int64_t)r * p.N]);
                   else if (p.epi == LVAE_EPI_BIAS_RES) x = __fadd_rn(rsrc[(int64_t)r * p.N], x);
                   dst[(int64_t)r * p.N] = x;
+                  if (p.out_pl[0] != nullptr) store_planes(p, (int64_t)(row0 + r) * p.N + n, x);
                 }
               }
             } else if (shuffle) {
@@ -506,6 +565,21 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, 
   return 0;
 }
 
+// NHWC bf16 plane viewed as (C, W, H, B); box = (bk channels, CONV_TW, CONV_TH, 1) = 128 rows of one swizzle row
+static int make_map_conv(CUtensorMap* map, const void* ptr, int B, int H, int W, int C, int bk) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LVAE_E_UNSUPPORTED; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bk, CONV_TW, CONV_TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (conv planes) failed (%d)", (int)r); return LVAE_E_BADARG; }
+  return 0;
+}
+
 static void tc_geometry(const lvae_gemm_desc* d, int* Ho, int* Wo, int64_t* M, int* K) {
   *Ho = (d->H + 2 * d->pad - d->ksize) / d->stride + 1;
   *Wo = (d->W + 2 * d->pad - d->ksize) / d->stride + 1;
@@ -559,11 +633,21 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
     for (int i = 0; i < npl; ++i) LVAE_CHECK_ARG(a_pl[i] != nullptr);
   }
 
+  // implicit 3x3 conv straight from NHWC planes (no im2col workspace): 9 shifted TMA box loads per channel block
+  const bool conv = d->a_planes[0] != nullptr && d->ksize == 3 && d->stride == 1 && d->pad == 1 && d->a1 == nullptr &&
+                    d->C0 % 64 == 0 && d->epilogue == LVAE_EPI_BIAS && d->out != nullptr;
+  if (d->a_planes[0] != nullptr && d->ksize != 1 && !conv) {
+    set_error("pre-split A planes support 1x1 (plain [M,K]) and 3x3 stride-1 pad-1 convolutions with C %% 64 == 0 only");
+    return LVAE_E_UNSUPPORTED;
+  }
   TcParams p;
   p.M = M; p.N = d->N; p.K = K;
   p.BN = pick_bn(d->N, npl);
   p.n_tiles = (d->N + p.BN - 1) / p.BN;
-  p.num_tiles = ((M + TC_BM - 1) / TC_BM) * p.n_tiles;
+  p.conv = conv ? 1 : 0; p.cH = d->H; p.cW = d->W; p.cC = d->C0;
+  p.tiles_w = conv ? (d->W + CONV_TW - 1) / CONV_TW : 1;
+  p.tiles_h = conv ? (d->H + CONV_TH - 1) / CONV_TH : 1;
+  p.num_tiles = (conv ? d->B * p.tiles_w * p.tiles_h : (M + TC_BM - 1) / TC_BM) * p.n_tiles;
   p.acc_cols = (npl >= 2 ? 2 : 1) * p.BN;
   int cols = 32; while (cols < 2 * p.acc_cols) cols <<= 1;
   p.tmem_cols = cols;
@@ -594,7 +678,8 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   int rc;
   for (int i = 0; i < 3; ++i) {
     const int j = i < npl ? i : 0;
-    if ((rc = make_map(&maps.a[i], a_pl[j], M, K, TC_BM, p.BK))) return rc;
+    if (conv) { if ((rc = make_map_conv(&maps.a[i], a_pl[j], d->B, d->H, d->W, d->C0, p.BK))) return rc; }
+    else if ((rc = make_map(&maps.a[i], a_pl[j], M, K, TC_BM, p.BK))) return rc;
     if ((rc = make_map(&maps.b[i], d->w_planes[j], d->N, K, p.BN, p.BK))) return rc;
   }
 

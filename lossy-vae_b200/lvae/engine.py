@@ -220,8 +220,9 @@ class QarvEngine:
         P.op(name, self.lib.lvae_gemm, C.byref(d), keep=(d, a0, a1, went, out, gamma, res, a_planes, out_planes, ws),
              meta=meta)
 
-    def _block(self, P, blk, x, B, Hs, Ws, out=None):
-        """x: [M, C] fp32 NHWC; returns the output buffer (x itself when out is None: in place)."""
+    def _block(self, P, blk, x, B, Hs, Ws, out=None, out_planes=None):
+        """x: [M, C] fp32 NHWC; returns the output buffer (x itself when out is None: in place).  out_planes: bf16
+        planes of the result, written by the fc2 epilogue for a tensor-core consumer (the 3x3 posterior conv)."""
         wb = self.w[id(blk)]
         C_, hid, k = blk.dim, blk.hidden, blk.kernel_size
         M = B * Hs * Ws
@@ -238,7 +239,7 @@ class QarvEngine:
                  keep=(x, A), meta=dw_meta)
             self._gemm(P, 'fc1', None, (1, 1, M, C_, 1, 1, 0), wb['fc1'], None, epi=N.EPI_BIAS_GELU, a_planes=A, out_planes=Hd)
             self._gemm(P, 'fc2', None, (1, 1, M, hid, 1, 1, 0), wb['fc2'], out, epi=N.EPI_SCALE_RES,
-                       gamma=wb['gamma'], res=x, a_planes=Hd)
+                       gamma=wb['gamma'], res=x, a_planes=Hd, out_planes=out_planes)
             return out
         A = P.named('scratch_a', M * C_)
         Hd = P.named('scratch_h', M * hid)
@@ -357,9 +358,16 @@ class QarvEngine:
         f = self._block(P, blk.posterior1, x, B, Hs, Ws, out=P.named('post_f', M * Cc)[:M * Cc])
         mg = P.named('post_m', M * Cc)[:M * Cc]
         self._gemm(P, 'post_merge', f, (B, Hs, Ws, Cc, 1, 1, 0), wl['post_merge'], mg, a1=e, C1=We)
-        mg = self._block(P, blk.posterior2, mg, B, Hs, Ws)
         qm = P.f32(M, wl['posterior']['N'])          # qarv: zdim means; rd: (mean_raw | std_raw) = 2 * zdim
-        self._gemm(P, 'posterior', mg, (B, Hs, Ws, Cc, 3, 1, 1), wl['posterior'], qm)
+        if self.npl and Cc % 64 == 0:
+            # tensor-core modes: posterior2's fc2 epilogue also writes its result as bf16 planes, which the 3x3
+            # head convolves implicitly (shifted TMA boxes) -- no im2col workspace
+            mp = [P.named(f'post_m_pl{i}', M * Cc, dtype=torch.bfloat16)[:M * Cc] for i in range(self.npl)]
+            mg = self._block(P, blk.posterior2, mg, B, Hs, Ws, out_planes=mp)
+            self._gemm(P, 'posterior', None, (B, Hs, Ws, Cc, 3, 1, 1), wl['posterior'], qm, a_planes=mp)
+        else:
+            mg = self._block(P, blk.posterior2, mg, B, Hs, Ws)
+            self._gemm(P, 'posterior', mg, (B, Hs, Ws, Cc, 3, 1, 1), wl['posterior'], qm)
         return qm
 
     # ------------------------------------------------------------------ plans
