@@ -147,7 +147,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='images per GPU per step (BASELINE configs[1]: 8)')
-    ap.add_argument('--precision', default=None, help="bf16x6 | bf16x3 | bf16 | fp32 (default: the model's default, bf16x6)")
+    ap.add_argument('--precision', default=None, help="f16x3 | bf16x6 | bf16x3 | bf16 | fp32 (default: the model's default, f16x3)")
     ap.add_argument('--workload', default='qarv', choices=['qarv', 'rd'],
                     help='qarv: BASELINE configs[1] (headline, default); rd: configs[4] rd_model_base 256x256, batch 32 per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -259,7 +259,7 @@ def main():
             k = by_kind.setdefault(meta.get('kind', 'misc'), dict(ms=0.0, flops=0, bytes=0, n=0))
             k['ms'] += ms; k['flops'] += meta.get('flops', 0); k['bytes'] += meta.get('bytes', 0); k['n'] += 1
         gm, lt, dw = by_kind['gemm'], by_kind['latent'], by_kind['dwln']
-        issued = {'fp32': 1, 'bf16': 1, 'bf16x3': 3, 'bf16x6': 6}[model.precision]
+        issued = {'fp32': 1, 'bf16': 1, 'bf16x3': 3, 'bf16x6': 6, 'f16x3': 3}[model.precision]
         roof = dict(bound='tensor', kernel=f'lvae_gemm ({model.precision})', achieved=gm['flops'] / gm['ms'] / 1e9,
                     peak=pk['tensor_sustained'], unit='TFLOP/s', traffic=None, peak_source=pk['src'] + ' (sustained bf16 cuBLAS)',
                     launches=gm['n'], share_of_step=gm['ms'] / tot_ms, issued_mma_multiplier=issued,
@@ -286,7 +286,8 @@ def main():
             'metric': METRIC if not rd else '256x256 images/sec (rd forward)', 'value': n_img / (ms_dev / 1e3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': {'fp32': 'f32', 'bf16x6': 'f32-class (3 bf16 planes per operand, 6 tcgen05 MMAs per product, f32 accumulate)',
-                      'bf16x3': 'bf16x3 (2 bf16 planes, 3 MMAs, f32 accumulate)', 'bf16': 'bf16'}[model.precision],
+                      'bf16x3': 'bf16x3 (2 bf16 planes, 3 MMAs, f32 accumulate)', 'bf16': 'bf16',
+                      'f16x3': 'f32-class (2 fp16 planes per operand = 22 significand bits, 3 tcgen05 MMAs per product, f32 accumulate)'}[model.precision],
             'data': 'synthetic',
             'config': {'workload': (f'rd_model_base forward (KL + MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 256 (BASELINE configs[4])'
                                     if rd else

@@ -58,11 +58,18 @@ enum lvae_precision {
   LVAE_PREC_FP32 = 0,         /* fp32 FFMA on CUDA cores                                                      */
   LVAE_PREC_BF16X3 = 1,       /* tcgen05 kind::f16, 2 bf16 planes per operand, 3 MMAs (hh + hm + mh): ~2^-17  */
   LVAE_PREC_BF16 = 2,         /* tcgen05, 1 plane, 1 MMA: ~2^-8 (non-parity fast mode)                        */
-  LVAE_PREC_BF16X6 = 3        /* tcgen05, 3 bf16 planes, 6 MMAs (hh + hm + mh + mm + hl + lh): ~2^-23, the    */
+  LVAE_PREC_BF16X6 = 3,       /* tcgen05, 3 bf16 planes, 6 MMAs (hh + hm + mh + mm + hl + lh): ~2^-23, the    */
                               /* fp32-class mode in which quantised symbols match the fp32 CPU reference      */
+  LVAE_PREC_F16X3 = 4         /* tcgen05 kind::f16 on fp16 planes: 2 planes of 11 significand bits each, 3    */
+                              /* MMAs (hh + hl + lh): ~2^-22 per product -- fp32-class at half the MMAs of    */
+                              /* BF16X6.  Weight planes carry w * LVAE_F16_WEIGHT_SCALE (keeps the low plane  */
+                              /* of small weights out of the fp16 subnormal range); the epilogue undoes it.   */
 };
-/* planes per operand for a precision mode: fp32 0, bf16 1, bf16x3 2, bf16x6 3 */
+/* planes per operand for a precision mode: fp32 0, bf16 1, bf16x3 2, bf16x6 3, f16x3 2 */
 #define LVAE_MAX_PLANES 3
+/* element format of operand planes */
+enum lvae_plane_format { LVAE_PLANES_BF16 = 0, LVAE_PLANES_F16 = 1 };
+#define LVAE_F16_WEIGHT_SCALE 256.0f
 
 typedef struct lvae_gemm_desc {
   const float* a0;     /* segment 0 activations, NHWC [B,H,W,C0] */
@@ -98,6 +105,11 @@ int lvae_gemm(const lvae_gemm_desc* d, void* stream);
 int64_t lvae_gemm_workspace_bytes(const lvae_gemm_desc* d);
 /* split fp32 -> bf16 planes p0 = rn(x), p1 = rn(x - p0), p2 = rn(x - p0 - p1); p1 / p2 may be NULL */
 int lvae_split_bf16(const float* x, void* p0, void* p1, void* p2, int64_t n, void* stream);
+/* the same split of (x * scale) into planes of `plane_format` (enum lvae_plane_format); weights of an
+ * LVAE_PREC_F16X3 GEMM are split with plane_format = LVAE_PLANES_F16, scale = LVAE_F16_WEIGHT_SCALE, activations with
+ * scale = 1.  fp16 conversion saturates at +-65504.  n % 2 == 0. */
+int lvae_split_planes(const float* x, void* p0, void* p1, void* p2, int64_t n, int plane_format, float scale,
+                      void* stream);
 
 /* ---- depthwise conv + LayerNorm + AdaLN (common.py:145-152) ------------------------------------
  * y[m, c] = LN_c( dwconv_kxk(x)[m, c] + dw_bias[c] ) * (1 + scale[b, c]) + shift[b, c]
@@ -109,12 +121,13 @@ int lvae_dwconv_ln_adaln(const float* x, const float* dw_w, const float* dw_b,
                          const float* ada, int64_t ada_stride, int64_t ada_off,
                          const float* ln_w, const float* ln_b,
                          float* y, int B, int H, int W, int C, int k, void* stream);
-/* Same operator writing the result as bf16 planes [M, C] -- the A operand of the tensor-core fc1 GEMM
- * (y1 / y2 may be NULL when the precision mode reads fewer planes). */
+/* Same operator writing the result as 16-bit planes [M, C] (enum lvae_plane_format) -- the A operand of the
+ * tensor-core fc1 GEMM (y1 / y2 may be NULL when the precision mode reads fewer planes). */
 int lvae_dwconv_ln_adaln_planes(const float* x, const float* dw_w, const float* dw_b,
                                 const float* ada, int64_t ada_stride, int64_t ada_off,
                                 const float* ln_w, const float* ln_b,
-                                void* y0, void* y1, void* y2, int B, int H, int W, int C, int k, void* stream);
+                                void* y0, void* y1, void* y2, int plane_format,
+                                int B, int H, int W, int C, int k, void* stream);
 
 /* ---- fused latent-layer kernels (qarv/model.py:51-53,90-96,104-113; CompressAI GaussianConditional) --
  * prior [M, 2*zdim] (pm | plogv_raw) and qm [M, zdim] are NHWC matrices; hw = h*w positions per image.

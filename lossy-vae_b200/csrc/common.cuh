@@ -126,6 +126,34 @@ __device__ __forceinline__ float erf_torch_cpu(float x) {
   return copysignf(r, x);
 }
 
+// ---- 16-bit operand planes of the tensor-core GEMM (lvae_plane_format).  pack2<F16>(a, b) rounds two fp32 values to
+// bf16 (F16 = false) or fp16 (F16 = true; saturating, so an out-of-range activation becomes +-65504 instead of inf)
+// and returns them as one 32-bit word, a in the low half; unpack2 is the exact inverse widening.
+template <bool F16> __device__ __forceinline__ uint32_t pack2(float a, float b) {
+  uint32_t d;
+  if (F16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+template <bool F16> __device__ __forceinline__ float2 unpack2(uint32_t d) {
+  if (F16) {
+    float2 r;
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "r"(d));
+    return r;
+  }
+  return make_float2(__uint_as_float(d << 16), __uint_as_float(d & 0xffff0000u));
+}
+// plane i of the pair (v.x, v.y); v is replaced by the exact residual v - plane for the next plane
+template <bool F16> __device__ __forceinline__ uint32_t split_next(float2& v) {
+  const uint32_t w = pack2<F16>(v.x, v.y);
+  const float2 f = unpack2<F16>(w);
+  v.x = __fsub_rn(v.x, f.x);
+  v.y = __fsub_rn(v.y, f.y);
+  return w;
+}
+__device__ __forceinline__ uint32_t split_next(float2& v, bool f16) { return f16 ? split_next<true>(v) : split_next<false>(v); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) dwln_kernel(
     const float* __restrict__ ada, int64_t ada_stride, int64_t ada_off,
     const float* __restrict__ ln_w, const float* __restrict__ ln_b,
     float* __restrict__ y, __nv_bfloat16* __restrict__ y0, __nv_bfloat16* __restrict__ y1, __nv_bfloat16* __restrict__ y2,
-    int H, int W, int tiles_x, int tiles_y) {
+    int f16, int H, int W, int tiles_x, int tiles_y) {
   constexpr int C = NJ * DW_CH * CL, PAD = (KS - 1) / 2, HT = DW_T + KS - 1;   // halo tile edge
   constexpr int CHUNK_FLOATS = HT * HT * DW_CH;
   extern __shared__ __align__(128) float dw_smem[];                          // [DW_NBUF][HT][HT][64]
@@ -198,18 +198,11 @@ __global__ void __launch_bounds__(256) dwln_kernel(
       const int64_t o = (((int64_t)b * H + h) * W + w) * C + c;
       if (y != nullptr) *reinterpret_cast<float2*>(y + o) = v;
       if (y0 != nullptr) {
-        // A operand of the tensor-core fc1 GEMM: p0 = rn_bf16(v), p1 = rn_bf16(v - p0), p2 = rn_bf16(v - p0 - p1)
-        const __nv_bfloat162 hv = __floats2bfloat162_rn(v.x, v.y);
-        *reinterpret_cast<__nv_bfloat162*>(y0 + o) = hv;
+        // A operand of the tensor-core fc1 GEMM: p0 = rn16(v), p1 = rn16(v - p0), p2 = rn16(v - p0 - p1)
+        *reinterpret_cast<uint32_t*>(y0 + o) = split_next(v, f16 != 0);
         if (y1 != nullptr) {
-          const float2 hf = __bfloat1622float2(hv);
-          const float2 r1 = make_float2(__fsub_rn(v.x, hf.x), __fsub_rn(v.y, hf.y));
-          const __nv_bfloat162 mv = __floats2bfloat162_rn(r1.x, r1.y);
-          *reinterpret_cast<__nv_bfloat162*>(y1 + o) = mv;
-          if (y2 != nullptr) {
-            const float2 mf = __bfloat1622float2(mv);
-            *reinterpret_cast<__nv_bfloat162*>(y2 + o) = __floats2bfloat162_rn(__fsub_rn(r1.x, mf.x), __fsub_rn(r1.y, mf.y));
-          }
+          *reinterpret_cast<uint32_t*>(y1 + o) = split_next(v, f16 != 0);
+          if (y2 != nullptr) *reinterpret_cast<uint32_t*>(y2 + o) = split_next(v, f16 != 0);
         }
       }
     }
@@ -235,7 +228,7 @@ static DwEncodeTiledFn dw_encode_fn() {
 template <int NJ, int KS, int CL>
 static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, const float* ada,
                        int64_t ada_stride, int64_t ada_off, const float* ln_w, const float* ln_b,
-                       float* y, __nv_bfloat16* y0, __nv_bfloat16* y1, __nv_bfloat16* y2,
+                       float* y, __nv_bfloat16* y0, __nv_bfloat16* y1, __nv_bfloat16* y2, int f16,
                        int B, int H, int W, cudaStream_t stream) {
   constexpr int HT = DW_T + KS - 1, C = NJ * DW_CH * CL;
   constexpr int smem = DW_NBUF * HT * HT * DW_CH * 4;
@@ -260,7 +253,7 @@ static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, con
   const int64_t blocks = (int64_t)B * tiles_x * tiles_y;
   if (CL == 1) {
     dwln_kernel<NJ, KS, CL><<<(unsigned)blocks, 256, smem, stream>>>(
-        map, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, H, W, tiles_x, tiles_y);
+        map, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, f16, H, W, tiles_x, tiles_y);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(blocks * CL)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -269,7 +262,7 @@ static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, con
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     LVAE_CUDA_CALL(cudaLaunchKernelEx(&cfg, dwln_kernel<NJ, KS, CL>, map, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b,
-                                      y, y0, y1, y2, H, W, tiles_x, tiles_y));
+                                      y, y0, y1, y2, f16, H, W, tiles_x, tiles_y));
   }
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
@@ -278,13 +271,13 @@ static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, con
 template <int NJ, int CL>
 static int dispatch_k(int k, const float* x, const float* dw_w, const float* dw_b, const float* ada,
                       int64_t ada_stride, int64_t ada_off, const float* ln_w, const float* ln_b,
-                      float* y, __nv_bfloat16* y0, __nv_bfloat16* y1, __nv_bfloat16* y2,
+                      float* y, __nv_bfloat16* y0, __nv_bfloat16* y1, __nv_bfloat16* y2, int f16,
                       int B, int H, int W, cudaStream_t stream) {
   switch (k) {
-    case 1: return launch_dwln<NJ, 1, CL>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, B, H, W, stream);
-    case 3: return launch_dwln<NJ, 3, CL>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, B, H, W, stream);
-    case 5: return launch_dwln<NJ, 5, CL>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, B, H, W, stream);
-    case 7: return launch_dwln<NJ, 7, CL>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, B, H, W, stream);
+    case 1: return launch_dwln<NJ, 1, CL>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, f16, B, H, W, stream);
+    case 3: return launch_dwln<NJ, 3, CL>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, f16, B, H, W, stream);
+    case 5: return launch_dwln<NJ, 5, CL>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, f16, B, H, W, stream);
+    case 7: return launch_dwln<NJ, 7, CL>(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, f16, B, H, W, stream);
     default: set_error("dwconv kernel size %d unsupported", k); return LVAE_E_UNSUPPORTED;
   }
 }
@@ -293,7 +286,7 @@ static int dispatch_k(int k, const float* x, const float* dw_w, const float* dw_
 
 static int dwln_dispatch(const float* x, const float* dw_w, const float* dw_b,
                          const float* ada, int64_t ada_stride, int64_t ada_off,
-                         const float* ln_w, const float* ln_b, float* y, void* y0, void* y1, void* y2,
+                         const float* ln_w, const float* ln_b, float* y, void* y0, void* y1, void* y2, int f16,
                          int B, int H, int W, int C, int k, void* stream) {
   using namespace lvae;
   LVAE_CHECK_ARG(x && dw_w && dw_b && (y || y0) && (ada || ln_w));
@@ -301,15 +294,15 @@ static int dwln_dispatch(const float* x, const float* dw_w, const float* dw_b,
   LVAE_CHECK_ARG(ln_w != nullptr || (ada_off % 2 == 0 && ada_stride % 2 == 0));      // float2 loads of shift / scale
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* p0 = (__nv_bfloat16*)y0; __nv_bfloat16* p1 = (__nv_bfloat16*)y1; __nv_bfloat16* p2 = (__nv_bfloat16*)y2;
-#define LVAE_DWLN_CASE(nj) case nj: return dispatch_k<nj, 1>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, B, H, W, st);
+#define LVAE_DWLN_CASE(nj) case nj: return dispatch_k<nj, 1>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, f16, B, H, W, st);
   switch (C / 64) {
     LVAE_DWLN_CASE(1) LVAE_DWLN_CASE(2) LVAE_DWLN_CASE(3) LVAE_DWLN_CASE(4)
     LVAE_DWLN_CASE(6)
     // C = 512 as a 2-CTA cluster of 4 chunks each: 168 -> ~100 registers per thread doubles the resident CTAs
     // (measured 25-40 % faster on the s16 / s32 / s64 layers; C = 384 was not faster split)
-    case 8: return dispatch_k<4, 2>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, B, H, W, st);
-    case 10: return dispatch_k<5, 2>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, B, H, W, st);
-    case 12: return dispatch_k<6, 2>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, B, H, W, st);
+    case 8: return dispatch_k<4, 2>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, f16, B, H, W, st);
+    case 10: return dispatch_k<5, 2>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, f16, B, H, W, st);
+    case 12: return dispatch_k<6, 2>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, f16, B, H, W, st);
     default: set_error("dwconv channel count %d unsupported (need C/64 in {1,2,3,4,6,8,10,12})", C); return LVAE_E_UNSUPPORTED;
   }
 #undef LVAE_DWLN_CASE
@@ -320,13 +313,16 @@ extern "C" int lvae_dwconv_ln_adaln(const float* x, const float* dw_w, const flo
                                     const float* ln_w, const float* ln_b,
                                     float* y, int B, int H, int W, int C, int k, void* stream) {
   LVAE_CHECK_ARG(y != nullptr);
-  return dwln_dispatch(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, nullptr, nullptr, nullptr, B, H, W, C, k, stream);
+  return dwln_dispatch(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, nullptr, nullptr, nullptr, 0, B, H, W, C, k, stream);
 }
 
 extern "C" int lvae_dwconv_ln_adaln_planes(const float* x, const float* dw_w, const float* dw_b,
                                            const float* ada, int64_t ada_stride, int64_t ada_off,
                                            const float* ln_w, const float* ln_b,
-                                           void* y0, void* y1, void* y2, int B, int H, int W, int C, int k, void* stream) {
+                                           void* y0, void* y1, void* y2, int plane_format,
+                                           int B, int H, int W, int C, int k, void* stream) {
   LVAE_CHECK_ARG(y0 != nullptr && (y2 == nullptr || y1 != nullptr));
-  return dwln_dispatch(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, nullptr, y0, y1, y2, B, H, W, C, k, stream);
+  LVAE_CHECK_ARG(plane_format == LVAE_PLANES_BF16 || plane_format == LVAE_PLANES_F16);
+  return dwln_dispatch(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, nullptr, y0, y1, y2,
+                       plane_format == LVAE_PLANES_F16, B, H, W, C, k, stream);
 }

@@ -45,6 +45,8 @@ struct TcParams {
   const float* bias; const float* gamma; const float* res;
   float* out; __nv_bfloat16* out_pl[3];
   int epi, r, Ho, Wo;
+  int f16;               // plane element format: 0 bf16, 1 fp16 (LVAE_PREC_F16X3)
+  float acc_scale;       // 1 / (scale the weight planes carry): 1, or 2^-8 in the fp16 mode -- exact
   // implicit 3x3 conv (stride 1, pad 1) from NHWC planes: an M-tile is a CONV_TH x CONV_TW pixel patch of one image
   int conv, cH, cW, cC, tiles_w, tiles_h;
 };
@@ -140,13 +142,12 @@ __device__ __forceinline__ float epi_value(const TcParams& p, int m, int n, floa
 }
 
 __device__ __forceinline__ void store_planes(const TcParams& p, int64_t o, float v) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  p.out_pl[0][o] = h;
+  float2 r = make_float2(v, 0.f);
+  const bool f16 = p.f16 != 0;
+  reinterpret_cast<uint16_t*>(p.out_pl[0])[o] = (uint16_t)split_next(r, f16);
   if (p.out_pl[1]) {
-    const float r1 = __fsub_rn(v, __bfloat162float(h));
-    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-    p.out_pl[1][o] = m;
-    if (p.out_pl[2]) p.out_pl[2][o] = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(m)));
+    reinterpret_cast<uint16_t*>(p.out_pl[1])[o] = (uint16_t)split_next(r, f16);
+    if (p.out_pl[2]) reinterpret_cast<uint16_t*>(p.out_pl[2])[o] = (uint16_t)split_next(r, f16);
   }
 }
 
@@ -162,16 +163,7 @@ __device__ __forceinline__ void epi_store(const TcParams& p, int m, int n, float
   }
   const int64_t o = (int64_t)m * p.N + n;
   if (p.out) p.out[o] = v;
-  if (p.out_pl[0]) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    p.out_pl[0][o] = h;
-    if (p.out_pl[1]) {
-      const float r1 = __fsub_rn(v, __bfloat162float(h));
-      const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-      p.out_pl[1][o] = m;
-      if (p.out_pl[2]) p.out_pl[2][o] = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(m)));
-    }
-  }
+  if (p.out_pl[0]) store_planes(p, o, v);
 }
 
 template <int NPL>
@@ -248,7 +240,9 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D fp32, A/B bf16, both K-major
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    // a_format / b_format (bits 7-9 / 10-12): 0 = fp16, 1 = bf16
+    const uint32_t fmt = p.f16 ? 0u : 1u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     int s = 0; uint32_t ph = 0; int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -321,7 +315,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            v[j] = (j < 16 || width == 32) ? __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(u[j]))) : 0u;
+            v[j] = (j < 16 || width == 32)
+                       ? __float_as_uint(__fmul_rn(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(u[j])), p.acc_scale)) : 0u;
         } else {
           if (width == 32) tc_ld32(taddr, v);
           else {
@@ -388,11 +383,9 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int j = j4 * 8 + e * 2;
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(g[j], g[j + 1]);
-                w[e] = *reinterpret_cast<const uint32_t*>(&h2);
-                const float2 hf = __bfloat1622float2(h2);
-                g[j] = __fsub_rn(g[j], hf.x);                // exact residual for the next plane
-                g[j + 1] = __fsub_rn(g[j + 1], hf.y);
+                float2 gv = make_float2(g[j], g[j + 1]);
+                w[e] = split_next(gv, p.f16 != 0);           // leaves the exact residual for the next plane
+                g[j] = gv.x; g[j + 1] = gv.y;
               }
               *reinterpret_cast<uint4*>(stg + lane * 20 + j4 * 4) = make_uint4(w[0], w[1], w[2], w[3]);
             }
@@ -501,7 +494,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 __global__ void __launch_bounds__(256) split_im2col_kernel(
     const float* __restrict__ a0, const float* __restrict__ a1, int B, int H, int W, int Ho, int Wo,
     int C0, int C1, int ks, int stride, int pad, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-    __nv_bfloat16* __restrict__ l2, int64_t total4, int K) {
+    __nv_bfloat16* __restrict__ l2, int64_t total4, int K, int f16) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int K4 = K >> 2;
@@ -517,18 +510,13 @@ __global__ void __launch_bounds__(256) split_im2col_kernel(
   } else {
     v = __ldg(reinterpret_cast<const float4*>(a1 + m * C1 + (k - K0)));
   }
-  const float f[4] = {v.x, v.y, v.z, v.w};
-  __align__(8) __nv_bfloat16 h[4], l[4], t[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    h[j] = __float2bfloat16_rn(f[j]);
-    const float r1 = __fsub_rn(f[j], __bfloat162float(h[j]));
-    l[j] = __float2bfloat16_rn(r1);
-    t[j] = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(l[j])));
-  }
-  *reinterpret_cast<uint2*>(hi + m * K + k) = *reinterpret_cast<const uint2*>(h);
-  if (lo) *reinterpret_cast<uint2*>(lo + m * K + k) = *reinterpret_cast<const uint2*>(l);
-  if (l2) *reinterpret_cast<uint2*>(l2 + m * K + k) = *reinterpret_cast<const uint2*>(t);
+  float2 a = make_float2(v.x, v.y), b = make_float2(v.z, v.w);
+  const bool h16 = f16 != 0;
+  uint2 w;
+  w.x = split_next(a, h16); w.y = split_next(b, h16);
+  *reinterpret_cast<uint2*>(hi + m * K + k) = w;
+  if (lo) { w.x = split_next(a, h16); w.y = split_next(b, h16); *reinterpret_cast<uint2*>(lo + m * K + k) = w; }
+  if (l2) { w.x = split_next(a, h16); w.y = split_next(b, h16); *reinterpret_cast<uint2*>(l2 + m * K + k) = w; }
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -588,7 +576,7 @@ static void tc_geometry(const lvae_gemm_desc* d, int* Ho, int* Wo, int64_t* M, i
 }
 
 static int num_planes(int precision) {
-  return precision == LVAE_PREC_BF16X6 ? 3 : (precision == LVAE_PREC_BF16X3 ? 2 : 1);
+  return precision == LVAE_PREC_BF16X6 ? 3 : ((precision == LVAE_PREC_BF16X3 || precision == LVAE_PREC_F16X3) ? 2 : 1);
 }
 
 int64_t gemm_tc_workspace_bytes(const lvae_gemm_desc* d) {
@@ -626,7 +614,7 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
     const int64_t total4 = (int64_t)M * (K / 4);
     split_im2col_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, stream>>>(
         d->a0, d->a1, d->B, d->H, d->W, Ho, Wo, d->C0, d->a1 ? d->C1 : 0, d->ksize, d->stride, d->pad,
-        pl[0], pl[1], pl[2], total4, K);
+        pl[0], pl[1], pl[2], total4, K, d->precision == LVAE_PREC_F16X3);
     LVAE_CUDA_LAUNCH_CHECK();
     for (int i = 0; i < 3; ++i) a_pl[i] = pl[i];
   } else {
@@ -672,6 +660,8 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   if (p.out_pl[0] == nullptr) p.out_pl[1] = p.out_pl[2] = nullptr;
   if (p.out_pl[1] == nullptr) p.out_pl[2] = nullptr;
   p.epi = d->epilogue; p.r = d->shuffle_r; p.Ho = Ho; p.Wo = Wo;
+  p.f16 = d->precision == LVAE_PREC_F16X3 ? 1 : 0;
+  p.acc_scale = p.f16 ? 1.0f / LVAE_F16_WEIGHT_SCALE : 1.0f;
   LVAE_CHECK_ARG(p.out != nullptr || p.out_pl[0] != nullptr);
 
   TcMaps maps;

@@ -174,11 +174,25 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __
   }
 }
 
+// two elements per thread: planes of (x * scale) in either 16-bit format (split_next, common.cuh)
+__global__ void split_planes_kernel(const float* __restrict__ x, uint32_t* __restrict__ p0, uint32_t* __restrict__ p1,
+                                    uint32_t* __restrict__ p2, int64_t n2, int f16, float scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  float2 v = __ldg(reinterpret_cast<const float2*>(x) + i);
+  v.x = __fmul_rn(v.x, scale); v.y = __fmul_rn(v.y, scale);
+  p0[i] = split_next(v, f16 != 0);
+  if (p1) {
+    p1[i] = split_next(v, f16 != 0);
+    if (p2) p2[i] = split_next(v, f16 != 0);
+  }
+}
+
 }  // namespace lvae
 
 using namespace lvae;
 
-extern "C" int lvae_version(void) { return 100; }
+extern "C" int lvae_version(void) { return 101; }
 extern "C" const char* lvae_last_error(void) { return lvae::g_err; }
 
 extern "C" int lvae_lmb_sinusoid(const float* lmb, const float* freqs, float* emb0, int B, int dim,
@@ -239,6 +253,17 @@ extern "C" int lvae_split_bf16(const float* x, void* p0, void* p1, void* p2, int
   LVAE_CHECK_ARG(x && p0 && n > 0 && (p2 == nullptr || p1 != nullptr));
   split_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       x, (__nv_bfloat16*)p0, (__nv_bfloat16*)p1, (__nv_bfloat16*)p2, n);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lvae_split_planes(const float* x, void* p0, void* p1, void* p2, int64_t n, int plane_format, float scale,
+                                 void* stream) {
+  LVAE_CHECK_ARG(x && p0 && n > 0 && n % 2 == 0 && (p2 == nullptr || p1 != nullptr));
+  LVAE_CHECK_ARG(plane_format == LVAE_PLANES_BF16 || plane_format == LVAE_PLANES_F16);
+  LVAE_CHECK_ARG(scale > 0.f);
+  split_planes_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, (uint32_t*)p0, (uint32_t*)p1, (uint32_t*)p2, n / 2, plane_format == LVAE_PLANES_F16, scale);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

@@ -9,10 +9,14 @@ _LIB_PATH = Path(__file__).resolve().parent.parent / 'lib' / 'liblvae_b200.so'
 _lib = None
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_SCALE_RES, EPI_BIAS_RES, EPI_SHUFFLE_NHWC, EPI_SHUFFLE_NCHW = range(6)
-PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_BF16X6 = range(4)
-PRECISIONS = {'fp32': PREC_FP32, 'bf16x3': PREC_BF16X3, 'bf16': PREC_BF16, 'bf16x6': PREC_BF16X6}
-NUM_PLANES = {PREC_FP32: 0, PREC_BF16: 1, PREC_BF16X3: 2, PREC_BF16X6: 3}
-MMA_TERMS = {PREC_FP32: 1, PREC_BF16: 1, PREC_BF16X3: 3, PREC_BF16X6: 6}
+PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_BF16X6, PREC_F16X3 = range(5)
+PRECISIONS = {'fp32': PREC_FP32, 'bf16x3': PREC_BF16X3, 'bf16': PREC_BF16, 'bf16x6': PREC_BF16X6, 'f16x3': PREC_F16X3}
+NUM_PLANES = {PREC_FP32: 0, PREC_BF16: 1, PREC_BF16X3: 2, PREC_BF16X6: 3, PREC_F16X3: 2}
+MMA_TERMS = {PREC_FP32: 1, PREC_BF16: 1, PREC_BF16X3: 3, PREC_BF16X6: 6, PREC_F16X3: 3}
+PLANES_BF16, PLANES_F16 = 0, 1
+PLANE_FORMAT = {PREC_FP32: PLANES_BF16, PREC_BF16: PLANES_BF16, PREC_BF16X3: PLANES_BF16, PREC_BF16X6: PLANES_BF16,
+                PREC_F16X3: PLANES_F16}
+F16_WEIGHT_SCALE = 256.0      # LVAE_F16_WEIGHT_SCALE
 
 _fp = C.c_void_p   # device / host pointers are passed as integers
 
@@ -40,7 +44,8 @@ _PROTOS = {
     'lvae_split_bf16': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp]),
     'lvae_dwconv_ln_adaln': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
-    'lvae_dwconv_ln_adaln_planes': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp, _fp, _fp,
+    'lvae_split_planes': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_float, _fp]),
+    'lvae_dwconv_ln_adaln_planes': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_int,
                                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_latent_num_partials': (C.c_int, [C.c_int, C.c_int]),
     'lvae_latent_eval': (C.c_int, [_fp, _fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp, _fp,

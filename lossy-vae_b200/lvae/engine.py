@@ -119,7 +119,9 @@ class QarvEngine:
             n = ent['w'].numel()
             pl = [torch.empty(n, dtype=torch.bfloat16, device=self.device) for _ in range(self.npl)]
             ptrs = [_ptr(t) for t in pl] + [0] * (3 - self.npl)
-            N.check(self.lib.lvae_split_bf16(_ptr(ent['w']), ptrs[0], ptrs[1], ptrs[2], n, self._stream()), 'split_bf16')
+            f16 = self.pfmt == N.PLANES_F16       # fp16 planes carry w * 2^8 (include/lvae_b200.h LVAE_PREC_F16X3)
+            N.check(self.lib.lvae_split_planes(_ptr(ent['w']), ptrs[0], ptrs[1], ptrs[2], n, self.pfmt,
+                                               N.F16_WEIGHT_SCALE if f16 else 1.0, self._stream()), 'split_planes')
             ent['planes'] = pl
         return ent
 
@@ -144,7 +146,8 @@ class QarvEngine:
             self._plans.clear()
         self.device = dev
         self.prec = N.PRECISIONS[m.precision]
-        self.npl = N.NUM_PLANES[self.prec]        # bf16 planes per tensor-core operand (0: fp32 CUDA-core path)
+        self.npl = N.NUM_PLANES[self.prec]        # 16-bit planes per tensor-core operand (0: fp32 CUDA-core path)
+        self.pfmt = N.PLANE_FORMAT[self.prec]     # their element format (bf16 | fp16)
         w = {}
         with torch.cuda.device(dev):
             for b in self.blocks:
@@ -235,7 +238,7 @@ class QarvEngine:
             Hd = [P.named(f'scratch_h{i}', M * hid, dtype=torch.bfloat16) for i in range(self.npl)]
             ap = [_ptr(t) for t in A] + [0] * (3 - self.npl)
             P.op('dwln', self.lib.lvae_dwconv_ln_adaln_planes, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']),
-                 _ptr(P.ada), self.ada_total, self.ada_off[id(blk)], 0, 0, ap[0], ap[1], ap[2], B, Hs, Ws, C_, k,
+                 _ptr(P.ada), self.ada_total, self.ada_off[id(blk)], 0, 0, ap[0], ap[1], ap[2], self.pfmt, B, Hs, Ws, C_, k,
                  keep=(x, A), meta=dw_meta)
             self._gemm(P, 'fc1', None, (1, 1, M, C_, 1, 1, 0), wb['fc1'], None, epi=N.EPI_BIAS_GELU, a_planes=A, out_planes=Hd)
             self._gemm(P, 'fc2', None, (1, 1, M, hid, 1, 1, 0), wb['fc2'], out, epi=N.EPI_SCALE_RES,

@@ -88,11 +88,12 @@ class VariableRateLossyVAE(nn.Module):
         self._logging_images = config.get('log_images', [])
         self._flops_mode = False
         # arithmetic of the dense contractions (DESIGN.md "Precision modes"):
-        #   'bf16x6'  tcgen05, 3 bf16 planes per operand, 6 MMAs, split main/cross TMEM accumulators: fp32-class,
-        #             the parity mode (default)
+        #   'f16x3'   tcgen05, 2 fp16 planes per operand (22 significand bits), 3 MMAs, split main/cross TMEM
+        #             accumulators: fp32-class, the parity mode (default)
+        #   'bf16x6'  tcgen05, 3 bf16 planes per operand, 6 MMAs: fp32-class, the first parity mode (kept: wider range)
         #   'bf16x3'  tcgen05, 2 planes, 3 MMAs (~2^-17 per product)      'bf16'  tcgen05 single pass (fast, non-parity)
         #   'fp32'    fp32 FFMA on CUDA cores
-        self.precision = config.get('precision', 'bf16x6')
+        self.precision = config.get('precision', 'f16x3')
         self.__dict__['_engine'] = None   # not a submodule / not deep-copied state
 
     # ------------------------------------------------------------------ engine plumbing

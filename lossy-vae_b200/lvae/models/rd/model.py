@@ -78,7 +78,7 @@ class VariableRateLossyVAE(nn.Module):
         self.register_buffer('_dummy', torch.zeros(1), persistent=False)
         self._logging_images = config.get('log_images', [])
         self._flops_mode = False
-        self.precision = config.get('precision', 'bf16x6')        # see qarv/model.py
+        self.precision = config.get('precision', 'f16x3')        # see qarv/model.py
         self.__dict__['_engine'] = None
 
     # ------------------------------------------------------------------ engine plumbing

@@ -61,16 +61,18 @@ def _check_integer_parity(syms, idxs, ref_syms, ref_idxs, oracle_records):
                 s = torch.max(rec['pv'], torch.tensor(0.11))[mi]
                 edge = O.default_scale_table()
                 rel = ((s[:, None] - edge[None]).abs() / edge[None]).min(dim=1).values
-                assert bool((rel < 1e-6).all()) and int(mi.sum()) <= 2, f'layer {li}: index mismatch away from a table edge'
+                # ln(scale) = plogv is a feature-map value with the same ~1e-6..1e-5 absolute summation noise as
+                # qm - pm above, i.e. the same *relative* noise on the scale itself -> same 2e-5 bound
+                assert bool((rel < 2e-5).all()) and int(mi.sum()) <= 2, f'layer {li}: index mismatch away from a table edge'
             flips += int(ms.sum()) + int(mi.sum())
         else:
             assert ms.float().mean() < 2e-3 and mi.float().mean() < 2e-3, f'layer {li} diverged after an upstream flip'
     return flips
 
 
-@pytest.fixture(params=['bf16x6', 'fp32'])
+@pytest.fixture(params=['bf16x6', 'f16x3', 'fp32'])
 def model_in_precision(request, gpu_model):
-    """The parity modes: tensor-core bf16x6 (default) and the fp32 CUDA-core path."""
+    """The parity modes: tensor-core bf16x6 / f16x3 (fp32-class operand splits) and the fp32 CUDA-core path."""
     old = gpu_model.precision
     gpu_model.precision = request.param
     yield gpu_model
