@@ -35,9 +35,20 @@
 namespace lvae {
 
 constexpr int TC_BM = 128;
-constexpr int TC_EPI_WARPS = 8;                  // two per TMEM lane quarter, alternating 32-column chunks
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr int TC_EPI_STAGE = TC_EPI_WARPS * 32 * 33 * 4;    // per-warp 32 x 33 word transpose buffers
+// Epilogue specialisations (template parameter EK): each instantiation carries only its own epilogue code -- the
+// all-in-one kernel was 9 k SASS instructions and spent 27-32 % of its stall samples on instruction fetch.
+//   EK_GELU  fc1: bias + GELU -> 16-bit planes.  CUDA-core bound (17 instructions per element for the ATen erf
+//            formula alone), so it runs 16 epilogue warps: four per TMEM lane quarter, one 32 x 32 chunk each
+//   EK_ROWS  bias | layer-scale + residual | bias + residual -> fp32 rows (+ planes), 128-bit accesses
+//   EK_MISC  pixel-shuffle stores, implicit-conv pixel tiles, odd N: scalar lane = column path
+constexpr int EK_GELU = 0, EK_ROWS = 1, EK_MISC = 2;
+__host__ __device__ constexpr int tc_epi_warps(int ek) { return ek == EK_GELU ? 16 : 8; }
+__host__ __device__ constexpr int tc_threads(int ek) { return 64 + 32 * tc_epi_warps(ek); }
+// per-warp transpose buffer in words: GELU 32 rows x 64 B (one 16-bit plane of 32 columns), ROWS 32 rows x 128 B --
+// both XOR-swizzled at 16-byte granularity instead of padded (conflict-free 128-bit row writes and row-segment
+// reads; padding would cost the third 64 KB pipeline stage at BN = 128) -- MISC 32 x 33 words
+__host__ __device__ constexpr int tc_stage_words(int ek) { return ek == EK_GELU ? 32 * 16 : (ek == EK_ROWS ? 32 * 32 : 32 * 33); }
+__host__ __device__ constexpr int tc_epi_stage_bytes(int ek) { return tc_epi_warps(ek) * tc_stage_words(ek) * 4; }
 
 struct TcParams {
   int M, N, K;
@@ -166,9 +177,11 @@ __device__ __forceinline__ void epi_store(const TcParams& p, int m, int n, float
   if (p.out_pl[0]) store_planes(p, o, v);
 }
 
-template <int NPL>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int NPL, int EK>
+__global__ void __launch_bounds__(tc_threads(EK), 1)
 gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  constexpr int TC_EPI_WARPS = tc_epi_warps(EK);
+  constexpr int TC_EPI_STAGE = tc_epi_stage_bytes(EK);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment of the swizzled tiles
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // (pointer arithmetic keeps the shared address space)
@@ -288,9 +301,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const int ew = warp - 2;
     const int q = warp & 3;                                  // TMEM lane quarter this warp may access
     const int cpar = ew >> 2, cstep = TC_EPI_WARPS / 4;      // this warp takes chunks cpar, cpar + cstep, ...
-    uint32_t* stg = reinterpret_cast<uint32_t*>(epi_smem) + ew * (32 * 33);
-    const bool gelu_planes = (p.epi == LVAE_EPI_BIAS_GELU) && p.out_pl[0] != nullptr && p.out == nullptr && (p.N % 2 == 0);
-    const bool shuffle = (p.epi == LVAE_EPI_SHUFFLE_NHWC || p.epi == LVAE_EPI_SHUFFLE_NCHW);
+    uint32_t* stg = reinterpret_cast<uint32_t*>(epi_smem) + ew * tc_stage_words(EK);
+    const bool f16 = p.f16 != 0;
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -313,10 +325,16 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           if (width == 32) { tc_ld32(taddr, v); tc_ld32(taddr + (uint32_t)p.BN, u); }
           else { tc_ld16(taddr, v); tc_ld16(taddr + (uint32_t)p.BN, u); }
           tc_wait_ld();
+          const float2 sc = splat2(p.acc_scale);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = (j < 16 || width == 32)
-                       ? __float_as_uint(__fmul_rn(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(u[j])), p.acc_scale)) : 0u;
+          for (int j = 0; j < 32; j += 2) {
+            // (main + cross) * 2^-s: the scale is a power of two, so the product is exact
+            const float2 sum = mul2(add2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                                         make_float2(__uint_as_float(u[j]), __uint_as_float(u[j + 1]))), sc);
+            const bool ok = (j < 16 || width == 32);
+            v[j] = ok ? __float_as_uint(sum.x) : 0u;
+            v[j + 1] = ok ? __float_as_uint(sum.y) : 0u;
+          }
         } else {
           if (width == 32) tc_ld32(taddr, v);
           else {
@@ -332,50 +350,30 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
         }
         const int nb = n0 + c * 32;                          // first column of the chunk
-        if (p.conv) {
-          // rows of the tile are the pixels of a CONV_TH x CONV_TW patch: row -> (h, w) -> m; N is small here
-#pragma unroll
-          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
-          __syncwarp();
-          const int mt = t / p.n_tiles;
-          const int ctx = mt % p.tiles_w, cty = (mt / p.tiles_w) % p.tiles_h, cb = mt / (p.tiles_w * p.tiles_h);
-          const int n = nb + lane;
-          if (lane < width && n < p.N) {
-            const float b = p.bias ? __ldg(p.bias + n) : 0.f;
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-              const int row = q * 32 + r;
-              const int hh = cty * CONV_TH + row / CONV_TW, ww = ctx * CONV_TW + row % CONV_TW;
-              if (hh < p.cH && ww < p.cW)
-                p.out[(((int64_t)cb * p.cH + hh) * p.cW + ww) * p.N + n] = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
-            }
-          }
-          __syncwarp();
-        } else if (gelu_planes) {
-          // ---- fc1: bias + GELU in the row-owner layout (32 independent chains per thread), then per plane
-          //      pack bf16 pairs, transpose through shared memory (80-byte rows: conflict-free 128-bit stores),
+        if constexpr (EK == EK_GELU) {
+          // ---- fc1: bias + GELU in the row-owner layout (16 independent pair chains per thread), then per plane
+          //      pack 16-bit pairs, transpose through shared memory (80-byte rows: conflict-free 128-bit stores),
           //      and store 64-byte row segments with 64-bit accesses
-          float g[32];
           if (nb + 32 <= p.N && p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.bias + nb + j));
               const float2 o = gelu_erf2(add2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), b2));
-              g[j] = o.x; g[j + 1] = o.y;
+              v[j] = __float_as_uint(o.x); v[j + 1] = __float_as_uint(o.y);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int n = nb + j;
               const float b = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
-              g[j] = gelu_erf(__fadd_rn(__uint_as_float(v[j]), b));
+              v[j] = __float_as_uint(gelu_erf(__fadd_rn(__uint_as_float(v[j]), b)));
             }
           }
           const int sub = lane >> 3, l8 = lane & 7;          // 4 rows per pass, 8 lanes x 4 columns per row
           const int n = nb + 4 * l8;
           const bool full = (row0 + 32 <= p.M) && (nb + 32 <= p.N) && (width == 32);
 #pragma unroll
-          for (int pl = 0; pl < 3; ++pl) {
+          for (int pl = 0; pl < NPL; ++pl) {
             if (p.out_pl[pl] == nullptr) break;
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
@@ -383,21 +381,26 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int j = j4 * 8 + e * 2;
-                float2 gv = make_float2(g[j], g[j + 1]);
-                w[e] = split_next(gv, p.f16 != 0);           // leaves the exact residual for the next plane
-                g[j] = gv.x; g[j + 1] = gv.y;
+                float2 gv = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                if (pl + 1 < NPL) {                          // leaves the exact residual for the next plane
+                  w[e] = split_next(gv, f16);
+                  v[j] = __float_as_uint(gv.x); v[j + 1] = __float_as_uint(gv.y);
+                } else {
+                  w[e] = f16 ? pack2<true>(gv.x, gv.y) : pack2<false>(gv.x, gv.y);
+                }
               }
-              *reinterpret_cast<uint4*>(stg + lane * 20 + j4 * 4) = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(stg + lane * 16 + ((j4 ^ ((lane >> 1) & 3)) << 2)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
             __syncwarp();
             __nv_bfloat16* dst = p.out_pl[pl] + (int64_t)(row0 + sub) * p.N + n;
             if (full) {
 #pragma unroll
               for (int r = 0; r < 32; r += 4)
-                *reinterpret_cast<uint2*>(dst + (int64_t)r * p.N) = *reinterpret_cast<const uint2*>(stg + (r + sub) * 20 + l8 * 2);
+                *reinterpret_cast<uint2*>(dst + (int64_t)r * p.N) =
+                    *reinterpret_cast<const uint2*>(stg + (r + sub) * 16 + ((((l8 >> 1) ^ (((r + sub) >> 1) & 3)) << 2) | ((l8 & 1) << 1)));
             } else {
               for (int r = 0; r < 32; r += 4) {
-                const uint2 w2 = *reinterpret_cast<const uint2*>(stg + (r + sub) * 20 + l8 * 2);
+                const uint2 w2 = *reinterpret_cast<const uint2*>(stg + (r + sub) * 16 + ((((l8 >> 1) ^ (((r + sub) >> 1) & 3)) << 2) | ((l8 & 1) << 1)));
                 if (row0 + r + sub < p.M && 4 * l8 < width) {
                   if (n + 3 < p.N) *reinterpret_cast<uint2*>(dst + (int64_t)r * p.N) = w2;
                   else if (n + 1 < p.N) *reinterpret_cast<uint32_t*>(dst + (int64_t)r * p.N) = w2.x;
@@ -406,73 +409,100 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             }
             __syncwarp();
           }
+        } else if constexpr (EK == EK_ROWS) {
+          // ---- bias | layer-scale + residual | bias + residual -> fp32 rows (+ planes).  The row-owner registers
+          //      go through shared memory as 128-bit rows (XOR-swizzled: conflict-free both ways); then lane =
+          //      4 consecutive columns, 4 rows per pass, all residual loads in flight before the first is consumed
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<uint4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) = make_uint4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          __syncwarp();
+          const int sub = lane >> 3, l8 = lane & 7;
+          const int n = nb + 4 * l8;
+          if (4 * l8 < width && n < p.N) {                   // N % 4 == 0 (host-checked): n + 3 < N
+            const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool scale_res = p.epi == LVAE_EPI_SCALE_RES;
+            const bool has_res = scale_res || p.epi == LVAE_EPI_BIAS_RES;
+            const float4 g4 = scale_res ? __ldg(reinterpret_cast<const float4*>(p.gamma + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const int64_t o0 = (int64_t)(row0 + sub) * p.N + n;
+            const int rows = p.M - row0 - sub;               // valid while 4 * i < rows
+            float4 rr[8];
+            if (has_res) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                rr[i] = (4 * i < rows) ? *reinterpret_cast<const float4*>(p.res + o0 + (int64_t)(4 * i) * p.N) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (4 * i >= rows) break;
+              const float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + sub) * 32 + ((l8 ^ ((4 * i + sub) & 7)) << 2));
+              float4 x = make_float4(__fadd_rn(a.x, b4.x), __fadd_rn(a.y, b4.y), __fadd_rn(a.z, b4.z), __fadd_rn(a.w, b4.w));
+              if (scale_res) {
+                x.x = __fadd_rn(__fmul_rn(x.x, g4.x), rr[i].x); x.y = __fadd_rn(__fmul_rn(x.y, g4.y), rr[i].y);
+                x.z = __fadd_rn(__fmul_rn(x.z, g4.z), rr[i].z); x.w = __fadd_rn(__fmul_rn(x.w, g4.w), rr[i].w);
+              } else if (has_res) {
+                x.x = __fadd_rn(rr[i].x, x.x); x.y = __fadd_rn(rr[i].y, x.y);
+                x.z = __fadd_rn(rr[i].z, x.z); x.w = __fadd_rn(rr[i].w, x.w);
+              } else if (p.epi == LVAE_EPI_BIAS_GELU) {
+                x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
+              }
+              const int64_t o = o0 + (int64_t)(4 * i) * p.N;
+              if (p.out != nullptr) *reinterpret_cast<float4*>(p.out + o) = x;
+              if (p.out_pl[0] != nullptr) {
+                float2 lo = make_float2(x.x, x.y), hi = make_float2(x.z, x.w);
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl) {
+                  if (p.out_pl[pl] == nullptr) break;
+                  uint2 w;
+                  w.x = split_next(lo, f16); w.y = split_next(hi, f16);
+                  *reinterpret_cast<uint2*>(p.out_pl[pl] + o) = w;
+                }
+              }
+            }
+          }
+          __syncwarp();
         } else {
-          // ---- generic: transpose first, then bias / layer-scale + residual / shuffle with lane = column
+          // ---- shuffle stores, implicit-conv pixel tiles, odd N: transpose, then lane = column
 #pragma unroll
           for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
           __syncwarp();
           const int n = nb + lane;
           const bool n_ok = (lane < width) && (n < p.N);
-          if (n_ok) {
+          if (n_ok && p.conv) {
+            // rows of the tile are the pixels of a CONV_TH x CONV_TW patch: row -> (h, w) -> m; N is small here
+            const int mt = t / p.n_tiles;
+            const int ctx = mt % p.tiles_w, cty = (mt / p.tiles_w) % p.tiles_h, cb = mt / (p.tiles_w * p.tiles_h);
             const float b = p.bias ? __ldg(p.bias + n) : 0.f;
-            if (!shuffle && p.out != nullptr && p.epi != LVAE_EPI_BIAS_GELU) {
-              const float gm = (p.epi == LVAE_EPI_SCALE_RES) ? __ldg(p.gamma + n) : 1.f;
-              const bool has_res = (p.epi == LVAE_EPI_SCALE_RES || p.epi == LVAE_EPI_BIAS_RES);
-              const int rows = (p.M - row0) < 32 ? (p.M - row0) : 32;
-              float* dst = p.out + (int64_t)row0 * p.N + n;
-              const float* rsrc = has_res ? p.res + (int64_t)row0 * p.N + n : nullptr;
-              if (rows == 32) {
-                if (has_res) {
-                  float rr[32];                               // all 32 residual loads in flight before any is consumed
-#pragma unroll
-                  for (int r = 0; r < 32; ++r) rr[r] = rsrc[(int64_t)r * p.N];
-#pragma unroll
-                  for (int r = 0; r < 32; ++r) {
-                    float x = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
-                    x = (p.epi == LVAE_EPI_SCALE_RES) ? __fadd_rn(__fmul_rn(x, gm), rr[r]) : __fadd_rn(rr[r], x);
-                    dst[(int64_t)r * p.N] = x;
-                    if (p.out_pl[0] != nullptr) store_planes(p, (int64_t)(row0 + r) * p.N + n, x);
-                  }
-                } else {
-#pragma unroll 8
-                  for (int r = 0; r < 32; ++r) {
-                    const float x = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
-                    dst[(int64_t)r * p.N] = x;
-                    if (p.out_pl[0] != nullptr) store_planes(p, (int64_t)(row0 + r) * p.N + n, x);
-                  }
-                }
-              } else {
-                for (int r = 0; r < rows; ++r) {
-                  float x = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
-                  if (p.epi == LVAE_EPI_SCALE_RES) x = __fadd_rn(__fmul_rn(x, gm), rsrc[(int64_t)r * p.N]);
-                  else if (p.epi == LVAE_EPI_BIAS_RES) x = __fadd_rn(rsrc[(int64_t)r * p.N], x);
-                  dst[(int64_t)r * p.N] = x;
-                  if (p.out_pl[0] != nullptr) store_planes(p, (int64_t)(row0 + r) * p.N + n, x);
-                }
-              }
-            } else if (shuffle) {
-              // PixelShuffle(r) store: address = base(m) + offset(n), both separable (common.py:33-38)
-              const int rr = p.r, Co = p.N / (rr * rr);
-              const int qq = n / Co, cc = n - qq * Co, si = qq / rr, sj = qq - si * rr;
-              const int Hr = p.Ho * rr, Wr = p.Wo * rr;
-              const bool nhwc = p.epi == LVAE_EPI_SHUFFLE_NHWC;
-              const int64_t coff = nhwc ? ((int64_t)si * Wr + sj) * Co + cc : ((int64_t)cc * Hr + si) * Wr + sj;
-              int wo = row0 % p.Wo; int tq = row0 / p.Wo; int ho = tq % p.Ho; int bb = tq / p.Ho;
 #pragma unroll 4
-              for (int r = 0; r < 32; ++r) {
-                if (row0 + r < p.M) {
-                  const int64_t base = nhwc ? (((int64_t)bb * Hr + ho * rr) * Wr + wo * rr) * Co
-                                            : ((int64_t)bb * Co * Hr + ho * rr) * Wr + wo * rr;
-                  p.out[base + coff] = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
-                }
-                if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; ++bb; } }
-              }
-            } else {
+            for (int r = 0; r < 32; ++r) {
+              const int row = q * 32 + r;
+              const int hh = cty * CONV_TH + row / CONV_TW, ww = ctx * CONV_TW + row % CONV_TW;
+              if (hh < p.cH && ww < p.cW)
+                p.out[(((int64_t)cb * p.cH + hh) * p.cW + ww) * p.N + n] = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
+            }
+          } else if (n_ok && (p.epi == LVAE_EPI_SHUFFLE_NHWC || p.epi == LVAE_EPI_SHUFFLE_NCHW)) {
+            // PixelShuffle(r) store: address = base(m) + offset(n), both separable (common.py:33-38)
+            const float b = p.bias ? __ldg(p.bias + n) : 0.f;
+            const int rr = p.r, Co = p.N / (rr * rr);
+            const int qq = n / Co, cc = n - qq * Co, si = qq / rr, sj = qq - si * rr;
+            const int Hr = p.Ho * rr, Wr = p.Wo * rr;
+            const bool nhwc = p.epi == LVAE_EPI_SHUFFLE_NHWC;
+            const int64_t coff = nhwc ? ((int64_t)si * Wr + sj) * Co + cc : ((int64_t)cc * Hr + si) * Wr + sj;
+            int wo = row0 % p.Wo; int tq = row0 / p.Wo; int ho = tq % p.Ho; int bb = tq / p.Ho;
 #pragma unroll 4
-              for (int r = 0; r < 32; ++r) {
-                const int m = row0 + r;
-                if (m < p.M) epi_store(p, m, n, epi_value(p, m, n, __uint_as_float(stg[r * 33 + lane])));
+            for (int r = 0; r < 32; ++r) {
+              if (row0 + r < p.M) {
+                const int64_t base = nhwc ? (((int64_t)bb * Hr + ho * rr) * Wr + wo * rr) * Co
+                                          : ((int64_t)bb * Co * Hr + ho * rr) * Wr + wo * rr;
+                p.out[base + coff] = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
               }
+              if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; ++bb; } }
+            }
+          } else if (n_ok) {
+#pragma unroll 2
+            for (int r = 0; r < 32; ++r) {
+              const int m = row0 + r;
+              if (m < p.M) epi_store(p, m, n, epi_value(p, m, n, __uint_as_float(stg[r * 33 + lane])));
             }
           }
           __syncwarp();
@@ -639,7 +669,16 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   p.acc_cols = (npl >= 2 ? 2 : 1) * p.BN;
   int cols = 32; while (cols < 2 * p.acc_cols) cols <<= 1;
   p.tmem_cols = cols;
-  const int fixed = 1024 + TC_EPI_STAGE + 256;                 // alignment slack + transpose buffers + barriers
+  p.out = d->out;
+  for (int i = 0; i < 3; ++i) p.out_pl[i] = (i < npl) ? (__nv_bfloat16*)d->out_planes[i] : nullptr;
+  if (p.out_pl[0] == nullptr) p.out_pl[1] = p.out_pl[2] = nullptr;
+  if (p.out_pl[1] == nullptr) p.out_pl[2] = nullptr;
+  // epilogue specialisation
+  const bool shuffle = d->epilogue == LVAE_EPI_SHUFFLE_NHWC || d->epilogue == LVAE_EPI_SHUFFLE_NCHW;
+  int ek = EK_MISC;
+  if (d->epilogue == LVAE_EPI_BIAS_GELU && p.out_pl[0] != nullptr && p.out == nullptr && d->N % 2 == 0) ek = EK_GELU;
+  else if (!conv && !shuffle && d->N % 4 == 0) ek = EK_ROWS;
+  const int fixed = 1024 + tc_epi_stage_bytes(ek) + 256;       // alignment slack + transpose buffers + barriers
   const int budget = 227 * 1024 - fixed;
   // k-block: a 128-byte swizzle row (64 bf16) whenever two such stages fit (measured: 2 x 64 beats 4 x 32 on every
   // qarv shape), else 64-byte rows (32 bf16)
@@ -655,10 +694,6 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   LVAE_CHECK_ARG(stages * stage_bytes <= budget);
   p.stages = stages;
   p.bias = d->bias; p.gamma = d->gamma; p.res = d->res;
-  p.out = d->out;
-  for (int i = 0; i < 3; ++i) p.out_pl[i] = (i < npl) ? (__nv_bfloat16*)d->out_planes[i] : nullptr;
-  if (p.out_pl[0] == nullptr) p.out_pl[1] = p.out_pl[2] = nullptr;
-  if (p.out_pl[1] == nullptr) p.out_pl[2] = nullptr;
   p.epi = d->epilogue; p.r = d->shuffle_r; p.Ho = Ho; p.Wo = Wo;
   p.f16 = d->precision == LVAE_PREC_F16X3 ? 1 : 0;
   p.acc_scale = p.f16 ? 1.0f / LVAE_F16_WEIGHT_SCALE : 1.0f;
@@ -677,15 +712,22 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   if (n_sm == 0) {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    LVAE_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    LVAE_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    LVAE_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define LVAE_TC_ATTR(npl_, ek_) LVAE_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<npl_, ek_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LVAE_TC_ATTR(1, EK_GELU) LVAE_TC_ATTR(1, EK_ROWS) LVAE_TC_ATTR(1, EK_MISC)
+    LVAE_TC_ATTR(2, EK_GELU) LVAE_TC_ATTR(2, EK_ROWS) LVAE_TC_ATTR(2, EK_MISC)
+    LVAE_TC_ATTR(3, EK_GELU) LVAE_TC_ATTR(3, EK_ROWS) LVAE_TC_ATTR(3, EK_MISC)
+#undef LVAE_TC_ATTR
   }
   const int smem = fixed + stages * stage_bytes;
   const int grid = p.num_tiles < n_sm ? p.num_tiles : n_sm;
-  if (npl == 3) gemm_tc_kernel<3><<<grid, TC_THREADS, smem, stream>>>(maps, p);
-  else if (npl == 2) gemm_tc_kernel<2><<<grid, TC_THREADS, smem, stream>>>(maps, p);
-  else gemm_tc_kernel<1><<<grid, TC_THREADS, smem, stream>>>(maps, p);
+#define LVAE_TC_LAUNCH(npl_, ek_) gemm_tc_kernel<npl_, ek_><<<grid, tc_threads(ek_), smem, stream>>>(maps, p)
+#define LVAE_TC_LAUNCH_EK(npl_) \
+  do { if (ek == EK_GELU) LVAE_TC_LAUNCH(npl_, EK_GELU); else if (ek == EK_ROWS) LVAE_TC_LAUNCH(npl_, EK_ROWS); else LVAE_TC_LAUNCH(npl_, EK_MISC); } while (0)
+  if (npl == 3) LVAE_TC_LAUNCH_EK(3);
+  else if (npl == 2) LVAE_TC_LAUNCH_EK(2);
+  else LVAE_TC_LAUNCH_EK(1);
+#undef LVAE_TC_LAUNCH_EK
+#undef LVAE_TC_LAUNCH
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

@@ -7,8 +7,8 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / 'lossy-vae_b200'))
 from lvae import _native as N
 lib = N.lib()
-NPL = {1: 2, 2: 1, 3: 3}
-TERMS = {0: 1, 1: 3, 2: 1, 3: 6}
+NPL = {1: 2, 2: 1, 3: 3, 4: 2}
+TERMS = {0: 1, 1: 3, 2: 1, 3: 6, 4: 3}
 precs = [int(a) for a in sys.argv[1].split(',')] if len(sys.argv) > 1 else [1, 2]
 only = sys.argv[2].split(',') if len(sys.argv) > 2 else None
 SHAPES = [  # (name, M, K, N, epi)
@@ -19,10 +19,11 @@ SHAPES = [  # (name, M, K, N, epi)
     ('s4 dec fc1', 196608, 128, 192, 1), ('s4 dec fc2', 196608, 192, 128, 2),
     ('s8 dec fc1', 49152, 256, 448, 1), ('s8 dec fc2', 49152, 448, 256, 2),
 ]
-def planes(x, n):
+def planes(x, n, prec=3, weight=False):
     ps = [torch.empty(x.shape, dtype=torch.bfloat16, device='cuda') for _ in range(n)]
     args = [p.data_ptr() for p in ps] + [0] * (3 - n)
-    N.check(lib.lvae_split_bf16(x.data_ptr(), args[0], args[1], args[2], x.numel(), 0))
+    N.check(lib.lvae_split_planes(x.data_ptr(), args[0], args[1], args[2], x.numel(), 1 if prec == 4 else 0,
+                                  256.0 if (prec == 4 and weight) else 1.0, 0))
     return ps
 for prec in precs:
     for name, M, K, Nn, epi in SHAPES:
@@ -32,11 +33,11 @@ for prec in precs:
         g = torch.Generator().manual_seed(0)
         w = (torch.randn(Nn, K, generator=g) / K ** 0.5).cuda(); b = torch.randn(Nn, generator=g).cuda()
         gamma = torch.rand(Nn, generator=g).cuda()
-        wp = planes(w, NPL.get(prec, 1)) if prec else []
+        wp = planes(w, NPL.get(prec, 1), prec, True) if prec else []
         bufs = []
         for i in range(nbuf):
             x = torch.randn(M, K, device='cuda')
-            ap = planes(x, NPL[prec]) if prec else []
+            ap = planes(x, NPL[prec], prec) if prec else []
             out = torch.randn(M, Nn, device='cuda')
             op = [torch.empty(M, Nn, dtype=torch.bfloat16, device='cuda') for _ in range(NPL[prec])] if (prec and epi == 1) else []
             d = N.GemmDesc()
