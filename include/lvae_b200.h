@@ -99,6 +99,10 @@ typedef struct lvae_gemm_desc {
   void* workspace;            /* device scratch >= lvae_gemm_workspace_bytes(): im2col + split of a0/a1 when
                                * a_planes[0] == NULL */
   int64_t workspace_bytes;
+  int32_t a_act;              /* 0: none; 1: GELU (erf form) applied to every element of a0 / a1 as it is read --
+                               * VDBlock's c_i(gelu(x)) (lvae/models/qresvae/model.py:143-149).  Requires a0
+                               * (not a_planes). */
+  int32_t reserved;
 } lvae_gemm_desc;
 
 int lvae_gemm(const lvae_gemm_desc* d, void* stream);
@@ -137,9 +141,14 @@ int lvae_dwconv_ln_adaln_planes(const float* x, const float* dw_w, const float* 
  * [B, kl_stride] matrix, each at its own column offset.  Optional outputs (NULL to skip): kl_elem [M,zdim];
  * sym (int32) and idx (int32) in NCHW order [B,zdim,h,w] for the host coder (K14). */
 int lvae_latent_num_partials(int hw, int zdim);
+/* cdf_kind selects how the standard normal CDF is evaluated, because that is where the two reference families differ:
+ * LVAE_CDF_NORMAL: 0.5 * (1 + erf(t / sqrt 2)) = td.Normal(0,1).cdf, the override of qarv's DiscretizedGaussian
+ * (lvae/models/entropy_coding.py:77-82); LVAE_CDF_ERFC: 0.5 * erfc(-t / sqrt 2), CompressAI's
+ * GaussianConditional._standardized_cumulative, which qres34m uses unmodified (lvae/models/qresvae/model.py:241). */
+enum lvae_cdf_kind { LVAE_CDF_NORMAL = 0, LVAE_CDF_ERFC = 1 };
 int lvae_latent_eval(const float* qm, const float* prior, const float* scale_table, int n_scales,
                      float* z, float* kl_partial, int kl_stride, float* kl_elem, int32_t* sym, int32_t* idx,
-                     int B, int hw, int zdim, void* stream);
+                     int B, int hw, int zdim, int cdf_kind, void* stream);
 /* Training (K13): z = qm + noise; kl = -gaussian_log_prob_mass(pm, pv, z) (entropy_coding.py:17-49) */
 int lvae_latent_train(const float* qm, const float* prior, const float* noise,
                       float* z, float* kl_partial, int kl_stride, float* kl_elem,
@@ -193,6 +202,9 @@ int lvae_rd_finalize(const float* kl_partial, int kl_stride, int kl_cols,
                      const float* lmb, int B, int64_t ndims, float* stats, void* stream);
 /* feature[b,h,w,c] = bias[c] (qarv/model.py:289-292) */
 int lvae_broadcast_bias(const float* bias, float* out, int64_t M, int C, void* stream);
+/* dst[m, 0:C] = src[m, 0:C], dst[m, C:Cp] = 0: latent tensors whose channel count is not a multiple of 8 (qres34m
+ * zdim 14 / 12 / 10) are padded before the 3x3 z_proj conv (lvae/models/qresvae/model.py:236-240) */
+int lvae_pad_channels(const float* src, float* dst, int64_t M, int C, int Cp, void* stream);
 /* out[i] = sum_j partial[i, j] in fixed order (double accumulation), n rows of `cols` */
 int lvae_sum_partials(const float* partial, float* out, int n, int cols, void* stream);
 

@@ -16,6 +16,7 @@ struct GemmParams {
   int B, H, W, Ho, Wo, C0, C1, ks, stride, pad;
   const float* w; const float* bias; int N, K, M;
   int epi; const float* gamma; const float* res; float* out; int r;
+  int a_act;     // 1: GELU on every A element as it is read (VDBlock c_i(gelu(x)))
 };
 
 constexpr int BM = 128, BK = 16, NT = 256;
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(NT) gemm_f32_kernel(const GemmParams p) {
         if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W)
           v = __ldg(reinterpret_cast<const float4*>(base + (((int64_t)a_b[i] * p.H + hh) * p.W + ww) * C + c));
       }
+      if (p.a_act) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
       ra[i] = v;
     }
 #pragma unroll
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(256) gemm_smallk_kernel(const GemmParams p) {
 bool gemm_smallk_applicable(const lvae_gemm_desc* d) {
   const int K = d->ksize * d->ksize * d->C0 + (d->a1 ? d->C1 : 0);
   return d->ksize == 1 && d->stride == 1 && d->pad == 0 && d->a1 == nullptr && d->a0 != nullptr && d->out != nullptr &&
-         K <= 32 && d->N >= 128 && d->out_planes[0] == nullptr &&
+         K <= 32 && d->N >= 128 && d->out_planes[0] == nullptr && d->a_act == 0 &&
          (d->epilogue == LVAE_EPI_BIAS || d->epilogue == LVAE_EPI_BIAS_RES || d->epilogue == LVAE_EPI_SCALE_RES);
 }
 
@@ -237,7 +239,7 @@ int gemm_smallk_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   p.a0 = d->a0; p.a1 = nullptr; p.B = d->B; p.H = d->H; p.W = d->W; p.Ho = d->H; p.Wo = d->W;
   p.C0 = d->C0; p.C1 = 0; p.ks = 1; p.stride = 1; p.pad = 0;
   p.w = d->w; p.bias = d->bias; p.N = d->N; p.K = d->C0; p.M = d->B * d->H * d->W;
-  p.epi = d->epilogue; p.gamma = d->gamma; p.res = d->res; p.out = d->out; p.r = 0;
+  p.epi = d->epilogue; p.gamma = d->gamma; p.res = d->res; p.out = d->out; p.r = 0; p.a_act = 0;
   if (p.M == 0) return 0;
   const int smem = (256 * (p.K + 1) + 32 * p.K) * 4;
   static bool configured = false;
@@ -262,7 +264,7 @@ int gemm_f32_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   p.Wo = (d->W + 2 * d->pad - d->ksize) / d->stride + 1;
   p.w = d->w; p.bias = d->bias; p.N = d->N; p.K = d->ksize * d->ksize * d->C0 + p.C1;
   p.M = d->B * p.Ho * p.Wo;
-  p.epi = d->epilogue; p.gamma = d->gamma; p.res = d->res; p.out = d->out; p.r = d->shuffle_r;
+  p.epi = d->epilogue; p.gamma = d->gamma; p.res = d->res; p.out = d->out; p.r = d->shuffle_r; p.a_act = d->a_act;
   if (p.M == 0) return 0;
   dim3 block(NT);
   if (p.N > 64) {

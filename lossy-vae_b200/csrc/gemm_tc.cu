@@ -524,7 +524,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 __global__ void __launch_bounds__(256) split_im2col_kernel(
     const float* __restrict__ a0, const float* __restrict__ a1, int B, int H, int W, int Ho, int Wo,
     int C0, int C1, int ks, int stride, int pad, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-    __nv_bfloat16* __restrict__ l2, int64_t total4, int K, int f16) {
+    __nv_bfloat16* __restrict__ l2, int64_t total4, int K, int f16, int act) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int K4 = K >> 2;
@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(256) split_im2col_kernel(
   } else {
     v = __ldg(reinterpret_cast<const float4*>(a1 + m * C1 + (k - K0)));
   }
+  if (act) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }   // gelu(0) = 0: padding stays 0
   float2 a = make_float2(v.x, v.y), b = make_float2(v.z, v.w);
   const bool h16 = f16 != 0;
   uint2 w;
@@ -644,7 +645,7 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
     const int64_t total4 = (int64_t)M * (K / 4);
     split_im2col_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, stream>>>(
         d->a0, d->a1, d->B, d->H, d->W, Ho, Wo, d->C0, d->a1 ? d->C1 : 0, d->ksize, d->stride, d->pad,
-        pl[0], pl[1], pl[2], total4, K, d->precision == LVAE_PREC_F16X3);
+        pl[0], pl[1], pl[2], total4, K, d->precision == LVAE_PREC_F16X3, d->a_act);
     LVAE_CUDA_LAUNCH_CHECK();
     for (int i = 0; i < 3; ++i) a_pl[i] = pl[i];
   } else {

@@ -35,6 +35,11 @@ __device__ __forceinline__ float std_normal_cdf(float t) {
   return __fmul_rn(0.5f, __fadd_rn(1.0f, erf_torch_cpu(a)));
 }
 
+// CompressAI GaussianConditional._standardized_cumulative: 0.5 * erfc(-(2^-0.5) * t)
+__device__ __forceinline__ float std_normal_cdf_erfc(float t) {
+  return __fmul_rn(0.5f, erfcf(__fmul_rn(-0.70710678118654752440f, t)));
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -54,7 +59,7 @@ __global__ void __launch_bounds__(LT) latent_kernel(
     const float* __restrict__ qm, const float* __restrict__ prior, const float* __restrict__ noise,
     const float* __restrict__ table, int n_scales,
     float* __restrict__ z, float* __restrict__ kl_partial, float* __restrict__ kl_elem,
-    int32_t* __restrict__ sym, int32_t* __restrict__ idx, int hw, int zdim, int kl_stride) {
+    int32_t* __restrict__ sym, int32_t* __restrict__ idx, int hw, int zdim, int kl_stride, int cdf_kind) {
   __shared__ float red[LT / 32];
   __shared__ float stab[64];
   if (MODE == 0 && idx != nullptr) {
@@ -79,8 +84,9 @@ __global__ void __launch_bounds__(LT) latent_kernel(
         zz = __fadd_rn(r, pm);
         const float v = fabsf(__fsub_rn(zz, pm));
         const float s = fmaxf(pv, 0.11f);
-        const float up = std_normal_cdf(__fdiv_rn(__fsub_rn(0.5f, v), s));
-        const float lo = std_normal_cdf(__fdiv_rn(__fsub_rn(-0.5f, v), s));
+        const float tu = __fdiv_rn(__fsub_rn(0.5f, v), s), tl = __fdiv_rn(__fsub_rn(-0.5f, v), s);
+        const float up = cdf_kind ? std_normal_cdf_erfc(tu) : std_normal_cdf(tu);
+        const float lo = cdf_kind ? std_normal_cdf_erfc(tl) : std_normal_cdf(tl);
         const float P = fmaxf(__fsub_rn(up, lo), 1e-9f);
         kl = -logf(P);
         if (sym != nullptr) {
@@ -228,14 +234,15 @@ extern "C" int lvae_latent_num_partials(int hw, int zdim) {
 
 extern "C" int lvae_latent_eval(const float* qm, const float* prior, const float* scale_table, int n_scales,
                                 float* z, float* kl_partial, int kl_stride, float* kl_elem,
-                                int32_t* sym, int32_t* idx, int B, int hw, int zdim, void* stream) {
+                                int32_t* sym, int32_t* idx, int B, int hw, int zdim, int cdf_kind, void* stream) {
   LVAE_CHECK_ARG(qm && prior && z && kl_partial && B > 0 && hw > 0 && zdim > 0);
+  LVAE_CHECK_ARG(cdf_kind == LVAE_CDF_NORMAL || cdf_kind == LVAE_CDF_ERFC);
   LVAE_CHECK_ARG((sym == nullptr) == (idx == nullptr));
   LVAE_CHECK_ARG(sym == nullptr || (scale_table != nullptr && n_scales >= 1 && n_scales <= 64));
   const int np = lvae_latent_num_partials(hw, zdim);
   LVAE_CHECK_ARG(kl_stride >= np);
   latent_kernel<0><<<dim3(np, B), LT, 0, (cudaStream_t)stream>>>(qm, prior, nullptr, scale_table, n_scales,
-                                                                  z, kl_partial, kl_elem, sym, idx, hw, zdim, kl_stride);
+                                                                  z, kl_partial, kl_elem, sym, idx, hw, zdim, kl_stride, cdf_kind);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -247,7 +254,7 @@ extern "C" int lvae_latent_train(const float* qm, const float* prior, const floa
   const int np = lvae_latent_num_partials(hw, zdim);
   LVAE_CHECK_ARG(kl_stride >= np);
   latent_kernel<1><<<dim3(np, B), LT, 0, (cudaStream_t)stream>>>(qm, prior, noise, nullptr, 0,
-                                                                  z, kl_partial, kl_elem, nullptr, nullptr, hw, zdim, kl_stride);
+                                                                  z, kl_partial, kl_elem, nullptr, nullptr, hw, zdim, kl_stride, 0);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

@@ -174,6 +174,13 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __
   }
 }
 
+__global__ void pad_channels_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t total, int C, int Cp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t m = i / Cp; const int c = (int)(i - m * Cp);
+  dst[i] = c < C ? src[m * C + c] : 0.f;
+}
+
 // two elements per thread: planes of (x * scale) in either 16-bit format (split_next, common.cuh)
 __global__ void split_planes_kernel(const float* __restrict__ x, uint32_t* __restrict__ p0, uint32_t* __restrict__ p1,
                                     uint32_t* __restrict__ p2, int64_t n2, int f16, float scale) {
@@ -238,6 +245,14 @@ extern "C" int lvae_broadcast_bias(const float* bias, float* out, int64_t M, int
   LVAE_CHECK_ARG(bias && out && M > 0 && C > 0 && C % 4 == 0);
   const int64_t total4 = M * (C / 4);
   broadcast_bias_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bias, out, total4, C / 4);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lvae_pad_channels(const float* src, float* dst, int64_t M, int C, int Cp, void* stream) {
+  LVAE_CHECK_ARG(src && dst && M > 0 && C > 0 && Cp >= C);
+  const int64_t total = M * Cp;
+  pad_channels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, total, C, Cp);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

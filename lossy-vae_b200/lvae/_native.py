@@ -14,6 +14,7 @@ PRECISIONS = {'fp32': PREC_FP32, 'bf16x3': PREC_BF16X3, 'bf16': PREC_BF16, 'bf16
 NUM_PLANES = {PREC_FP32: 0, PREC_BF16: 1, PREC_BF16X3: 2, PREC_BF16X6: 3, PREC_F16X3: 2}
 MMA_TERMS = {PREC_FP32: 1, PREC_BF16: 1, PREC_BF16X3: 3, PREC_BF16X6: 6, PREC_F16X3: 3}
 PLANES_BF16, PLANES_F16 = 0, 1
+CDF_NORMAL, CDF_ERFC = 0, 1
 PLANE_FORMAT = {PREC_FP32: PLANES_BF16, PREC_BF16: PLANES_BF16, PREC_BF16X3: PLANES_BF16, PREC_BF16X6: PLANES_BF16,
                 PREC_F16X3: PLANES_F16}
 F16_WEIGHT_SCALE = 256.0      # LVAE_F16_WEIGHT_SCALE
@@ -33,6 +34,7 @@ class GemmDesc(C.Structure):
         ('shuffle_r', C.c_int32), ('precision', C.c_int32),
         ('w_planes', _fp * 3), ('a_planes', _fp * 3), ('out_planes', _fp * 3),
         ('workspace', _fp), ('workspace_bytes', C.c_int64),
+        ('a_act', C.c_int32), ('reserved', C.c_int32),
     ]
 
 
@@ -49,7 +51,8 @@ _PROTOS = {
                                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_latent_num_partials': (C.c_int, [C.c_int, C.c_int]),
     'lvae_latent_eval': (C.c_int, [_fp, _fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp, _fp,
-                                   C.c_int, C.c_int, C.c_int, _fp]),
+                                   C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_pad_channels': (C.c_int, [_fp, _fp, C.c_int64, C.c_int, C.c_int, _fp]),
     'lvae_latent_train': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_latent_prior_index': (C.c_int, [_fp, _fp, C.c_int, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_latent_dequant': (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),

@@ -1,2 +1,3 @@
 from . import qarv
 from . import rd
+from . import qresvae

@@ -105,6 +105,28 @@ class ConvNeXtBlockAdaLN(nn.Module):
         self.requires_embedding = True
 
 
+class ParamLayerNorm(nn.LayerNorm):
+    """Holds the affine parameters of a LayerNorm (eps 1e-6); compute lives in liblvae_b200 (dwln kernel)."""
+    def forward(self, x):
+        raise RuntimeError('ParamLayerNorm is a parameter container; run the owning model (lvae.engine)')
+
+
+class ConvNeXtBlockLN(nn.Module):
+    """timm ConvNeXtBlock key set (conv_dw, norm, mlp.fc1/fc2, gamma [C]) as used by qresvae's MyConvNeXtBlock:
+    dwconv kxk -> affine LayerNorm(C) -> Linear -> GELU -> Linear -> layer scale -> residual
+    (reference lvae/models/qresvae/model.py:163-182; timm.models.convnext.ConvNeXtBlock)."""
+    def __init__(self, dim, mlp_ratio=2, kernel_size=7, ls_init_value=1e-6):
+        super().__init__()
+        pad = (kernel_size - 1) // 2
+        self.conv_dw = ParamConv2d(dim, dim, kernel_size=kernel_size, padding=pad, groups=dim)
+        self.norm = ParamLayerNorm(dim, eps=1e-6)
+        hidden = int(mlp_ratio * dim)
+        self.mlp = Mlp(dim, hidden, dim)
+        self.gamma = nn.Parameter(ls_init_value * torch.ones(dim))
+        self.dim, self.hidden, self.kernel_size = dim, hidden, kernel_size
+        self.requires_embedding = False
+
+
 class FeatureExtractorWithEmbedding(nn.Module):
     """Bottom-up path container (reference common.py:84-98)."""
     def __init__(self, blocks):

@@ -27,6 +27,7 @@ def default_scale_table():
 
 
 class DiscretizedGaussian(nn.Module):
+    cdf_kind = 'normal'
     tail_mass = 1e-9
     entropy_coder_precision = 16
 
@@ -63,12 +64,47 @@ class DiscretizedGaussian(nn.Module):
                 np.ascontiguousarray(self._offset.cpu().numpy()))
 
 
+class GaussianConditional(DiscretizedGaussian):
+    """CompressAI's stock `GaussianConditional(None)` as qres34m uses it (lvae/models/qresvae/model.py:241,317-325):
+    buffer set `_offset, _quantized_cdf, _cdf_length, scale_table (persistent, empty until update_scale_table),
+    scale_bound, likelihood_lower_bound.bound, lower_bound_scale.bound`; scale lower bound 0.11; the CDF is
+    0.5 * erfc(-x / sqrt 2) (`cdf_kind = 'erfc'`: the fused latent kernel and the table builder follow it)."""
+    cdf_kind = 'erfc'
+
+    def __init__(self, scale_table=None, scale_bound=0.11):
+        nn.Module.__init__(self)
+        assert scale_table is None, 'qres34m constructs the entropy model without a table (set in update())'
+        self.likelihood_lower_bound = _Bound(1e-9)
+        self.register_buffer('_offset', torch.IntTensor())
+        self.register_buffer('_quantized_cdf', torch.IntTensor())
+        self.register_buffer('_cdf_length', torch.IntTensor())
+        self.register_buffer('scale_table', torch.Tensor())
+        self.register_buffer('scale_bound', torch.Tensor([float(scale_bound)]))
+        self.lower_bound_scale = _Bound(scale_bound)
+
+    def update_scale_table(self, scale_table, force=False):
+        if self._offset.numel() > 0 and not force:
+            return False
+        device = self.scale_table.device
+        self.scale_table = torch.Tensor(tuple(float(s) for s in scale_table)).to(device)
+        self.update()
+        return True
+
+    def update(self):
+        cdf, length, offset = build_cdf_tables(self.scale_table.detach().cpu(), self.tail_mass,
+                                               self.entropy_coder_precision, cdf_kind='erfc')
+        dev = self.scale_table.device
+        self._quantized_cdf = cdf.to(dev)
+        self._cdf_length = length.to(dev)
+        self._offset = offset.to(dev)
+
+
 _table_cache = {}
 
 
-def build_cdf_tables(scale_table, tail_mass=1e-9, precision=16):
+def build_cdf_tables(scale_table, tail_mass=1e-9, precision=16, cdf_kind='normal'):
     """pmf of the integer offsets around each table scale -> 16-bit quantised CDF rows."""
-    key = (scale_table.numpy().tobytes(), tail_mass, precision)
+    key = (scale_table.numpy().tobytes(), tail_mass, precision, cdf_kind)
     if key in _table_cache:
         return tuple(t.clone() for t in _table_cache[key])
     lib = _native.lib()
@@ -78,9 +114,13 @@ def build_cdf_tables(scale_table, tail_mass=1e-9, precision=16):
     max_length = int(length.max())
     samples = torch.abs(torch.arange(max_length).int() - center[:, None]).float()
     sc = scale_table.unsqueeze(1).float()
-    normal = torch.distributions.Normal(0.0, 1.0)
-    upper = normal.cdf((0.5 - samples) / sc)
-    lower = normal.cdf((-0.5 - samples) / sc)
+    if cdf_kind == 'erfc':        # CompressAI GaussianConditional._standardized_cumulative
+        def cdf_fn(t):
+            return float(0.5) * torch.erfc(float(-(2 ** -0.5)) * t)
+    else:                         # td.Normal(0, 1).cdf (lvae/models/entropy_coding.py:77-82)
+        cdf_fn = torch.distributions.Normal(0.0, 1.0).cdf
+    upper = cdf_fn((0.5 - samples) / sc)
+    lower = cdf_fn((-0.5 - samples) / sc)
     pmf = upper - lower
     tail = 2 * lower[:, :1]
     cdf = np.zeros((len(length), max_length + 2), dtype=np.int32)

@@ -19,8 +19,9 @@ import lvae_oracle as O    # noqa: E402
 OUT = HERE.parent / 'tests' / 'golden'
 
 
-from oracle_inputs import CASES, RD_CASES, make_input, synth_image   # noqa: E402,F401
+from oracle_inputs import CASES, RD_CASES, QRES_CASES, QRES_LMB, make_input, synth_image   # noqa: E402,F401
 import rd_oracle as R      # noqa: E402
+import qres_oracle as Q    # noqa: E402
 
 
 def main():
@@ -124,9 +125,69 @@ def main_rd():
         print(name, 'loss', float(rec['loss']), 'bppix', float(rec['bppix']), 'psnr', float(rec['psnr']))
 
 
+def main_qres():
+    """qres34m fixtures: the unmodified reference in eval mode (forward, latents, compress / decompress) and in train
+    mode with torch.manual_seed(noise_seed) before the forward (its uniform_ draws are then reproducible)."""
+    ref = ref_loader.load_reference()
+    torch.manual_seed(0)
+    model = ref.get_model('qres34m', lmb=QRES_LMB).eval()
+    sd = O.sensitised_state_dict(Q.qres_param_shapes(), seed=0)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all('discrete_gaussian' in k for k in missing)
+    model.compress_mode()
+    for name, (kind, nB, H, W, seed, nseed) in QRES_CASES.items():
+        im = make_input(kind, nB, H, W, seed)
+        with torch.no_grad():
+            model.eval()
+            stats = model(im, return_rec=True)
+            lat = model.forward_get_latents(im)
+            obj = model.compress(im)
+            dec = model.decompress(obj)
+            # symbols / indexes from the reference's own block pieces
+            feats = model.encoder(model.preprocess_input(im))
+            feature = model.decoder.bias.expand(feats[min(feats.keys())].shape)
+            syms, idxs = [], []
+            for blk in model.decoder.dec_blocks:
+                if hasattr(blk, 'forward_train'):
+                    f_enc = feats[int(feature.shape[2])]
+                    f2, pm, plogv = blk.transform_prior(feature)
+                    qm = blk.posterior(torch.cat([f2, f_enc], dim=1))
+                    syms.append(blk.discrete_gaussian.quantize(qm, 'symbols', pm).numpy().astype(np.int16))
+                    idxs.append(blk.discrete_gaussian.build_indexes(torch.exp(plogv)).numpy().astype(np.uint8))
+                    feature, _ = blk.forward_train(feature, f_enc)
+                else:
+                    feature = blk(feature)
+            model.train()
+            torch.manual_seed(nseed)
+            tstats = model(im)
+            torch.manual_seed(nseed)
+            tlat = model.forward_get_latents(im)
+            model.eval()
+        rec = dict(loss=np.float32(stats['loss'].item()), kl=np.float64(stats['kl']), mse=np.float64(stats['mse']),
+                   bppix=np.float64(stats['bppix']), psnr=np.float64(stats['psnr']), im_hat=stats['im_hat'].numpy(),
+                   dec_im_hat=dec.numpy(), shape=np.array(obj[-1]),
+                   kl_per_image=np.stack([st['kl'].sum(dim=(1, 2, 3)).numpy() for st in lat]),
+                   train_loss=np.float32(tstats['loss'].item()), train_bppix=np.float64(tstats['bppix']),
+                   train_psnr=np.float64(tstats['psnr']),
+                   train_kl_per_image=np.stack([st['kl'].sum(dim=(1, 2, 3)).numpy() for st in tlat]))
+        for li in range(len(lat)):
+            rec[f'z{li}'] = lat[li]['z'].numpy()
+            rec[f'sym{li}'], rec[f'idx{li}'] = syms[li], idxs[li]
+            for b in range(nB):
+                rec[f'bytes{li}_{b}'] = np.frombuffer(obj[li][b], dtype=np.uint8)
+        np.savez_compressed(OUT / f'{name}.npz', **rec)
+        print(name, 'loss', float(rec['loss']), 'bppix', float(rec['bppix']), 'psnr', float(rec['psnr']),
+              'train loss', float(rec['train_loss']), 'bytes', sum(len(s) for l in obj[:-1] for s in l))
+    dg = [b for b in model.decoder.dec_blocks if hasattr(b, 'forward_train')][0].discrete_gaussian
+    np.savez_compressed(OUT / 'qres_tables.npz', scale_table=dg.scale_table.numpy(), cdf=dg._quantized_cdf.numpy(),
+                        cdf_length=dg._cdf_length.numpy(), offset=dg._offset.numpy())
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'rd':
-        main_rd()
-    else:
+    which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    if which in ('qarv', 'all'):
         main()
+    if which in ('rd', 'all'):
         main_rd()
+    if which in ('qres', 'all'):
+        main_qres()

@@ -82,18 +82,20 @@ def sensitised_tensor(key, shape, seed=0, wide_heads=True):
     shape = tuple(shape)
     if key.endswith('gamma'):
         return torch.rand(shape, generator=g) * 0.4 + 0.2
-    if key == 'bias':
+    if key == 'bias' or key == 'decoder.bias':
         return torch.randn(shape, generator=g) * 0.5
-    if key.endswith('prior.bias'):          # spread prior means and log-scales
+    if key.endswith('norm.weight'):         # affine LayerNorm gain (qres): around 1
+        return 1.0 + (torch.rand(shape, generator=g) * 2 - 1) * 0.3
+    if key.endswith('prior.bias') or key.endswith('prior.c4.bias'):          # spread prior means and log-scales
         return torch.randn(shape, generator=g) * 0.7
     if key.endswith('.bias'):
         return torch.randn(shape, generator=g) * 0.05
     assert key.endswith('.weight'), key
     fan_in = int(np.prod(shape[1:]))
     bound = 1.0 / math.sqrt(fan_in)
-    if wide_heads and key.endswith('posterior.weight'):    # wider posterior means -> symbols beyond {-1,0,1}
-        bound *= 3.0
-    if wide_heads and key.endswith('prior.weight'):
+    if wide_heads and (key.endswith('posterior.weight') or key.endswith('posterior.c4.weight')):
+        bound *= 3.0                                       # wider posterior means -> symbols beyond {-1,0,1}
+    if wide_heads and (key.endswith('prior.weight') or key.endswith('prior.c4.weight')):
         bound *= 2.0
     return (torch.rand(shape, generator=g) * 2 - 1) * bound
 
@@ -176,8 +178,14 @@ def prior_transform(prior_out):
     return pm, pv
 
 
-def eval_quantize_likelihood(qm, pm, pv, scale_bound=0.11, likelihood_bound=1e-9):
+def std_normal_cdf_erfc(t):
+    # CompressAI GaussianConditional._standardized_cumulative (what qres34m runs, unmodified)
+    return float(0.5) * torch.erfc(float(-(2 ** -0.5)) * t)
+
+
+def eval_quantize_likelihood(qm, pm, pv, scale_bound=0.11, likelihood_bound=1e-9, cdf=None):
     """GaussianConditional.forward(training=False): returns z, P."""
+    std_normal_cdf = cdf or globals()['std_normal_cdf']
     z = qm.clone()
     z -= pm
     z = torch.round(z)
@@ -241,9 +249,10 @@ def pmf_to_quantized_cdf(pmf, precision=16):
     return cdf
 
 
-def build_cdf_tables(scale_table=None, tail_mass=1e-9, precision=16):
+def build_cdf_tables(scale_table=None, tail_mass=1e-9, precision=16, cdf=None):
     """GaussianConditional.update() (Appendix A.4) -> (cdf [n, L+2] int32, cdf_length [n], offset [n])."""
     import scipy.stats
+    std_normal_cdf = cdf or globals()['std_normal_cdf']
     scale_table = default_scale_table() if scale_table is None else scale_table
     multiplier = -scipy.stats.norm.ppf(tail_mass / 2)
     center = torch.ceil(scale_table * multiplier).int()

@@ -41,3 +41,10 @@ RD_CASES = {
     'rd_rand_1x64x64': ('rand', 1, 64, 64, [256.0], 10, 5),
     'rd_synth_2x128x128': ('synth', 2, 128, 128, [16.0, 1024.0], 11, 6),
 }
+
+# qres34m fixtures (lambda fixed at 2048): name -> (kind, nB, H, W, image seed, train-noise seed)
+QRES_LMB = 2048
+QRES_CASES = {
+    'qres_rand_2x64x128': ('rand', 2, 64, 128, 3, 21),
+    'qres_synth_1x192x256': ('synth', 1, 192, 256, 12, 22),
+}

@@ -29,7 +29,7 @@ def test_bad_arguments_are_rejected_without_a_gpu(native_lib):
     # argument validation happens before any CUDA call
     assert native_lib.lvae_gemm(None, None) == -1
     assert b'bad argument' in native_lib.lvae_last_error()
-    assert native_lib.lvae_latent_eval(None, None, None, 0, None, None, 0, None, None, None, 1, 1, 1, None) == -1
+    assert native_lib.lvae_latent_eval(None, None, None, 0, None, None, 0, None, None, None, 1, 1, 1, 0, None) == -1
     assert native_lib.lvae_rans_decode(None, 0, None, 0, None, 0, None, None, 0, None) == -1
 
 

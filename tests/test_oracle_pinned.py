@@ -159,3 +159,61 @@ def test_rd_scalar_functions_known_answers():
     assert abs(R.std_smooth(torch.tensor([0.0])).item() - 1.0) < 1e-6  # softplus_beta=ln2 (0) = ln2 / ln2
     kl = R.gaussian_kl(torch.tensor([0.3]), torch.tensor([0.5]), torch.tensor([0.1]), torch.tensor([2.0]))
     assert abs(kl.item() - (-0.5 + math.log(2.0) - math.log(0.5) + 0.5 * (0.25 + 0.04) / 4.0)) < 1e-6
+
+
+# ----------------------------------------------------------------------------- qres34m (fixed rate, VDBlock heads)
+def _qres_noise(Q, arch, nB, H, W, nseed):
+    """What `torch.empty_like(qm).uniform_(-0.5, 0.5)` yields layer by layer after torch.manual_seed(nseed)."""
+    g = torch.Generator().manual_seed(nseed)
+    out, h, w = [], H // 64, W // 64
+    for ent in arch['dec']:
+        if ent[0] == 'lat':
+            out.append(torch.empty(nB, ent[2], h, w).uniform_(-0.5, 0.5, generator=g))
+        elif ent[0] == 'up':
+            h, w = h * ent[3], w * ent[3]
+    return out
+
+
+def test_qres_param_count_matches_readme():
+    import qres_oracle as Q
+    shapes = Q.qres_param_shapes()     # lvae/models/qresvae/README.md: qres34m, 34.0 M parameters
+    assert round(sum(int(np.prod(s)) for _, s in shapes) / 1e6, 2) == 34.04
+
+
+def test_qres_cdf_tables_match_reference_fixture(golden):
+    import qres_oracle as Q
+    t = golden('qres_tables')
+    assert np.array_equal(Q.qres_scale_table().numpy(), t['scale_table'])
+    cdf, length, offset = Q.qres_tables()
+    assert np.array_equal(cdf.numpy(), t['cdf']) and np.array_equal(length.numpy(), t['cdf_length'])
+    assert np.array_equal(offset.numpy(), t['offset'])
+
+
+@pytest.mark.parametrize('name', ['qres_rand_2x64x128', 'qres_synth_1x192x256'])
+def test_qres_oracle_matches_golden(name, golden):
+    import qres_oracle as Q
+    from oracle_inputs import QRES_CASES, QRES_LMB
+    g = golden(name)
+    kind, nB, H, W, seed, nseed = QRES_CASES[name]
+    sd = O.sensitised_state_dict(Q.qres_param_shapes(), seed=0)
+    im = make_input(kind, nB, H, W, seed)
+    out = Q.qres_forward(sd, im, QRES_LMB)
+    assert np.float32(out['loss'].item()) == g['loss']
+    assert out['bppix'] == float(g['bppix']) and out['psnr'] == float(g['psnr']) and out['mse'] == float(g['mse'])
+    assert torch.equal(out['im_hat'], torch.from_numpy(g['im_hat']))
+    for li, r in enumerate(out['records']):
+        assert torch.equal(r['z'], torch.from_numpy(g[f'z{li}']))
+        assert torch.equal(r['kl'].sum(dim=(1, 2, 3)), torch.from_numpy(g['kl_per_image'][li]))
+        assert np.array_equal(r['sym'].numpy(), g[f'sym{li}']) and np.array_equal(r['idx'].numpy(), g[f'idx{li}'])
+    noise = _qres_noise(Q, Q.qres34m_arch(), nB, H, W, nseed)
+    tr = Q.qres_forward(sd, im, QRES_LMB, mode='train', noise=noise)
+    assert np.float32(tr['loss'].item()) == g['train_loss'] and tr['bppix'] == float(g['train_bppix'])
+    for li, r in enumerate(tr['records']):
+        assert torch.equal(r['kl'].sum(dim=(1, 2, 3)), torch.from_numpy(g['train_kl_per_image'][li]))
+    if H * W <= 64 * 128:          # the pure-python coder is slow: small case only
+        obj = Q.qres_compress(sd, im)
+        assert tuple(obj[-1]) == tuple(g['shape'])
+        for li in range(12):
+            for b in range(nB):
+                assert obj[li][b] == g[f'bytes{li}_{b}'].tobytes()
+        assert torch.equal(Q.qres_decompress(sd, obj), torch.from_numpy(g['dec_im_hat']))
