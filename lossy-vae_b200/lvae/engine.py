@@ -87,26 +87,31 @@ class Plan:
 class QarvEngine:
     def __init__(self, model):
         self.model = model
-        self.family = getattr(model, 'family', 'qarv')      # 'qarv' (discretised-Gaussian latents) | 'rd' (continuous)
+        # 'qarv' (AdaLN blocks, discretised-Gaussian latents) | 'rd' (continuous latents) | 'qres' (affine-LN blocks,
+        # VDBlock heads, CompressAI's stock erfc likelihood, no lambda embedding)
+        self.family = getattr(model, 'family', 'qarv')
         self.lib = N.lib()
         self.device = None
         self._wver = None
         self._plans = {}
         self.use_graphs = True
-        self.blocks = [m for m in model.modules() if isinstance(m, common.ConvNeXtBlockAdaLN)]
+        self.blocks = [m for m in model.modules() if isinstance(m, (common.ConvNeXtBlockAdaLN, common.ConvNeXtBlockLN))]
         self.ada_off = {}
         off = 0
         for b in self.blocks:
-            self.ada_off[id(b)] = off
-            off += 2 * b.dim
+            if isinstance(b, common.ConvNeXtBlockAdaLN):
+                self.ada_off[id(b)] = off
+                off += 2 * b.dim
         self.ada_total = off
         self.w = {}
 
     # ------------------------------------------------------------------ weights
     def _weights_version(self):
+        tables = tuple(b.discrete_gaussian.scale_table.numel() for b in self.model.dec_blocks
+                       if hasattr(b, 'discrete_gaussian'))[:1]      # qres: the table appears with compress_mode()
         return (self.model._dummy.device, self.model.precision,
                 sum(p._version for p in self.model.parameters()),
-                tuple(p.data_ptr() for p in (self.model.bias, self.blocks[0].gamma)))
+                tuple(p.data_ptr() for p in (self.model.bias, self.blocks[0].gamma)), tables)
 
     def _dev_f32(self, t):
         return t.detach().to(self.device, torch.float32).contiguous()
@@ -125,10 +130,26 @@ class QarvEngine:
             ent['planes'] = pl
         return ent
 
-    def _conv_weight(self, conv):
+    def _conv_weight(self, conv, pad_c=0):
+        """pad_c: zero input channels appended (the operand is channel-padded by lvae_pad_channels)."""
         w = self._dev_f32(conv.weight)                    # [N, C, kh, kw]
+        if pad_c:
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, pad_c))
         n, c, kh, kw = w.shape
-        return self._pack_gemm_weight(w.permute(0, 2, 3, 1).reshape(n, kh * kw * c), conv.bias)
+        ent = self._pack_gemm_weight(w.permute(0, 2, 3, 1).reshape(n, kh * kw * c), conv.bias)
+        ent['ks'] = kh
+        return ent
+
+    def _vd_weights(self, vd):
+        return {k: self._conv_weight(getattr(vd, k)) for k in ('c1', 'c2', 'c3', 'c4')}
+
+    @staticmethod
+    def _z_pad(zdim, ks):
+        """channels lvae_pad_channels appends to z before the z_proj conv: the GEMM needs C % 4 == 0 and K % 8 == 0"""
+        zp = zdim
+        while zp % 4 or (ks * ks * zp) % 8:
+            zp += 1
+        return zp - zdim
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -159,12 +180,16 @@ class QarvEngine:
                     fc2=self._pack_gemm_weight(self._dev_f32(b.mlp.fc2.weight), b.mlp.fc2.bias),
                     gamma=self._dev_f32(b.gamma).reshape(C_),
                 )
-            w['ada_w'] = torch.cat([self._dev_f32(b.embedding_layer[1].weight) for b in self.blocks], 0).contiguous()
-            w['ada_b'] = torch.cat([self._dev_f32(b.embedding_layer[1].bias) for b in self.blocks], 0).contiguous()
-            for j in (0, 2):
-                w[f'emb{j}_w'] = self._dev_f32(m.lmb_embedding[j].weight)
-                w[f'emb{j}_b'] = self._dev_f32(m.lmb_embedding[j].bias)
-            w['freqs'] = common.sinusoidal_frequencies(m.lmb_embed_dim[0], m._sin_period).to(dev)
+                if isinstance(b, common.ConvNeXtBlockLN):       # affine LayerNorm instead of AdaLN
+                    w[id(b)]['ln_w'], w[id(b)]['ln_b'] = self._dev_f32(b.norm.weight), self._dev_f32(b.norm.bias)
+            if self.ada_total:
+                ada = [b for b in self.blocks if id(b) in self.ada_off]
+                w['ada_w'] = torch.cat([self._dev_f32(b.embedding_layer[1].weight) for b in ada], 0).contiguous()
+                w['ada_b'] = torch.cat([self._dev_f32(b.embedding_layer[1].bias) for b in ada], 0).contiguous()
+                for j in (0, 2):
+                    w[f'emb{j}_w'] = self._dev_f32(m.lmb_embedding[j].weight)
+                    w[f'emb{j}_b'] = self._dev_f32(m.lmb_embedding[j].bias)
+                w['freqs'] = common.sinusoidal_frequencies(m.lmb_embed_dim[0], m._sin_period).to(dev)
             w['bias'] = self._dev_f32(m.bias).reshape(-1)
             mods = list(m.encoder.enc_blocks) + list(m.dec_blocks)
             for mod in mods:
@@ -180,6 +205,14 @@ class QarvEngine:
                     # packed row (i*r+j)*Co + c  <-  reference row c*r*r + i*r + j  (PixelShuffle, common.py:33-38)
                     perm = torch.arange(conv.out_channels, device=dev).reshape(co, r * r).t().reshape(-1)
                     w[id(mod)] = self._pack_gemm_weight(wt[perm], self._dev_f32(conv.bias)[perm])
+                elif getattr(mod, 'is_latent_block', False) and self.family == 'qres':
+                    ks0 = mod.z_proj[0].kernel_size[0]
+                    zpad = self._z_pad(mod.zdim, ks0)
+                    tab = mod.discrete_gaussian.scale_table
+                    w[id(mod)] = dict(posterior=self._vd_weights(mod.posterior), prior=self._vd_weights(mod.prior),
+                                      z_proj0=self._conv_weight(mod.z_proj[0], pad_c=zpad), z_pad=zpad,
+                                      z_proj2=self._conv_weight(mod.z_proj[2]),
+                                      table=tab.detach().to(dev, torch.float32).contiguous() if tab.numel() else None)
                 elif getattr(mod, 'is_latent_block', False):
                     w[id(mod)] = dict(post_merge=self._conv_weight(mod.post_merge),
                                       posterior=self._conv_weight(mod.posterior),
@@ -194,7 +227,7 @@ class QarvEngine:
 
     # ------------------------------------------------------------------ plan construction helpers
     def _gemm(self, P, name, a0, geom, went, out, epi=N.EPI_BIAS, a1=None, C1=0, gamma=None, res=None, r=0,
-              a_planes=None, out_planes=None):
+              a_planes=None, out_planes=None, a_act=0):
         """geom = (B, H, W, C0, ksize, stride, pad) of the NHWC input a0.  In a tensor-core mode the A operand is
         either `a_planes` (bf16 planes written by the producing kernel) or a0/a1, which the library im2col-splits
         into the plan's workspace first."""
@@ -205,7 +238,7 @@ class QarvEngine:
         d.ksize, d.stride, d.pad = ks, st, pad
         d.w, d.bias, d.N = _ptr(went['w']), _ptr(went['bias']), went['N']
         d.epilogue, d.gamma, d.res, d.out = epi, _ptr(gamma), _ptr(res), _ptr(out)
-        d.shuffle_r, d.precision = r, self.prec
+        d.shuffle_r, d.precision, d.a_act = r, self.prec, a_act
         assert went['K'] == ks * ks * C0 + C1, (name, went['K'], ks, C0, C1)
         Mo = B * ((H + 2 * pad - ks) // st + 1) * ((W + 2 * pad - ks) // st + 1)
         ws = None
@@ -230,6 +263,8 @@ class QarvEngine:
         C_, hid, k = blk.dim, blk.hidden, blk.kernel_size
         M = B * Hs * Ws
         out = x if out is None else out
+        ln_w, ln_b = _ptr(wb.get('ln_w')), _ptr(wb.get('ln_b'))        # affine LayerNorm (qres) | 0: AdaLN
+        ada_off = self.ada_off.get(id(blk), 0)
         # algorithmic bytes: read x fp32, write the GEMM operand (fp32, or npl bf16 planes)
         dw_meta = dict(kind='dwln', bytes=M * C_ * (4 + (2 * self.npl if self.npl else 4)), flops=2 * M * C_ * k * k)
         if self.npl:
@@ -238,7 +273,7 @@ class QarvEngine:
             Hd = [P.named(f'scratch_h{i}', M * hid, dtype=torch.bfloat16) for i in range(self.npl)]
             ap = [_ptr(t) for t in A] + [0] * (3 - self.npl)
             P.op('dwln', self.lib.lvae_dwconv_ln_adaln_planes, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']),
-                 _ptr(P.ada), self.ada_total, self.ada_off[id(blk)], 0, 0, ap[0], ap[1], ap[2], self.pfmt, B, Hs, Ws, C_, k,
+                 _ptr(P.ada), self.ada_total, ada_off, ln_w, ln_b, ap[0], ap[1], ap[2], self.pfmt, B, Hs, Ws, C_, k,
                  keep=(x, A), meta=dw_meta)
             self._gemm(P, 'fc1', None, (1, 1, M, C_, 1, 1, 0), wb['fc1'], None, epi=N.EPI_BIAS_GELU, a_planes=A, out_planes=Hd)
             self._gemm(P, 'fc2', None, (1, 1, M, hid, 1, 1, 0), wb['fc2'], out, epi=N.EPI_SCALE_RES,
@@ -247,7 +282,7 @@ class QarvEngine:
         A = P.named('scratch_a', M * C_)
         Hd = P.named('scratch_h', M * hid)
         P.op('dwln', self.lib.lvae_dwconv_ln_adaln, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']),
-             _ptr(P.ada), self.ada_total, self.ada_off[id(blk)], 0, 0, _ptr(A), B, Hs, Ws, C_, k,
+             _ptr(P.ada), self.ada_total, ada_off, ln_w, ln_b, _ptr(A), B, Hs, Ws, C_, k,
              keep=(x, A), meta=dw_meta)
         self._gemm(P, 'fc1', A, (1, 1, M, C_, 1, 1, 0), wb['fc1'], Hd, epi=N.EPI_BIAS_GELU)
         self._gemm(P, 'fc2', Hd, (1, 1, M, hid, 1, 1, 0), wb['fc2'], out, epi=N.EPI_SCALE_RES,
@@ -256,6 +291,9 @@ class QarvEngine:
 
     def _embedding(self, P, lmb):
         m, w, B = self.model, self.w, P.B
+        P.ada = None
+        if not self.ada_total:          # qres: no lambda embedding
+            return
         E0, E1 = m.lmb_embed_dim
         emb0, e1, emb = P.f32(B, E0), P.f32(B, E1), P.f32(B, E1)
         P.ada = P.f32(B, self.ada_total)
@@ -299,7 +337,7 @@ class QarvEngine:
                 out = P.f32(B * (Hs // r) * (Ws // r), conv.out_channels)
                 self._gemm(P, 'down', y, (B, Hs, Ws, Cc, r, r, 0), self.w[id(conv)], out)
                 x, Cc, pinned = out, conv.out_channels, False
-            elif isinstance(mod, common.ConvNeXtBlockAdaLN):
+            elif isinstance(mod, (common.ConvNeXtBlockAdaLN, common.ConvNeXtBlockLN)):
                 Hs, Ws = H // s, W // s
                 x = self._block(P, mod, x, B, Hs, Ws, out=P.f32(B * Hs * Ws, Cc) if pinned else None)
                 pinned = False
@@ -308,8 +346,8 @@ class QarvEngine:
                 pinned = True
             else:
                 raise TypeError(f'unsupported encoder module {type(mod)}')
-            if self.family == 'rd':
-                feats[H // s] = x          # keyed by feature height, last writer wins (rd/model.py:236-244)
+            if self.family in ('rd', 'qres'):
+                feats[H // s] = x          # keyed by feature height, last writer wins (rd/model.py:236-244, qresvae/model.py:200-206)
         return feats
 
     def _top_down(self, P, feats, nH, nW, latent_fn, stop_at_flag=False):
@@ -329,12 +367,28 @@ class QarvEngine:
                 zd = mod.zdim
                 x = self._block(P, mod.resnet_front, x, B, Hs, Ws)
                 prior = P.f32(M, 2 * zd)
-                self._gemm(P, 'prior', x, (B, Hs, Ws, Cc, 1, 1, 0), wl['prior'], prior)
+                if self.family == 'qres':
+                    self._vdblock(P, 'prior', wl['prior'], x, (B, Hs, Ws, Cc), prior)
+                else:
+                    self._gemm(P, 'prior', x, (B, Hs, Ws, Cc, 1, 1, 0), wl['prior'], prior)
                 z = latent_fn(P, mod, li, x, prior, (B, Hs, Ws, Cc))
                 li += 1
-                self._gemm(P, 'z_proj', z, (B, Hs, Ws, zd, 1, 1, 0), wl['z_proj'], x, epi=N.EPI_BIAS_RES, res=x)
+                if self.family == 'qres':
+                    # z_proj = conv (3x3 | 1x1) -> GELU -> 1x1, added to the feature (qresvae/model.py:236-240,278)
+                    zp, ks0 = wl['z_pad'], wl['z_proj0']['ks']
+                    if zp:
+                        zz = P.named('z_padded', M * (zd + zp))[:M * (zd + zp)]
+                        P.op('pad_z', self.lib.lvae_pad_channels, _ptr(z), _ptr(zz), M, zd, zd + zp, keep=(z, zz))
+                    else:
+                        zz = z
+                    hz = wl['z_proj0']['N']
+                    t = P.named('z_hidden', M * hz)[:M * hz]
+                    self._gemm(P, 'z_proj0', zz, (B, Hs, Ws, zd + zp, ks0, 1, (ks0 - 1) // 2), wl['z_proj0'], t, epi=N.EPI_BIAS_GELU)
+                    self._gemm(P, 'z_proj2', t, (B, Hs, Ws, hz, 1, 1, 0), wl['z_proj2'], x, epi=N.EPI_BIAS_RES, res=x)
+                else:
+                    self._gemm(P, 'z_proj', z, (B, Hs, Ws, zd, 1, 1, 0), wl['z_proj'], x, epi=N.EPI_BIAS_RES, res=x)
                 x = self._block(P, mod.resnet_end, x, B, Hs, Ws)
-            elif isinstance(mod, common.ConvNeXtBlockAdaLN):
+            elif isinstance(mod, (common.ConvNeXtBlockAdaLN, common.ConvNeXtBlockLN)):
                 x = self._block(P, mod, x, B, Hs, Ws)
             elif kind == 'up':
                 r = mod.rate
@@ -351,11 +405,27 @@ class QarvEngine:
                 raise TypeError(f'unsupported decoder module {type(mod)}')
         return x
 
+    def _vdblock(self, P, name, wv, a0, geom, out, a1=None, C1=0):
+        """VDBlock without residual (qresvae/model.py:143-149): c4(gelu(c3(gelu(c2(gelu(c1(gelu(x)))))))).  The first
+        GELU is applied to the operand as it is read (a_act), the others ride in the producing GEMM's epilogue."""
+        B, Hs, Ws, C0 = geom
+        M = B * Hs * Ws
+        hid, ks = wv['c1']['N'], wv['c2']['ks']
+        h1, h2 = P.named('vd_h1', M * hid)[:M * hid], P.named('vd_h2', M * hid)[:M * hid]
+        self._gemm(P, name + '.c1', a0, (B, Hs, Ws, C0, 1, 1, 0), wv['c1'], h1, epi=N.EPI_BIAS_GELU, a1=a1, C1=C1, a_act=1)
+        self._gemm(P, name + '.c2', h1, (B, Hs, Ws, hid, ks, 1, (ks - 1) // 2), wv['c2'], h2, epi=N.EPI_BIAS_GELU)
+        self._gemm(P, name + '.c3', h2, (B, Hs, Ws, hid, ks, 1, (ks - 1) // 2), wv['c3'], h1, epi=N.EPI_BIAS_GELU)
+        self._gemm(P, name + '.c4', h1, (B, Hs, Ws, hid, 1, 1, 0), wv['c4'], out)
+
     def _posterior(self, P, blk, x, enc_feat, geom):
         """transform_posterior (qarv/model.py:56-70) -> qm [M, zdim]"""
         B, Hs, Ws, Cc = geom
         M = B * Hs * Ws
         wl = self.w[id(blk)]
+        if self.family == 'qres':        # posterior(cat([feature, enc_feature])) (qresvae/model.py:270)
+            qm = P.f32(M, blk.zdim)
+            self._vdblock(P, 'posterior', wl['posterior'], x, geom, qm, a1=enc_feat, C1=blk.enc_width)
+            return qm
         We = blk.enc_width
         e = self._block(P, blk.posterior0, enc_feat, B, Hs, Ws, out=P.named('post_e', M * We)[:M * We])
         f = self._block(P, blk.posterior1, x, B, Hs, Ws, out=P.named('post_f', M * Cc)[:M * Cc])
@@ -430,8 +500,11 @@ class QarvEngine:
                     P.sym.append(sym)
                     P.idx.append(idx)
                 tab = self.w[id(blk)]['table']
-                P.op('latent_eval', self.lib.lvae_latent_eval, _ptr(qm), _ptr(prior), _ptr(tab), tab.numel(), _ptr(z),
-                     klp.data_ptr(), kl_cols, _ptr(kle), _ptr(sym), _ptr(idx), B, hw, zd, keep=(qm, prior, z, kle),
+                if tab is None and mode == 'compress':
+                    raise ValueError('Uninitialized CDFs. Run update() first')      # CompressAI's message
+                cdf_kind = N.CDF_ERFC if blk.discrete_gaussian.cdf_kind == 'erfc' else N.CDF_NORMAL
+                P.op('latent_eval', self.lib.lvae_latent_eval, _ptr(qm), _ptr(prior), _ptr(tab), 0 if tab is None else tab.numel(),
+                     _ptr(z), klp.data_ptr(), kl_cols, _ptr(kle), _ptr(sym), _ptr(idx), B, hw, zd, cdf_kind, keep=(qm, prior, z, kle),
                      meta=dict(kind='latent', elems=B * hw * zd,
                                bytes=B * hw * zd * (16 + (4 if want_elem else 0) + (8 if mode == 'compress' else 0))))
             return z
@@ -544,6 +617,8 @@ class QarvEngine:
             torch.cuda.current_stream(self.device).synchronize()
             self._assert_range(rng)
             res = dict(stats=P.stats.clone(), stats_host=P.stats_host.numpy().copy(), x_hat=P.x_hat)
+            if self.family == 'qres':     # per-layer rate log of HierarchicalVAE.forward (qresvae/model.py:551-557)
+                res['kl_layers'] = [P.kl_partial[:, off:off + np_].sum(dim=1) for (_, _, np_, off, _, _) in P.layout]
             if want_im_hat:
                 res['im_hat'] = P.im_hat.clone()
             if want_elem:
@@ -616,6 +691,8 @@ class QarvEngine:
             P.idx.append(idx)
             P.sym.append(sym)
             tab = self.w[id(blk)]['table']
+            if tab is None:
+                raise ValueError('Uninitialized CDFs. Run update() first')
             P.op('prior_index', self.lib.lvae_latent_prior_index, _ptr(prior), _ptr(tab), tab.numel(), _ptr(idx),
                  B, hw, zd, keep=(prior, idx))
             P.cut()              # host: D2H idx -> rANS decode -> H2D sym
@@ -631,7 +708,7 @@ class QarvEngine:
         """strings: one byte string per latent layer (batch 1, as the reference container holds)."""
         self.refresh_weights()
         B, nH, nW = bhw
-        assert B == 1, 'the container format carries one image (qarv/model.py:521)'
+        assert B == 1 or self.family == 'qres', 'the container format carries one image (qarv/model.py:521)'
         blocks = [b for b in self.model.dec_blocks if getattr(b, 'is_latent_block', False)]
         with torch.cuda.device(self.device):
             P = self._get_plan(('dec', B, nH, nW), lambda: self._build_decode_plan(B, nH, nW))
@@ -642,12 +719,15 @@ class QarvEngine:
                 idx = P.idx[li].to('cpu', non_blocking=True)
                 stream.synchronize()
                 cdf, clen, coff = self._tables(blk)
-                idx_np = idx.numpy().reshape(-1)
-                sym_np = np.empty(idx_np.size, dtype=np.int32)
-                data = np.frombuffer(strings[li], dtype=np.uint8)
-                N.check(self.lib.lvae_rans_decode(data.ctypes.data, data.size, idx_np.ctypes.data, idx_np.size,
-                                                  cdf.ctypes.data, cdf.shape[1], clen.ctypes.data, coff.ctypes.data,
-                                                  cdf.shape[0], sym_np.ctypes.data), 'rans_decode')
+                idx_np = idx.numpy().reshape(B, -1)
+                sym_np = np.empty(idx_np.shape, dtype=np.int32)
+                per_layer = strings[li] if isinstance(strings[li], (list, tuple)) else [strings[li]]
+                assert len(per_layer) == B
+                for b in range(B):            # one stream per (image, layer)
+                    data = np.frombuffer(per_layer[b], dtype=np.uint8)
+                    N.check(self.lib.lvae_rans_decode(data.ctypes.data, data.size, idx_np[b].ctypes.data, idx_np.shape[1],
+                                                      cdf.ctypes.data, cdf.shape[1], clen.ctypes.data, coff.ctypes.data,
+                                                      cdf.shape[0], sym_np[b].ctypes.data), 'rans_decode')
                 P.sym[li].copy_(torch.from_numpy(sym_np).view_as(P.sym[li]), non_blocking=False)
             self._launch(P, len(blocks))
             return P.x_hat.clone().clamp_(min=-1.0, max=1.0).mul_(0.5).add_(0.5)

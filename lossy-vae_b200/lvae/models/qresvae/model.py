@@ -195,7 +195,6 @@ class HierarchicalVAE(nn.Module):
         res = self.engine.run(im, self._lmb(nB), mode=mode, want_elem=False, want_im_hat=return_rec, noise=noise)
         host = res['stats_host']
         ndims = imC * imH * imW
-        P = res['plan']
         kls = torch.stack([res['kl_layers'][li].mean(0) / ndims for li in range(self.num_latents)])
         bpdim = kls * self.log2_e
         self._stats_log[f'{mode}_bpdim'] = bpdim.tolist()

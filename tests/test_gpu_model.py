@@ -39,7 +39,7 @@ def _symbols_from_model(model, im, lmb):
     return [s.cpu() for s in P.sym], [i.cpu() for i in P.idx]
 
 
-def _check_integer_parity(syms, idxs, ref_syms, ref_idxs, oracle_records):
+def _check_integer_parity(syms, idxs, ref_syms, ref_idxs, oracle_records, scale_table=None):
     """Bit-exact symbols / indexes -- except at rounding-boundary elements: the fp32 contractions upstream sum in a
     different order than the host BLAS (|d(qm-pm)| ~ 1e-6), so an element whose oracle value qm-pm lies within 2e-5 of
     a half-integer can round the other way.  Every mismatch in the first differing layer must be such an element
@@ -59,7 +59,7 @@ def _check_integer_parity(syms, idxs, ref_syms, ref_idxs, oracle_records):
             assert int(ms.sum()) <= 2, f'layer {li}: {int(ms.sum())} symbol mismatches'
             if mi.any():
                 s = torch.max(rec['pv'], torch.tensor(0.11))[mi]
-                edge = O.default_scale_table()
+                edge = O.default_scale_table() if scale_table is None else scale_table
                 rel = ((s[:, None] - edge[None]).abs() / edge[None]).min(dim=1).values
                 # ln(scale) = plogv is a feature-map value with the same ~1e-6..1e-5 absolute summation noise as
                 # qm - pm above, i.e. the same *relative* noise on the scale itself -> same 2e-5 bound

@@ -1,0 +1,115 @@
+"""End-to-end parity of the qres34m path on a B200 against the fixtures produced by the
+unmodified reference (tests/golden/qres_*.npz, oracle/gen_golden.py): eval forward, train forward with the
+reference's noise, integer symbols / table indexes, bit streams and decompression."""
+import numpy as np
+import pytest
+import torch
+
+import lvae_oracle as O
+import qres_oracle as Q
+from oracle_inputs import QRES_CASES, QRES_LMB, make_input
+from test_gpu_model import PSNR_TOL, bpp_tol, _check_integer_parity
+from test_oracle_pinned import _qres_noise
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module')
+def qres_sd():
+    return O.sensitised_state_dict(Q.qres_param_shapes(), seed=0)
+
+
+@pytest.fixture(scope='module')
+def qres_model(native_lib, qres_sd):
+    import lvae
+    torch.manual_seed(0)
+    model = lvae.get_model('qres34m', lmb=QRES_LMB)
+    missing, unexpected = model.load_state_dict(qres_sd, strict=False)
+    assert not unexpected and all('discrete_gaussian' in k for k in missing), (missing, unexpected)
+    model = model.to(DEV).eval()
+    model.compress_mode()
+    return model
+
+
+@pytest.mark.parametrize('precision', ['f16x3', 'bf16x6', 'fp32'])
+@pytest.mark.parametrize('name', list(QRES_CASES))
+def test_qres_forward_matches_reference_fixture(name, precision, qres_model, qres_sd, golden):
+    g = golden(name)
+    kind, nB, H, W, seed, nseed = QRES_CASES[name]
+    im_cpu = make_input(kind, nB, H, W, seed)
+    im = im_cpu.to(DEV)
+    qres_model.precision = precision
+    try:
+        st = qres_model(im, return_rec=True)
+        lat = qres_model.forward_get_latents(im)
+        obj = qres_model.compress(im)
+        P = qres_model.engine._plans[(nB, H, W, 'compress', False)]
+        torch.cuda.synchronize()
+        syms, idxs = [s.cpu() for s in P.sym], [i.cpu() for i in P.idx]
+        rec = qres_model.decompress(obj)
+        qres_model.train()
+        noise = _qres_noise(Q, Q.qres34m_arch(), nB, H, W, nseed)
+        tr = qres_model(im, noise=noise)
+    finally:
+        qres_model.eval()
+        qres_model.precision = 'f16x3'
+    assert abs(st['bppix'] - float(g['bppix'])) <= bpp_tol(H, W), (st['bppix'], float(g['bppix']))
+    assert abs(st['psnr'] - float(g['psnr'])) <= PSNR_TOL
+    assert abs(st['loss'].item() - float(g['loss'])) <= 1e-4 * abs(float(g['loss']))
+    assert abs(st['mse'] - float(g['mse'])) <= 1e-4 * float(g['mse']) and abs(st['kl'] - float(g['kl'])) <= 1e-4
+    flips = _check_integer_parity(
+        syms, idxs, [torch.from_numpy(g[f'sym{li}'].astype(np.int32)) for li in range(12)],
+        [torch.from_numpy(g[f'idx{li}'].astype(np.int32)) for li in range(12)],
+        lambda: Q.qres_forward(qres_sd, im_cpu, QRES_LMB)['records'], scale_table=Q.qres_scale_table())
+    tol_nats = bpp_tol(H, W) * H * W / 1.4427
+    for li, stl in enumerate(lat):
+        kl = stl['kl'].sum(dim=(1, 2, 3)).cpu().numpy()
+        assert np.all(np.abs(kl - g['kl_per_image'][li]) <= tol_nats + 2e-5 * g['kl_per_image'][li]), li
+    assert tuple(obj[-1]) == tuple(g['shape'])
+    assert (rec - st['im_hat']).abs().max().item() < 1e-5          # decoder reproduces the encoder's reconstruction
+    if flips == 0:
+        assert (st['im_hat'].cpu() - torch.from_numpy(g['im_hat'])).abs().max().item() < 1e-5
+        for li, stl in enumerate(lat):
+            assert (stl['z'].cpu() - torch.from_numpy(g[f'z{li}'])).abs().max().item() < 2e-5, f'layer {li} latents differ'
+            for b in range(nB):
+                assert obj[li][b] == g[f'bytes{li}_{b}'].tobytes(), f'bit stream of layer {li} image {b} differs'
+        assert (rec.cpu() - torch.from_numpy(g['dec_im_hat'])).abs().max().item() < 1e-5
+    # training branch (uniform noise + gaussian_log_prob_mass): smooth in the activations -> fp32 round-off only
+    assert abs(tr['loss'].item() - float(g['train_loss'])) <= 2e-5 * abs(float(g['train_loss']))
+    assert abs(tr['bppix'] - float(g['train_bppix'])) <= 1e-4 and abs(tr['psnr'] - float(g['train_psnr'])) <= PSNR_TOL
+
+
+def test_qres_batched_container_roundtrip_and_errors(qres_model, tmp_path):
+    from PIL import Image
+    im = make_input('synth', 3, 64, 128, 30).to(DEV)
+    obj = qres_model.compress(im)
+    assert len(obj) == 13 and all(len(layer) == 3 for layer in obj[:-1]) and obj[-1] == (3, 384, 1, 2)
+    rec = qres_model.decompress(obj)
+    ref = qres_model(im, return_rec=True)['im_hat']
+    assert (rec - ref).abs().max().item() < 1e-5
+    one = qres_model.compress(im[1:2])
+    assert all(one[li][0] == obj[li][1] for li in range(12))      # batch invariance of the bit stream
+    # file container: pickle of the list + (h, w), cropped on decode (qresvae/model.py:689-725)
+    arr = (make_input('synth', 1, 100, 150, 8)[0].permute(1, 2, 0).numpy() * 255).round().astype(np.uint8)
+    src, bits = tmp_path / 'x.png', tmp_path / 'x.bits'
+    Image.fromarray(arr).save(src)
+    qres_model.compress_file(src, bits)
+    out = qres_model.decompress_file(bits)
+    assert tuple(out.shape) == (1, 3, 100, 150)
+    mse = ((out.cpu()[0].permute(1, 2, 0).numpy() - arr / 255.0) ** 2).mean()
+    assert np.isfinite(mse)
+    with pytest.raises(AssertionError):
+        qres_model(torch.rand(1, 3, 60, 64, device=DEV))
+    with pytest.raises(AssertionError):
+        qres_model(torch.rand(1, 3, 64, 64, device=DEV) * 2)
+
+
+def test_qres_sampling_with_given_latents_reproduces_decoder(qres_model):
+    im = make_input('rand', 1, 64, 64, 31).to(DEV)
+    lat = qres_model.forward_get_latents(im)
+    rec = qres_model.cond_sample([s['z'] for s in lat])
+    ref = qres_model(im, return_rec=True)['im_hat']
+    assert (rec - ref).abs().max().item() < 1e-5
+    smp = qres_model.uncond_sample((2, 1, 1), temprature=0.0)
+    assert tuple(smp.shape) == (2, 3, 64, 64) and bool(torch.isfinite(smp).all())

@@ -182,3 +182,41 @@ def test_no_cpu_fallback_and_error_conventions(native_lib):
     m.compress_mode()
     cdf, clen, off = blk.discrete_gaussian.host_tables()
     assert cdf.shape == (64, 249) and clen.max() == 249 and off.min() == -123
+
+
+def test_qres_model_surface_and_state_dict_contract(native_lib, golden):
+    """qres34m: parameter / buffer names of the reference's HierarchicalVAE, its default init, the
+    CompressAI table set built by compress_mode(), and the no-CPU-path error."""
+    import lvae
+    import qres_oracle as Q
+    torch.manual_seed(0)
+    m = lvae.get_model('qres34m', lmb=64)
+    want = dict(Q.qres_param_shapes())
+    names = [k for k, _ in m.named_parameters()]
+    assert sorted(names) == sorted(want)
+    for k, p in m.named_parameters():
+        assert tuple(p.shape) == tuple(want[k]), k
+    sd = m.state_dict()
+    assert len(sd) == 813 and round(sum(p.numel() for p in m.parameters()) / 1e6, 2) == 34.04
+    for suffix in ('_offset', '_quantized_cdf', '_cdf_length', 'scale_table', 'scale_bound',
+                   'likelihood_lower_bound.bound', 'lower_bound_scale.bound'):
+        assert f'decoder.dec_blocks.0.discrete_gaussian.{suffix}' in sd
+    assert sd['decoder.dec_blocks.0.discrete_gaussian.scale_table'].numel() == 0
+    # default init conventions: zero-initialised prior head (zero_last), residual scaling of z_proj.2, gamma 1e-6
+    assert torch.count_nonzero(sd['decoder.dec_blocks.0.prior.c4.weight']) == 0
+    assert float(sd['encoder.enc_blocks.1.gamma'][0]) == pytest.approx(1e-6)
+    assert m.out_net.mse_lmb == 64.0 and m.num_latents == 12 and m.max_stride == 64
+    for attr in ('forward', 'forward_eval', 'forward_get_latents', 'uncond_sample', 'cond_sample', 'compress_mode',
+                 'compress', 'decompress', 'compress_file', 'decompress_file'):
+        assert callable(getattr(m, attr))
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        m.eval()(torch.rand(1, 3, 64, 64))
+    m.compress_mode()
+    t = golden('qres_tables')
+    dg = m.decoder.dec_blocks[3].discrete_gaussian
+    assert np.array_equal(dg.scale_table.numpy(), t['scale_table'])
+    cdf, clen, off = dg.host_tables()
+    assert np.array_equal(cdf, t['cdf']) and np.array_equal(clen, t['cdf_length']) and np.array_equal(off, t['offset'])
+    m2 = copy.deepcopy(m)
+    assert m2.__dict__['_engine'] is None and torch.equal(m2.decoder.bias, m.decoder.bias)
+    str(m)
