@@ -153,6 +153,13 @@ int lvae_latent_eval(const float* qm, const float* prior, const float* scale_tab
 int lvae_latent_train(const float* qm, const float* prior, const float* noise,
                       float* z, float* kl_partial, int kl_stride, float* kl_elem,
                       int B, int hw, int zdim, void* stream);
+/* Backward of lvae_latent_train (entropy_coding.py:17-49 under autograd).  Upstream gradients:
+ * dz [M,zdim] = dL/dz arriving through z_proj (NULL: 0) and dL/dkl, either per element (dkl_elem [M,zdim]) or the
+ * constant dkl_scale (the loss uses 1 / (ndims * B), qarv/model.py:338-346).  Outputs: dqm [M,zdim] = dL/dqm and
+ * dprior [M,2*zdim] = (dL/dpm | dL/dplogv_raw), the gradient w.r.t. the prior head's output. */
+int lvae_latent_train_bwd(const float* qm, const float* prior, const float* noise,
+                          const float* dz, const float* dkl_elem, float dkl_scale,
+                          float* dqm, float* dprior, int B, int hw, int zdim, void* stream);
 /* Decompress side: idx from the prior only (NCHW int32), then z = float(sym) + pm from decoded symbols */
 int lvae_latent_prior_index(const float* prior, const float* scale_table, int n_scales,
                             int32_t* idx, int B, int hw, int zdim, void* stream);

@@ -1,20 +1,22 @@
-// Depthwise kxk conv + LayerNorm(C, eps 1e-6) + AdaLN (or affine LN), NHWC fp32 in, fp32 and/or bf16 planes out.
+// Depthwise kxk conv + LayerNorm(C, eps 1e-6) + AdaLN (or affine LN), NHWC fp32 in, fp32 and/or 16-bit planes out.
 // Reference: ConvNeXtBlockAdaLN.forward, lvae/models/common.py:145-152 (conv_dw -> permute -> norm ->
 // x*(1+scale)+shift); qresvae MyConvNeXtBlock (affine LayerNorm, no AdaLN) qresvae/model.py:163-182.
 //
-// HBM-bound stage (algorithmic bytes per position: read 4C, write 4C fp32 or 2C per bf16 plane).  One CTA of
-// 8 warps owns an 8 x 8 tile of output pixels of one image, all C channels:
-//   * channels are processed in chunks of 64; the (8+k-1)^2 halo of a chunk is one TMA box load
-//     (cp.async.bulk.tensor.4d over the [C, W, H, B] view; coordinates outside the image are zero-filled by the
-//     hardware = the conv's zero padding), double-buffered on mbarriers so chunk j+1 streams in while chunk j is
-//     convolved -- no fill loop, no index arithmetic, every input element is read once per tile;
-//   * warp w convolves output row w: lane l owns channels {64 j + 2 l, 64 j + 2 l + 1}, a sliding window of the
-//     shared-memory row feeds the 8 pixels, results stay in registers (8 pixels x 2 channels x C/64 chunks);
-//   * LayerNorm is then warp-local: two-pass (mean, centred second moment) warp-shuffle reductions in fp32,
-//     followed by the modulation and the split into bf16 planes for the tensor-core GEMM that consumes it;
-//   * wide layers (C > 512, the rd model's 640 / 768) run as a 2-CTA thread-block cluster: each CTA convolves half
-//     of the channels of the same pixel tile and the two exchange their per-pixel LayerNorm partial sums through
-//     distributed shared memory (always added in rank order, so both CTAs -- and every launch -- agree bit for bit).
+// Balanced between HBM (algorithmic bytes per position: read 4C, write 4C fp32 or 2C per 16-bit plane) and the fp32
+// FMA pipe (49 MACs per output at k = 7).  One CTA of 4 warps owns an 8 x 8 tile of output pixels of one image and
+// 64 channels (128 for the rd model's 640 / 768); a thread-block cluster of C / 64 CTAs covers all channels:
+//   * the (8+k-1)^2 x 64 halo is one TMA box load (cp.async.bulk.tensor.4d over the [C, W, H, B] view;
+//     coordinates outside the image are zero-filled by the hardware = the conv's zero padding): no fill loop, no
+//     index arithmetic; at 49 KB per CTA four CTAs share an SM, so loads, convolution, the cluster exchange and the
+//     stores of different tiles overlap (measured: 4 warps x 4 CTAs beats 8 x 2 and 6 x 3 by 10-15 %);
+//   * warp w convolves output rows 2w and 2w+1 together, lane l owns channels {2l, 2l+1}: rolling over the k+1 input
+//     rows, every shared-memory row and every filter row is loaded once and feeds both outputs -- 161 loads per 784
+//     packed FFMA2 instead of 294, which moves the bound from the L1/shared pipe (62 % busy before) to the FMA pipe;
+//   * LayerNorm: per-CTA two-pass statistics in registers (16-value halving warp reduction: 16 shuffles instead of
+//     80), then Chan's parallel-variance combination of the CL partial (sum, M2) pairs read through distributed
+//     shared memory, always in rank order, so every CTA of the cluster -- and every launch -- agrees bit for bit;
+//     one cluster barrier before the exchange, one before exit;
+//   * modulation (AdaLN or affine) and the split into 16-bit planes for the tensor-core GEMM that consumes them.
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <cuda.h>
@@ -24,9 +26,14 @@
 
 namespace lvae {
 
-constexpr int DW_T = 8;                 // output tile edge
-constexpr int DW_CH = 64;               // channels per chunk
-constexpr int DW_NBUF = 2;              // halo buffers per CTA (chunk j+1 streams in while chunk j is convolved)
+#ifndef LVAE_DW_WARPS
+#define LVAE_DW_WARPS 4
+#endif
+constexpr int DW_WARPS = LVAE_DW_WARPS; // warps per CTA
+constexpr int DW_TW = 8;                // output tile: 8 columns x 2 * DW_WARPS rows, warp w owns rows 2w and 2w + 1
+constexpr int DW_TH = 2 * DW_WARPS;
+constexpr int DW_CH = 64;               // channels per chunk (lane l owns channels 2l, 2l + 1 of the chunk)
+constexpr int DW_PIX = 2 * DW_TW;       // pixels per warp
 
 __device__ __forceinline__ uint32_t dw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dw_mbar_init(uint32_t bar, uint32_t count) {
@@ -59,25 +66,57 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return *reinterpret_cast<float2*>(&d);
 }
 
+// Sum of 16 per-lane values over the 32 lanes of a warp in 16 shuffles (instead of 16 x 5): at every butterfly step a
+// lane keeps the half of the values its partner does not.  Lane l ends with the total of value (l >> 1) & 15; the
+// additions are the same pairs in the same order as the xor-butterfly warp_sum(), so the totals are bit-identical.
+__device__ __forceinline__ float warp_sum16(const float (&v)[DW_PIX], int lane) {
+  float a[8], b[4], c[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = h16 ? v[i + 8] : v[i], send = h16 ? v[i] : v[i + 8];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = h8 ? a[i + 4] : a[i], send = h8 ? a[i] : a[i + 4];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = h4 ? b[i + 2] : b[i], send = h4 ? b[i] : b[i + 2];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float keep = h2 ? c[1] : c[0], send = h2 ? c[0] : c[1];
+  float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
+}
+
+// One CTA (8 warps) = one 16 x 8 pixel tile x (NJ * 64) channels; a cluster of CL CTAs covers all C = NJ * 64 * CL
+// channels of the tile and exchanges LayerNorm partial statistics through distributed shared memory.
 template <int NJ, int KS, int CL>
-__global__ void __launch_bounds__(256) dwln_kernel(
+__global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
     const __grid_constant__ CUtensorMap x_map, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
     const float* __restrict__ ada, int64_t ada_stride, int64_t ada_off,
     const float* __restrict__ ln_w, const float* __restrict__ ln_b,
     float* __restrict__ y, __nv_bfloat16* __restrict__ y0, __nv_bfloat16* __restrict__ y1, __nv_bfloat16* __restrict__ y2,
     int f16, int H, int W, int tiles_x, int tiles_y) {
-  constexpr int C = NJ * DW_CH * CL, PAD = (KS - 1) / 2, HT = DW_T + KS - 1;   // halo tile edge
-  constexpr int CHUNK_FLOATS = HT * HT * DW_CH;
-  extern __shared__ __align__(128) float dw_smem[];                          // [DW_NBUF][HT][HT][64]
+  constexpr int C = NJ * DW_CH * CL, NLOC = NJ * DW_CH, PAD = (KS - 1) / 2;
+  constexpr int HW_ = DW_TW + KS - 1, HH_ = DW_TH + KS - 1;                  // halo tile width / height
+  constexpr int CHUNK_FLOATS = HH_ * HW_ * DW_CH;
+  constexpr int NBUF = NJ > 1 ? 2 : 1;
+  extern __shared__ __align__(128) float dw_smem[];                          // [NBUF][HH_][HW_][64]
   __shared__ __align__(8) uint64_t dw_bar[2];
-  __shared__ float ln_part[2][8][DW_T];                                      // [pass][warp][pixel] partial sums (CL > 1)
+  __shared__ __align__(16) float ln_pub[2][DW_WARPS * DW_PIX];                      // this CTA's (sum, M2) per tile pixel, read by the cluster
+  __shared__ __align__(16) float ln_loc[DW_WARPS][2][DW_PIX];                       // per warp: broadcast scratch
   const int tid = threadIdx.x, lane = tid & 31, wrow = tid >> 5;
   const int crank = (CL > 1) ? (int)(blockIdx.x % CL) : 0;                   // cluster dims (CL,1,1): rank == blockIdx.x % CL
-  const int cbase = crank * NJ * DW_CH;                                      // first channel of this CTA
+  const int cbase = crank * NLOC;                                            // first channel of this CTA
   int t = blockIdx.x / CL;
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y; const int b = t / tiles_y;
-  const int h0 = ty * DW_T, w0 = tx * DW_T;
+  const int h0 = ty * DW_TH, w0 = tx * DW_TW;
 
   if (tid == 0) {
     dw_mbar_init(dw_smem_u32(&dw_bar[0]), 1);
@@ -91,90 +130,141 @@ __global__ void __launch_bounds__(256) dwln_kernel(
     dw_tma_load_4d(dw_smem_u32(dw_smem + buf * CHUNK_FLOATS), &x_map, bar, cbase + j * DW_CH, w0 - PAD, h0 - PAD, b);
   };
 
-  float2 res[NJ][DW_T];
+  // res[j][p]: conv output of pixel p = r * 8 + s (r = 0, 1: rows 2 wrow + r; s: column) for this lane's 2 channels
+  float2 res[NJ][DW_PIX];
   if (tid == 0) load_chunk(0, 0);
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     // buffer (j+1)&1 was last read in iteration j-1, which ended with __syncthreads()
-    if (tid == 0 && j + 1 < NJ) load_chunk(j + 1, (j + 1) & 1);
-    dw_mbar_wait(dw_smem_u32(&dw_bar[j & 1]), (uint32_t)((j >> 1) & 1));
-    const float* tile = dw_smem + (j & 1) * CHUNK_FLOATS;
+    if (NJ > 1 && tid == 0 && j + 1 < NJ) load_chunk(j + 1, (j + 1) & 1);
+    dw_mbar_wait(dw_smem_u32(&dw_bar[j & (NBUF - 1)]), (uint32_t)((j >> 1) & 1));
+    const float* tile = dw_smem + (j & (NBUF - 1)) * CHUNK_FLOATS;
     const int c = cbase + j * DW_CH + lane * 2;
     const float2 bias = __ldg(reinterpret_cast<const float2*>(dw_b + c));
-    float2 acc[DW_T];
 #pragma unroll
-    for (int s = 0; s < DW_T; ++s) acc[s] = bias;
+    for (int p = 0; p < DW_PIX; ++p) res[j][p] = bias;
+    // rolling over the KS + 1 halo rows that feed output rows o1 = 2 wrow (tap row ky = i) and o2 = o1 + 1 (ky = i - 1):
+    // every input row is read from shared memory once, every filter row is loaded once and used for both outputs;
+    // per output the taps still accumulate in (ky, kx) order, i.e. the sums are those of the one-row-per-warp kernel
+    float2 wprev[KS];
 #pragma unroll
-    for (int ky = 0; ky < KS; ++ky) {
-      const float* row = tile + ((wrow + ky) * HT) * DW_CH + lane * 2;
-      float2 xv[HT];
+    for (int i = 0; i <= KS; ++i) {
+      const float* row = tile + ((2 * wrow + i) * HW_) * DW_CH + lane * 2;
+      float2 xv[HW_];
 #pragma unroll
-      for (int i = 0; i < HT; ++i) xv[i] = *reinterpret_cast<const float2*>(row + i * DW_CH);
+      for (int q = 0; q < HW_; ++q) xv[q] = *reinterpret_cast<const float2*>(row + q * DW_CH);
+      float2 wcur[KS];
+      if (i < KS) {
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) wcur[kx] = __ldg(reinterpret_cast<const float2*>(dw_w + (i * KS + kx) * C + c));
+      }
 #pragma unroll
       for (int kx = 0; kx < KS; ++kx) {
-        const float2 wv = __ldg(reinterpret_cast<const float2*>(dw_w + (ky * KS + kx) * C + c));
+        if (i >= 1) {
 #pragma unroll
-        for (int s = 0; s < DW_T; ++s) acc[s] = ffma2(xv[s + kx], wv, acc[s]);
+          for (int s = 0; s < DW_TW; ++s) res[j][DW_TW + s] = ffma2(xv[s + kx], wprev[kx], res[j][DW_TW + s]);
+        }
       }
-    }
 #pragma unroll
-    for (int s = 0; s < DW_T; ++s) res[j][s] = acc[s];
-    __syncthreads();                       // everyone is done with this buffer before chunk j+2 overwrites it
+      for (int kx = 0; kx < KS; ++kx) {
+        if (i < KS) {
+#pragma unroll
+          for (int s = 0; s < DW_TW; ++s) res[j][s] = ffma2(xv[s + kx], wcur[kx], res[j][s]);
+        }
+      }
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) wprev[kx] = wcur[kx];
+    }
+    if (NJ > 1) __syncthreads();           // everyone is done with this buffer before chunk j+2 overwrites it
   }
 
-  const int h = h0 + wrow;
-  if (CL == 1 && h >= H) return;           // warp-uniform (cluster CTAs stay for the exchanges below)
+  // ---- LayerNorm statistics: two-pass over this CTA's channels (registers), Chan's combination across the cluster
   namespace cg = cooperative_groups;
-  float mean[DW_T], rstd[DW_T];
-  float part[DW_T];
+  float v16[DW_PIX];
 #pragma unroll
-  for (int s = 0; s < DW_T; ++s) {
+  for (int p = 0; p < DW_PIX; ++p) {
     float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) sum += res[j][s].x + res[j][s].y;
-    part[s] = warp_sum(sum);
+    for (int j = 0; j < NJ; ++j) sum += res[j][p].x + res[j][p].y;
+    v16[p] = sum;
   }
-  if (CL > 1) {
-    if (lane == 0) {
+  float tot = warp_sum16(v16, lane);                           // lane l: sum of pixel (l >> 1) & 15 over NLOC channels
+  if ((lane & 1) == 0) ln_loc[wrow][0][lane >> 1] = tot;
+  __syncwarp();
+  float mean[DW_PIX], rstd[DW_PIX];
 #pragma unroll
-      for (int s = 0; s < DW_T; ++s) ln_part[0][wrow][s] = part[s];
-    }
-    cg::this_cluster().sync();
-#pragma unroll
-    for (int s = 0; s < DW_T; ++s) {
-      float tot = 0.f;
-      for (int r = 0; r < CL; ++r) tot += cg::this_cluster().map_shared_rank(&ln_part[0][wrow][s], r)[0];
-      part[s] = tot;
-    }
+  for (int p4 = 0; p4 < DW_PIX; p4 += 4) {
+    const float4 s4 = *reinterpret_cast<const float4*>(&ln_loc[wrow][0][p4]);
+    mean[p4] = s4.x; mean[p4 + 1] = s4.y; mean[p4 + 2] = s4.z; mean[p4 + 3] = s4.w;     // local sums for now
   }
 #pragma unroll
-  for (int s = 0; s < DW_T; ++s) {
-    mean[s] = part[s] * (1.0f / C);
+  for (int p = 0; p < DW_PIX; ++p) {
+    const float mloc = mean[p] * (1.0f / NLOC);
     float sq = 0.f;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const float dx = res[j][s].x - mean[s], dy = res[j][s].y - mean[s];
+      const float dx = res[j][p].x - mloc, dy = res[j][p].y - mloc;
       sq = fmaf(dx, dx, sq); sq = fmaf(dy, dy, sq);
     }
-    part[s] = warp_sum(sq);
+    v16[p] = sq;
   }
-  if (CL > 1) {
-    if (lane == 0) {
+  const float m2 = warp_sum16(v16, lane);                      // centred second moment about the LOCAL mean
+  if (CL == 1) {
+    __syncwarp();
+    if ((lane & 1) == 0) ln_loc[wrow][1][lane >> 1] = m2;
+    __syncwarp();
 #pragma unroll
-      for (int s = 0; s < DW_T; ++s) ln_part[1][wrow][s] = part[s];
+    for (int p4 = 0; p4 < DW_PIX; p4 += 4) {
+      const float4 q4 = *reinterpret_cast<const float4*>(&ln_loc[wrow][1][p4]);
+      rstd[p4] = q4.x; rstd[p4 + 1] = q4.y; rstd[p4 + 2] = q4.z; rstd[p4 + 3] = q4.w;
     }
-    cg::this_cluster().sync();
 #pragma unroll
-    for (int s = 0; s < DW_T; ++s) {
-      float tot = 0.f;
-      for (int r = 0; r < CL; ++r) tot += cg::this_cluster().map_shared_rank(&ln_part[1][wrow][s], r)[0];
-      part[s] = tot;
+    for (int p = 0; p < DW_PIX; ++p) {
+      mean[p] = mean[p] * (1.0f / C);
+      rstd[p] = 1.0f / sqrtf(rstd[p] * (1.0f / C) + 1e-6f);
     }
-    cg::this_cluster().sync();               // nobody exits while a peer may still read its shared memory
-    if (h >= H) return;
+  } else {
+    if ((lane & 1) == 0) {
+      ln_pub[0][wrow * DW_PIX + (lane >> 1)] = tot;
+      ln_pub[1][wrow * DW_PIX + (lane >> 1)] = m2;
+    }
+    // publish -> read: release / acquire cluster barrier (orders the shared-memory writes above)
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (lane < DW_PIX) {
+      // pixel `lane` of this warp: combine the CL partial (sum, M2) pairs in rank order (identical in every CTA)
+      float s_r[CL], q_r[CL];
+#pragma unroll
+      for (int r = 0; r < CL; ++r) {
+        s_r[r] = *cg::this_cluster().map_shared_rank(&ln_pub[0][wrow * DW_PIX + lane], r);
+        q_r[r] = *cg::this_cluster().map_shared_rank(&ln_pub[1][wrow * DW_PIX + lane], r);
+      }
+      float S = 0.f;
+#pragma unroll
+      for (int r = 0; r < CL; ++r) S += s_r[r];
+      const float mu = S * (1.0f / C);
+      float M2 = 0.f;
+#pragma unroll
+      for (int r = 0; r < CL; ++r) {
+        const float dm = s_r[r] * (1.0f / NLOC) - mu;
+        M2 += fmaf((float)NLOC * dm, dm, q_r[r]);
+      }
+      ln_loc[wrow][0][lane] = mu;
+      ln_loc[wrow][1][lane] = 1.0f / sqrtf(M2 * (1.0f / C) + 1e-6f);
+    }
+    // this warp's remote reads have returned (their values were consumed above): arrive now, without memory ordering,
+    // and wait only before exit -- the output stores below overlap the barrier and no fence has to drain them
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int p4 = 0; p4 < DW_PIX; p4 += 4) {
+      const float4 s4 = *reinterpret_cast<const float4*>(&ln_loc[wrow][0][p4]);
+      const float4 q4 = *reinterpret_cast<const float4*>(&ln_loc[wrow][1][p4]);
+      mean[p4] = s4.x; mean[p4 + 1] = s4.y; mean[p4 + 2] = s4.z; mean[p4 + 3] = s4.w;
+      rstd[p4] = q4.x; rstd[p4 + 1] = q4.y; rstd[p4 + 2] = q4.z; rstd[p4 + 3] = q4.w;
+    }
   }
-#pragma unroll
-  for (int s = 0; s < DW_T; ++s) rstd[s] = 1.0f / sqrtf(part[s] * (1.0f / C) + 1e-6f);
+
+  // ---- modulation + output
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     const int c = cbase + j * DW_CH + lane * 2;
@@ -189,12 +279,12 @@ __global__ void __launch_bounds__(256) dwln_kernel(
       mul = make_float2(__fadd_rn(1.0f, sc.x), __fadd_rn(1.0f, sc.y));
     }
 #pragma unroll
-    for (int s = 0; s < DW_T; ++s) {
-      const int w = w0 + s;
-      if (w >= W) break;                   // warp-uniform
+    for (int p = 0; p < DW_PIX; ++p) {
+      const int h = h0 + 2 * wrow + p / DW_TW, w = w0 + p % DW_TW;
+      if (h >= H || w >= W) continue;      // warp-uniform
       float2 v;
-      v.x = __fadd_rn(__fmul_rn(__fmul_rn(res[j][s].x - mean[s], rstd[s]), mul.x), add.x);
-      v.y = __fadd_rn(__fmul_rn(__fmul_rn(res[j][s].y - mean[s], rstd[s]), mul.y), add.y);
+      v.x = __fadd_rn(__fmul_rn(__fmul_rn(res[j][p].x - mean[p], rstd[p]), mul.x), add.x);
+      v.y = __fadd_rn(__fmul_rn(__fmul_rn(res[j][p].y - mean[p], rstd[p]), mul.y), add.y);
       const int64_t o = (((int64_t)b * H + h) * W + w) * C + c;
       if (y != nullptr) *reinterpret_cast<float2*>(y + o) = v;
       if (y0 != nullptr) {
@@ -207,6 +297,7 @@ __global__ void __launch_bounds__(256) dwln_kernel(
       }
     }
   }
+  if (CL > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // nobody exits while a peer may still read its shared memory
 }
 
 typedef CUresult (*DwEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -230,8 +321,8 @@ static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, con
                        int64_t ada_stride, int64_t ada_off, const float* ln_w, const float* ln_b,
                        float* y, __nv_bfloat16* y0, __nv_bfloat16* y1, __nv_bfloat16* y2, int f16,
                        int B, int H, int W, cudaStream_t stream) {
-  constexpr int HT = DW_T + KS - 1, C = NJ * DW_CH * CL;
-  constexpr int smem = DW_NBUF * HT * HT * DW_CH * 4;
+  constexpr int HW_ = DW_TW + KS - 1, HH_ = DW_TH + KS - 1, C = NJ * DW_CH * CL;
+  constexpr int smem = (NJ > 1 ? 2 : 1) * HH_ * HW_ * DW_CH * 4;
   static bool configured = false;
   if (!configured) {
     LVAE_CUDA_CALL(cudaFuncSetAttribute(dwln_kernel<NJ, KS, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -239,24 +330,24 @@ static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, con
   }
   DwEncodeTiledFn enc = dw_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LVAE_E_UNSUPPORTED; }
-  // NHWC fp32 viewed as a 4-D tensor (C, W, H, B); box = (64 channels, HT, HT, 1); out-of-image coordinates -> 0
+  // NHWC fp32 viewed as a 4-D tensor (C, W, H, B); box = (64 channels, 8 + k - 1, 16 + k - 1, 1); out-of-image -> 0
   CUtensorMap map;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[4] = {DW_CH, HT, HT, 1};
+  cuuint32_t box[4] = {DW_CH, HW_, HH_, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (dwconv input) failed: %d", (int)r); return LVAE_E_BADARG; }
-  const int tiles_x = (W + DW_T - 1) / DW_T, tiles_y = (H + DW_T - 1) / DW_T;
+  const int tiles_x = (W + DW_TW - 1) / DW_TW, tiles_y = (H + DW_TH - 1) / DW_TH;
   const int64_t blocks = (int64_t)B * tiles_x * tiles_y;
   if (CL == 1) {
-    dwln_kernel<NJ, KS, CL><<<(unsigned)blocks, 256, smem, stream>>>(
+    dwln_kernel<NJ, KS, CL><<<(unsigned)blocks, 32 * DW_WARPS, smem, stream>>>(
         map, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, f16, H, W, tiles_x, tiles_y);
   } else {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(blocks * CL)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3((unsigned)(blocks * CL)); cfg.blockDim = dim3(32 * DW_WARPS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -294,15 +385,12 @@ static int dwln_dispatch(const float* x, const float* dw_w, const float* dw_b,
   LVAE_CHECK_ARG(ln_w != nullptr || (ada_off % 2 == 0 && ada_stride % 2 == 0));      // float2 loads of shift / scale
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* p0 = (__nv_bfloat16*)y0; __nv_bfloat16* p1 = (__nv_bfloat16*)y1; __nv_bfloat16* p2 = (__nv_bfloat16*)y2;
-#define LVAE_DWLN_CASE(nj) case nj: return dispatch_k<nj, 1>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, f16, B, H, W, st);
+#define LVAE_DWLN_CASE(n64, nj, cl) case n64: return dispatch_k<nj, cl>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, f16, B, H, W, st);
+  // C = 64 * NJ * CL: one 64-channel chunk per CTA (everything stays in registers, two CTAs per SM), the channel
+  // dimension spread over a thread-block cluster; the rd model's 640 / 768 use two chunks per CTA (cluster <= 8)
   switch (C / 64) {
-    LVAE_DWLN_CASE(1) LVAE_DWLN_CASE(2) LVAE_DWLN_CASE(3) LVAE_DWLN_CASE(4)
-    LVAE_DWLN_CASE(6)
-    // C = 512 as a 2-CTA cluster of 4 chunks each: 168 -> ~100 registers per thread doubles the resident CTAs
-    // (measured 25-40 % faster on the s16 / s32 / s64 layers; C = 384 was not faster split)
-    case 8: return dispatch_k<4, 2>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, f16, B, H, W, st);
-    case 10: return dispatch_k<5, 2>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, f16, B, H, W, st);
-    case 12: return dispatch_k<6, 2>(k, x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, p0, p1, p2, f16, B, H, W, st);
+    LVAE_DWLN_CASE(1, 1, 1) LVAE_DWLN_CASE(2, 1, 2) LVAE_DWLN_CASE(3, 1, 3) LVAE_DWLN_CASE(4, 1, 4)
+    LVAE_DWLN_CASE(6, 1, 6) LVAE_DWLN_CASE(8, 1, 8) LVAE_DWLN_CASE(10, 2, 5) LVAE_DWLN_CASE(12, 2, 6)
     default: set_error("dwconv channel count %d unsupported (need C/64 in {1,2,3,4,6,8,10,12})", C); return LVAE_E_UNSUPPORTED;
   }
 #undef LVAE_DWLN_CASE

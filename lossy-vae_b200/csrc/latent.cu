@@ -124,6 +124,51 @@ __global__ void __launch_bounds__(LT) latent_kernel(
   if (threadIdx.x == 0) kl_partial[(int64_t)b * kl_stride + blockIdx.x] = t;
 }
 
+// Backward of the training branch: kl = -gaussian_log_prob_mass(pm, sigma, z), z = qm + noise,
+// sigma = exp(softplus(raw + 2.3) - 2.3).  torch.where routes the gradient through the selected branch only
+// (lvae/models/entropy_coding.py:17-26; the unselected branch's gradient is finite, so it contributes exactly 0):
+//   mass branch (mass > 1e-6), u, l = (z +- 1/2 - pm) / sigma, phi = standard normal pdf:
+//     d lnP/dz = (phi(u) - phi(l)) / (sigma P),  d lnP/dpm = -d lnP/dz,  d lnP/dsigma = -(u phi(u) - l phi(l)) / (sigma P)
+//   tail branch: lnP = Normal(pm, sigma).log_prob(z):  d/dz = -(z - pm)/sigma^2,  d/dsigma = (z - pm)^2/sigma^3 - 1/sigma
+// and d sigma/d raw = sigma * sigmoid(raw + 2.3) (softplus with torch's threshold 20).
+__global__ void __launch_bounds__(LT) latent_train_bwd_kernel(
+    const float* __restrict__ qm, const float* __restrict__ prior, const float* __restrict__ noise,
+    const float* __restrict__ dz, const float* __restrict__ dkl_elem, float dkl_scale,
+    float* __restrict__ dqm, float* __restrict__ dprior, int64_t total, int zdim) {
+  const int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x;
+  if (i >= total) return;
+  const int64_t m = i / zdim; const int c = (int)(i - m * zdim);
+  const float q = qm[i];
+  const float pm = prior[m * 2 * zdim + c];
+  const float raw = prior[m * 2 * zdim + zdim + c];
+  const float pv = prior_scale(raw);
+  const float zz = __fadd_rn(q, noise[i]);
+  const float rcp = __frcp_rn(pv);
+  const float u = __fmul_rn(__fsub_rn(__fadd_rn(zz, 0.5f), pm), rcp);
+  const float l = __fmul_rn(__fsub_rn(__fsub_rn(zz, 0.5f), pm), rcp);
+  const float cu = __fmul_rn(0.5f, __fadd_rn(1.0f, erf_torch_cpu(__fdiv_rn(u, 1.4142135623730951f))));
+  const float cl = __fmul_rn(0.5f, __fadd_rn(1.0f, erf_torch_cpu(__fdiv_rn(l, 1.4142135623730951f))));
+  const float mass = __fsub_rn(cu, cl);
+  float dlp_dz, dlp_ds;
+  if (mass > 1e-6f) {
+    const float pu = 0.3989422804014327f * expf(-0.5f * u * u), pl = 0.3989422804014327f * expf(-0.5f * l * l);
+    const float inv = rcp / mass;
+    dlp_dz = (pu - pl) * inv;
+    dlp_ds = -(u * pu - l * pl) * inv;
+  } else {
+    const float d = __fsub_rn(zz, pm);
+    dlp_dz = -d * rcp * rcp;
+    dlp_ds = d * d * rcp * rcp * rcp - rcp;
+  }
+  const float g = dkl_elem ? dkl_elem[i] : dkl_scale;       // dL/dkl, kl = -lnP
+  const float x = __fadd_rn(raw, 2.3f);
+  const float sig = x > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-x));
+  const float dzt = (dz ? dz[i] : 0.f) - g * dlp_dz;
+  dqm[i] = dzt;
+  dprior[m * 2 * zdim + c] = g * dlp_dz;                    // dL/dpm = -g * dlnP/dpm = +g * dlnP/dz
+  dprior[m * 2 * zdim + zdim + c] = -g * dlp_ds * pv * sig;
+}
+
 __global__ void __launch_bounds__(LT) prior_index_kernel(
     const float* __restrict__ prior, const float* __restrict__ table, int n_scales,
     int32_t* __restrict__ idx, int hw, int zdim) {
@@ -255,6 +300,17 @@ extern "C" int lvae_latent_train(const float* qm, const float* prior, const floa
   LVAE_CHECK_ARG(kl_stride >= np);
   latent_kernel<1><<<dim3(np, B), LT, 0, (cudaStream_t)stream>>>(qm, prior, noise, nullptr, 0,
                                                                   z, kl_partial, kl_elem, nullptr, nullptr, hw, zdim, kl_stride, 0);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lvae_latent_train_bwd(const float* qm, const float* prior, const float* noise,
+                                     const float* dz, const float* dkl_elem, float dkl_scale,
+                                     float* dqm, float* dprior, int B, int hw, int zdim, void* stream) {
+  LVAE_CHECK_ARG(qm && prior && noise && dqm && dprior && B > 0 && hw > 0 && zdim > 0);
+  const int64_t total = (int64_t)B * hw * zdim;
+  latent_train_bwd_kernel<<<(unsigned)((total + LT - 1) / LT), LT, 0, (cudaStream_t)stream>>>(
+      qm, prior, noise, dz, dkl_elem, dkl_scale, dqm, dprior, total, zdim);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

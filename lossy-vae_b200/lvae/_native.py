@@ -54,6 +54,7 @@ _PROTOS = {
                                    C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_pad_channels': (C.c_int, [_fp, _fp, C.c_int64, C.c_int, C.c_int, _fp]),
     'lvae_latent_train': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_latent_train_bwd': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_float, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_latent_prior_index': (C.c_int, [_fp, _fp, C.c_int, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_latent_dequant': (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_latent_sample': (C.c_int, [_fp, _fp, _fp, C.c_float, _fp, C.c_int, C.c_int, C.c_int, _fp]),

@@ -6,6 +6,9 @@ import torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / 'lossy-vae_b200'))
 from lvae import _native as N
+import os
+if os.environ.get('LVAE_LIB_PATH'):      # tuning builds (scripts only)
+    N._LIB_PATH = Path(os.environ['LVAE_LIB_PATH'])
 lib = N.lib()
 only = sys.argv[1].split(',') if len(sys.argv) > 1 else None
 npl = int(sys.argv[2]) if len(sys.argv) > 2 else 2
