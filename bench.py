@@ -148,8 +148,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='images per GPU per step (BASELINE configs[1]: 8)')
     ap.add_argument('--precision', default=None, help="f16x3 | bf16x6 | bf16x3 | bf16 | fp32 (default: the model's default, f16x3)")
-    ap.add_argument('--workload', default='qarv', choices=['qarv', 'rd'],
-                    help='qarv: BASELINE configs[1] (headline, default); rd: configs[4] rd_model_base 256x256, batch 32 per GPU')
+    ap.add_argument('--workload', default='qarv', choices=['qarv', 'rd', 'qres'],
+                    help='qarv: BASELINE configs[1] (headline, default); rd: configs[4] rd_model_base 256x256, batch 32 per GPU; '
+                         'qres: the forward half of configs[2], qres34m lambda 2048, 512x768, batch 16 per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-samples', type=int, default=5)
     args = ap.parse_args()
@@ -177,6 +178,12 @@ def main():
     B = args.batch
     global H, W, DENSE_GFLOP_PER_IMAGE
     rd = args.workload == 'rd'
+    qres = args.workload == 'qres'
+    if qres:
+        import qres_oracle as Q
+        DENSE_GFLOP_PER_IMAGE = 269.2              # 278.65 GFLOP total, 269.2 dense
+        if B == 8:
+            B = 16                                   # configs[2]: batch 16
     if rd:
         import rd_oracle as R
         H = W = 256
@@ -188,6 +195,9 @@ def main():
     if rd:
         model = lvae.get_model('rd_model_base')
         model.load_state_dict(O.sensitised_state_dict(R.rd_param_shapes(), seed=0, wide_heads=False), strict=True)
+    elif qres:
+        model = lvae.get_model('qres34m', lmb=2048)
+        model.load_state_dict(O.sensitised_state_dict(Q.qres_param_shapes(), seed=0), strict=False)
     else:
         model = lvae.get_model('qarv_base')
         model.load_state_dict(O.sensitised_state_dict(O.qarv_param_shapes(), seed=0), strict=False)
@@ -231,14 +241,15 @@ def main():
     stats = P.stats.cpu()
 
     # ---- end to end through the public API: pinned host batch in, stats out, every step
+    call = (lambda: model(im_host)) if qres else (lambda: model(im_host, lmb=lmb_dev))
     for _ in range(warmup):
-        out = model(im_host, lmb=lmb_dev)
+        out = call()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e2.record(st)
     for _ in range(args.steps):
-        out = model(im_host, lmb=lmb_dev)
+        out = call()
     e3.record(st)
     barrier()
     ms_e2e = e2.elapsed_time(e3)
@@ -277,20 +288,21 @@ def main():
                       frac=dw['bytes'] / dw['ms'] / 1e6 / pk['hbm'], share_of_step=dw['ms'] / tot_ms, traffic=None)
 
         cpu = None
-        if not args.no_cpu_baseline and not rd:
+        if not args.no_cpu_baseline and not rd and not qres:
             v, cores, sample = cpu_reference_images_per_s(args.cpu_samples)
             cpu = dict(value=v, unit='images/s', cores=cores, kind='port', sample=sample)
 
         n_img = B * world * args.steps
         line = {
-            'metric': METRIC if not rd else '256x256 images/sec (rd forward)', 'value': n_img / (ms_dev / 1e3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+            'metric': '256x256 images/sec (rd forward)' if rd else ('512x768 images/sec (qres34m forward)' if qres else METRIC), 'value': n_img / (ms_dev / 1e3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': {'fp32': 'f32', 'bf16x6': 'f32-class (3 bf16 planes per operand, 6 tcgen05 MMAs per product, f32 accumulate)',
                       'bf16x3': 'bf16x3 (2 bf16 planes, 3 MMAs, f32 accumulate)', 'bf16': 'bf16',
                       'f16x3': 'f32-class (2 fp16 planes per operand = 22 significand bits, 3 tcgen05 MMAs per product, f32 accumulate)'}[model.precision],
             'data': 'synthetic',
             'config': {'workload': (f'rd_model_base forward (KL + MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 256 (BASELINE configs[4])'
-                                    if rd else
+                                    if rd else f'qres34m eval forward (rate + lambda * MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 2048 '
+                                               f'(forward half of BASELINE configs[2]; the backward pass is not built)' if qres else
                                     f'qarv_base eval forward (rate + MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 2048 '
                                     f'(BASELINE configs[1])'), 'batch_per_gpu': B, 'global_batch': B * world, 'precision': model.precision,
                        'parallelism': f'batch-shard x{world}, no data-path collective', 'weights': 'seeded sensitised init (no checkpoint offline)',

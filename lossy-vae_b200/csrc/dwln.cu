@@ -23,6 +23,7 @@
 #include <cooperative_groups.h>
 #include <mutex>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace lvae {
 
@@ -264,39 +265,63 @@ __global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
     }
   }
 
-  // ---- modulation + output
+  // ---- modulation + output: one specialised store loop per (output kind, interior / border tile) so that the
+  //      per-pixel work carries no pointer tests or bounds checks (they were 18 % of the kernel's instructions)
+  const bool interior = (h0 + DW_TH <= H) && (w0 + DW_TW <= W);
+  const int64_t o00 = (((int64_t)b * H + h0 + 2 * wrow) * W + w0) * C;        // pixel (row 2 wrow, column 0) of the tile
+  auto emit = [&](auto mode_c, auto interior_c) {
+    constexpr int MODE = decltype(mode_c)::value;          // 0: fp32 | 1-3: bf16 planes | 4: two fp16 planes
+    constexpr bool INTERIOR = decltype(interior_c)::value;
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    const int c = cbase + j * DW_CH + lane * 2;
-    float2 mul, add;                       // v * mul + add with mul = (1 + scale) | gamma, add = shift | beta
-    if (ln_w != nullptr) {
-      mul = __ldg(reinterpret_cast<const float2*>(ln_w + c));
-      add = __ldg(reinterpret_cast<const float2*>(ln_b + c));
-    } else {
-      const float* e = ada + (int64_t)b * ada_stride + ada_off + c;
-      add = __ldg(reinterpret_cast<const float2*>(e));
-      const float2 sc = __ldg(reinterpret_cast<const float2*>(e + C));
-      mul = make_float2(__fadd_rn(1.0f, sc.x), __fadd_rn(1.0f, sc.y));
-    }
+    for (int j = 0; j < NJ; ++j) {
+      const int c = cbase + j * DW_CH + lane * 2;
+      float2 mul, add;                       // v * mul + add with mul = (1 + scale) | gamma, add = shift | beta
+      if (ln_w != nullptr) {
+        mul = __ldg(reinterpret_cast<const float2*>(ln_w + c));
+        add = __ldg(reinterpret_cast<const float2*>(ln_b + c));
+      } else {
+        const float* e = ada + (int64_t)b * ada_stride + ada_off + c;
+        add = __ldg(reinterpret_cast<const float2*>(e));
+        const float2 sc = __ldg(reinterpret_cast<const float2*>(e + C));
+        mul = make_float2(__fadd_rn(1.0f, sc.x), __fadd_rn(1.0f, sc.y));
+      }
 #pragma unroll
-    for (int p = 0; p < DW_PIX; ++p) {
-      const int h = h0 + 2 * wrow + p / DW_TW, w = w0 + p % DW_TW;
-      if (h >= H || w >= W) continue;      // warp-uniform
-      float2 v;
-      v.x = __fadd_rn(__fmul_rn(__fmul_rn(res[j][p].x - mean[p], rstd[p]), mul.x), add.x);
-      v.y = __fadd_rn(__fmul_rn(__fmul_rn(res[j][p].y - mean[p], rstd[p]), mul.y), add.y);
-      const int64_t o = (((int64_t)b * H + h) * W + w) * C + c;
-      if (y != nullptr) *reinterpret_cast<float2*>(y + o) = v;
-      if (y0 != nullptr) {
-        // A operand of the tensor-core fc1 GEMM: p0 = rn16(v), p1 = rn16(v - p0), p2 = rn16(v - p0 - p1)
-        *reinterpret_cast<uint32_t*>(y0 + o) = split_next(v, f16 != 0);
-        if (y1 != nullptr) {
-          *reinterpret_cast<uint32_t*>(y1 + o) = split_next(v, f16 != 0);
-          if (y2 != nullptr) *reinterpret_cast<uint32_t*>(y2 + o) = split_next(v, f16 != 0);
+      for (int p = 0; p < DW_PIX; ++p) {
+        if (!INTERIOR && (h0 + 2 * wrow + p / DW_TW >= H || w0 + p % DW_TW >= W)) continue;      // warp-uniform
+        float2 v;
+        v.x = __fadd_rn(__fmul_rn(__fmul_rn(res[j][p].x - mean[p], rstd[p]), mul.x), add.x);
+        v.y = __fadd_rn(__fmul_rn(__fmul_rn(res[j][p].y - mean[p], rstd[p]), mul.y), add.y);
+        const int64_t o = o00 + ((int64_t)(p / DW_TW) * W + p % DW_TW) * C + c;
+        if constexpr (MODE == 0) {
+          *reinterpret_cast<float2*>(y + o) = v;
+        } else {
+          // A operand of the tensor-core fc1 GEMM: p0 = rn16(v), p1 = rn16(v - p0), p2 = rn16(v - p0 - p1)
+          constexpr bool F16 = MODE == 4;
+          constexpr int NP = MODE == 4 ? 2 : MODE;
+          if constexpr (NP == 1) {
+            *reinterpret_cast<uint32_t*>(y0 + o) = pack2<F16>(v.x, v.y);
+          } else {
+            *reinterpret_cast<uint32_t*>(y0 + o) = split_next<F16>(v);
+            if constexpr (NP == 2) {
+              *reinterpret_cast<uint32_t*>(y1 + o) = pack2<F16>(v.x, v.y);
+            } else {
+              *reinterpret_cast<uint32_t*>(y1 + o) = split_next<F16>(v);
+              *reinterpret_cast<uint32_t*>(y2 + o) = pack2<F16>(v.x, v.y);
+            }
+          }
         }
       }
     }
-  }
+  };
+  auto emit_mode = [&](auto interior_c) {
+    using std::integral_constant;
+    if (y != nullptr) emit(integral_constant<int, 0>{}, interior_c);
+    else if (f16) emit(integral_constant<int, 4>{}, interior_c);
+    else if (y2 != nullptr) emit(integral_constant<int, 3>{}, interior_c);
+    else if (y1 != nullptr) emit(integral_constant<int, 2>{}, interior_c);
+    else emit(integral_constant<int, 1>{}, interior_c);
+  };
+  if (interior) emit_mode(std::true_type{}); else emit_mode(std::false_type{});
   if (CL > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // nobody exits while a peer may still read its shared memory
 }
 
@@ -411,6 +436,7 @@ extern "C" int lvae_dwconv_ln_adaln_planes(const float* x, const float* dw_w, co
                                            int B, int H, int W, int C, int k, void* stream) {
   LVAE_CHECK_ARG(y0 != nullptr && (y2 == nullptr || y1 != nullptr));
   LVAE_CHECK_ARG(plane_format == LVAE_PLANES_BF16 || plane_format == LVAE_PLANES_F16);
+  LVAE_CHECK_ARG(plane_format != LVAE_PLANES_F16 || (y1 != nullptr && y2 == nullptr));    // fp16 operands travel as 2 planes
   return dwln_dispatch(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, nullptr, y0, y1, y2,
                        plane_format == LVAE_PLANES_F16, B, H, W, C, k, stream);
 }

@@ -85,7 +85,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (!done) __nanosleep(20);                              // free issue slots for the epilogue warps while waiting
+#ifndef LVAE_TC_SPIN_NS
+#define LVAE_TC_SPIN_NS 20
+#endif
+    if (LVAE_TC_SPIN_NS > 0 && !done) __nanosleep(LVAE_TC_SPIN_NS);   // free issue slots for the epilogue warps while waiting
   } while (!done);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {

@@ -6,6 +6,9 @@ import torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / 'lossy-vae_b200'))
 from lvae import _native as N
+import os
+if os.environ.get('LVAE_LIB_PATH'):      # tuning builds (scripts only)
+    N._LIB_PATH = Path(os.environ['LVAE_LIB_PATH'])
 lib = N.lib()
 NPL = {1: 2, 2: 1, 3: 3, 4: 2}
 TERMS = {0: 1, 1: 3, 2: 1, 3: 6, 4: 3}
