@@ -140,6 +140,51 @@ def run_reference(args):
     }))
 
 
+def run_codec(args):
+    """compress() + decompress() images/s through the public API with the host coder's share broken out.
+    One step = one 512x768 image: compress (encoder + top-down to the stop flag, D2H symbols, 9 host rANS streams) and
+    decompress (9 x [graph segment, D2H indexes, host rANS decode, H2D symbols] + tail decoder)."""
+    import torch
+    import lvae
+    import lvae_oracle as O
+    from oracle_inputs import make_input
+    dev = torch.device('cuda', 0)
+    torch.manual_seed(0)
+    model = lvae.get_model('qarv_base')
+    model.load_state_dict(O.sensitised_state_dict(O.qarv_param_shapes(), seed=0), strict=False)
+    if args.precision:
+        model.precision = args.precision
+    model = model.to(dev).eval()
+    model.compress_mode()
+    im = make_input('synth', 1, H, W, 5).to(dev)
+    for _ in range(max(args.warmup, 3)):
+        blob = model.compress(im, lmb=2048.0)
+        rec = model.decompress(blob)
+    torch.cuda.synchronize()
+    eng = model.engine
+    eng.host_coder_s = 0.0
+    t_c = t_d = 0.0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        blob = model.compress(im, lmb=2048.0)
+        t1 = time.perf_counter()
+        rec = model.decompress(blob)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        t_c += t1 - t0; t_d += t2 - t1
+    ref = model(im, lmb=torch.tensor([2048.0], device=dev), return_rec=True)
+    err = (rec - ref['im_hat']).abs().max().item()
+    print(json.dumps({
+        'metric': '512x768 images/sec (compress + decompress, real bit stream)', 'value': args.steps / (t_c + t_d), 'unit': 'images/s',
+        'n_gpus': 1, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': (t_c + t_d) / args.steps * 1e3,
+        'higher_is_better': True, 'dtype': model.precision, 'data': 'synthetic',
+        'config': {'workload': 'qarv_base compress() + decompress(), one synthetic 512x768 image per step, lambda 2048'},
+        'compress_ms': t_c / args.steps * 1e3, 'decompress_ms': t_d / args.steps * 1e3,
+        'host_coder_ms': eng.host_coder_s / args.steps * 1e3, 'bytes': len(blob), 'bpp': len(blob) * 8 / (H * W),
+        'decoder_vs_forward_max_abs_err': err,
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -148,14 +193,17 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='images per GPU per step (BASELINE configs[1]: 8)')
     ap.add_argument('--precision', default=None, help="f16x3 | bf16x6 | bf16x3 | bf16 | fp32 (default: the model's default, f16x3)")
-    ap.add_argument('--workload', default='qarv', choices=['qarv', 'rd', 'qres'],
+    ap.add_argument('--workload', default='qarv', choices=['qarv', 'rd', 'qres', 'codec'],
                     help='qarv: BASELINE configs[1] (headline, default); rd: configs[4] rd_model_base 256x256, batch 32 per GPU; '
-                         'qres: the forward half of configs[2], qres34m lambda 2048, 512x768, batch 16 per GPU')
+                         'qres: the forward half of configs[2], qres34m lambda 2048, 512x768, batch 16 per GPU; '
+                         'codec: qarv_base compress() + decompress() of one 512x768 image per step (real bit stream, host rANS)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-samples', type=int, default=5)
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.workload == 'codec':
+        return run_codec(args)
 
     import torch
     import torch.distributed as dist

@@ -226,6 +226,12 @@ int64_t lvae_rans_bound(int64_t n);
 int lvae_rans_encode(const int32_t* sym, const int32_t* idx, int64_t n,
                      const int32_t* cdf, int cdf_stride, const int32_t* cdf_len, const int32_t* offset,
                      int n_cdf, uint8_t* out, int64_t out_cap, int64_t* out_len);
+/* n_streams independent streams on up to n_threads host threads (largest streams should come first): stream i covers
+ * symbols [begin[i], begin[i+1]) and writes out_len[i] bytes at out + out_begin[i] (capacity out_begin[i+1] -
+ * out_begin[i] >= lvae_rans_bound of its symbol count).  SURVEY 8(f)-1. */
+int lvae_rans_encode_streams(const int32_t* sym, const int32_t* idx, const int64_t* begin, int n_streams,
+                             const int32_t* cdf, int cdf_stride, const int32_t* cdf_len, const int32_t* offset,
+                             int n_cdf, uint8_t* out, const int64_t* out_begin, int64_t* out_len, int n_threads);
 int lvae_rans_decode(const uint8_t* in, int64_t in_len, const int32_t* idx, int64_t n,
                      const int32_t* cdf, int cdf_stride, const int32_t* cdf_len, const int32_t* offset,
                      int n_cdf, int32_t* sym_out);

@@ -10,6 +10,8 @@
 #include <stdint.h>
 #include <math.h>
 #include <string.h>
+#include <atomic>
+#include <thread>
 #include <vector>
 #include "lvae_b200.h"
 
@@ -146,10 +148,24 @@ extern "C" int lvae_rans_decode(const uint8_t* in, int64_t in_len, const int32_t
     const int32_t size = cdf_len[ci];
     const int32_t max_value = size - 2;
     const uint32_t cum = (uint32_t)(x & mask);
-    // first entry > cum, minus one (cdf rows are strictly increasing); binary search
-    int lo = 0, hi = size - 1;           // invariant: c[lo] <= cum < c[hi]
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((uint32_t)c[mid] <= cum) lo = mid; else hi = mid; }
-    const int32_t s = lo;
+    // the entry s with c[s] <= cum < c[s+1] (rows are strictly increasing).  The tables are discretised Gaussians
+    // centred on the row: walk outwards from the mode (1-3 comparisons for almost every symbol), falling back to a
+    // binary search once the walk has left the bulk
+    int s = -offset[ci];                 // centre of the row (offset = -ceil(6.1 sigma))
+    if (s < 0 || s > size - 2) s = (size - 2) >> 1;
+    if ((uint32_t)c[s] <= cum) {
+      int steps = 0;
+      while ((uint32_t)c[s + 1] <= cum) {
+        if (++steps > 4) { int lo = s + 1, hi = size - 1; while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((uint32_t)c[mid] <= cum) lo = mid; else hi = mid; } s = lo; break; }
+        ++s;
+      }
+    } else {
+      int steps = 0;
+      do {
+        if (++steps > 4) { int lo = 0, hi = s; while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((uint32_t)c[mid] <= cum) lo = mid; else hi = mid; } s = lo; break; }
+        --s;
+      } while ((uint32_t)c[s] > cum);
+    }
     x = (uint64_t)(c[s + 1] - c[s]) * (x >> kPrecision) + cum - (uint32_t)c[s];
     renorm();
     int32_t value = s;
@@ -167,4 +183,32 @@ extern "C" int lvae_rans_decode(const uint8_t* in, int64_t in_len, const int32_t
     sym_out[i] = value + offset[ci];
   }
   return 0;
+}
+
+// Encode `n_streams` independent streams (one per (image, layer)) on up to `n_threads` host threads.  Stream i
+// covers symbols [begin[i], begin[i+1]) of sym / idx and uses table set table_of[i] (cdf_sets[k] etc. describe table
+// set k; all streams of a model usually share one).  Its bytes are written at out + out_begin[i] (capacity
+// out_begin[i+1] - out_begin[i] >= lvae_rans_bound(count)), their count to out_len[i].
+extern "C" int lvae_rans_encode_streams(const int32_t* sym, const int32_t* idx, const int64_t* begin, int n_streams,
+                                        const int32_t* cdf, int cdf_stride, const int32_t* cdf_len,
+                                        const int32_t* offset, int n_cdf, uint8_t* out, const int64_t* out_begin,
+                                        int64_t* out_len, int n_threads) {
+  if (!sym || !idx || !begin || !out || !out_begin || !out_len || n_streams < 0) return LVAE_E_BADARG;
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > n_streams) n_threads = n_streams;
+  std::atomic<int> next(0), status(0);
+  auto work = [&]() {
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n_streams) return;
+      const int rc = lvae_rans_encode(sym + begin[i], idx + begin[i], begin[i + 1] - begin[i], cdf, cdf_stride, cdf_len,
+                                      offset, n_cdf, out + out_begin[i], out_begin[i + 1] - out_begin[i], out_len + i);
+      if (rc != 0) status.store(rc);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+  return status.load();
 }

@@ -20,6 +20,7 @@ Dense contractions run in one of three precisions (model.precision):
 """
 import ctypes as C
 import math
+import time
 
 import numpy as np
 import torch
@@ -95,6 +96,8 @@ class QarvEngine:
         self._wver = None
         self._plans = {}
         self.use_graphs = True
+        self.host_coder_s = 0.0        # seconds spent in the host rANS coder (bench.py --workload codec reads it)
+        self.coder_threads = min(16, __import__('os').cpu_count() or 1)
         self.blocks = [m for m in model.modules() if isinstance(m, (common.ConvNeXtBlockAdaLN, common.ConvNeXtBlockLN))]
         self.ada_off = {}
         off = 0
@@ -469,6 +472,12 @@ class QarvEngine:
         P.layout = lay
         P.kl_partial = torch.zeros(B, kl_cols, dtype=torch.float32, device=self.device)
         P.z, P.kl_elem, P.sym, P.idx, P.noise = [], [], [], [], []
+        if mode == 'compress':      # all layers' symbols / indexes in one buffer each: one D2H copy, one coder call
+            total = sum(B * hw * zd for (hw, zd, _, _, _, _) in lay)
+            P.sym_all, P.idx_all, P.sym_used = P.i32(total), P.i32(total), 0
+            P.sym_host = torch.empty(total, dtype=torch.int32, pin_memory=True)
+            P.idx_host = torch.empty(total, dtype=torch.int32, pin_memory=True)
+            P.enc_layout = None
         self._embedding(P, P.lmb)
         feats = self._encoder(P, P.im)
 
@@ -496,7 +505,10 @@ class QarvEngine:
             else:
                 sym = idx = None
                 if mode == 'compress':
-                    sym, idx = P.i32(B, zd, Hs, Ws), P.i32(B, zd, Hs, Ws)
+                    n_el = B * zd * Hs * Ws
+                    sym = P.sym_all[P.sym_used:P.sym_used + n_el].view(B, zd, Hs, Ws)
+                    idx = P.idx_all[P.sym_used:P.sym_used + n_el].view(B, zd, Hs, Ws)
+                    P.sym_used += n_el
                     P.sym.append(sym)
                     P.idx.append(idx)
                 tab = self.w[id(blk)]['table']
@@ -645,28 +657,45 @@ class QarvEngine:
 
     def _encode_strings(self, P):
         """per latent layer: list (over the batch) of rANS byte strings.  Symbols / indexes arrive in NCHW
-        order, the order CompressAI flattens them in (qarv/model.py:106-108)."""
+        order, the order CompressAI flattens them in (qarv/model.py:106-108).  All layers' symbols travel to the
+        host in one pinned copy and the (layer, image) streams are coded in parallel by the C coder
+        (lvae_rans_encode_streams)."""
         blocks = [b for b in self.model.dec_blocks if getattr(b, 'is_latent_block', False)]
-        host = []
-        for sym, idx in zip(P.sym, P.idx):
-            host.append((sym.to('cpu', non_blocking=True), idx.to('cpu', non_blocking=True)))
+        P.sym_host.copy_(P.sym_all, non_blocking=True)
+        P.idx_host.copy_(P.idx_all, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        out = []
-        for blk, (sym, idx) in zip(blocks, host):
-            cdf, clen, coff = self._tables(blk)
-            sym, idx = sym.numpy(), idx.numpy()
-            per_image = sym[0].size
-            cap = int(self.lib.lvae_rans_bound(per_image))
-            buf = np.empty(cap, dtype=np.uint8)
-            strings = []
-            for b in range(P.B):
-                n = C.c_int64(0)
-                s_b, i_b = np.ascontiguousarray(sym[b]).reshape(-1), np.ascontiguousarray(idx[b]).reshape(-1)
-                N.check(self.lib.lvae_rans_encode(s_b.ctypes.data, i_b.ctypes.data, per_image, cdf.ctypes.data,
-                                                  cdf.shape[1], clen.ctypes.data, coff.ctypes.data, cdf.shape[0],
-                                                  buf.ctypes.data, cap, C.byref(n)), 'rans_encode')
-                strings.append(buf[:n.value].tobytes())
-            out.append(strings)
+        t0 = time.perf_counter()
+        cdf, clen, coff = self._tables(blocks[0])
+        for blk in blocks[1:]:      # one table set for the whole model (true for every registered model)
+            assert blk.discrete_gaussian._quantized_cdf.shape == blocks[0].discrete_gaussian._quantized_cdf.shape
+        if P.enc_layout is None:
+            # streams sorted by size (largest first) for the thread pool; begin[] needs contiguous ranges, so the
+            # stream table holds explicit (start, count) pairs through a begin array per stream
+            streams = []
+            off = 0
+            for li, (sym, _) in enumerate(zip(P.sym, P.idx)):
+                per = sym[0].numel()
+                for b in range(P.B):
+                    streams.append((li, b, off + b * per, per))
+                off += sym.numel()
+            P.enc_layout = streams
+            P.enc_cap = [int(self.lib.lvae_rans_bound(per)) for (_, _, _, per) in streams]
+            P.enc_out = np.empty(sum(P.enc_cap), dtype=np.uint8)
+        streams = P.enc_layout
+        sym_np, idx_np = P.sym_host.numpy(), P.idx_host.numpy()
+        n = len(streams)
+        # streams are laid out back to back in layer-major order, so begin[i] / begin[i+1] are simply cumulative
+        begin = np.array([st[2] for st in streams] + [streams[-1][2] + streams[-1][3]], dtype=np.int64)
+        out_begin = np.concatenate([[0], np.cumsum(P.enc_cap)]).astype(np.int64)
+        out_len = np.zeros(n, dtype=np.int64)
+        N.check(self.lib.lvae_rans_encode_streams(sym_np.ctypes.data, idx_np.ctypes.data, begin.ctypes.data, n,
+                                                  cdf.ctypes.data, cdf.shape[1], clen.ctypes.data, coff.ctypes.data,
+                                                  cdf.shape[0], P.enc_out.ctypes.data, out_begin.ctypes.data,
+                                                  out_len.ctypes.data, self.coder_threads), 'rans_encode_streams')
+        out = [[None] * P.B for _ in P.sym]
+        for i, (li, b, _, _) in enumerate(streams):
+            out[li][b] = P.enc_out[out_begin[i]:out_begin[i] + out_len[i]].tobytes()
+        self.host_coder_s += time.perf_counter() - t0
         return out
 
     def _build_decode_plan(self, B, nH, nW, sampling=False):
@@ -723,11 +752,13 @@ class QarvEngine:
                 sym_np = np.empty(idx_np.shape, dtype=np.int32)
                 per_layer = strings[li] if isinstance(strings[li], (list, tuple)) else [strings[li]]
                 assert len(per_layer) == B
+                t0 = time.perf_counter()
                 for b in range(B):            # one stream per (image, layer)
                     data = np.frombuffer(per_layer[b], dtype=np.uint8)
                     N.check(self.lib.lvae_rans_decode(data.ctypes.data, data.size, idx_np[b].ctypes.data, idx_np.shape[1],
                                                       cdf.ctypes.data, cdf.shape[1], clen.ctypes.data, coff.ctypes.data,
                                                       cdf.shape[0], sym_np[b].ctypes.data), 'rans_decode')
+                self.host_coder_s += time.perf_counter() - t0
                 P.sym[li].copy_(torch.from_numpy(sym_np).view_as(P.sym[li]), non_blocking=False)
             self._launch(P, len(blocks))
             return P.x_hat.clone().clamp_(min=-1.0, max=1.0).mul_(0.5).add_(0.5)

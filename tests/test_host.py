@@ -220,3 +220,30 @@ def test_qres_model_surface_and_state_dict_contract(native_lib, golden):
     m2 = copy.deepcopy(m)
     assert m2.__dict__['_engine'] is None and torch.equal(m2.decoder.bias, m.decoder.bias)
     str(m)
+
+
+def test_c_rans_encode_streams_equals_single_stream_calls(native_lib, tables):
+    """the threaded multi-stream entry point produces, per stream, exactly the bytes of
+    lvae_rans_encode, for ragged stream sizes (including an empty stream) and any thread count."""
+    rng = np.random.default_rng(3)
+    sizes = [5000, 1, 0, 777, 20000, 64]
+    idx = rng.integers(0, 64, size=sum(sizes)).astype(np.int32)
+    sym = np.rint(rng.normal(size=sum(sizes)) * (1 + idx * 0.3)).astype(np.int32)
+    sym[::97] *= 40                                   # bypass-coded outliers
+    cdf, clen, off = (np.ascontiguousarray(t.numpy()) for t in tables)
+    begin = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    caps = [int(native_lib.lvae_rans_bound(n)) for n in sizes]
+    out_begin = np.concatenate([[0], np.cumsum(caps)]).astype(np.int64)
+    want = [_enc(native_lib, sym[begin[i]:begin[i + 1]], idx[begin[i]:begin[i + 1]], tables) for i in range(len(sizes))]
+    for threads in (1, 3, 16):
+        out = np.zeros(sum(caps), dtype=np.uint8)
+        out_len = np.zeros(len(sizes), dtype=np.int64)
+        rc = native_lib.lvae_rans_encode_streams(sym.ctypes.data, idx.ctypes.data, begin.ctypes.data, len(sizes),
+                                                 cdf.ctypes.data, cdf.shape[1], clen.ctypes.data, off.ctypes.data, cdf.shape[0],
+                                                 out.ctypes.data, out_begin.ctypes.data, out_len.ctypes.data, threads)
+        assert rc == 0
+        got = [out[out_begin[i]:out_begin[i] + out_len[i]].tobytes() for i in range(len(sizes))]
+        assert got == want
+    for i, n in enumerate(sizes):                     # and every stream decodes back
+        rc, dec = _dec(native_lib, want[i], idx[begin[i]:begin[i + 1]], tables)
+        assert rc == 0 and np.array_equal(dec, sym[begin[i]:begin[i + 1]])
