@@ -324,6 +324,11 @@ def main():
                     launches=gm['n'], share_of_step=gm['ms'] / tot_ms, issued_mma_multiplier=issued,
                     note='achieved = sum over the GEMM launches of 2*M*N*K / sum of their CUDA-event durations')
         roof['frac'] = roof['achieved'] / roof['peak']
+        # DRAM traffic per launch from the committed ncu --set full captures (profiles/r1_final_ncu_summary.md): the class
+        # has 226 launches of ~40 shapes, so the two largest are quoted instead of one number
+        roof['traffic_examples'] = {
+            'fc2 H/4 M=196608 K=384 N=192': {'dram_bytes': 573.1e6, 'algorithmic_bytes': 604.0e6, 'us': 125.6},
+            'fc1 H/4 M=196608 K=192 N=384': {'dram_bytes': 402.1e6, 'algorithmic_bytes': 453.0e6, 'us': 161.6}}
         roof['issued_tflops'] = roof['achieved'] * issued          # MMA FLOPs actually issued to the tensor pipe
         roof['issued_frac'] = roof['issued_tflops'] / roof['peak']
         # biggest latent layer alone (the only ones large enough to be bandwidth- rather than latency-bound)
@@ -333,7 +338,8 @@ def main():
                       all_layers_gbs=lt['bytes'] / lt['ms'] / 1e6, share_of_step=lt['ms'] / tot_ms)
         roof_e['frac'] = roof_e['achieved'] / roof_e['peak']
         roof_d = dict(bound='hbm', kernel='dwln_kernel', achieved=dw['bytes'] / dw['ms'] / 1e6, peak=pk['hbm'], unit='GB/s',
-                      frac=dw['bytes'] / dw['ms'] / 1e6 / pk['hbm'], share_of_step=dw['ms'] / tot_ms, traffic=None)
+                      frac=dw['bytes'] / dw['ms'] / 1e6 / pk['hbm'], share_of_step=dw['ms'] / tot_ms, traffic=262.8e6,
+                      traffic_of='H/4 C=192 k=7 launch: 151.1 MB read + 111.6 MB written (ncu), 302 MB algorithmic')
 
         cpu = None
         if not args.no_cpu_baseline and not rd and not qres:

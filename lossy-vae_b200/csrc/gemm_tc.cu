@@ -56,6 +56,8 @@ struct TcParams {
   const float* bias; const float* gamma; const float* res;
   float* out; __nv_bfloat16* out_pl[3];
   int epi, r, Ho, Wo;
+  int prefetch;          // L2-prefetch the next tile's A k-blocks (tuning knob LVAE_TC_PREFETCH=1; measured: no gain --
+                         // the large-K GEMMs sit on the ~6.3 kB/clk L2->SM cap (85 B/clk/SM wanted at BN = 128), not on latency)
   int f16;               // plane element format: 0 bf16, 1 fp16 (LVAE_PREC_F16X3)
   float acc_scale;       // 1 / (scale the weight planes carry): 1, or 2^-8 in the fp16 mode -- exact
   // implicit 3x3 conv (stride 1, pad 1) from NHWC planes: an M-tile is a CONV_TH x CONV_TW pixel patch of one image
@@ -100,6 +102,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// pull the box into L2 only (no shared-memory destination, no barrier): hides HBM latency behind the current tile
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -247,6 +253,15 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             for (int pl = 0; pl < NPL; ++pl) {
               tma_load_2d(base + pl * a_tile, &maps.a[pl], fb, kb * p.BK, m0);
               tma_load_2d(base + NPL * a_tile + pl * b_tile, &maps.b[pl], fb, kb * p.BK, n0);
+            }
+            // optional: pull the same k-block of this CTA's NEXT tile into L2 (off by default, see TcParams::prefetch)
+            if (p.prefetch) {
+              const int tn = t + gridDim.x;
+              if (tn < p.num_tiles && (tn / p.n_tiles) != mt) {
+                const int m1 = (tn / p.n_tiles) * TC_BM;
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl) tma_prefetch_2d(&maps.a[pl], kb * p.BK, m1);
+              }
             }
           }
           if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -699,6 +714,7 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   p.stages = stages;
   p.bias = d->bias; p.gamma = d->gamma; p.res = d->res;
   p.epi = d->epilogue; p.r = d->shuffle_r; p.Ho = Ho; p.Wo = Wo;
+  { static const char* e = getenv("LVAE_TC_PREFETCH"); p.prefetch = e ? atoi(e) : 0; }
   p.f16 = d->precision == LVAE_PREC_F16X3 ? 1 : 0;
   p.acc_scale = p.f16 ? 1.0f / LVAE_F16_WEIGHT_SCALE : 1.0f;
   LVAE_CHECK_ARG(p.out != nullptr || p.out_pl[0] != nullptr);
