@@ -137,6 +137,26 @@ def test_against_live_oracle_new_input(gpu_model, sensitised_sd):
                           lambda: ref['records'])
 
 
+def test_against_live_oracle_at_baseline_size(gpu_model, sensitised_sd):
+    """BASELINE configs[1] image size (512x768), one image: the oracle takes a few seconds on the host CPU.  The
+    north-star tolerances (bpp 1e-4, PSNR 0.01 dB) hold here without any widening; the 617 472 latent symbols and
+    table indexes are compared one by one."""
+    H, W = 512, 768
+    im = make_input('synth', 1, H, W, 33)
+    lmb = torch.tensor([700.0])
+    ref = O.qarv_forward(sensitised_sd, im, lmb)
+    st = gpu_model(im.to(DEV), lmb=lmb.to(DEV), return_rec=True)
+    assert bpp_tol(H, W) == 1e-4
+    assert abs(st['bppix'] - ref['bppix']) <= 1e-4, (st['bppix'], ref['bppix'])
+    assert abs(st['psnr'] - ref['psnr']) <= PSNR_TOL
+    syms, idxs = _symbols_from_model(gpu_model, im.to(DEV), lmb.to(DEV))
+    assert sum(s.numel() for s in syms) == 617472
+    flips = _check_integer_parity(syms, idxs, [r['sym'] for r in ref['records']], [r['idx'] for r in ref['records']],
+                                  lambda: ref['records'])
+    if flips == 0:
+        assert (st['im_hat'].cpu() - ref['im_hat']).abs().max().item() < 1e-5
+
+
 def test_compress_decompress_roundtrip_equals_forward_at_kodak_shape(gpu_model):
     """BASELINE config 2 shape: decode(encode(x)) reproduces forward()'s reconstruction and the coded
     size tracks the estimated rate (coding overhead of 16-bit tables is < 2 %)."""
