@@ -42,7 +42,10 @@ constexpr int TC_BM = 128;
 //   EK_ROWS  bias | layer-scale + residual | bias + residual -> fp32 rows (+ planes), 128-bit accesses
 //   EK_MISC  pixel-shuffle stores, implicit-conv pixel tiles, odd N: scalar lane = column path
 constexpr int EK_GELU = 0, EK_ROWS = 1, EK_MISC = 2;
-__host__ __device__ constexpr int tc_epi_warps(int ek) { return ek == EK_GELU ? 16 : 8; }
+#ifndef LVAE_TC_GELU_WARPS
+#define LVAE_TC_GELU_WARPS 16
+#endif
+__host__ __device__ constexpr int tc_epi_warps(int ek) { return ek == EK_GELU ? LVAE_TC_GELU_WARPS : 8; }
 __host__ __device__ constexpr int tc_threads(int ek) { return 64 + 32 * tc_epi_warps(ek); }
 // per-warp transpose buffer in words: GELU 32 rows x 64 B (one 16-bit plane of 32 columns), ROWS 32 rows x 128 B --
 // both XOR-swizzled at 16-byte granularity instead of padded (conflict-free 128-bit row writes and row-segment
