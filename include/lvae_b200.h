@@ -115,6 +115,15 @@ int lvae_split_bf16(const float* x, void* p0, void* p1, void* p2, int64_t n, voi
 int lvae_split_planes(const float* x, void* p0, void* p1, void* p2, int64_t n, int plane_format, float scale,
                       void* stream);
 
+/* Fused ConvNeXt MLP (common.py:154-160) for narrow layers: out = res + gamma * (W2 gelu(W1 a + b1) + b2) in one
+ * kernel; the hidden activation stays on chip.  a_p*: the two 16-bit planes [M, C] of the MLP input (written by
+ * lvae_dwconv_ln_adaln_planes), w1_p* / w2_p*: planes of fc1.weight [hidden, C] / fc2.weight [C, hidden]
+ * (lvae_split_planes; fp16 planes carry LVAE_F16_WEIGHT_SCALE).  C in {64, 128, 192}, hidden % 32 == 0, precision
+ * LVAE_PREC_F16X3 or LVAE_PREC_BF16X3.  Bit-identical to the two lvae_gemm calls it replaces.  out may alias res. */
+int lvae_convnext_mlp(const void* a_p0, const void* a_p1, const void* w1_p0, const void* w1_p1, const float* b1,
+                      const void* w2_p0, const void* w2_p1, const float* b2, const float* gamma,
+                      const float* res, float* out, int64_t M, int C, int hidden, int precision, void* stream);
+
 /* ---- depthwise conv + LayerNorm + AdaLN (common.py:145-152) ------------------------------------
  * y[m, c] = LN_c( dwconv_kxk(x)[m, c] + dw_bias[c] ) * (1 + scale[b, c]) + shift[b, c]
  * x NHWC [B,H,W,C]; dw_w packed [k*k, C]; ada = [B, ada_stride] with shift at ada[b, ada_off + c]

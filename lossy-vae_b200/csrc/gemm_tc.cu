@@ -5,7 +5,7 @@
 // Operands are bf16 PLANES: an fp32 value x is carried as p0 = rn(x), p1 = rn(x - p0), p2 = rn(x - p0 - p1)
 // (24 mantissa bits in three 8-bit pieces).  Per logical product, with fp32 accumulation in TMEM:
 //   BF16    1 plane,  1 MMA   p0*p0                                        ~2^-8
-//   BF16X3  2 planes, 3 MMAs  p0*p0 + p0*p1 + p1*p0                        ~2^-17
+//   BF16X3  2 planes, 3 products p0*p0 + p0*p1 + p1*p0 (2 MMAs: p0 * [p0; p1] is one)   ~2^-17
 //   BF16X6  3 planes, 6 MMAs  ... + p1*p1 + p0*p2 + p2*p0                  ~2^-23 (fp32-class: the mode in which
 //                                                                          the quantised symbols match the CPU oracle)
 //
@@ -26,8 +26,7 @@
 // Two such buffers in TMEM (2 x 2 x BN <= 512 columns, BN <= 128; 2 x BN with BN <= 256 for single-plane bf16)
 // let the epilogue of tile i overlap the MMAs of tile i+1.  K order is fixed, there is no split-K and BN depends on N only, so results are bit-reproducible
 // and do not depend on the batch an image travels in.
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 #include <cuda_bf16.h>
 #include <mutex>
 #include <stdlib.h>
@@ -69,88 +68,6 @@ struct TcParams {
 constexpr int CONV_TW = 16, CONV_TH = 8;       // 128 output pixels per tile
 
 struct TcMaps { CUtensorMap a[3]; CUtensorMap b[3]; };
-
-// ---------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-#ifndef LVAE_TC_SPIN_NS
-#define LVAE_TC_SPIN_NS 20
-#endif
-    if (LVAE_TC_SPIN_NS > 0 && !done) __nanosleep(LVAE_TC_SPIN_NS);   // free issue slots for the epilogue warps while waiting
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-// pull the box into L2 only (no shared-memory destination, no barrier): hides HBM latency behind the current tile
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major operand tile in shared memory, one swizzle row per matrix row (what the TMA box writes): descriptor
-// fields per cute/arch/mma_sm100_desc.hpp SmemDescriptor -- start address >> 4, LBO (unused for swizzled
-// K-major, 1), SBO = 8 rows * row bytes >> 4, version 1 (sm_100), layout type 2 (SWIZZLE_128B) / 4 (SWIZZLE_64B).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int bk) {
-  const uint64_t sbo = (uint64_t)(8 * bk * 2) >> 4;
-  const uint64_t layout = bk == 64 ? 2ull : 4ull;
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
 
 __device__ __forceinline__ float epi_value(const TcParams& p, int m, int n, float acc) {
   float v = acc;
@@ -277,6 +194,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // a_format / b_format (bits 7-9 / 10-12): 0 = fp16, 1 = bf16
     const uint32_t fmt = p.f16 ? 0u : 1u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t idesc2n = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 2) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // N = 2 * BN
     int s = 0; uint32_t ph = 0; int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -299,16 +217,20 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t ko = (uint64_t)(k * 2);           // 16 bf16 = 32 bytes = 2 x 16-byte units along K
             const uint32_t first = (kb | k) ? 1u : 0u;
-            if (NPL == 3) {
-              tc_mma(d_cross, da[2] + ko, db[0] + ko, idesc, first);
-              tc_mma(d_cross, da[0] + ko, db[2] + ko, idesc, 1u);
-              tc_mma(d_cross, da[1] + ko, db[1] + ko, idesc, 1u);
-            }
             if (NPL >= 2) {
-              tc_mma(d_cross, da[1] + ko, db[0] + ko, idesc, NPL == 3 ? 1u : first);
-              tc_mma(d_cross, da[0] + ko, db[1] + ko, idesc, 1u);
+              // one tcgen05.mma costs ~142 cycles whatever its N (scripts/probe/mma_probe.cu), so a0 * b0 (-> main) and
+              // a0 * b1 (-> cross) ride in ONE instruction of N = 2 * BN: the B planes 0 and 1 are adjacent in the stage
+              // and main | cross are adjacent in TMEM.  2 MMAs per k-step instead of 3 (5 instead of 6 with 3 planes).
+              tc_mma(d_tmem, da[0] + ko, db[0] + ko, idesc2n, first);
+              tc_mma(d_cross, da[1] + ko, db[0] + ko, idesc, 1u);
+              if (NPL == 3) {
+                tc_mma(d_cross, da[1] + ko, db[1] + ko, idesc, 1u);
+                tc_mma(d_cross, da[2] + ko, db[0] + ko, idesc, 1u);
+                tc_mma(d_cross, da[0] + ko, db[2] + ko, idesc, 1u);
+              }
+            } else {
+              tc_mma(d_tmem, da[0] + ko, db[0] + ko, idesc, first);
             }
-            tc_mma(d_tmem, da[0] + ko, db[0] + ko, idesc, first);
           }
           tc_commit(smem_u32(empty_bar + s));               // frees the stage once these MMAs have read it
           if (kb == nkb - 1) tc_commit(smem_u32(tfull_bar + acc));
@@ -590,7 +512,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // [rows, K] bf16 row-major, box = [box_rows x 64], SWIZZLE_128B, zero fill outside the tensor
-static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box_rows, int bk) {
+int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box_rows, int bk) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LVAE_E_UNSUPPORTED; }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};

@@ -43,6 +43,7 @@ _PROTOS = {
     'lvae_last_error': (C.c_char_p, []),
     'lvae_gemm': (C.c_int, [C.POINTER(GemmDesc), _fp]),
     'lvae_gemm_workspace_bytes': (C.c_int64, [C.POINTER(GemmDesc)]),
+    'lvae_convnext_mlp': (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_split_bf16': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp]),
     'lvae_dwconv_ln_adaln': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),

@@ -96,6 +96,8 @@ class QarvEngine:
         self._wver = None
         self._plans = {}
         self.use_graphs = True
+        # lvae_convnext_mlp for C <= 192 (False / LVAE_FUSE_MLP=0: the unfused GEMM pair, bit-identical)
+        self.fuse_mlp = __import__('os').environ.get('LVAE_FUSE_MLP', '1') != '0'
         self.host_coder_s = 0.0        # seconds spent in the host rANS coder (bench.py --workload codec reads it)
         self.coder_threads = min(16, __import__('os').cpu_count() or 1)
         self.blocks = [m for m in model.modules() if isinstance(m, (common.ConvNeXtBlockAdaLN, common.ConvNeXtBlockLN))]
@@ -278,6 +280,15 @@ class QarvEngine:
             P.op('dwln', self.lib.lvae_dwconv_ln_adaln_planes, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']),
                  _ptr(P.ada), self.ada_total, ada_off, ln_w, ln_b, ap[0], ap[1], ap[2], self.pfmt, B, Hs, Ws, C_, k,
                  keep=(x, A), meta=dw_meta)
+            if self.fuse_mlp and self.npl == 2 and C_ % 64 == 0 and C_ <= 192 and hid % 32 == 0 and out_planes is None:
+                # narrow layers (H/4 stages): fc1 -> GELU -> fc2 -> layer scale + residual in one kernel, the hidden
+                # tensor never leaves the SM (bit-identical to the two GEMMs below)
+                w1, w2 = wb['fc1'], wb['fc2']
+                P.op('mlp', self.lib.lvae_convnext_mlp, ap[0], ap[1], _ptr(w1['planes'][0]), _ptr(w1['planes'][1]),
+                     _ptr(w1['bias']), _ptr(w2['planes'][0]), _ptr(w2['planes'][1]), _ptr(w2['bias']), _ptr(wb['gamma']),
+                     _ptr(x), _ptr(out), M, C_, hid, self.prec, keep=(x, out, A, wb),
+                     meta=dict(kind='gemm', flops=4 * M * C_ * hid, M=M, N=C_, K=hid, bytes=M * C_ * (4 + 4 + 4)))
+                return out
             self._gemm(P, 'fc1', None, (1, 1, M, C_, 1, 1, 0), wb['fc1'], None, epi=N.EPI_BIAS_GELU, a_planes=A, out_planes=Hd)
             self._gemm(P, 'fc2', None, (1, 1, M, hid, 1, 1, 0), wb['fc2'], out, epi=N.EPI_SCALE_RES,
                        gamma=wb['gamma'], res=x, a_planes=Hd, out_planes=out_planes)

@@ -21,6 +21,7 @@ SHAPES = [  # (name, M, K, N, epi)
     ('s32 fc1', 3072, 512, 1024, 1), ('s64 fc1', 768, 512, 2048, 1),
     ('s4 dec fc1', 196608, 128, 192, 1), ('s4 dec fc2', 196608, 192, 128, 2),
     ('s8 dec fc1', 49152, 256, 448, 1), ('s8 dec fc2', 49152, 448, 256, 2),
+    ('n32 probe', 196608, 192, 32, 0), ('n64 probe', 196608, 192, 64, 0), ('n128 probe', 196608, 192, 128, 0),
 ]
 def planes(x, n, prec=3, weight=False):
     ps = [torch.empty(x.shape, dtype=torch.bfloat16, device='cuda') for _ in range(n)]
