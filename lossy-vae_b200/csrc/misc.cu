@@ -26,38 +26,49 @@ __global__ void sinusoid_kernel(const float* __restrict__ lmb, const float* __re
   emb0[(int64_t)b * dim + half + f] = sinf(arg);
 }
 
-// one warp per output column n, all batch rows; K % 4 == 0
+// Small-batch linear layer: out[b, n] = act_out(sum_k act_in(x[b, k]) w[n, k] + bias[n]).  The (activated) input
+// [B, K] is staged once per block in shared memory -- with act_in = GELU (all 90 AdaLN projections in one launch,
+// N ~ 63 k) the old one-warp-per-column kernel evaluated the GELU N * K * B = 129 M times and was compute-bound at
+// 0.4 TB/s of weight traffic.  Each warp then streams SL_COLS weight rows; per-lane K order and the warp reduction
+// are unchanged, so results are bit-identical to the previous kernel.
+constexpr int SL_COLS = 8;                  // output columns per warp
 template <int BCHUNK>
 __global__ void __launch_bounds__(256) small_linear_kernel(
     const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
     float* __restrict__ out, int B, int K, int N, int act_in, int act_out) {
+  extern __shared__ float sl_x[];            // [B][K]
+  for (int i = threadIdx.x; i < B * K; i += blockDim.x) {
+    const float v = __ldg(x + i);
+    sl_x[i] = act_in ? gelu_erf(v) : v;
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (n >= N) return;
-  const float* wr = w + (int64_t)n * K;
-  for (int b0 = 0; b0 < B; b0 += BCHUNK) {
-    float acc[BCHUNK];
+  const int n0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * SL_COLS;
+  for (int n = n0; n < n0 + SL_COLS && n < N; ++n) {
+    const float* wr = w + (int64_t)n * K;
+    for (int b0 = 0; b0 < B; b0 += BCHUNK) {
+      float acc[BCHUNK];
 #pragma unroll
-    for (int i = 0; i < BCHUNK; ++i) acc[i] = 0.f;
-    for (int k = lane * 4; k < K; k += 128) {
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + k));
+      for (int i = 0; i < BCHUNK; ++i) acc[i] = 0.f;
+      for (int k = lane * 4; k < K; k += 128) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + k));
 #pragma unroll
-      for (int i = 0; i < BCHUNK; ++i) {
-        if (b0 + i < B) {
-          float4 xv = __ldg(reinterpret_cast<const float4*>(x + (int64_t)(b0 + i) * K + k));
-          if (act_in) { xv.x = gelu_erf(xv.x); xv.y = gelu_erf(xv.y); xv.z = gelu_erf(xv.z); xv.w = gelu_erf(xv.w); }
-          acc[i] = fmaf(xv.x, wv.x, acc[i]); acc[i] = fmaf(xv.y, wv.y, acc[i]);
-          acc[i] = fmaf(xv.z, wv.z, acc[i]); acc[i] = fmaf(xv.w, wv.w, acc[i]);
+        for (int i = 0; i < BCHUNK; ++i) {
+          if (b0 + i < B) {
+            const float4 xv = *reinterpret_cast<const float4*>(sl_x + (b0 + i) * K + k);
+            acc[i] = fmaf(xv.x, wv.x, acc[i]); acc[i] = fmaf(xv.y, wv.y, acc[i]);
+            acc[i] = fmaf(xv.z, wv.z, acc[i]); acc[i] = fmaf(xv.w, wv.w, acc[i]);
+          }
         }
       }
-    }
 #pragma unroll
-    for (int i = 0; i < BCHUNK; ++i) {
-      const float s = warp_sum(acc[i]);
-      if (lane == 0 && b0 + i < B) {
-        float v = bias ? __fadd_rn(s, bias[n]) : s;
-        if (act_out) v = gelu_erf(v);
-        out[(int64_t)(b0 + i) * N + n] = v;
+      for (int i = 0; i < BCHUNK; ++i) {
+        const float s = warp_sum(acc[i]);
+        if (lane == 0 && b0 + i < B) {
+          float v = bias ? __fadd_rn(s, bias[n]) : s;
+          if (act_out) v = gelu_erf(v);
+          out[(int64_t)(b0 + i) * N + n] = v;
+        }
       }
     }
   }
@@ -215,8 +226,11 @@ extern "C" int lvae_lmb_sinusoid(const float* lmb, const float* freqs, float* em
 extern "C" int lvae_small_linear(const float* x, const float* w, const float* bias, float* out,
                                  int B, int K, int N, int act_in, int act_out, void* stream) {
   LVAE_CHECK_ARG(x && w && out && B > 0 && K > 0 && K % 4 == 0 && N > 0);
-  const int warps = 8;
-  small_linear_kernel<8><<<(N + warps - 1) / warps, warps * 32, 0, (cudaStream_t)stream>>>(x, w, bias, out, B, K, N, act_in, act_out);
+  const int warps = 8, cols = warps * SL_COLS;
+  const size_t smem = (size_t)B * K * sizeof(float);
+  LVAE_CHECK_ARG(smem <= 160 * 1024);
+  if (smem > 48 * 1024) LVAE_CUDA_CALL(cudaFuncSetAttribute(small_linear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  small_linear_kernel<8><<<(N + cols - 1) / cols, warps * 32, smem, (cudaStream_t)stream>>>(x, w, bias, out, B, K, N, act_in, act_out);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
