@@ -103,6 +103,9 @@ typedef struct lvae_gemm_desc {
                                * VDBlock's c_i(gelu(x)) (lvae/models/qresvae/model.py:143-149).  Requires a0
                                * (not a_planes). */
   int32_t reserved;
+  const void* a1_planes[3];   /* optional pre-split planes [M, C1] of segment 1 (the K-concat of post_merge): with
+                               * a_planes (then [M, C0]) the tensor-core path reads both segments without an im2col /
+                               * split pass.  ksize == 1, C0 % 64 == 0. */
 } lvae_gemm_desc;
 
 int lvae_gemm(const lvae_gemm_desc* d, void* stream);

@@ -58,6 +58,7 @@ struct TcParams {
   const float* bias; const float* gamma; const float* res;
   float* out; __nv_bfloat16* out_pl[3];
   int epi, r, Ho, Wo;
+  int k_split;           // k >= k_split comes from the a1 maps (K-concat of two plane sets); = K when there is one segment
   int prefetch;          // L2-prefetch the next tile's A k-blocks (tuning knob LVAE_TC_PREFETCH=1; measured: no gain --
                          // the large-K GEMMs sit on the ~6.3 kB/clk L2->SM cap (85 B/clk/SM wanted at BN = 128), not on latency)
   int f16;               // plane element format: 0 bf16, 1 fp16 (LVAE_PREC_F16X3)
@@ -67,7 +68,7 @@ struct TcParams {
 };
 constexpr int CONV_TW = 16, CONV_TH = 8;       // 128 output pixels per tile
 
-struct TcMaps { CUtensorMap a[3]; CUtensorMap b[3]; };
+struct TcMaps { CUtensorMap a[3]; CUtensorMap b[3]; CUtensorMap a1[3]; };   // a1: second K segment (K-concat from planes)
 
 __device__ __forceinline__ float epi_value(const TcParams& p, int m, int n, float acc) {
   float v = acc;
@@ -170,9 +171,11 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             }
           } else {
 #pragma unroll
+            const int k0 = kb * p.BK;
+            const bool seg1 = k0 >= p.k_split;
             for (int pl = 0; pl < NPL; ++pl) {
-              tma_load_2d(base + pl * a_tile, &maps.a[pl], fb, kb * p.BK, m0);
-              tma_load_2d(base + NPL * a_tile + pl * b_tile, &maps.b[pl], fb, kb * p.BK, n0);
+              tma_load_2d(base + pl * a_tile, seg1 ? &maps.a1[pl] : &maps.a[pl], fb, seg1 ? k0 - p.k_split : k0, m0);
+              tma_load_2d(base + NPL * a_tile + pl * b_tile, &maps.b[pl], fb, k0, n0);
             }
             // optional: pull the same k-block of this CTA's NEXT tile into L2 (off by default, see TcParams::prefetch)
             if (p.prefetch) {
@@ -546,7 +549,7 @@ static void tc_geometry(const lvae_gemm_desc* d, int* Ho, int* Wo, int64_t* M, i
   *Ho = (d->H + 2 * d->pad - d->ksize) / d->stride + 1;
   *Wo = (d->W + 2 * d->pad - d->ksize) / d->stride + 1;
   *M = (int64_t)d->B * *Ho * *Wo;
-  *K = d->ksize * d->ksize * d->C0 + (d->a1 ? d->C1 : 0);
+  *K = d->ksize * d->ksize * d->C0 + ((d->a1 || d->a1_planes[0]) ? d->C1 : 0);
 }
 
 static int num_planes(int precision) {
@@ -602,8 +605,14 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
     set_error("pre-split A planes support 1x1 (plain [M,K]) and 3x3 stride-1 pad-1 convolutions with C %% 64 == 0 only");
     return LVAE_E_UNSUPPORTED;
   }
+  const bool concat_planes = d->a_planes[0] != nullptr && d->a1_planes[0] != nullptr;
+  if (concat_planes) {
+    LVAE_CHECK_ARG(d->ksize == 1 && d->stride == 1 && d->pad == 0 && d->C0 % 64 == 0 && d->C1 > 0 && d->C1 % 8 == 0);
+    for (int i = 0; i < npl; ++i) LVAE_CHECK_ARG(d->a1_planes[i] != nullptr);
+  }
   TcParams p;
   p.M = M; p.N = d->N; p.K = K;
+  p.k_split = concat_planes ? d->C0 : K;
   p.BN = pick_bn(d->N, npl);
   p.n_tiles = (d->N + p.BN - 1) / p.BN;
   p.conv = conv ? 1 : 0; p.cH = d->H; p.cW = d->W; p.cC = d->C0;
@@ -649,8 +658,10 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   for (int i = 0; i < 3; ++i) {
     const int j = i < npl ? i : 0;
     if (conv) { if ((rc = make_map_conv(&maps.a[i], a_pl[j], d->B, d->H, d->W, d->C0, p.BK))) return rc; }
-    else if ((rc = make_map(&maps.a[i], a_pl[j], M, K, TC_BM, p.BK))) return rc;
+    else if ((rc = make_map(&maps.a[i], a_pl[j], M, concat_planes ? d->C0 : K, TC_BM, p.BK))) return rc;
     if ((rc = make_map(&maps.b[i], d->w_planes[j], d->N, K, p.BN, p.BK))) return rc;
+    if (concat_planes) { if ((rc = make_map(&maps.a1[i], d->a1_planes[j], M, d->C1, TC_BM, p.BK))) return rc; }
+    else maps.a1[i] = maps.a[i];
   }
 
   static int n_sm = 0;

@@ -35,6 +35,7 @@ class GemmDesc(C.Structure):
         ('w_planes', _fp * 3), ('a_planes', _fp * 3), ('out_planes', _fp * 3),
         ('workspace', _fp), ('workspace_bytes', C.c_int64),
         ('a_act', C.c_int32), ('reserved', C.c_int32),
+        ('a1_planes', _fp * 3),
     ]
 
 

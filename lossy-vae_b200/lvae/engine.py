@@ -98,6 +98,8 @@ class QarvEngine:
         self.use_graphs = True
         # lvae_convnext_mlp for C <= 192 (False / LVAE_FUSE_MLP=0: the unfused GEMM pair, bit-identical)
         self.fuse_mlp = __import__('os').environ.get('LVAE_FUSE_MLP', '1') != '0'
+        # producers write operand planes for prior / post_merge (False / LVAE_PLANE_CHAIN=0: fp32 + split pass)
+        self.plane_chain = __import__('os').environ.get('LVAE_PLANE_CHAIN', '1') != '0'
         self.host_coder_s = 0.0        # seconds spent in the host rANS coder (bench.py --workload codec reads it)
         self.coder_threads = min(16, __import__('os').cpu_count() or 1)
         self.blocks = [m for m in model.modules() if isinstance(m, (common.ConvNeXtBlockAdaLN, common.ConvNeXtBlockLN))]
@@ -232,7 +234,7 @@ class QarvEngine:
 
     # ------------------------------------------------------------------ plan construction helpers
     def _gemm(self, P, name, a0, geom, went, out, epi=N.EPI_BIAS, a1=None, C1=0, gamma=None, res=None, r=0,
-              a_planes=None, out_planes=None, a_act=0):
+              a_planes=None, out_planes=None, a_act=0, a1_planes=None):
         """geom = (B, H, W, C0, ksize, stride, pad) of the NHWC input a0.  In a tensor-core mode the A operand is
         either `a_planes` (bf16 planes written by the producing kernel) or a0/a1, which the library im2col-splits
         into the plan's workspace first."""
@@ -251,6 +253,9 @@ class QarvEngine:
             N.set_planes(d, 'w', went['planes'])
             N.set_planes(d, 'a', a_planes)
             N.set_planes(d, 'out', out_planes)
+            N.set_planes(d, 'a1', a1_planes)
+            if a1_planes is not None:
+                d.C1 = C1
             if a_planes is None:
                 ws = P.named('tc_ws', Mo * went['K'] * self.npl, dtype=torch.bfloat16)
                 d.workspace, d.workspace_bytes = _ptr(ws), ws.numel() * 2
@@ -258,10 +263,10 @@ class QarvEngine:
             assert a_planes is None and out_planes is None
         meta = dict(kind='gemm', flops=2 * Mo * went['N'] * went['K'], M=Mo, N=went['N'], K=went['K'],
                     bytes=4 * (B * H * W * (C0 + C1) + went['N'] * went['K'] + Mo * went['N'] * (2 if res is not None else 1)))
-        P.op(name, self.lib.lvae_gemm, C.byref(d), keep=(d, a0, a1, went, out, gamma, res, a_planes, out_planes, ws),
+        P.op(name, self.lib.lvae_gemm, C.byref(d), keep=(d, a0, a1, went, out, gamma, res, a_planes, out_planes, ws, a1_planes),
              meta=meta)
 
-    def _block(self, P, blk, x, B, Hs, Ws, out=None, out_planes=None):
+    def _block(self, P, blk, x, B, Hs, Ws, out=None, out_planes=None, planes_only=False):
         """x: [M, C] fp32 NHWC; returns the output buffer (x itself when out is None: in place).  out_planes: bf16
         planes of the result, written by the fc2 epilogue for a tensor-core consumer (the 3x3 posterior conv)."""
         wb = self.w[id(blk)]
@@ -290,7 +295,8 @@ class QarvEngine:
                      meta=dict(kind='gemm', flops=4 * M * C_ * hid, M=M, N=C_, K=hid, bytes=M * C_ * (4 + 4 + 4)))
                 return out
             self._gemm(P, 'fc1', None, (1, 1, M, C_, 1, 1, 0), wb['fc1'], None, epi=N.EPI_BIAS_GELU, a_planes=A, out_planes=Hd)
-            self._gemm(P, 'fc2', None, (1, 1, M, hid, 1, 1, 0), wb['fc2'], out, epi=N.EPI_SCALE_RES,
+            # planes_only: the consumer reads the 16-bit planes, the fp32 result is never written
+            self._gemm(P, 'fc2', None, (1, 1, M, hid, 1, 1, 0), wb['fc2'], None if planes_only else out, epi=N.EPI_SCALE_RES,
                        gamma=wb['gamma'], res=x, a_planes=Hd, out_planes=out_planes)
             return out
         A = P.named('scratch_a', M * C_)
@@ -302,6 +308,9 @@ class QarvEngine:
         self._gemm(P, 'fc2', Hd, (1, 1, M, hid, 1, 1, 0), wb['fc2'], out, epi=N.EPI_SCALE_RES,
                    gamma=wb['gamma'], res=x)
         return out
+
+    def _mlp_fused(self, blk):
+        return (self.fuse_mlp and self.npl == 2 and blk.dim % 64 == 0 and blk.dim <= 192 and blk.hidden % 32 == 0)
 
     def _embedding(self, P, lmb):
         m, w, B = self.model, self.w, P.B
@@ -379,11 +388,17 @@ class QarvEngine:
             if getattr(mod, 'is_latent_block', False):
                 wl = self.w[id(mod)]
                 zd = mod.zdim
-                x = self._block(P, mod.resnet_front, x, B, Hs, Ws)
                 prior = P.f32(M, 2 * zd)
                 if self.family == 'qres':
+                    x = self._block(P, mod.resnet_front, x, B, Hs, Ws)
                     self._vdblock(P, 'prior', wl['prior'], x, (B, Hs, Ws, Cc), prior)
+                elif self.npl and self.plane_chain and not self._mlp_fused(mod.resnet_front):
+                    # resnet_front's fc2 epilogue also writes its result as planes: the prior head reads them directly
+                    xp = [P.named(f'x_pl{i}', M * Cc, dtype=torch.bfloat16)[:M * Cc] for i in range(self.npl)]
+                    x = self._block(P, mod.resnet_front, x, B, Hs, Ws, out_planes=xp)
+                    self._gemm(P, 'prior', None, (B, Hs, Ws, Cc, 1, 1, 0), wl['prior'], prior, a_planes=xp)
                 else:
+                    x = self._block(P, mod.resnet_front, x, B, Hs, Ws)
                     self._gemm(P, 'prior', x, (B, Hs, Ws, Cc, 1, 1, 0), wl['prior'], prior)
                 z = latent_fn(P, mod, li, x, prior, (B, Hs, Ws, Cc))
                 li += 1
@@ -441,10 +456,20 @@ class QarvEngine:
             self._vdblock(P, 'posterior', wl['posterior'], x, geom, qm, a1=enc_feat, C1=blk.enc_width)
             return qm
         We = blk.enc_width
-        e = self._block(P, blk.posterior0, enc_feat, B, Hs, Ws, out=P.named('post_e', M * We)[:M * We])
-        f = self._block(P, blk.posterior1, x, B, Hs, Ws, out=P.named('post_f', M * Cc)[:M * Cc])
         mg = P.named('post_m', M * Cc)[:M * Cc]
-        self._gemm(P, 'post_merge', f, (B, Hs, Ws, Cc, 1, 1, 0), wl['post_merge'], mg, a1=e, C1=We)
+        if self.npl and Cc % 64 == 0 and We % 8 == 0 and self.plane_chain:
+            # the two branch blocks hand their results to post_merge as 16-bit planes (written by their fc2
+            # epilogues, never as fp32): the K-concat reads both plane sets, no im2col / split pass
+            pdt = torch.bfloat16
+            ep = [P.named(f'post_e_pl{i}', M * We, dtype=pdt)[:M * We] for i in range(self.npl)]
+            fp = [P.named(f'post_f_pl{i}', M * Cc, dtype=pdt)[:M * Cc] for i in range(self.npl)]
+            self._block(P, blk.posterior0, enc_feat, B, Hs, Ws, out=mg, out_planes=ep, planes_only=True)
+            self._block(P, blk.posterior1, x, B, Hs, Ws, out=mg, out_planes=fp, planes_only=True)
+            self._gemm(P, 'post_merge', None, (B, Hs, Ws, Cc, 1, 1, 0), wl['post_merge'], mg, a_planes=fp, a1_planes=ep, C1=We)
+        else:
+            e = self._block(P, blk.posterior0, enc_feat, B, Hs, Ws, out=P.named('post_e', M * We)[:M * We])
+            f = self._block(P, blk.posterior1, x, B, Hs, Ws, out=P.named('post_f', M * Cc)[:M * Cc])
+            self._gemm(P, 'post_merge', f, (B, Hs, Ws, Cc, 1, 1, 0), wl['post_merge'], mg, a1=e, C1=We)
         qm = P.f32(M, wl['posterior']['N'])          # qarv: zdim means; rd: (mean_raw | std_raw) = 2 * zdim
         if self.npl and Cc % 64 == 0:
             # tensor-core modes: posterior2's fc2 epilogue also writes its result as bf16 planes, which the 3x3
