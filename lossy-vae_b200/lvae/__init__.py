@@ -7,5 +7,6 @@ Same import surface as the reference package (`/root/reference/lvae/__init__.py:
 from .paths import known_datasets
 from .models.registry import get_model, register_model
 from . import models
+from . import evaluation
 
-__all__ = ['get_model', 'register_model', 'known_datasets', 'models']
+__all__ = ['get_model', 'register_model', 'known_datasets', 'models', 'evaluation']

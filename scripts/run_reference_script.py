@@ -1,0 +1,18 @@
+"""Run one of the reference's own scripts, unmodified, against this package:
+
+    python scripts/run_reference_script.py /path/to/lossy-vae/eval-var-rate.py -m qarv_base -a "pretrained='ckpt.pt'" -n kodak
+    python scripts/run_reference_script.py /path/to/lossy-vae/scripts/speedtest-lvae.py -a "pretrained='ckpt.pt'"
+
+`python /path/to/lossy-vae/<script>` would put the reference's own `lvae` first on sys.path; this runner
+puts ours there instead and hands over with runpy.  Datasets: set LVAE_DATASETS (lvae/paths.py)."""
+import runpy
+import sys
+from pathlib import Path
+
+if __name__ == '__main__':
+    if len(sys.argv) < 2:
+        raise SystemExit(__doc__)
+    script = sys.argv[1]
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / 'lossy-vae_b200'))
+    sys.argv = sys.argv[1:]
+    runpy.run_path(script, run_name='__main__')
