@@ -156,31 +156,40 @@ def run_codec(args):
         model.precision = args.precision
     model = model.to(dev).eval()
     model.compress_mode()
-    im = make_input('synth', 1, H, W, 5).to(dev)
+    nb = args.codec_batch
+    im = make_input('synth', nb, H, W, 5).to(dev)
+    if nb == 1:          # the reference's API: one image per call
+        enc = lambda: [model.compress(im, lmb=2048.0)]
+        dec = lambda blobs: model.decompress(blobs[0])
+    else:                # batched extension: same bit streams, B images per call
+        enc = lambda: model.compress_batch(im, lmb=2048.0)
+        dec = lambda blobs: model.decompress_batch(blobs)
     for _ in range(max(args.warmup, 3)):
-        blob = model.compress(im, lmb=2048.0)
-        rec = model.decompress(blob)
+        blobs = enc()
+        rec = dec(blobs)
     torch.cuda.synchronize()
     eng = model.engine
     eng.host_coder_s = 0.0
     t_c = t_d = 0.0
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        blob = model.compress(im, lmb=2048.0)
+        blobs = enc()
         t1 = time.perf_counter()
-        rec = model.decompress(blob)
+        rec = dec(blobs)
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         t_c += t1 - t0; t_d += t2 - t1
-    ref = model(im, lmb=torch.tensor([2048.0], device=dev), return_rec=True)
+    ref = model(im, lmb=torch.full((nb,), 2048.0, device=dev), return_rec=True)
     err = (rec - ref['im_hat']).abs().max().item()
+    nbytes = sum(len(b) for b in blobs)
     print(json.dumps({
-        'metric': '512x768 images/sec (compress + decompress, real bit stream)', 'value': args.steps / (t_c + t_d), 'unit': 'images/s',
+        'metric': '512x768 images/sec (compress + decompress, real bit stream)', 'value': nb * args.steps / (t_c + t_d), 'unit': 'images/s',
         'n_gpus': 1, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': (t_c + t_d) / args.steps * 1e3,
         'higher_is_better': True, 'dtype': model.precision, 'data': 'synthetic',
-        'config': {'workload': 'qarv_base compress() + decompress(), one synthetic 512x768 image per step, lambda 2048'},
+        'config': {'workload': f'qarv_base compress + decompress, {nb} synthetic 512x768 image(s) per step, lambda 2048'
+                               + ('' if nb == 1 else ' (compress_batch / decompress_batch)')},
         'compress_ms': t_c / args.steps * 1e3, 'decompress_ms': t_d / args.steps * 1e3,
-        'host_coder_ms': eng.host_coder_s / args.steps * 1e3, 'bytes': len(blob), 'bpp': len(blob) * 8 / (H * W),
+        'host_coder_ms': eng.host_coder_s / args.steps * 1e3, 'bytes': nbytes, 'bpp': nbytes * 8 / (nb * H * W),
         'decoder_vs_forward_max_abs_err': err,
     }))
 
@@ -199,6 +208,7 @@ def main():
                          'codec: qarv_base compress() + decompress() of one 512x768 image per step (real bit stream, host rANS)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-samples', type=int, default=5)
+    ap.add_argument('--codec-batch', type=int, default=1, help='--workload codec: images per compress / decompress call')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

@@ -244,6 +244,10 @@ int lvae_rans_encode(const int32_t* sym, const int32_t* idx, int64_t n,
 int lvae_rans_encode_streams(const int32_t* sym, const int32_t* idx, const int64_t* begin, int n_streams,
                              const int32_t* cdf, int cdf_stride, const int32_t* cdf_len, const int32_t* offset,
                              int n_cdf, uint8_t* out, const int64_t* out_begin, int64_t* out_len, int n_threads);
+/* the decoding counterpart: stream i = bytes [in_begin[i], in_begin[i+1]) of `in` -> symbols [begin[i], begin[i+1]) */
+int lvae_rans_decode_streams(const uint8_t* in, const int64_t* in_begin, const int32_t* idx, const int64_t* begin,
+                             int n_streams, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len,
+                             const int32_t* offset, int n_cdf, int32_t* sym_out, int n_threads);
 int lvae_rans_decode(const uint8_t* in, int64_t in_len, const int32_t* idx, int64_t n,
                      const int32_t* cdf, int cdf_stride, const int32_t* cdf_len, const int32_t* offset,
                      int n_cdf, int32_t* sym_out);

@@ -212,3 +212,28 @@ extern "C" int lvae_rans_encode_streams(const int32_t* sym, const int32_t* idx, 
   for (auto& th : pool) th.join();
   return status.load();
 }
+
+// Decode `n_streams` independent streams on up to `n_threads` host threads: stream i reads bytes
+// [in_begin[i], in_begin[i+1]) of `in` and produces symbols [begin[i], begin[i+1]) of sym_out from the same range of idx.
+extern "C" int lvae_rans_decode_streams(const uint8_t* in, const int64_t* in_begin, const int32_t* idx, const int64_t* begin,
+                                        int n_streams, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len,
+                                        const int32_t* offset, int n_cdf, int32_t* sym_out, int n_threads) {
+  if (!in || !in_begin || !idx || !begin || !sym_out || n_streams < 0) return LVAE_E_BADARG;
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > n_streams) n_threads = n_streams;
+  std::atomic<int> next(0), status(0);
+  auto work = [&]() {
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n_streams) return;
+      const int rc = lvae_rans_decode(in + in_begin[i], in_begin[i + 1] - in_begin[i], idx + begin[i], begin[i + 1] - begin[i],
+                                      cdf, cdf_stride, cdf_len, offset, n_cdf, sym_out + begin[i]);
+      if (rc != 0) status.store(rc);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+  return status.load();
+}

@@ -75,6 +75,7 @@ _PROTOS = {
     'lvae_rans_encode': (C.c_int, [_fp, _fp, C.c_int64, _fp, C.c_int, _fp, _fp, C.c_int, _fp, C.c_int64,
                                    C.POINTER(C.c_int64)]),
     'lvae_rans_encode_streams': (C.c_int, [_fp, _fp, _fp, C.c_int, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp, _fp, C.c_int]),
+    'lvae_rans_decode_streams': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, _fp, C.c_int, _fp, _fp, C.c_int, _fp, C.c_int]),
     'lvae_rans_decode': (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, _fp, C.c_int, _fp, _fp, C.c_int, _fp]),
 }
 

@@ -741,7 +741,7 @@ class QarvEngine:
         P.lmb = P.f32(B)
         lay, _ = self._latent_layout(B, nH, nW)
         P.layout = lay
-        P.z, P.idx, P.sym, P.prior = [], [], [], []
+        P.z, P.idx, P.sym, P.prior, P.idx_host, P.sym_host = [], [], [], [], [], []
         self._embedding(P, P.lmb)
 
         def latent_fn(P, blk, li, x, prior, geom):
@@ -755,6 +755,8 @@ class QarvEngine:
             idx, sym = P.i32(B, zd, Hs, Ws), P.i32(B, zd, Hs, Ws)
             P.idx.append(idx)
             P.sym.append(sym)
+            P.idx_host.append(torch.empty(B * zd * Hs * Ws, dtype=torch.int32, pin_memory=True))
+            P.sym_host.append(torch.empty(B * zd * Hs * Ws, dtype=torch.int32, pin_memory=True))
             tab = self.w[id(blk)]['table']
             if tab is None:
                 raise ValueError('Uninitialized CDFs. Run update() first')
@@ -770,10 +772,11 @@ class QarvEngine:
 
     @torch.no_grad()
     def decompress(self, lmb, strings, bhw):
-        """strings: one byte string per latent layer (batch 1, as the reference container holds)."""
+        """strings[li]: the byte string of latent layer li, or a list of B of them (one per image).  The B streams of a
+        layer are decoded on a thread pool (lvae_rans_decode_streams); layers stay sequential, because the prior of
+        layer i + 1 needs z_i (qarv/model.py:546-554)."""
         self.refresh_weights()
         B, nH, nW = bhw
-        assert B == 1 or self.family == 'qres', 'the container format carries one image (qarv/model.py:521)'
         blocks = [b for b in self.model.dec_blocks if getattr(b, 'is_latent_block', False)]
         with torch.cuda.device(self.device):
             P = self._get_plan(('dec', B, nH, nW), lambda: self._build_decode_plan(B, nH, nW))
@@ -781,21 +784,24 @@ class QarvEngine:
             stream = torch.cuda.current_stream(self.device)
             for li, blk in enumerate(blocks):
                 self._launch(P, li)
-                idx = P.idx[li].to('cpu', non_blocking=True)
+                P.idx_host[li].copy_(P.idx[li].view(-1), non_blocking=True)
                 stream.synchronize()
                 cdf, clen, coff = self._tables(blk)
-                idx_np = idx.numpy().reshape(B, -1)
-                sym_np = np.empty(idx_np.shape, dtype=np.int32)
+                idx_np = P.idx_host[li].numpy().reshape(-1)
+                sym_np = P.sym_host[li].numpy().reshape(-1)
                 per_layer = strings[li] if isinstance(strings[li], (list, tuple)) else [strings[li]]
                 assert len(per_layer) == B
                 t0 = time.perf_counter()
-                for b in range(B):            # one stream per (image, layer)
-                    data = np.frombuffer(per_layer[b], dtype=np.uint8)
-                    N.check(self.lib.lvae_rans_decode(data.ctypes.data, data.size, idx_np[b].ctypes.data, idx_np.shape[1],
-                                                      cdf.ctypes.data, cdf.shape[1], clen.ctypes.data, coff.ctypes.data,
-                                                      cdf.shape[0], sym_np[b].ctypes.data), 'rans_decode')
+                per = idx_np.size // B
+                data = np.frombuffer(b''.join(per_layer), dtype=np.uint8)
+                in_begin = np.concatenate([[0], np.cumsum([len(s_) for s_ in per_layer])]).astype(np.int64)
+                begin = (np.arange(B + 1, dtype=np.int64) * per)
+                N.check(self.lib.lvae_rans_decode_streams(data.ctypes.data, in_begin.ctypes.data, idx_np.ctypes.data,
+                                                          begin.ctypes.data, B, cdf.ctypes.data, cdf.shape[1],
+                                                          clen.ctypes.data, coff.ctypes.data, cdf.shape[0],
+                                                          sym_np.ctypes.data, self.coder_threads), 'rans_decode_streams')
                 self.host_coder_s += time.perf_counter() - t0
-                P.sym[li].copy_(torch.from_numpy(sym_np).view_as(P.sym[li]), non_blocking=False)
+                P.sym[li].copy_(P.sym_host[li].view_as(P.sym[li]), non_blocking=True)
             self._launch(P, len(blocks))
             return P.x_hat.clone().clamp_(min=-1.0, max=1.0).mul_(0.5).add_(0.5)
 

@@ -331,6 +331,38 @@ class VariableRateLossyVAE(nn.Module):
         lmb = self.expand_to_tensor(lmb, n=nB)
         return self.engine.decompress(lmb, all_lv_strings, (nB, nH, nW))
 
+    # ---- batched variants (an extension: SURVEY 8(f)-2; the reference codes one image per call).  Every blob is a
+    #      standard single-image bit stream, byte-identical to what compress() gives for that image (the kernels are
+    #      batch-invariant), so blobs can be mixed freely between the two APIs.
+    @torch.no_grad()
+    def compress_batch(self, im, lmb=None):
+        """[B,3,H,W] in [0,1] -> list of B byte strings.  lmb: None (default_lmb), a float, or a [B] tensor."""
+        nB, _, imH, imW = im.shape
+        lmb = self.default_lmb if lmb is None else lmb
+        lmb_t = self.expand_to_tensor(lmb, n=nB)
+        results = self.forward_end2end(im, lmb=lmb_t, mode='compress')
+        assert len(results) == self.num_latents
+        lmbs = lmb_t.tolist()
+        head = struct.pack('3H', 1, imH // self.max_stride, imW // self.max_stride)
+        return [struct.pack('f', lmbs[b]) + head + coding.pack_byte_strings([res['strings'][b] for res in results])
+                for b in range(nB)]
+
+    @torch.no_grad()
+    def decompress_batch(self, blobs):
+        """list of B byte strings of same-size images -> [B,3,H,W] in [0,1]."""
+        lmbs, shapes, layers = [], set(), []
+        for blob in blobs:
+            lmbs.append(struct.unpack('f', blob[:4])[0])
+            nB, nH, nW = struct.unpack('3H', blob[4:10])
+            assert nB == 1
+            shapes.add((nH, nW))
+            layers.append(coding.unpack_byte_string(blob[10:]))
+        assert len(shapes) == 1, f'decompress_batch needs images of one size, got {sorted(shapes)}'
+        nH, nW = shapes.pop()
+        strings = [[layers[b][li] for b in range(len(blobs))] for li in range(self.num_latents)]
+        lmb = torch.tensor(lmbs, device=self._device())
+        return self.engine.decompress(lmb, strings, (len(blobs), nH, nW))
+
     @torch.no_grad()
     def compress_file(self, img_path, output_path, lmb=None):
         import torchvision.transforms.functional as tvf

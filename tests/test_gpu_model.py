@@ -281,3 +281,21 @@ def test_evaluation_helpers_on_a_synthetic_dataset(gpu_model, tmp_path):
     assert set(one) >= {'loss', 'bppix', 'psnr'}
     # sample_lmb() draws a random lambda per call when none is given (reference behaviour), so only sanity here
     assert all(np.isfinite(v) for v in list(one.values()) + list(two.values()))
+
+
+def test_batched_codec_equals_per_image_codec(gpu_model):
+    """compress_batch / decompress_batch: every blob is byte-identical to compress() of that image
+    alone (batch-invariant kernels, same coder), and the batched decoder returns what decompress() returns."""
+    im = make_input('synth', 3, 128, 192, 50).to(DEV)
+    lmb = torch.tensor([32.0, 500.0, 2048.0], device=DEV)
+    blobs = gpu_model.compress_batch(im, lmb=lmb)
+    assert len(blobs) == 3
+    singles = [gpu_model.compress(im[b:b + 1], lmb=float(lmb[b])) for b in range(3)]
+    assert blobs == singles
+    rec = gpu_model.decompress_batch(blobs)
+    assert tuple(rec.shape) == (3, 3, 128, 192)
+    for b in range(3):
+        one = gpu_model.decompress(singles[b])
+        assert torch.equal(rec[b:b + 1], one)
+    with pytest.raises(AssertionError):
+        gpu_model.decompress_batch([blobs[0], gpu_model.compress(make_input('synth', 1, 64, 64, 1).to(DEV))])
