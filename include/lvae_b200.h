@@ -92,8 +92,9 @@ typedef struct lvae_gemm_desc {
   const void* w_planes[3];    /* bf16 [N,K] planes of w */
   const void* a_planes[3];    /* optional pre-split A planes (written by lvae_dwconv_ln_adaln_planes or by a previous
                                * lvae_gemm through out_planes); when [0] is set, a0/a1 are not read.  ksize == 1: plain
-                               * [M,K] bf16.  ksize == 3, stride 1, pad 1, C0 % 64 == 0, LVAE_EPI_BIAS: NHWC [B,H,W,C0]
-                               * planes, convolved implicitly (9 shifted TMA box loads, no im2col workspace) */
+                               * [M,K] planes.  ksize == 3, stride 1, pad 1, C0 % 16 == 0, LVAE_EPI_BIAS or _BIAS_GELU:
+                               * NHWC [B,H,W,C0] planes, convolved implicitly (9 shifted TMA box loads per channel
+                               * block, no im2col workspace); the result may go to `out`, `out_planes` or both */
   void* out_planes[3];        /* optional bf16 [M,N] planes of the epilogue result (non-shuffle epilogues); `out`
                                * may then be NULL */
   void* workspace;            /* device scratch >= lvae_gemm_workspace_bytes(): im2col + split of a0/a1 when

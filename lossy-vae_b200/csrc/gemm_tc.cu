@@ -419,12 +419,18 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             const int mt = t / p.n_tiles;
             const int ctx = mt % p.tiles_w, cty = (mt / p.tiles_w) % p.tiles_h, cb = mt / (p.tiles_w * p.tiles_h);
             const float b = p.bias ? __ldg(p.bias + n) : 0.f;
+            const bool gelu = p.epi == LVAE_EPI_BIAS_GELU;
 #pragma unroll 4
             for (int r = 0; r < 32; ++r) {
               const int row = q * 32 + r;
               const int hh = cty * CONV_TH + row / CONV_TW, ww = ctx * CONV_TW + row % CONV_TW;
-              if (hh < p.cH && ww < p.cW)
-                p.out[(((int64_t)cb * p.cH + hh) * p.cW + ww) * p.N + n] = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
+              if (hh < p.cH && ww < p.cW) {
+                float x = __fadd_rn(__uint_as_float(stg[r * 33 + lane]), b);
+                if (gelu) x = gelu_erf(x);
+                const int64_t o = (((int64_t)cb * p.cH + hh) * p.cW + ww) * p.N + n;
+                if (p.out != nullptr) p.out[o] = x;
+                if (p.out_pl[0] != nullptr) store_planes(p, o, x);
+              }
             }
           } else if (n_ok && (p.epi == LVAE_EPI_SHUFFLE_NHWC || p.epi == LVAE_EPI_SHUFFLE_NCHW)) {
             // PixelShuffle(r) store: address = base(m) + offset(n), both separable (common.py:33-38)
@@ -523,7 +529,8 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box
   cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld box=%d", (int)r, (long long)rows, (long long)K, box_rows); return LVAE_E_BADARG; }
@@ -539,7 +546,8 @@ static int make_map_conv(CUtensorMap* map, const void* ptr, int B, int H, int W,
   cuuint32_t box[4] = {(cuuint32_t)bk, CONV_TW, CONV_TH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (conv planes) failed (%d)", (int)r); return LVAE_E_BADARG; }
   return 0;
@@ -600,9 +608,10 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
 
   // implicit 3x3 conv straight from NHWC planes (no im2col workspace): 9 shifted TMA box loads per channel block
   const bool conv = d->a_planes[0] != nullptr && d->ksize == 3 && d->stride == 1 && d->pad == 1 && d->a1 == nullptr &&
-                    d->C0 % 64 == 0 && d->epilogue == LVAE_EPI_BIAS && d->out != nullptr;
+                    d->C0 % 16 == 0 && (d->epilogue == LVAE_EPI_BIAS || d->epilogue == LVAE_EPI_BIAS_GELU) &&
+                    (d->out != nullptr || d->out_planes[0] != nullptr);
   if (d->a_planes[0] != nullptr && d->ksize != 1 && !conv) {
-    set_error("pre-split A planes support 1x1 (plain [M,K]) and 3x3 stride-1 pad-1 convolutions with C %% 64 == 0 only");
+    set_error("pre-split A planes support 1x1 (plain [M,K]) and 3x3 stride-1 pad-1 convolutions with C %% 16 == 0 only");
     return LVAE_E_UNSUPPORTED;
   }
   const bool concat_planes = d->a_planes[0] != nullptr && d->a1_planes[0] != nullptr;
@@ -629,14 +638,16 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   // epilogue specialisation
   const bool shuffle = d->epilogue == LVAE_EPI_SHUFFLE_NHWC || d->epilogue == LVAE_EPI_SHUFFLE_NCHW;
   int ek = EK_MISC;
-  if (d->epilogue == LVAE_EPI_BIAS_GELU && p.out_pl[0] != nullptr && p.out == nullptr && d->N % 2 == 0) ek = EK_GELU;
-  else if (!conv && !shuffle && d->N % 4 == 0) ek = EK_ROWS;
+  if (conv) ek = EK_MISC;                                      // tile rows are pixel patches: its own store loop
+  else if (d->epilogue == LVAE_EPI_BIAS_GELU && p.out_pl[0] != nullptr && p.out == nullptr && d->N % 2 == 0) ek = EK_GELU;
+  else if (!shuffle && d->N % 4 == 0) ek = EK_ROWS;
   const int fixed = 1024 + tc_epi_stage_bytes(ek) + 256;       // alignment slack + transpose buffers + barriers
   const int budget = 227 * 1024 - fixed;
   // k-block: a 128-byte swizzle row (64 bf16) whenever two such stages fit (measured: 2 x 64 beats 4 x 32 on every
   // qarv shape), else 64-byte rows (32 bf16)
   p.BK = (2 * npl * (TC_BM + p.BN) * 64 * 2 <= budget) ? 64 : 32;
   if (K <= 32) p.BK = 32;
+  if (conv) p.BK = d->C0 % 64 == 0 ? p.BK : (d->C0 % 32 == 0 ? 32 : 16);   // a k-block never straddles two filter taps
   { static const char* e = getenv("LVAE_TC_BK"); if (e) { const int v = atoi(e); if ((v == 64 || v == 32) && 2 * npl * (TC_BM + p.BN) * v * 2 <= budget) p.BK = v; } }   // tuning knob
   const int stage_bytes = npl * (TC_BM + p.BN) * p.BK * 2;
   int stages = budget / stage_bytes;

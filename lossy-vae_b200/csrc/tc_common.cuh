@@ -83,12 +83,12 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 // K-major, 1), SBO = 8 rows * row bytes >> 4, version 1 (sm_100), layout type 2 (SWIZZLE_128B) / 4 (SWIZZLE_64B).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int bk) {
   const uint64_t sbo = (uint64_t)(8 * bk * 2) >> 4;
-  const uint64_t layout = bk == 64 ? 2ull : 4ull;
+  const uint64_t layout = bk == 64 ? 2ull : (bk == 32 ? 4ull : 6ull);      // SWIZZLE_128B | 64B | 32B (16 elements per row)
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
 
-// [rows, K] 16-bit row-major, box = [box_rows x bk] (bk = 64: SWIZZLE_128B, 32: SWIZZLE_64B), zero fill outside
+// [rows, K] 16-bit row-major, box = [box_rows x bk] (bk = 64: SWIZZLE_128B, 32: SWIZZLE_64B, 16: SWIZZLE_32B), zero fill outside
 int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box_rows, int bk);
 
 }  // namespace lvae

@@ -440,6 +440,17 @@ class QarvEngine:
         B, Hs, Ws, C0 = geom
         M = B * Hs * Ws
         hid, ks = wv['c1']['N'], wv['c2']['ks']
+        if self.npl and ks == 3 and hid % 16 == 0 and self.plane_chain:
+            # tensor-core modes: the hidden maps travel as 16-bit planes from epilogue to epilogue and the two 3x3 convs
+            # read them implicitly (shifted TMA boxes) -- no fp32 round trip, no 9x im2col workspace
+            h1 = [P.named(f'vd_h1_pl{i}', M * hid, dtype=torch.bfloat16)[:M * hid] for i in range(self.npl)]
+            h2 = [P.named(f'vd_h2_pl{i}', M * hid, dtype=torch.bfloat16)[:M * hid] for i in range(self.npl)]
+            self._gemm(P, name + '.c1', a0, (B, Hs, Ws, C0, 1, 1, 0), wv['c1'], None, epi=N.EPI_BIAS_GELU, a1=a1, C1=C1, a_act=1,
+                       out_planes=h1)
+            self._gemm(P, name + '.c2', None, (B, Hs, Ws, hid, 3, 1, 1), wv['c2'], None, epi=N.EPI_BIAS_GELU, a_planes=h1, out_planes=h2)
+            self._gemm(P, name + '.c3', None, (B, Hs, Ws, hid, 3, 1, 1), wv['c3'], None, epi=N.EPI_BIAS_GELU, a_planes=h2, out_planes=h1)
+            self._gemm(P, name + '.c4', None, (B, Hs, Ws, hid, 1, 1, 0), wv['c4'], out, a_planes=h1)
+            return
         h1, h2 = P.named('vd_h1', M * hid)[:M * hid], P.named('vd_h2', M * hid)[:M * hid]
         self._gemm(P, name + '.c1', a0, (B, Hs, Ws, C0, 1, 1, 0), wv['c1'], h1, epi=N.EPI_BIAS_GELU, a1=a1, C1=C1, a_act=1)
         self._gemm(P, name + '.c2', h1, (B, Hs, Ws, hid, ks, 1, (ks - 1) // 2), wv['c2'], h2, epi=N.EPI_BIAS_GELU)

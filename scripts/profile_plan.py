@@ -10,7 +10,12 @@ import lvae, lvae_oracle as O
 from oracle_inputs import make_input
 prec = sys.argv[1] if len(sys.argv) > 1 else 'bf16x6'
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-m = lvae.get_model('qarv_base'); m.load_state_dict(O.sensitised_state_dict(O.qarv_param_shapes(), seed=0), strict=False)
+name = sys.argv[3] if len(sys.argv) > 3 else 'qarv_base'
+if name == 'qres34m':
+    import qres_oracle as Q
+    m = lvae.get_model('qres34m', lmb=2048); m.load_state_dict(O.sensitised_state_dict(Q.qres_param_shapes(), seed=0), strict=False)
+else:
+    m = lvae.get_model('qarv_base'); m.load_state_dict(O.sensitised_state_dict(O.qarv_param_shapes(), seed=0), strict=False)
 m.precision = prec
 m = m.cuda().eval()
 eng = m.engine
