@@ -103,7 +103,8 @@ typedef struct lvae_gemm_desc {
   int32_t a_act;              /* 0: none; 1: GELU (erf form) applied to every element of a0 / a1 as it is read --
                                * VDBlock's c_i(gelu(x)) (lvae/models/qresvae/model.py:143-149).  Requires a0
                                * (not a_planes). */
-  int32_t reserved;
+  int32_t out_planes_act;     /* 1: out_planes hold gelu(result) instead of the result (the consumer is a VDBlock, whose first
+                               * conv reads gelu(x), qresvae/model.py:144); `out` still receives the plain result */
   const void* a1_planes[3];   /* optional pre-split planes [M, C1] of segment 1 (the K-concat of post_merge): with
                                * a_planes (then [M, C0]) the tensor-core path reads both segments without an im2col /
                                * split pass.  ksize == 1, C0 % 64 == 0. */
@@ -118,6 +119,8 @@ int lvae_split_bf16(const float* x, void* p0, void* p1, void* p2, int64_t n, voi
  * scale = 1.  fp16 conversion saturates at +-65504.  n % 2 == 0. */
 int lvae_split_planes(const float* x, void* p0, void* p1, void* p2, int64_t n, int plane_format, float scale,
                       void* stream);
+/* planes of gelu(x) (erf form): the operand of a VDBlock's first conv, computed once per encoder feature */
+int lvae_gelu_split_planes(const float* x, void* p0, void* p1, void* p2, int64_t n, int plane_format, void* stream);
 
 /* Fused ConvNeXt MLP (common.py:154-160) for narrow layers: out = res + gamma * (W2 gelu(W1 a + b1) + b2) in one
  * kernel; the hidden activation stays on chip.  a_p*: the two 16-bit planes [M, C] of the MLP input (written by
@@ -127,6 +130,12 @@ int lvae_split_planes(const float* x, void* p0, void* p1, void* p2, int64_t n, i
 int lvae_convnext_mlp(const void* a_p0, const void* a_p1, const void* w1_p0, const void* w1_p1, const float* b1,
                       const void* w2_p0, const void* w2_p1, const float* b2, const float* gamma,
                       const float* res, float* out, int64_t M, int C, int hidden, int precision, void* stream);
+/* the same, additionally writing the two 16-bit planes [M, C] of the result (out_planes_gelu = 0) or of gelu(result)
+ * (out_planes_gelu = 1) for a tensor-core consumer */
+int lvae_convnext_mlp_planes(const void* a_p0, const void* a_p1, const void* w1_p0, const void* w1_p1, const float* b1,
+                             const void* w2_p0, const void* w2_p1, const float* b2, const float* gamma,
+                             const float* res, float* out, void* out_p0, void* out_p1, int out_planes_gelu,
+                             int64_t M, int C, int hidden, int precision, void* stream);
 
 /* ---- depthwise conv + LayerNorm + AdaLN (common.py:145-152) ------------------------------------
  * y[m, c] = LN_c( dwconv_kxk(x)[m, c] + dw_bias[c] ) * (1 + scale[b, c]) + shift[b, c]

@@ -25,6 +25,8 @@ extern "C" int lvae_gemm(const lvae_gemm_desc* d, void* stream) {
   LVAE_CHECK_ARG(d->C0 > 0 && d->C0 % 4 == 0);
   LVAE_CHECK_ARG(d->a1 == nullptr || d->a_planes[0] != nullptr || (d->C1 > 0 && d->C1 % 4 == 0 && d->ksize == 1 && d->stride == 1 && d->pad == 0));
   LVAE_CHECK_ARG(d->ksize >= 1 && d->stride >= 1 && d->pad >= 0);
+  LVAE_CHECK_ARG(d->out_planes_act == 0 || (d->out_planes_act == 1 && d->out_planes[0] != nullptr && d->precision != LVAE_PREC_FP32 &&
+                                            d->epilogue != LVAE_EPI_BIAS_GELU && d->N % 4 == 0 && d->ksize == 1));
   LVAE_CHECK_ARG(d->a_act == 0 || (d->a_act == 1 && d->a0 != nullptr && d->a_planes[0] == nullptr));
   LVAE_CHECK_ARG(d->H + 2 * d->pad >= d->ksize && d->W + 2 * d->pad >= d->ksize);
   LVAE_CHECK_ARG(d->epilogue >= LVAE_EPI_BIAS && d->epilogue <= LVAE_EPI_SHUFFLE_NCHW);

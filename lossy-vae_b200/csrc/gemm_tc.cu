@@ -58,6 +58,7 @@ struct TcParams {
   const float* bias; const float* gamma; const float* res;
   float* out; __nv_bfloat16* out_pl[3];
   int epi, r, Ho, Wo;
+  int pl_act;            // out planes hold gelu(result) (EK_ROWS)
   int k_split;           // k >= k_split comes from the a1 maps (K-concat of two plane sets); = K when there is one segment
   int prefetch;          // L2-prefetch the next tile's A k-blocks (tuning knob LVAE_TC_PREFETCH=1; measured: no gain --
                          // the large-K GEMMs sit on the ~6.3 kB/clk L2->SM cap (85 B/clk/SM wanted at BN = 128), not on latency)
@@ -395,6 +396,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               const int64_t o = o0 + (int64_t)(4 * i) * p.N;
               if (p.out != nullptr) *reinterpret_cast<float4*>(p.out + o) = x;
               if (p.out_pl[0] != nullptr) {
+                if (p.pl_act) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
                 float2 lo = make_float2(x.x, x.y), hi = make_float2(x.z, x.w);
 #pragma unroll
                 for (int pl = 0; pl < NPL; ++pl) {
@@ -622,6 +624,7 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   TcParams p;
   p.M = M; p.N = d->N; p.K = K;
   p.k_split = concat_planes ? d->C0 : K;
+  p.pl_act = d->out_planes_act;
   p.BN = pick_bn(d->N, npl);
   p.n_tiles = (d->N + p.BN - 1) / p.BN;
   p.conv = conv ? 1 : 0; p.cH = d->H; p.cW = d->W; p.cC = d->C0;

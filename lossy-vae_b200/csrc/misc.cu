@@ -194,10 +194,11 @@ __global__ void pad_channels_kernel(const float* __restrict__ src, float* __rest
 
 // two elements per thread: planes of (x * scale) in either 16-bit format (split_next, common.cuh)
 __global__ void split_planes_kernel(const float* __restrict__ x, uint32_t* __restrict__ p0, uint32_t* __restrict__ p1,
-                                    uint32_t* __restrict__ p2, int64_t n2, int f16, float scale) {
+                                    uint32_t* __restrict__ p2, int64_t n2, int f16, float scale, int act) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n2) return;
   float2 v = __ldg(reinterpret_cast<const float2*>(x) + i);
+  if (act) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); }
   v.x = __fmul_rn(v.x, scale); v.y = __fmul_rn(v.y, scale);
   p0[i] = split_next(v, f16 != 0);
   if (p1) {
@@ -292,7 +293,16 @@ extern "C" int lvae_split_planes(const float* x, void* p0, void* p1, void* p2, i
   LVAE_CHECK_ARG(plane_format == LVAE_PLANES_BF16 || plane_format == LVAE_PLANES_F16);
   LVAE_CHECK_ARG(scale > 0.f);
   split_planes_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      x, (uint32_t*)p0, (uint32_t*)p1, (uint32_t*)p2, n / 2, plane_format == LVAE_PLANES_F16, scale);
+      x, (uint32_t*)p0, (uint32_t*)p1, (uint32_t*)p2, n / 2, plane_format == LVAE_PLANES_F16, scale, 0);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lvae_gelu_split_planes(const float* x, void* p0, void* p1, void* p2, int64_t n, int plane_format, void* stream) {
+  LVAE_CHECK_ARG(x && p0 && n > 0 && n % 2 == 0 && (p2 == nullptr || p1 != nullptr));
+  LVAE_CHECK_ARG(plane_format == LVAE_PLANES_BF16 || plane_format == LVAE_PLANES_F16);
+  split_planes_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, (uint32_t*)p0, (uint32_t*)p1, (uint32_t*)p2, n / 2, plane_format == LVAE_PLANES_F16, 1.0f, 1);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

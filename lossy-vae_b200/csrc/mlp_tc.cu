@@ -36,6 +36,7 @@ constexpr int ML_THREADS = 128 + 32 * ML_EPI_WARPS;     // A/W1 producer, fc1 is
 struct MlpParams {
   int M, C, HID, num_tiles;
   const float* b1; const float* b2; const float* gamma; const float* res; float* out;
+  uint16_t* out_pl[2]; int pl_act;       // optional planes of the result (pl_act: of gelu(result))
   float acc_scale; int f16;
 };
 struct MlpMaps { CUtensorMap a[2]; CUtensorMap w1[2]; CUtensorMap w2[2]; };
@@ -344,6 +345,16 @@ mlp_tc_kernel(const __grid_constant__ MlpMaps maps, const MlpParams p) {
           x.x = __fadd_rn(__fmul_rn(__fadd_rn(a.x, b4.x), g4.x), rr[i].x); x.y = __fadd_rn(__fmul_rn(__fadd_rn(a.y, b4.y), g4.y), rr[i].y);
           x.z = __fadd_rn(__fmul_rn(__fadd_rn(a.z, b4.z), g4.z), rr[i].z); x.w = __fadd_rn(__fmul_rn(__fadd_rn(a.w, b4.w), g4.w), rr[i].w);
           *reinterpret_cast<float4*>(p.out + o0 + (int64_t)(8 * i) * C) = x;
+          if (p.out_pl[0] != nullptr) {
+            if (p.pl_act) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+            float2 lo = make_float2(x.x, x.y), hi = make_float2(x.z, x.w);
+            uint2 w;
+            w.x = split_next(lo, f16); w.y = split_next(hi, f16);
+            *reinterpret_cast<uint2*>(p.out_pl[0] + o0 + (int64_t)(8 * i) * C) = w;
+            w.x = f16 ? pack2<true>(lo.x, lo.y) : pack2<false>(lo.x, lo.y);
+            w.y = f16 ? pack2<true>(hi.x, hi.y) : pack2<false>(hi.x, hi.y);
+            *reinterpret_cast<uint2*>(p.out_pl[1] + o0 + (int64_t)(8 * i) * C) = w;
+          }
         }
         __syncwarp();
       }
@@ -367,13 +378,23 @@ using namespace lvae;
 extern "C" int lvae_convnext_mlp(const void* a_p0, const void* a_p1, const void* w1_p0, const void* w1_p1, const float* b1,
                                  const void* w2_p0, const void* w2_p1, const float* b2, const float* gamma,
                                  const float* res, float* out, int64_t M, int C, int hidden, int precision, void* stream) {
+  return lvae_convnext_mlp_planes(a_p0, a_p1, w1_p0, w1_p1, b1, w2_p0, w2_p1, b2, gamma, res, out, nullptr, nullptr, 0,
+                                  M, C, hidden, precision, stream);
+}
+
+extern "C" int lvae_convnext_mlp_planes(const void* a_p0, const void* a_p1, const void* w1_p0, const void* w1_p1, const float* b1,
+                                        const void* w2_p0, const void* w2_p1, const float* b2, const float* gamma,
+                                        const float* res, float* out, void* out_p0, void* out_p1, int out_planes_gelu,
+                                        int64_t M, int C, int hidden, int precision, void* stream) {
   LVAE_CHECK_ARG(a_p0 && a_p1 && w1_p0 && w1_p1 && w2_p0 && w2_p1 && b1 && b2 && gamma && res && out);
+  LVAE_CHECK_ARG((out_p0 == nullptr) == (out_p1 == nullptr));
   LVAE_CHECK_ARG(M > 0 && M < (1ll << 31));
   LVAE_CHECK_ARG(C % 64 == 0 && C >= 64 && C <= 192 && hidden % ML_HB == 0 && hidden >= ML_HB);
   LVAE_CHECK_ARG(precision == LVAE_PREC_F16X3 || precision == LVAE_PREC_BF16X3);
   MlpParams p;
   p.M = (int)M; p.C = C; p.HID = hidden; p.num_tiles = (int)((M + ML_BM - 1) / ML_BM);
   p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.res = res; p.out = out;
+  p.out_pl[0] = (uint16_t*)out_p0; p.out_pl[1] = (uint16_t*)out_p1; p.pl_act = out_planes_gelu;
   p.f16 = precision == LVAE_PREC_F16X3 ? 1 : 0;
   p.acc_scale = p.f16 ? 1.0f / LVAE_F16_WEIGHT_SCALE : 1.0f;
   MlpMaps maps;

@@ -34,7 +34,7 @@ class GemmDesc(C.Structure):
         ('shuffle_r', C.c_int32), ('precision', C.c_int32),
         ('w_planes', _fp * 3), ('a_planes', _fp * 3), ('out_planes', _fp * 3),
         ('workspace', _fp), ('workspace_bytes', C.c_int64),
-        ('a_act', C.c_int32), ('reserved', C.c_int32),
+        ('a_act', C.c_int32), ('out_planes_act', C.c_int32),
         ('a1_planes', _fp * 3),
     ]
 
@@ -45,6 +45,9 @@ _PROTOS = {
     'lvae_gemm': (C.c_int, [C.POINTER(GemmDesc), _fp]),
     'lvae_gemm_workspace_bytes': (C.c_int64, [C.POINTER(GemmDesc)]),
     'lvae_convnext_mlp': (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_convnext_mlp_planes': (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int,
+                                           C.c_int64, C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_gelu_split_planes': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int, _fp]),
     'lvae_split_bf16': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp]),
     'lvae_dwconv_ln_adaln': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),

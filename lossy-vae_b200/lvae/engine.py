@@ -47,6 +47,7 @@ class Plan:
         self.eng, self.B, self.H, self.W, self.mode, self.want_elem = engine, B, H, W, mode, want_elem
         self.dev = engine.device
         self.segments = [[]]      # op lists split at host interaction points
+        self.enc_gelu = {}        # qres: planes of gelu(encoder feature) per resolution
         self.bufs = {}
         self.retired = []
         self.graphs = None
@@ -58,6 +59,9 @@ class Plan:
 
     def i32(self, *shape):
         return torch.empty(shape, dtype=torch.int32, device=self.dev)
+
+    def i16(self, *shape):
+        return torch.empty(shape, dtype=torch.bfloat16, device=self.dev)      # raw 16-bit plane storage
 
     def named(self, name, numel, dtype=torch.float32):
         t = self.bufs.get(name)
@@ -234,7 +238,7 @@ class QarvEngine:
 
     # ------------------------------------------------------------------ plan construction helpers
     def _gemm(self, P, name, a0, geom, went, out, epi=N.EPI_BIAS, a1=None, C1=0, gamma=None, res=None, r=0,
-              a_planes=None, out_planes=None, a_act=0, a1_planes=None):
+              a_planes=None, out_planes=None, a_act=0, a1_planes=None, out_planes_act=0):
         """geom = (B, H, W, C0, ksize, stride, pad) of the NHWC input a0.  In a tensor-core mode the A operand is
         either `a_planes` (bf16 planes written by the producing kernel) or a0/a1, which the library im2col-splits
         into the plan's workspace first."""
@@ -245,7 +249,7 @@ class QarvEngine:
         d.ksize, d.stride, d.pad = ks, st, pad
         d.w, d.bias, d.N = _ptr(went['w']), _ptr(went['bias']), went['N']
         d.epilogue, d.gamma, d.res, d.out = epi, _ptr(gamma), _ptr(res), _ptr(out)
-        d.shuffle_r, d.precision, d.a_act = r, self.prec, a_act
+        d.shuffle_r, d.precision, d.a_act, d.out_planes_act = r, self.prec, a_act, out_planes_act
         assert went['K'] == ks * ks * C0 + C1, (name, went['K'], ks, C0, C1)
         Mo = B * ((H + 2 * pad - ks) // st + 1) * ((W + 2 * pad - ks) // st + 1)
         ws = None
@@ -266,7 +270,7 @@ class QarvEngine:
         P.op(name, self.lib.lvae_gemm, C.byref(d), keep=(d, a0, a1, went, out, gamma, res, a_planes, out_planes, ws, a1_planes),
              meta=meta)
 
-    def _block(self, P, blk, x, B, Hs, Ws, out=None, out_planes=None, planes_only=False):
+    def _block(self, P, blk, x, B, Hs, Ws, out=None, out_planes=None, planes_only=False, planes_act=0):
         """x: [M, C] fp32 NHWC; returns the output buffer (x itself when out is None: in place).  out_planes: bf16
         planes of the result, written by the fc2 epilogue for a tensor-core consumer (the 3x3 posterior conv)."""
         wb = self.w[id(blk)]
@@ -285,19 +289,20 @@ class QarvEngine:
             P.op('dwln', self.lib.lvae_dwconv_ln_adaln_planes, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']),
                  _ptr(P.ada), self.ada_total, ada_off, ln_w, ln_b, ap[0], ap[1], ap[2], self.pfmt, B, Hs, Ws, C_, k,
                  keep=(x, A), meta=dw_meta)
-            if self.fuse_mlp and self.npl == 2 and C_ % 64 == 0 and C_ <= 192 and hid % 32 == 0 and out_planes is None:
+            if self._mlp_fused(blk) and not planes_only:
                 # narrow layers (H/4 stages): fc1 -> GELU -> fc2 -> layer scale + residual in one kernel, the hidden
                 # tensor never leaves the SM (bit-identical to the two GEMMs below)
                 w1, w2 = wb['fc1'], wb['fc2']
-                P.op('mlp', self.lib.lvae_convnext_mlp, ap[0], ap[1], _ptr(w1['planes'][0]), _ptr(w1['planes'][1]),
+                op0, op1 = (_ptr(out_planes[0]), _ptr(out_planes[1])) if out_planes is not None else (0, 0)
+                P.op('mlp', self.lib.lvae_convnext_mlp_planes, ap[0], ap[1], _ptr(w1['planes'][0]), _ptr(w1['planes'][1]),
                      _ptr(w1['bias']), _ptr(w2['planes'][0]), _ptr(w2['planes'][1]), _ptr(w2['bias']), _ptr(wb['gamma']),
-                     _ptr(x), _ptr(out), M, C_, hid, self.prec, keep=(x, out, A, wb),
+                     _ptr(x), _ptr(out), op0, op1, planes_act, M, C_, hid, self.prec, keep=(x, out, A, wb, out_planes),
                      meta=dict(kind='gemm', flops=4 * M * C_ * hid, M=M, N=C_, K=hid, bytes=M * C_ * (4 + 4 + 4)))
                 return out
             self._gemm(P, 'fc1', None, (1, 1, M, C_, 1, 1, 0), wb['fc1'], None, epi=N.EPI_BIAS_GELU, a_planes=A, out_planes=Hd)
             # planes_only: the consumer reads the 16-bit planes, the fp32 result is never written
             self._gemm(P, 'fc2', None, (1, 1, M, hid, 1, 1, 0), wb['fc2'], None if planes_only else out, epi=N.EPI_SCALE_RES,
-                       gamma=wb['gamma'], res=x, a_planes=Hd, out_planes=out_planes)
+                       gamma=wb['gamma'], res=x, a_planes=Hd, out_planes=out_planes, out_planes_act=planes_act)
             return out
         A = P.named('scratch_a', M * C_)
         Hd = P.named('scratch_h', M * hid)
@@ -390,8 +395,12 @@ class QarvEngine:
                 zd = mod.zdim
                 prior = P.f32(M, 2 * zd)
                 if self.family == 'qres':
-                    x = self._block(P, mod.resnet_front, x, B, Hs, Ws)
-                    self._vdblock(P, 'prior', wl['prior'], x, (B, Hs, Ws, Cc), prior)
+                    P.cur_xg = None
+                    if self.npl == 2 and self.plane_chain and Cc % 64 == 0:
+                        # both VDBlock heads start with gelu(feature): resnet_front's epilogue writes those planes once
+                        P.cur_xg = [P.named(f'xg_pl{i}', M * Cc, dtype=torch.bfloat16)[:M * Cc] for i in range(self.npl)]
+                    x = self._block(P, mod.resnet_front, x, B, Hs, Ws, out_planes=P.cur_xg, planes_act=1 if P.cur_xg is not None else 0)
+                    self._vdblock(P, 'prior', wl['prior'], x, (B, Hs, Ws, Cc), prior, a_planes=P.cur_xg)
                 elif self.npl and self.plane_chain and not self._mlp_fused(mod.resnet_front):
                     # resnet_front's fc2 epilogue also writes its result as planes: the prior head reads them directly
                     xp = [P.named(f'x_pl{i}', M * Cc, dtype=torch.bfloat16)[:M * Cc] for i in range(self.npl)]
@@ -434,7 +443,7 @@ class QarvEngine:
                 raise TypeError(f'unsupported decoder module {type(mod)}')
         return x
 
-    def _vdblock(self, P, name, wv, a0, geom, out, a1=None, C1=0):
+    def _vdblock(self, P, name, wv, a0, geom, out, a1=None, C1=0, a_planes=None, a1_planes=None):
         """VDBlock without residual (qresvae/model.py:143-149): c4(gelu(c3(gelu(c2(gelu(c1(gelu(x)))))))).  The first
         GELU is applied to the operand as it is read (a_act), the others ride in the producing GEMM's epilogue."""
         B, Hs, Ws, C0 = geom
@@ -445,8 +454,12 @@ class QarvEngine:
             # read them implicitly (shifted TMA boxes) -- no fp32 round trip, no 9x im2col workspace
             h1 = [P.named(f'vd_h1_pl{i}', M * hid, dtype=torch.bfloat16)[:M * hid] for i in range(self.npl)]
             h2 = [P.named(f'vd_h2_pl{i}', M * hid, dtype=torch.bfloat16)[:M * hid] for i in range(self.npl)]
-            self._gemm(P, name + '.c1', a0, (B, Hs, Ws, C0, 1, 1, 0), wv['c1'], None, epi=N.EPI_BIAS_GELU, a1=a1, C1=C1, a_act=1,
-                       out_planes=h1)
+            if a_planes is not None:      # gelu(input) already travels as planes (written by the producers)
+                self._gemm(P, name + '.c1', None, (B, Hs, Ws, C0, 1, 1, 0), wv['c1'], None, epi=N.EPI_BIAS_GELU, C1=C1,
+                           a_planes=a_planes, a1_planes=a1_planes, out_planes=h1)
+            else:
+                self._gemm(P, name + '.c1', a0, (B, Hs, Ws, C0, 1, 1, 0), wv['c1'], None, epi=N.EPI_BIAS_GELU, a1=a1, C1=C1, a_act=1,
+                           out_planes=h1)
             self._gemm(P, name + '.c2', None, (B, Hs, Ws, hid, 3, 1, 1), wv['c2'], None, epi=N.EPI_BIAS_GELU, a_planes=h1, out_planes=h2)
             self._gemm(P, name + '.c3', None, (B, Hs, Ws, hid, 3, 1, 1), wv['c3'], None, epi=N.EPI_BIAS_GELU, a_planes=h2, out_planes=h1)
             self._gemm(P, name + '.c4', None, (B, Hs, Ws, hid, 1, 1, 0), wv['c4'], out, a_planes=h1)
@@ -464,7 +477,18 @@ class QarvEngine:
         wl = self.w[id(blk)]
         if self.family == 'qres':        # posterior(cat([feature, enc_feature])) (qresvae/model.py:270)
             qm = P.f32(M, blk.zdim)
-            self._vdblock(P, 'posterior', wl['posterior'], x, geom, qm, a1=enc_feat, C1=blk.enc_width)
+            eg = None
+            if getattr(P, 'cur_xg', None) is not None and blk.enc_width % 8 == 0:
+                # gelu(encoder feature) as planes, once per resolution (the latent blocks of a stage share the feature)
+                eg = P.enc_gelu.get(Hs)
+                if eg is None:
+                    eg = [P.i16(M * blk.enc_width) for _ in range(self.npl)]
+                    ptrs = [_ptr(t) for t in eg] + [0] * (3 - self.npl)
+                    P.op('enc_gelu', self.lib.lvae_gelu_split_planes, _ptr(enc_feat), ptrs[0], ptrs[1], ptrs[2],
+                         M * blk.enc_width, self.pfmt, keep=(enc_feat, eg))
+                    P.enc_gelu[Hs] = eg
+            self._vdblock(P, 'posterior', wl['posterior'], x, geom, qm, a1=enc_feat, C1=blk.enc_width,
+                          a_planes=P.cur_xg if eg is not None else None, a1_planes=eg)
             return qm
         We = blk.enc_width
         mg = P.named('post_m', M * Cc)[:M * Cc]
