@@ -112,7 +112,7 @@ class VariableRateLossyVAE(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = None if k == '_engine' else copy.deepcopy(v, memo)
+            new.__dict__[k] = None if k in ('_engine', '_train_path') else copy.deepcopy(v, memo)
         return new
 
     def _device(self):
@@ -181,6 +181,8 @@ class VariableRateLossyVAE(nn.Module):
             lmb = self.sample_lmb(n=nB)
         assert isinstance(lmb, torch.Tensor) and lmb.shape == (nB,)
         self._check_image(im)
+        if self.training and torch.is_grad_enabled():
+            return self._forward_train(im, lmb, return_rec)
         emode = 'train' if self.training else 'eval'
         res = self.engine.run(im, lmb.to(self._device(), torch.float32), mode=emode, want_elem=False,
                               want_im_hat=return_rec)
@@ -190,6 +192,28 @@ class VariableRateLossyVAE(nn.Module):
         stats['bppix'] = float(host[1]) * self.log2_e * imC
         stats[self.distortion_name] = float(host[2])
         stats['psnr'] = -10 * math.log10(float(host[3]))
+        if return_rec:
+            stats['im_hat'] = res['im_hat']
+        return stats
+
+    @property
+    def train_path(self):
+        if self.__dict__.get('_train_path') is None:
+            from ...training import TrainPath
+            self.__dict__['_train_path'] = TrainPath(self)
+        return self.__dict__['_train_path']
+
+    def _forward_train(self, im, lmb, return_rec=False, noise=None):
+        """Training step forward with the autograd graph attached to stats['loss'] (lvae.training): what
+        `loss.backward()` of lvae/trainer.py:262-270 differentiates."""
+        im = im.to(self._device())
+        assert 0 <= float(im.min()) <= float(im.max()) <= 1, 'image values must lie in [0, 1]'
+        res = self.train_path.objective(im, lmb.to(self._device(), torch.float32), noise=noise)
+        stats = OrderedDict()
+        stats['loss'] = res['loss']
+        stats['bppix'] = res['kl_mean'] * self.log2_e * im.shape[1]
+        stats[self.distortion_name] = res['mse']
+        stats['psnr'] = -10 * math.log10(res['im_mse'])
         if return_rec:
             stats['im_hat'] = res['im_hat']
         return stats

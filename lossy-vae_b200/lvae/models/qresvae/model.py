@@ -164,7 +164,7 @@ class HierarchicalVAE(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = None if k == '_engine' else copy.deepcopy(v, memo)
+            new.__dict__[k] = None if k in ('_engine', '_train_path') else copy.deepcopy(v, memo)
         return new
 
     def _device(self):
@@ -192,6 +192,8 @@ class HierarchicalVAE(nn.Module):
         self._check_image(im)
         nB, imC, imH, imW = im.shape
         mode = 'train' if self.training else 'eval'
+        if self.training and torch.is_grad_enabled():
+            return self._forward_train(im, return_rec, noise)
         res = self.engine.run(im, self._lmb(nB), mode=mode, want_elem=False, want_im_hat=return_rec, noise=noise)
         host = res['stats_host']
         ndims = imC * imH * imW
@@ -205,6 +207,34 @@ class HierarchicalVAE(nn.Module):
         stats[self.out_net.loss_name] = float(host[2]) * self.out_net.mse_lmb
         stats['bppix'] = float(host[1]) * self.log2_e * imC
         stats['psnr'] = -10 * math.log10(float(host[3]))
+        if return_rec:
+            stats['im_hat'] = res['im_hat']
+        return stats
+
+    @property
+    def train_path(self):
+        if self.__dict__.get('_train_path') is None:
+            from ...training import TrainPath
+            self.__dict__['_train_path'] = TrainPath(self)
+        return self.__dict__['_train_path']
+
+    def _forward_train(self, im, return_rec=False, noise=None):
+        """Training step forward with the autograd graph attached to stats['loss'] (lvae.training): what
+        `loss.backward()` of lvae/trainer.py:262-270 differentiates (reference model.py:517-569)."""
+        assert 0 <= float(im.min()) <= float(im.max()) <= 1, 'image values must lie in [0, 1]'
+        nB, imC, imH, imW = im.shape
+        res = self.train_path.objective(im, self._lmb(nB), noise=noise)
+        ndims = imC * imH * imW
+        kls = torch.stack([k.detach().reshape(nB, -1).sum(1).mean(0) / ndims for k in res['kl']])
+        bpdim = kls * self.log2_e
+        self._stats_log['train_bpdim'] = bpdim.tolist()
+        self._stats_log['train_bppix'] = (bpdim * imC).tolist()
+        stats = OrderedDict()
+        stats['loss'] = res['loss']
+        stats['kl'] = res['kl_mean']
+        stats[self.out_net.loss_name] = res['lmb_mse']
+        stats['bppix'] = res['kl_mean'] * self.log2_e * imC
+        stats['psnr'] = -10 * math.log10(res['im_mse'])
         if return_rec:
             stats['im_hat'] = res['im_hat']
         return stats

@@ -1,0 +1,432 @@
+"""Differentiable execution of the rate-distortion path (training step; BASELINE configs 2 and 3).
+
+`model.forward()` routes here when the model is in training mode and autograd is recording, so that
+`loss = model(batch)['loss']; loss.backward(); optimizer.step()` of train-var-rate.py / train-fix-rate.py works
+unchanged (reference lvae/trainer.py:255-300, qarv/model.py:317-363, qresvae/model.py:517-569).
+
+Forward: the SAME liblvae_b200 kernels as the inference plans (dwconv+LN+AdaLN, tcgen05 GEMMs / fused MLP, fused latent
+kernel), launched op by op through `torch.autograd.Function`s that keep only each op's inputs (activation checkpointing
+at op granularity: ConvNeXt block, convolution, VDBlock, latent layer).
+
+Backward -- STATE OF THIS ROUND, per op:
+  * latent layer: native (`lvae_latent_train_bwd`);
+  * ConvNeXt block: the pre-activation of fc1 is recomputed with the native kernels (dwconv+LN kernel, tcgen05 GEMM),
+    both data gradients (through fc2 and fc1) are native tcgen05 GEMMs on transposed packed weights; the weight
+    gradients are cuBLAS fp32 matmuls (`torch.mm`), GELU' is ATen's elementwise `gelu_backward`, and the
+    dwconv + LayerNorm + AdaLN part is differentiated by ATen on a recomputed sub-graph;
+  * convolutions (patch down / up, 1x1 and 3x3 heads) and qres VDBlocks: ATen autograd on a recomputed sub-graph.
+Everything ATen here is a LIBRARY call (cuBLAS / cuDNN), not this repo's product; it is what the native backward
+kernels of the next round replace, one op at a time, each against the gradient tests in tests/test_gpu_train.py.
+There is no CPU path: every Function launches CUDA kernels of liblvae_b200.so.
+"""
+import math
+import os
+
+import torch
+import torch.nn.functional as F
+
+from . import _native as N
+from .engine import Plan, _ptr
+from .models import common
+
+
+class _EagerPlan(Plan):
+    """A Plan whose ops run as they are emitted (on the current stream): lets the op Functions reuse the engine's
+    launch helpers (`_block`, `_gemm`, `_vdblock`) -- the inference code path -- one op at a time."""
+
+    def __init__(self, engine, B):
+        super().__init__(engine, B, 0, 0, 'train', True)
+        self.cur_xg = None
+
+    def op(self, name, fn, *args, keep=None, meta=None):
+        rc = fn(*args, self.eng._stream())
+        if rc != 0:
+            N.check(rc, name)
+        N.launch_count += 1
+
+
+def _grad_of(fn, inputs, gout):
+    """ATen autograd over a recomputed sub-graph: d fn(*inputs) . gout for every tensor input that needs it."""
+    with torch.enable_grad():
+        ins = [None if t is None else t.detach().requires_grad_(True) for t in inputs]
+        out = fn(*ins)
+        live = [t for t in ins if t is not None]
+        grads = torch.autograd.grad(out, live, gout, allow_unused=True)
+    it = iter(grads)
+    return [None if t is None else next(it) for t in ins]
+
+
+# ------------------------------------------------------------------------------------------ ATen restatements (backward only)
+def _dwln_aten(x, ada, dw_w, dw_b, ln_w, ln_b, k):
+    """x NHWC [B,H,W,C]; ada [B,2C] = (shift | scale) or None (affine LN).  common.py:145-152 / timm ConvNeXtBlock."""
+    C_ = x.shape[-1]
+    y = F.conv2d(x.permute(0, 3, 1, 2), dw_w, dw_b, padding=(k - 1) // 2, groups=C_).permute(0, 2, 3, 1)
+    if ada is None:
+        return F.layer_norm(y, (C_,), ln_w, ln_b, eps=1e-6)
+    y = F.layer_norm(y, (C_,), eps=1e-6)
+    shift, scale = ada[:, None, None, :C_], ada[:, None, None, C_:]
+    return y * (1 + scale) + shift
+
+
+def _conv_aten(x, x1, res, w, b, cfg):
+    a = x if x1 is None else torch.cat([x, x1], dim=-1)
+    if cfg.get('nchw_in'):
+        a_nchw = a
+    else:
+        if cfg.get('a_act'):
+            a = F.gelu(a)
+        a_nchw = a.permute(0, 3, 1, 2)
+    y = F.conv2d(a_nchw, w, b, stride=cfg['stride'], padding=cfg['pad'])
+    if cfg.get('gelu'):
+        y = F.gelu(y)
+    if cfg.get('r'):
+        y = F.pixel_shuffle(y, cfg['r'])
+    if cfg.get('nchw_out'):
+        return y
+    y = y.permute(0, 2, 3, 1)
+    return y if res is None else y + res
+
+
+def _vd_aten(x, x1, *p):
+    a = x if x1 is None else torch.cat([x, x1], dim=-1)
+    h = a.permute(0, 3, 1, 2)
+    pad = (p[2].shape[-1] - 1) // 2
+    h = F.conv2d(F.gelu(h), p[0], p[1])
+    h = F.conv2d(F.gelu(h), p[2], p[3], padding=pad)
+    h = F.conv2d(F.gelu(h), p[4], p[5], padding=pad)
+    return F.conv2d(F.gelu(h), p[6], p[7]).permute(0, 2, 3, 1)
+
+
+# ------------------------------------------------------------------------------------------ op Functions
+class _BlockFn(torch.autograd.Function):
+    """ConvNeXt block (AdaLN | affine LN).  x [B,H,W,C]; ada: the [B, ada_total] matrix of all blocks' (shift | scale)
+    rows (AdaLN) or None; params = conv_dw.weight, conv_dw.bias, fc1.weight, fc1.bias, fc2.weight, fc2.bias, gamma
+    [, norm.weight, norm.bias]."""
+
+    @staticmethod
+    def forward(ctx, T, blk, x, ada, *params):
+        B, H, W, C_ = x.shape
+        out = torch.empty_like(x)
+        T.P.ada = ada
+        T.eng._block(T.P, blk, x, B, H, W, out=out)
+        ctx.T, ctx.blk = T, blk
+        ctx.save_for_backward(x, ada, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        T, blk = ctx.T, ctx.blk
+        x, ada, *params = ctx.saved_tensors
+        gout = gout.contiguous()
+        if T.native_bwd and T.eng.npl:
+            return (None, None) + T.block_backward(blk, x, ada, params, gout)
+        off = T.eng.ada_off.get(id(blk), 0)
+        C_, k = blk.dim, blk.kernel_size
+        ada_s = None if ada is None else ada[:, off:off + 2 * C_]
+
+        def fn(x_, ada_, dw_w, dw_b, w1, b1, w2, b2, gamma, ln_w=None, ln_b=None):
+            y = _dwln_aten(x_, ada_, dw_w, dw_b, ln_w, ln_b, k)
+            y = F.linear(F.gelu(F.linear(y, w1, b1)), w2, b2)
+            return x_ + y * gamma.reshape(-1)
+        g = _grad_of(fn, [x, ada_s] + list(params), gout)
+        return (None, None, g[0], T.scatter_ada(ada, off, g[1])) + tuple(g[2:])
+
+
+class _ConvFn(torch.autograd.Function):
+    """One convolution through lvae_gemm.  cfg: ks, stride, pad, epi, r (pixel shuffle), a_act, gelu, nchw_in (image
+    patch embedding), nchw_out (the last pixel shuffle writes NCHW), pad_c (zero channels appended to x: z_proj of qres)."""
+
+    @staticmethod
+    def forward(ctx, T, went, cfg, x, x1, res, w, b):
+        eng, P = T.eng, T.P
+        if cfg.get('nchw_in'):                     # image -> space-to-depth operand (qarv/model.py:213-222 + patch conv)
+            B, _, H, W = x.shape
+            r = cfg['stride']
+            Ho, Wo, m = H // r, W // r, T.model
+            a = torch.empty(B * Ho * Wo, 3 * r * r, device=x.device)
+            P.op('im2patch', eng.lib.lvae_image_to_patches, _ptr(x), _ptr(a), B, H, W, r, float(m.im_shift), float(m.im_scale))
+            geom = (1, 1, B * Ho * Wo, 3 * r * r, 1, 1, 0)
+        else:
+            B, H, W, C0 = x.shape
+            a = x
+            if cfg.get('pad_c'):
+                a = torch.empty(B, H, W, C0 + cfg['pad_c'], device=x.device)
+                P.op('pad_z', eng.lib.lvae_pad_channels, _ptr(x), _ptr(a), B * H * W, C0, C0 + cfg['pad_c'])
+                C0 += cfg['pad_c']
+            ks, st, pad = cfg['ks'], cfg['stride'], cfg['pad']
+            Ho, Wo = (H + 2 * pad - ks) // st + 1, (W + 2 * pad - ks) // st + 1
+            geom = (B, H, W, C0, ks, st, pad)
+        Nn, r = went['N'], cfg.get('r', 0)
+        if cfg.get('nchw_out'):
+            out = torch.empty(B, Nn // (r * r), Ho * r, Wo * r, device=x.device)
+        elif r:
+            out = torch.empty(B, Ho * r, Wo * r, Nn // (r * r), device=x.device)
+        else:
+            out = torch.empty(B, Ho, Wo, Nn, device=x.device)
+        eng._gemm(P, cfg.get('name', 'conv'), a, geom, went, out, epi=cfg['epi'], a1=x1, C1=0 if x1 is None else x1.shape[-1],
+                  res=res, r=r, a_act=cfg.get('a_act', 0))
+        ctx.T, ctx.cfg = T, cfg
+        ctx.save_for_backward(x, x1, res, w, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, x1, res, w, b = ctx.saved_tensors
+        cfg, m = ctx.cfg, ctx.T.model
+        if cfg.get('nchw_in'):
+            xin = x.add(m.im_shift).mul_(m.im_scale)
+            g = _grad_of(lambda w_, b_: _conv_aten(xin, None, None, w_, b_, cfg), [w, b], gout)
+            return (None, None, None, None, None, None, g[0], g[1])
+        g = _grad_of(lambda *a: _conv_aten(*a, cfg), [x, x1, res, w, b], gout)
+        return (None, None, None) + tuple(g)
+
+
+class _VDFn(torch.autograd.Function):
+    """qres VDBlock head without residual (qresvae/model.py:143-149); params = c1..c4 (weight, bias)."""
+
+    @staticmethod
+    def forward(ctx, T, wv, x, x1, *params):
+        B, H, W, C0 = x.shape
+        out = torch.empty(B, H, W, wv['c4']['N'], device=x.device)
+        T.eng._vdblock(T.P, 'vd', wv, x, (B, H, W, C0), out, a1=x1, C1=0 if x1 is None else x1.shape[-1])
+        ctx.save_for_backward(x, x1, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        g = _grad_of(_vd_aten, list(ctx.saved_tensors), gout)
+        return (None, None) + tuple(g)
+
+
+class _LatentFn(torch.autograd.Function):
+    """z = qm + noise, kl = -gaussian_log_prob_mass(pm, pv, z) (entropy_coding.py:17-49); native both ways."""
+
+    @staticmethod
+    def forward(ctx, T, qm, prior, noise):
+        B, H, W, zd = qm.shape
+        z, kl = torch.empty_like(qm), torch.empty_like(qm)
+        scratch = T.P.named('kl_partial', B * T.eng.lib.lvae_latent_num_partials(H * W, zd))
+        T.P.op('latent_train', T.eng.lib.lvae_latent_train, _ptr(qm), _ptr(prior), _ptr(noise), _ptr(z), _ptr(scratch),
+               scratch.numel() // B, _ptr(kl), B, H * W, zd)
+        ctx.T = T
+        ctx.save_for_backward(qm, prior, noise)
+        return z, kl
+
+    @staticmethod
+    def backward(ctx, gz, gkl):
+        qm, prior, noise = ctx.saved_tensors
+        B, H, W, zd = qm.shape
+        gz = None if gz is None else gz.contiguous()
+        gkl = torch.zeros_like(qm) if gkl is None else gkl.contiguous()
+        dqm, dprior = torch.empty_like(qm), torch.empty_like(prior)
+        ctx.T.P.op('latent_train_bwd', ctx.T.eng.lib.lvae_latent_train_bwd, _ptr(qm), _ptr(prior), _ptr(noise), _ptr(gz),
+                   _ptr(gkl), 0.0, _ptr(dqm), _ptr(dprior), B, H * W, zd)
+        return None, dqm, dprior, None
+
+
+# ------------------------------------------------------------------------------------------ the executor
+class TrainPath:
+    def __init__(self, model):
+        self.model, self.eng = model, model.engine
+        self.family = self.eng.family
+        self.P = None
+        # LVAE_TRAIN_NATIVE_BWD=0: every backward through ATen on recomputed sub-graphs (the cross-check of the native pieces)
+        self.native_bwd = os.environ.get('LVAE_TRAIN_NATIVE_BWD', '1') != '0'
+        self._wt = {}
+
+    # ---- helpers
+    def scatter_ada(self, ada, off, g):
+        if ada is None or g is None:
+            return None
+        full = torch.zeros_like(ada)
+        full[:, off:off + g.shape[1]] = g
+        return full
+
+    def _block(self, blk, x, ada):
+        ps = [blk.conv_dw.weight, blk.conv_dw.bias, blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight,
+              blk.mlp.fc2.bias, blk.gamma]
+        if isinstance(blk, common.ConvNeXtBlockLN):
+            ps += [blk.norm.weight, blk.norm.bias]
+        return _BlockFn.apply(self, blk, x, ada, *ps)
+
+    def _conv(self, conv, went, x, x1=None, res=None, **cfg):
+        cfg.setdefault('ks', conv.kernel_size[0])
+        cfg.setdefault('stride', conv.stride[0])
+        cfg.setdefault('pad', conv.padding[0])
+        cfg.setdefault('epi', N.EPI_BIAS_RES if res is not None else N.EPI_BIAS)
+        return _ConvFn.apply(self, went, cfg, x, x1, res, conv.weight, conv.bias)
+
+    def _vd(self, vd, wv, x, x1=None):
+        ps = []
+        for k in ('c1', 'c2', 'c3', 'c4'):
+            ps += [getattr(vd, k).weight, getattr(vd, k).bias]
+        return _VDFn.apply(self, wv, x, x1, *ps)
+
+    def _transposed(self, key, w2d):
+        """packed operand planes of a transposed (and possibly row-scaled) weight for the data-gradient GEMMs"""
+        return self.eng._pack_gemm_weight(w2d.t().contiguous(), None)
+
+    def block_backward(self, blk, x, ada, params, gout):
+        """Gradients of one ConvNeXt block w.r.t. (x, ada, *params).  The two GEMM data gradients and the recomputation
+        of the fc1 pre-activation run on the tcgen05 GEMM; see the module docstring for what is still ATen."""
+        eng, P = self.eng, self.P
+        dw_w, dw_b, w1, b1, w2, b2, gamma = params[:7]
+        ln = params[7:]
+        B, H, W, C_ = x.shape
+        M, hid, k = B * H * W, blk.hidden, blk.kernel_size
+        wb = eng.w[id(blk)]
+        off = eng.ada_off.get(id(blk), 0)
+        gam = gamma.detach().reshape(-1)
+        # recompute: a = AdaLN(LN(dwconv(x))) as operand planes, h = a W1^T + b1 (pre-activation)
+        P.ada = ada
+        A = [P.named(f'scratch_a{i}', M * C_, dtype=torch.bfloat16) for i in range(eng.npl)]
+        ap = [_ptr(t) for t in A] + [0] * (3 - eng.npl)
+        P.op('dwln', eng.lib.lvae_dwconv_ln_adaln_planes, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']), _ptr(ada),
+             eng.ada_total, off, _ptr(wb.get('ln_w')), _ptr(wb.get('ln_b')), ap[0], ap[1], ap[2], eng.pfmt, B, H, W, C_, k)
+        h = torch.empty(M, hid, device=x.device)
+        eng._gemm(P, 'fc1.re', None, (1, 1, M, C_, 1, 1, 0), wb['fc1'], h, epi=N.EPI_BIAS, a_planes=A)
+        g = F.gelu(h)
+        go = gout.reshape(M, C_)
+        # fc2: out = x + gamma * (g W2^T + b2)
+        dw2_raw = go.t().mm(g)                                  # cuBLAS fp32  [C, hid]
+        db2_raw = go.sum(0)
+        d_w2 = gam[:, None] * dw2_raw
+        d_b2 = gam * db2_raw
+        d_gamma = ((w2.detach() * dw2_raw).sum(1) + b2.detach() * db2_raw).reshape(gamma.shape)
+        dg = torch.empty(M, hid, device=x.device)
+        eng._gemm(P, 'fc2.dgrad', go, (1, 1, M, C_, 1, 1, 0), self._transposed('w2', gam[:, None] * w2.detach()), dg, epi=N.EPI_BIAS)
+        dh = torch.ops.aten.gelu_backward(dg, h)
+        del dg, g
+        # fc1: h = a W1^T + b1;  a is needed for the weight gradient: one more (fp32) dwln launch
+        a32 = torch.empty(M, C_, device=x.device)
+        P.op('dwln', eng.lib.lvae_dwconv_ln_adaln, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']), _ptr(ada), eng.ada_total, off,
+             _ptr(wb.get('ln_w')), _ptr(wb.get('ln_b')), _ptr(a32), B, H, W, C_, k)
+        d_w1 = dh.t().mm(a32)
+        d_b1 = dh.sum(0)
+        da = torch.empty(M, C_, device=x.device)
+        eng._gemm(P, 'fc1.dgrad', dh, (1, 1, M, hid, 1, 1, 0), self._transposed('w1', w1.detach()), da, epi=N.EPI_BIAS)
+        del dh, h, a32
+        # dwconv + LN (+ AdaLN): ATen on the recomputed sub-graph
+        ada_s = None if ada is None else ada[:, off:off + 2 * C_]
+        lw, lb = (ln[0], ln[1]) if ln else (None, None)
+        gs = _grad_of(lambda x_, ada_, w_, b_, lw_, lb_: _dwln_aten(x_, ada_, w_, b_, lw_, lb_, k),
+                      [x, ada_s, dw_w, dw_b, lw, lb], da.view(B, H, W, C_))
+        dx = gs[0] + gout
+        out = (dx, self.scatter_ada(ada, off, gs[1]), gs[2], gs[3], d_w1, d_b1, d_w2, d_b2, d_gamma)
+        if ln:
+            out += (gs[4], gs[5])
+        return out
+
+    # ---- lambda embedding (tiny; ATen both ways): qarv/model.py:280-287, common.py:101-107,150
+    def _ada(self, lmb):
+        m, eng = self.model, self.eng
+        if not eng.ada_total:
+            return None
+        scaled = torch.log(lmb) * m._sin_period / math.log(m.MAX_LMB)
+        freqs = eng.w['freqs']
+        args = scaled.view(-1, 1) * freqs.view(1, -1)
+        e = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+        e = F.linear(e, m.lmb_embedding[0].weight, m.lmb_embedding[0].bias)
+        e = F.linear(F.gelu(e), m.lmb_embedding[2].weight, m.lmb_embedding[2].bias)
+        blocks = [b for b in eng.blocks if id(b) in eng.ada_off]
+        w_all = torch.cat([b.embedding_layer[1].weight for b in blocks], 0)
+        b_all = torch.cat([b.embedding_layer[1].bias for b in blocks], 0)
+        return F.linear(F.gelu(e), w_all, b_all).contiguous()
+
+    # ---- the pass
+    def forward(self, im, lmb, noise=None):
+        """im [B,3,H,W] on the device in [0,1]; lmb [B]; noise: optional per-layer [B,zdim,h,w] U(-.5,.5).
+        Returns dict(x_hat [B,3,H,W] (graph-attached), kl [per layer [B,h,w,zdim] graph-attached], z [per layer])."""
+        m, eng = self.model, self.eng
+        eng.refresh_weights()
+        B, _, H, W = im.shape
+        if self.P is None or self.P.B != B or self.P.dev != eng.device:
+            self.P = _EagerPlan(eng, B)
+        qres = self.family == 'qres'
+        with torch.cuda.device(eng.device), torch.autocast('cuda', enabled=False):
+            ada = self._ada(lmb)
+            # ---------------- bottom-up
+            feats, x, s, first = {}, im, 1, True
+            for mod in m.encoder.enc_blocks:
+                kind = getattr(mod, 'op_kind', None)
+                if kind == 'down':
+                    x = self._conv(mod, eng.w[id(mod)], x, nchw_in=first, name='down')
+                    s *= mod.rate
+                    first = False
+                elif getattr(mod, 'downsapmle', None) is not None:
+                    conv = mod.downsapmle
+                    x = self._conv(conv, eng.w[id(conv)], self._block(mod, x, ada), name='down')
+                    s *= conv.rate
+                elif isinstance(mod, (common.ConvNeXtBlockAdaLN, common.ConvNeXtBlockLN)):
+                    x = self._block(mod, x, ada)
+                elif isinstance(mod, common.SetKey):
+                    feats[mod.key] = x
+                else:
+                    raise TypeError(f'unsupported encoder module {type(mod)}')
+                if qres:
+                    feats[H // s] = x
+            # ---------------- top-down
+            nH, nW = H // m.max_stride, W // m.max_stride
+            x = m.bias.reshape(1, 1, 1, -1).expand(B, nH, nW, -1).contiguous()
+            kls, zs, li = [], [], 0
+            for mod in m.dec_blocks:
+                kind = getattr(mod, 'op_kind', None)
+                if getattr(mod, 'is_latent_block', False):
+                    wl = eng.w[id(mod)]
+                    Hs, Ws, zd = x.shape[1], x.shape[2], mod.zdim
+                    x = self._block(mod.resnet_front, x, ada)
+                    if qres:
+                        prior = self._vd(mod.prior, wl['prior'], x)
+                        qm = self._vd(mod.posterior, wl['posterior'], x, feats[Hs])
+                    else:
+                        prior = self._conv(mod.prior, wl['prior'], x, name='prior')
+                        e = self._block(mod.posterior0, feats[mod.enc_key], ada)
+                        f = self._block(mod.posterior1, x, ada)
+                        mg = self._conv(mod.post_merge, wl['post_merge'], f, e, name='post_merge')
+                        mg = self._block(mod.posterior2, mg, ada)
+                        qm = self._conv(mod.posterior, wl['posterior'], mg, name='posterior')
+                    if noise is not None:
+                        nz = noise[li].to(eng.device).permute(0, 2, 3, 1).contiguous()
+                    else:
+                        nz = torch.empty_like(qm).uniform_(-0.5, 0.5)       # same draw order as the reference: one per layer
+                    z, kl = _LatentFn.apply(self, qm, prior, nz)
+                    kls.append(kl)
+                    zs.append(z)
+                    li += 1
+                    if qres:
+                        t = self._conv(mod.z_proj[0], wl['z_proj0'], z, epi=N.EPI_BIAS_GELU, gelu=1, pad_c=wl['z_pad'], name='z_proj0')
+                        x = self._conv(mod.z_proj[2], wl['z_proj2'], t, res=x, name='z_proj2')
+                    else:
+                        x = self._conv(mod.z_proj, wl['z_proj'], z, res=x, name='z_proj')
+                    x = self._block(mod.resnet_end, x, ada)
+                elif isinstance(mod, (common.ConvNeXtBlockAdaLN, common.ConvNeXtBlockLN)):
+                    x = self._block(mod, x, ada)
+                elif kind == 'up':
+                    conv, r = mod[0], mod.rate
+                    last = conv.out_channels // (r * r) == 3
+                    x = self._conv(conv, eng.w[id(mod)], x, r=r, nchw_out=last, name='up',
+                                   epi=N.EPI_SHUFFLE_NCHW if last else N.EPI_SHUFFLE_NHWC)
+                elif isinstance(mod, common.CompresionStopFlag):
+                    pass
+                else:
+                    raise TypeError(f'unsupported decoder module {type(mod)}')
+        return dict(x_hat=x, kl=kls, z=zs)
+
+    def objective(self, im, lmb, noise=None):
+        """The loss of `forward()` of both model classes: mean_b( sum_layers kl_b / ndims + lmb_b * mse_b )
+        (qarv/model.py:338-346, qresvae/model.py:533-545) plus the logged statistics."""
+        res = self.forward(im, lmb, noise)
+        B, imC, imH, imW = im.shape
+        ndims = float(imC * imH * imW)
+        kl = sum(k.reshape(B, -1).sum(1) for k in res['kl']) / ndims
+        x_hat = res['x_hat']
+        target = im.sub(0.5).mul_(2.0)
+        distortion = (x_hat - target).square().mean(dim=(1, 2, 3))
+        loss = (kl + lmb * distortion).mean(0)
+        with torch.no_grad():
+            im_hat = x_hat.detach().clamp(-1.0, 1.0).mul_(0.5).add_(0.5)
+            host = torch.stack([kl.mean(0), distortion.mean(0), (im_hat - im).square().mean(),
+                                (lmb * distortion).mean(0)]).cpu()
+        res.update(loss=loss, kl_mean=float(host[0]), mse=float(host[1]), im_mse=float(host[2]),
+                   lmb_mse=float(host[3]), im_hat=im_hat, kl_img=kl.detach())
+        return res

@@ -234,7 +234,8 @@ def test_train_mode_forward_uses_noise_and_matches_oracle(gpu_model, sensitised_
     gpu_model.train()
     try:
         torch.manual_seed(123)
-        st = gpu_model(im.to(DEV), lmb=lmb.to(DEV))
+        with torch.no_grad():       # with autograd recording, train mode routes to lvae.training (tests/test_gpu_train.py)
+            st = gpu_model(im.to(DEV), lmb=lmb.to(DEV))
         P = gpu_model.engine._plans[(2, 64, 64, 'train', False)]
         noise = [n.view(2, l[4], l[5], l[1]).permute(0, 3, 1, 2).cpu() for n, l in zip(P.noise, P.layout)]
     finally:

@@ -50,7 +50,8 @@ def test_qres_forward_matches_reference_fixture(name, precision, qres_model, qre
         rec = qres_model.decompress(obj)
         qres_model.train()
         noise = _qres_noise(Q, Q.qres34m_arch(), nB, H, W, nseed)
-        tr = qres_model(im, noise=noise)
+        with torch.no_grad():       # the launch-plan train forward; with autograd recording see tests/test_gpu_train.py
+            tr = qres_model(im, noise=noise)
     finally:
         qres_model.eval()
         qres_model.precision = 'f16x3'

@@ -1,0 +1,113 @@
+"""Training step (BASELINE configs 2, 3): loss and parameter gradients of `model(batch)['loss'].backward()` on a B200
+against torch autograd over the CPU oracle (the restatement pinned to the unmodified reference) with the same weights,
+images, lambdas and uniform noise.  Tolerance: per parameter tensor, |g - g_ref|_2 <= GRAD_RTOL * |g_ref|_2 + GRAD_ATOL *
+sqrt(numel) -- fp32 round-off through ~110 blocks in a different summation order on both sides."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import lvae_oracle as O
+import qres_oracle as Q
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+GRAD_RTOL, GRAD_ATOL = 2e-3, 1e-7
+
+
+def _noise(model, B, H, W, seed):
+    lay, _ = model.engine._latent_layout(B, H // model.max_stride, W // model.max_stride)
+    g = torch.Generator().manual_seed(seed)
+    return [torch.rand(B, zd, Hs, Ws, generator=g) - 0.5 for (_, zd, _, _, Hs, Ws) in lay]
+
+
+def _oracle_grads(fwd, sd, *args, **kw):
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    with torch.enable_grad():
+        out = fwd.__wrapped__(sd, *args, **kw)
+        out['loss'].backward()
+    return out, {k: v.grad for k, v in sd.items()}
+
+
+def _compare(model, ref_grads, loss, ref_loss):
+    assert abs(loss - ref_loss) <= 1e-4 * abs(ref_loss), (loss, ref_loss)
+    worst, n = (0.0, None), 0
+    for name, p in model.named_parameters():
+        gr = ref_grads[name]
+        if gr is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        assert p.grad is not None, f'no gradient reached {name}'
+        g = p.grad.detach().cpu().reshape(gr.shape)
+        err, scale = float((g - gr).norm()), float(gr.norm())
+        tol = GRAD_RTOL * scale + GRAD_ATOL * gr.numel() ** 0.5
+        worst = max(worst, (err / max(scale, 1e-30), name))
+        assert err <= tol, (name, err, scale)
+        n += 1
+    assert n > 100
+    return worst
+
+
+@pytest.fixture()
+def train_model(gpu_model):
+    m = copy.deepcopy(gpu_model)
+    m.compressing = False
+    return m.train()
+
+
+@pytest.mark.parametrize('native_bwd', [True, False])
+def test_qarv_train_step_gradients_match_oracle_autograd(train_model, sensitised_sd, native_bwd):
+    m = train_model
+    m.train_path.native_bwd = native_bwd
+    B, H, W = 2, 64, 64
+    im = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(5))
+    lmb = torch.tensor([64.0, 1024.0])
+    noise = _noise(m, B, H, W, 17)
+    st = m._forward_train(im.to(DEV), lmb.to(DEV), noise=noise)
+    assert st['loss'].requires_grad
+    st['loss'].backward()
+    ref, grads = _oracle_grads(O.qarv_forward, sensitised_sd, im, lmb, mode='train', noise=noise)
+    assert abs(st['bppix'] - ref['bppix']) <= 1e-4 * max(1.0, ref['bppix'])
+    worst = _compare(m, grads, st['loss'].item(), ref['loss'].item())
+    print('worst relative gradient error', worst)
+
+
+def test_qarv_forward_routes_to_training_path_and_adam_reduces_the_loss(native_lib):
+    import lvae
+    torch.manual_seed(0)
+    m = lvae.get_model('qarv_base').to(DEV).train()
+    opt = torch.optim.Adam(m.parameters(), lr=2e-4)
+    im = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(1)).to(DEV)
+    lmb = torch.tensor([256.0, 256.0], device=DEV)
+    losses = []
+    for _ in range(6):
+        torch.manual_seed(7)                       # same noise draw every step
+        st = m(im, lmb=lmb)
+        opt.zero_grad(set_to_none=True)
+        st['loss'].backward()
+        opt.step()
+        losses.append(st['loss'].item())
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    m.eval()
+    with torch.no_grad():
+        ev = m(im, lmb=lmb)                        # the launch plans pick up the updated weights
+    assert np.isfinite(ev['loss'].item())
+
+
+@pytest.mark.parametrize('native_bwd', [True, False])
+def test_qres_train_step_gradients_match_oracle_autograd(native_lib, native_bwd):
+    import lvae
+    sd = O.sensitised_state_dict(Q.qres_param_shapes(), seed=0)
+    m = lvae.get_model('qres34m', lmb=2048)
+    m.load_state_dict(sd, strict=False)
+    m = m.to(DEV).train()
+    m.train_path.native_bwd = native_bwd
+    B, H, W = 1, 64, 64
+    im = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(9))
+    noise = _noise(m, B, H, W, 23)
+    st = m(im.to(DEV), noise=noise)
+    st['loss'].backward()
+    ref, grads = _oracle_grads(Q.qres_forward, sd, im, 2048, mode='train', noise=noise)
+    worst = _compare(m, grads, st['loss'].item(), float(ref['loss']))
+    print('worst relative gradient error', worst)
