@@ -194,6 +194,109 @@ def run_codec(args):
     }))
 
 
+def run_train(args):
+    """Training step images/s (BASELINE configs[2]: qres34m 512x768 batch 16 fwd+bwd on one GPU; configs[3]: qarv_base
+    train-var-rate step on 256x256 crops, 16 per GPU, gradients all-reduced over NCCL by DistributedDataParallel).
+    One step = forward (lvae.training: native kernels) + backward + Adam update.  `value`: batch resident on the device;
+    `e2e`: pinned host batch copied in and the loss read back every step.  Which parts of the backward are native and which
+    are ATen library calls: lvae/training.py docstring / DESIGN.md 4.6."""
+    import torch
+    import torch.distributed as dist
+    import lvae
+    from lvae import _native as N
+    from oracle_inputs import make_input
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (there is no CPU path)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    qres = args.workload == 'train-qres'
+    warmup = max(args.warmup, 3)
+    B = 16 if args.batch == 8 else args.batch
+    h, w = (512, 768) if qres else (256, 256)
+    torch.manual_seed(0)                                # same seeded default init on every rank
+    model = lvae.get_model('qres34m', lmb=2048) if qres else lvae.get_model('qarv_base')
+    if args.precision:
+        model.precision = args.precision
+    model = model.to(dev).train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    im_host = make_input('rand', B, h, w, 1000 + rank).pin_memory()
+    im_dev = im_host.to(dev)
+    torch.manual_seed(1234 + rank)                      # lambda / noise draws differ per rank
+
+    def step(im):
+        out = net(im) if qres else net(im)              # qarv: lmb=None -> sample_lmb (train-var-rate)
+        opt.zero_grad(set_to_none=True)
+        out['loss'].backward()
+        opt.step()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step(im_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    st = torch.cuda.current_stream()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    launches0 = N.launch_count
+    barrier()
+    e[0].record(st)
+    for _ in range(args.steps):
+        step(im_dev)
+    e[1].record(st)
+    barrier()
+    launches = N.launch_count - launches0
+    e[2].record(st)
+    for _ in range(args.steps):
+        out = step(im_host.to(dev, non_blocking=True))
+        loss = out['loss'].item()
+    e[3].record(st)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    if rank == 0:
+        n_img = B * world * args.steps
+        print(json.dumps({
+            'metric': f'{h}x{w} images/sec (training step: forward + backward + Adam)', 'value': n_img / (ms_dev / 1e3),
+            'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms_dev / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': model.precision, 'data': 'synthetic',
+            'config': {'workload': (f'qres34m lambda 2048 training step, synthetic {h}x{w} RGB, batch {B} per GPU (BASELINE configs[2])'
+                                    if qres else f'qarv_base train-var-rate step (lambda sampled per image), synthetic {h}x{w} crops, '
+                                                 f'batch {B} per GPU (BASELINE configs[3])'),
+                       'batch_per_gpu': B, 'global_batch': B * world,
+                       'parallelism': f'data parallel x{world}' + (', NCCL gradient all-reduce (DistributedDataParallel buckets)' if world > 1 else ''),
+                       'weights': 'seeded default init', 'optimizer': 'Adam (torch.optim)',
+                       'backward': 'latent layers and ConvNeXt-block GEMM data gradients native; weight gradients cuBLAS fp32; '
+                                   'dwconv/LN/AdaLN and head convolutions via ATen on recomputed sub-graphs (lvae/training.py)',
+                       'l2': 'no flush: per-step working set exceeds the 126 MB L2'},
+            'e2e': {'value': n_img / (ms_e2e / 1e3), 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,
+                    'h2d_bytes_per_step': im_host.numel() * 4, 'd2h_bytes_per_step': 4},
+            'gpu_launches': launches, 'launches_per_step': launches // max(1, args.steps),
+            'clocks': clocks, 'result': {'loss': loss, 'bppix': out['bppix'], 'psnr': out['psnr']},
+            'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30,
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -202,10 +305,12 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='images per GPU per step (BASELINE configs[1]: 8)')
     ap.add_argument('--precision', default=None, help="f16x3 | bf16x6 | bf16x3 | bf16 | fp32 (default: the model's default, f16x3)")
-    ap.add_argument('--workload', default='qarv', choices=['qarv', 'rd', 'qres', 'codec'],
+    ap.add_argument('--workload', default='qarv', choices=['qarv', 'rd', 'qres', 'codec', 'train', 'train-qres'],
                     help='qarv: BASELINE configs[1] (headline, default); rd: configs[4] rd_model_base 256x256, batch 32 per GPU; '
                          'qres: the forward half of configs[2], qres34m lambda 2048, 512x768, batch 16 per GPU; '
-                         'codec: qarv_base compress() + decompress() of one 512x768 image per step (real bit stream, host rANS)')
+                         'codec: qarv_base compress() + decompress() of one 512x768 image per step (real bit stream, host rANS); '
+                         'train: configs[3] qarv_base training step, 256x256 crops, 16 per GPU; train-qres: configs[2] qres34m '
+                         '512x768 batch 16 forward + backward + Adam')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-samples', type=int, default=5)
     ap.add_argument('--codec-batch', type=int, default=1, help='--workload codec: images per compress / decompress call')
@@ -214,6 +319,8 @@ def main():
         return run_reference(args)
     if args.workload == 'codec':
         return run_codec(args)
+    if args.workload in ('train', 'train-qres'):
+        return run_train(args)
 
     import torch
     import torch.distributed as dist

@@ -155,6 +155,23 @@ int lvae_dwconv_ln_adaln_planes(const float* x, const float* dw_w, const float* 
                                 void* y0, void* y1, void* y2, int plane_format,
                                 int B, int H, int W, int C, int k, void* stream);
 
+/* ---- backward of the dwconv + LayerNorm + modulation stage (training step; autograd of common.py:145-152 and of
+ * qresvae/model.py:163-182, which the reference gets from ATen) -------------------------------------------------
+ * lvae_dwconv: y = dwconv_kxk(x) [+ bias[c]] [+ add], NHWC fp32, filter packed [k*k, C] (bias / add may be NULL).
+ * flip = 0: the forward convolution (recomputes the conv output c for the LayerNorm backward); flip = 1: correlation with
+ * the spatially flipped filter = the data gradient dx = conv^T(dc), `add` carrying the residual branch's gradient. */
+int lvae_dwconv(const float* x, const float* dw_w, const float* bias, const float* add, float* y,
+                int B, int H, int W, int C, int k, int flip, void* stream);
+/* dw[t, c] = sum_p dc[p, c] * x[p + t, c] (packed [k*k, C]) and db[c] = sum_p dc[p, c]; both outputs are zeroed first,
+ * partial sums meet in fp32 atomics (order not fixed, like cuDNN's weight gradients). */
+int lvae_dwconv_wgrad(const float* dc, const float* x, float* dw, float* db,
+                      int B, int H, int W, int C, int k, void* stream);
+/* LayerNorm(C, eps 1e-6) + modulation a = yhat * g1 + g0 backward: from the conv output c [M,C] and da = dL/da [M,C],
+ * dc [M,C] = dL/dc and dmod = (sum da | sum da * yhat): one [2C] row per image for AdaLN (g1 = 1 + scale[b], g0 = shift[b]
+ * read from ada as in lvae_dwconv_ln_adaln: dmod row = (dshift | dscale)), a single row (d ln_b | d ln_w) when ln_w != NULL. */
+int lvae_ln_mod_bwd(const float* c, const float* da, const float* ada, int64_t ada_stride, int64_t ada_off,
+                    const float* ln_w, float* dc, float* dmod, int B, int HW, int C, void* stream);
+
 /* ---- fused latent-layer kernels (qarv/model.py:51-53,90-96,104-113; CompressAI GaussianConditional) --
  * prior [M, 2*zdim] (pm | plogv_raw) and qm [M, zdim] are NHWC matrices; hw = h*w positions per image.
  * Eval (K11+K12+K15): z = rint(qm-pm)+pm; kl = -ln max(Phi((.5-|z-pm|)/s) - Phi((-.5-|z-pm|)/s), 1e-9),

@@ -306,16 +306,22 @@ class TrainPath:
         da = torch.empty(M, C_, device=x.device)
         eng._gemm(P, 'fc1.dgrad', dh, (1, 1, M, hid, 1, 1, 0), self._transposed('w1', w1.detach()), da, epi=N.EPI_BIAS)
         del dh, h, a32
-        # dwconv + LN (+ AdaLN): ATen on the recomputed sub-graph
-        ada_s = None if ada is None else ada[:, off:off + 2 * C_]
-        lw, lb = (ln[0], ln[1]) if ln else (None, None)
-        gs = _grad_of(lambda x_, ada_, w_, b_, lw_, lb_: _dwln_aten(x_, ada_, w_, b_, lw_, lb_, k),
-                      [x, ada_s, dw_w, dw_b, lw, lb], da.view(B, H, W, C_))
-        dx = gs[0] + gout
-        out = (dx, self.scatter_ada(ada, off, gs[1]), gs[2], gs[3], d_w1, d_b1, d_w2, d_b2, d_gamma)
+        # dwconv + LayerNorm + modulation: recompute the conv output, LayerNorm / modulation backward, filter gradient,
+        # data gradient (transposed conv + the residual branch's gradient) -- csrc/dwln_bwd.cu
+        lib = eng.lib
+        c = torch.empty(M, C_, device=x.device)
+        P.op('dwconv', lib.lvae_dwconv, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']), 0, _ptr(c), B, H, W, C_, k, 0)
+        dmod, dc = torch.empty(1 if ln else B, 2 * C_, device=x.device), torch.empty(M, C_, device=x.device)
+        P.op('ln_mod_bwd', lib.lvae_ln_mod_bwd, _ptr(c), _ptr(da), _ptr(ada), eng.ada_total, off, _ptr(wb.get('ln_w')),
+             _ptr(dc), _ptr(dmod), B, H * W, C_)
+        dwp, d_dwb = torch.empty(k * k, C_, device=x.device), torch.empty(C_, device=x.device)
+        P.op('dwconv_wgrad', lib.lvae_dwconv_wgrad, _ptr(dc), _ptr(x), _ptr(dwp), _ptr(d_dwb), B, H, W, C_, k)
+        dx = torch.empty_like(x)
+        P.op('dwconv_dgrad', lib.lvae_dwconv, _ptr(dc), _ptr(wb['dw_w']), 0, _ptr(gout), _ptr(dx), B, H, W, C_, k, 1)
+        d_dww = dwp.t().reshape(C_, 1, k, k)
         if ln:
-            out += (gs[4], gs[5])
-        return out
+            return (dx, None, d_dww, d_dwb, d_w1, d_b1, d_w2, d_b2, d_gamma, dmod[0, C_:].clone(), dmod[0, :C_].clone())
+        return (dx, self.scatter_ada(ada, off, dmod), d_dww, d_dwb, d_w1, d_b1, d_w2, d_b2, d_gamma)
 
     # ---- lambda embedding (tiny; ATen both ways): qarv/model.py:280-287, common.py:101-107,150
     def _ada(self, lmb):
