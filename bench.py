@@ -227,7 +227,8 @@ def run_train(args):
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    graphed = world == 1 and not args.no_train_graph
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graphed)
     im_host = make_input('rand', B, h, w, 1000 + rank).pin_memory()
     im_dev = im_host.to(dev)
     torch.manual_seed(1234 + rank)                      # lambda / noise draws differ per rank
@@ -244,7 +245,12 @@ def run_train(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    resident = step
+    if graphed:          # lvae.training.GraphedTrainStep: the whole step as one CUDA graph (device-resident number)
+        from lvae.training import GraphedTrainStep
+        resident = GraphedTrainStep(model, opt, tuple(im_dev.shape))
     for _ in range(warmup):
+        resident(im_dev)
         step(im_dev)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -256,7 +262,7 @@ def run_train(args):
     barrier()
     e[0].record(st)
     for _ in range(args.steps):
-        step(im_dev)
+        resident(im_dev)
     e[1].record(st)
     barrier()
     launches = N.launch_count - launches0
@@ -283,6 +289,8 @@ def run_train(args):
                        'batch_per_gpu': B, 'global_batch': B * world,
                        'parallelism': f'data parallel x{world}' + (', NCCL gradient all-reduce (DistributedDataParallel buckets)' if world > 1 else ''),
                        'weights': 'seeded default init', 'optimizer': 'Adam (torch.optim)',
+                       'value_path': 'whole step replayed as one CUDA graph (lvae.training.GraphedTrainStep)' if graphed else 'eager step',
+                       'e2e_path': 'eager step through model.forward() / loss.backward() / optimizer.step()',
                        'backward': 'latent layers and ConvNeXt-block GEMM data gradients native; weight gradients cuBLAS fp32; '
                                    'dwconv/LN/AdaLN and head convolutions via ATen on recomputed sub-graphs (lvae/training.py)',
                        'l2': 'no flush: per-step working set exceeds the 126 MB L2'},
@@ -312,6 +320,7 @@ def main():
                          'train: configs[3] qarv_base training step, 256x256 crops, 16 per GPU; train-qres: configs[2] qres34m '
                          '512x768 batch 16 forward + backward + Adam')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train-graph', action='store_true', help='--workload train*: time the eager step also for `value`')
     ap.add_argument('--cpu-samples', type=int, default=5)
     ap.add_argument('--codec-batch', type=int, default=1, help='--workload codec: images per compress / decompress call')
     args = ap.parse_args()

@@ -200,7 +200,8 @@ class QarvEngine:
                 for j in (0, 2):
                     w[f'emb{j}_w'] = self._dev_f32(m.lmb_embedding[j].weight)
                     w[f'emb{j}_b'] = self._dev_f32(m.lmb_embedding[j].bias)
-                w['freqs'] = common.sinusoidal_frequencies(m.lmb_embed_dim[0], m._sin_period).to(dev)
+                fr = self.w.get('freqs')          # constant: kept across refreshes (no H2D copy inside a captured training step)
+                w['freqs'] = fr if fr is not None and fr.device == dev else common.sinusoidal_frequencies(m.lmb_embed_dim[0], m._sin_period).to(dev)
             w['bias'] = self._dev_f32(m.bias).reshape(-1)
             mods = list(m.encoder.enc_blocks) + list(m.dec_blocks)
             for mod in mods:

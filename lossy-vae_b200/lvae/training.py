@@ -53,7 +53,8 @@ def _grad_of(fn, inputs, gout):
         live = [t for t in ins if t is not None]
         grads = torch.autograd.grad(out, live, gout, allow_unused=True)
     it = iter(grads)
-    return [None if t is None else next(it) for t in ins]
+    out = [None if t is None else next(it) for t in ins]
+    return [None if g is None else g.contiguous() for g in out]      # cuDNN hands back channels-last strided filters
 
 
 # ------------------------------------------------------------------------------------------ ATen restatements (backward only)
@@ -232,7 +233,7 @@ class TrainPath:
         self.P = None
         # LVAE_TRAIN_NATIVE_BWD=0: every backward through ATen on recomputed sub-graphs (the cross-check of the native pieces)
         self.native_bwd = os.environ.get('LVAE_TRAIN_NATIVE_BWD', '1') != '0'
-        self._wt = {}
+        self.force_refresh = False      # GraphedTrainStep: the captured step must always re-pack the weights
 
     # ---- helpers
     def scatter_ada(self, ada, off, g):
@@ -344,7 +345,7 @@ class TrainPath:
         """im [B,3,H,W] on the device in [0,1]; lmb [B]; noise: optional per-layer [B,zdim,h,w] U(-.5,.5).
         Returns dict(x_hat [B,3,H,W] (graph-attached), kl [per layer [B,h,w,zdim] graph-attached], z [per layer])."""
         m, eng = self.model, self.eng
-        eng.refresh_weights()
+        eng.refresh_weights(force=self.force_refresh)
         B, _, H, W = im.shape
         if self.P is None or self.P.B != B or self.P.dev != eng.device:
             self.P = _EagerPlan(eng, B)
@@ -418,9 +419,10 @@ class TrainPath:
                     raise TypeError(f'unsupported decoder module {type(mod)}')
         return dict(x_hat=x, kl=kls, z=zs)
 
-    def objective(self, im, lmb, noise=None):
+    def objective(self, im, lmb, noise=None, stats=True):
         """The loss of `forward()` of both model classes: mean_b( sum_layers kl_b / ndims + lmb_b * mse_b )
-        (qarv/model.py:338-346, qresvae/model.py:533-545) plus the logged statistics."""
+        (qarv/model.py:338-346, qresvae/model.py:533-545) plus the logged statistics (stats=False: no host read-back,
+        which is what lets GraphedTrainStep capture the step)."""
         res = self.forward(im, lmb, noise)
         B, imC, imH, imW = im.shape
         ndims = float(imC * imH * imW)
@@ -429,6 +431,9 @@ class TrainPath:
         target = im.sub(0.5).mul_(2.0)
         distortion = (x_hat - target).square().mean(dim=(1, 2, 3))
         loss = (kl + lmb * distortion).mean(0)
+        res['loss'] = loss
+        if not stats:
+            return res
         with torch.no_grad():
             im_hat = x_hat.detach().clamp(-1.0, 1.0).mul_(0.5).add_(0.5)
             host = torch.stack([kl.mean(0), distortion.mean(0), (im_hat - im).square().mean(),
@@ -436,3 +441,57 @@ class TrainPath:
         res.update(loss=loss, kl_mean=float(host[0]), mse=float(host[1]), im_mse=float(host[2]),
                    lmb_mse=float(host[3]), im_hat=im_hat, kl_img=kl.detach())
         return res
+
+
+class GraphedTrainStep:
+    """One training step -- lambda draw, forward, backward, optimizer update, including the re-packing of the updated
+    weights into tensor-core operand planes -- captured once into a CUDA graph and replayed per batch: the training
+    counterpart of the inference launch plans (the eager step is bound by ~4000 host-side launches).  The optimizer must be
+    graph-capturable (torch.optim.Adam(..., capturable=True)); batch shape and lambda policy are fixed per instance.
+
+        step = GraphedTrainStep(model, optimizer, (16, 3, 256, 256))
+        loss = step(batch)            # 0-d device tensor, overwritten by the next call
+    """
+
+    def __init__(self, model, optimizer, batch_shape, warmup=3):
+        self.model, self.opt = model, optimizer
+        self.tp = model.train_path
+        self.im = torch.zeros(batch_shape, device=model._device())
+        self.graph, self.loss, self.warmup = None, None, max(1, warmup)   # >= 1: lazy state (packed weights, scratch) exists before capture
+
+    def _step(self):
+        m, B = self.model, self.im.shape[0]
+        lmb = m._lmb(B) if self.tp.family == 'qres' else m.sample_lmb(B)
+        self.tp.force_refresh = True
+        try:
+            res = self.tp.objective(self.im, lmb, stats=False)
+        finally:
+            self.tp.force_refresh = False
+        self.opt.zero_grad(set_to_none=True)
+        res['loss'].backward()
+        self.opt.step()
+        return res['loss'].detach()
+
+    def __call__(self, im):
+        assert self.model.training and tuple(im.shape) == tuple(self.im.shape)
+        self.im.copy_(im, non_blocking=True)
+        if self.graph is None:
+            dev = self.im.device
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(self.warmup):
+                    self._step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            self.opt.zero_grad(set_to_none=True)
+            n0 = N.launch_count
+            with torch.cuda.graph(self.graph):
+                self.loss = self._step()
+            self.launches_per_replay = N.launch_count - n0        # liblvae_b200 launches recorded in the graph
+            N.launch_count = n0
+        self.graph.replay()
+        N.launch_count += self.launches_per_replay
+        self.tp.eng._wver = None        # the replay updated the parameters in place: the next eager / inference use re-packs
+        return self.loss

@@ -111,3 +111,40 @@ def test_qres_train_step_gradients_match_oracle_autograd(native_lib, native_bwd)
     ref, grads = _oracle_grads(Q.qres_forward, sd, im, 2048, mode='train', noise=noise)
     worst = _compare(m, grads, st['loss'].item(), float(ref['loss']))
     print('worst relative gradient error', worst)
+
+
+def test_graphed_train_step_matches_eager_step(native_lib):
+    """GraphedTrainStep (whole step in one CUDA graph) against the eager step: three updates each from the same seeded
+    init (lambda / noise draws differ), and the inference plans see the weights the replays updated in place."""
+    import lvae
+    from lvae.training import GraphedTrainStep
+    im = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(4)).to(DEV)
+    lmb = torch.full((2,), 256.0, device=DEV)
+    finals = []
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        m = lvae.get_model('qarv_base').to(DEV)
+        with torch.no_grad():
+            before = m.eval()(im, lmb=lmb)['loss'].item()
+        m.train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True)
+        if graphed:
+            step = GraphedTrainStep(m, opt, tuple(im.shape), warmup=1)        # 1 eager warm-up update + 2 replays
+            losses = [float(step(im)) for _ in range(2)]
+            assert step.launches_per_replay > 300
+        else:
+            losses = []
+            for _ in range(3):
+                st = m(im)
+                opt.zero_grad(set_to_none=True)
+                st['loss'].backward()
+                opt.step()
+                losses.append(st['loss'].item())
+        assert all(np.isfinite(losses))
+        m.eval()
+        with torch.no_grad():
+            after = m(im, lmb=lmb)['loss'].item()
+        finals.append((before, after))
+    (b0, a0), (b1, a1) = finals
+    assert b0 == b1 and a0 < b0 and a1 < b1, finals            # both paths trained the weights the eval plans read
+    assert abs(a1 - a0) <= 0.25 * abs(b0 - a0), finals
