@@ -127,16 +127,18 @@ class QarvEngine:
     def _dev_f32(self, t):
         return t.detach().to(self.device, torch.float32).contiguous()
 
-    def _pack_gemm_weight(self, w2d, bias):
-        """w2d: [N, K] fp32 on device -> dict(w, bias, planes=[bf16 [N,K]] * npl)"""
+    def _pack_gemm_weight(self, w2d, bias, prec=None):
+        """w2d: [N, K] fp32 on device -> dict(w, bias, planes=[bf16 [N,K]] * npl); prec: precision mode the planes are
+        for (default: the model's)"""
         ent = dict(w=w2d.contiguous(), bias=None if bias is None else self._dev_f32(bias),
                    N=w2d.shape[0], K=w2d.shape[1], planes=[])
-        if self.npl:
+        npl, pfmt = (self.npl, self.pfmt) if prec is None else (N.NUM_PLANES[prec], N.PLANE_FORMAT[prec])
+        if npl:
             n = ent['w'].numel()
-            pl = [torch.empty(n, dtype=torch.bfloat16, device=self.device) for _ in range(self.npl)]
-            ptrs = [_ptr(t) for t in pl] + [0] * (3 - self.npl)
-            f16 = self.pfmt == N.PLANES_F16       # fp16 planes carry w * 2^8 (include/lvae_b200.h LVAE_PREC_F16X3)
-            N.check(self.lib.lvae_split_planes(_ptr(ent['w']), ptrs[0], ptrs[1], ptrs[2], n, self.pfmt,
+            pl = [torch.empty(n, dtype=torch.bfloat16, device=self.device) for _ in range(npl)]
+            ptrs = [_ptr(t) for t in pl] + [0] * (3 - npl)
+            f16 = pfmt == N.PLANES_F16       # fp16 planes carry w * 2^8 (include/lvae_b200.h LVAE_PREC_F16X3)
+            N.check(self.lib.lvae_split_planes(_ptr(ent['w']), ptrs[0], ptrs[1], ptrs[2], n, pfmt,
                                                N.F16_WEIGHT_SCALE if f16 else 1.0, self._stream()), 'split_planes')
             ent['planes'] = pl
         return ent
@@ -239,7 +241,7 @@ class QarvEngine:
 
     # ------------------------------------------------------------------ plan construction helpers
     def _gemm(self, P, name, a0, geom, went, out, epi=N.EPI_BIAS, a1=None, C1=0, gamma=None, res=None, r=0,
-              a_planes=None, out_planes=None, a_act=0, a1_planes=None, out_planes_act=0):
+              a_planes=None, out_planes=None, a_act=0, a1_planes=None, out_planes_act=0, prec=None):
         """geom = (B, H, W, C0, ksize, stride, pad) of the NHWC input a0.  In a tensor-core mode the A operand is
         either `a_planes` (bf16 planes written by the producing kernel) or a0/a1, which the library im2col-splits
         into the plan's workspace first."""
@@ -250,11 +252,13 @@ class QarvEngine:
         d.ksize, d.stride, d.pad = ks, st, pad
         d.w, d.bias, d.N = _ptr(went['w']), _ptr(went['bias']), went['N']
         d.epilogue, d.gamma, d.res, d.out = epi, _ptr(gamma), _ptr(res), _ptr(out)
-        d.shuffle_r, d.precision, d.a_act, d.out_planes_act = r, self.prec, a_act, out_planes_act
+        prec = self.prec if prec is None else prec
+        npl = N.NUM_PLANES[prec]
+        d.shuffle_r, d.precision, d.a_act, d.out_planes_act = r, prec, a_act, out_planes_act
         assert went['K'] == ks * ks * C0 + C1, (name, went['K'], ks, C0, C1)
         Mo = B * ((H + 2 * pad - ks) // st + 1) * ((W + 2 * pad - ks) // st + 1)
         ws = None
-        if self.npl:
+        if npl:
             N.set_planes(d, 'w', went['planes'])
             N.set_planes(d, 'a', a_planes)
             N.set_planes(d, 'out', out_planes)
@@ -262,7 +266,7 @@ class QarvEngine:
             if a1_planes is not None:
                 d.C1 = C1
             if a_planes is None:
-                ws = P.named('tc_ws', Mo * went['K'] * self.npl, dtype=torch.bfloat16)
+                ws = P.named('tc_ws', Mo * went['K'] * npl, dtype=torch.bfloat16)
                 d.workspace, d.workspace_bytes = _ptr(ws), ws.numel() * 2
         else:
             assert a_planes is None and out_planes is None

@@ -263,9 +263,15 @@ class TrainPath:
             ps += [getattr(vd, k).weight, getattr(vd, k).bias]
         return _VDFn.apply(self, wv, x, x1, *ps)
 
+    # Data-gradient GEMMs run in the 2-plane bf16 mode whatever the forward mode is: their A operand is a GRADIENT, whose
+    # magnitude (1e-3 ... 1e-9 at the default init, where the layer scale is 1e-6) is far outside what fp16 planes hold;
+    # bf16 planes have fp32's exponent range, and 16 significand bits are ample for a gradient (cuDNN's default for the
+    # reference's convolutions is TF32: 11 bits).
+    DGRAD_PREC = N.PREC_BF16X3
+
     def _transposed(self, key, w2d):
         """packed operand planes of a transposed (and possibly row-scaled) weight for the data-gradient GEMMs"""
-        return self.eng._pack_gemm_weight(w2d.t().contiguous(), None)
+        return self.eng._pack_gemm_weight(w2d.t().contiguous(), None, prec=self.DGRAD_PREC)
 
     def block_backward(self, blk, x, ada, params, gout):
         """Gradients of one ConvNeXt block w.r.t. (x, ada, *params).  The two GEMM data gradients and the recomputation
@@ -295,7 +301,8 @@ class TrainPath:
         d_b2 = gam * db2_raw
         d_gamma = ((w2.detach() * dw2_raw).sum(1) + b2.detach() * db2_raw).reshape(gamma.shape)
         dg = torch.empty(M, hid, device=x.device)
-        eng._gemm(P, 'fc2.dgrad', go, (1, 1, M, C_, 1, 1, 0), self._transposed('w2', gam[:, None] * w2.detach()), dg, epi=N.EPI_BIAS)
+        eng._gemm(P, 'fc2.dgrad', go, (1, 1, M, C_, 1, 1, 0), self._transposed('w2', gam[:, None] * w2.detach()), dg, epi=N.EPI_BIAS,
+                  prec=self.DGRAD_PREC)
         dh = torch.ops.aten.gelu_backward(dg, h)
         del dg, g
         # fc1: h = a W1^T + b1;  a is needed for the weight gradient: one more (fp32) dwln launch
@@ -305,7 +312,7 @@ class TrainPath:
         d_w1 = dh.t().mm(a32)
         d_b1 = dh.sum(0)
         da = torch.empty(M, C_, device=x.device)
-        eng._gemm(P, 'fc1.dgrad', dh, (1, 1, M, hid, 1, 1, 0), self._transposed('w1', w1.detach()), da, epi=N.EPI_BIAS)
+        eng._gemm(P, 'fc1.dgrad', dh, (1, 1, M, hid, 1, 1, 0), self._transposed('w1', w1.detach()), da, epi=N.EPI_BIAS, prec=self.DGRAD_PREC)
         del dh, h, a32
         # dwconv + LayerNorm + modulation: recompute the conv output, LayerNorm / modulation backward, filter gradient,
         # data gradient (transposed conv + the residual branch's gradient) -- csrc/dwln_bwd.cu

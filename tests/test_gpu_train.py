@@ -73,6 +73,39 @@ def test_qarv_train_step_gradients_match_oracle_autograd(train_model, sensitised
     print('worst relative gradient error', worst)
 
 
+@pytest.mark.parametrize('native_bwd', [True, False])
+def test_qarv_gradients_at_default_init_match_oracle_autograd(native_lib, native_bwd):
+    """Real training conditions: the reference's default initialisation has layer scale gamma = 1e-6, so the gradients
+    inside every residual branch are ~1e-6 of the trunk's.  Adam normalises them, so they must be RELATIVELY right:
+    no absolute tolerance here (this is what rules out fp16 operand planes for the gradient GEMMs)."""
+    import lvae
+    torch.manual_seed(0)
+    m = lvae.get_model('qarv_base')
+    sd = {k: v.detach().clone() for k, v in m.named_parameters()}
+    m = m.to(DEV).train()
+    m.train_path.native_bwd = native_bwd
+    B, H, W = 2, 64, 64
+    im = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(6))
+    lmb = torch.tensor([32.0, 2048.0])
+    noise = _noise(m, B, H, W, 3)
+    st = m._forward_train(im.to(DEV), lmb.to(DEV), noise=noise)
+    st['loss'].backward()
+    ref, grads = _oracle_grads(O.qarv_forward, sd, im, lmb, mode='train', noise=noise)
+    assert abs(st['loss'].item() - ref['loss'].item()) <= 1e-5 * abs(ref['loss'].item())
+    worst = (0.0, None)
+    for name, p in m.named_parameters():
+        gr = grads[name]
+        g = p.grad.detach().cpu().reshape(gr.shape)
+        scale = float(gr.norm())
+        if scale == 0.0:
+            assert float(g.norm()) == 0.0, name
+            continue
+        rel = float((g - gr).norm()) / scale
+        worst = max(worst, (rel, name, scale))
+        assert rel <= 5e-3, (name, rel, scale)
+    print('worst relative gradient error at default init', worst)
+
+
 def test_qarv_forward_routes_to_training_path_and_adam_reduces_the_loss(native_lib):
     import lvae
     torch.manual_seed(0)
