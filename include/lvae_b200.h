@@ -172,6 +172,14 @@ int lvae_dwconv_wgrad(const float* dc, const float* x, float* dw, float* db,
 int lvae_ln_mod_bwd(const float* c, const float* da, const float* ada, int64_t ada_stride, int64_t ada_off,
                     const float* ln_w, float* dc, float* dmod, int B, int HW, int C, void* stream);
 
+/* ---- weight gradients of the dense layers (training step; autograd of F.linear / 1x1 conv2d) -------------------
+ * dW[n, k] = sum_p dY[p, n] * X[p, k] on the tensor cores: lvae_split_planes_t transposes a pixel-major fp32 matrix
+ * [P, C] into two K-major bf16 planes [C, P] (hi | lo; P even), lvae_gemm_wgrad contracts two such operands over P
+ * (P % 8 == 0) with split-K over the grid and writes dw [n_out, k_in] fp32 (zeroed first, fp32 atomics). */
+int lvae_split_planes_t(const float* x, void* p0, void* p1, int64_t P, int C, void* stream);
+int lvae_gemm_wgrad(const void* dyt_p0, const void* dyt_p1, const void* xt_p0, const void* xt_p1,
+                    float* dw, int n_out, int k_in, int64_t P, void* stream);
+
 /* ---- fused latent-layer kernels (qarv/model.py:51-53,90-96,104-113; CompressAI GaussianConditional) --
  * prior [M, 2*zdim] (pm | plogv_raw) and qm [M, zdim] are NHWC matrices; hw = h*w positions per image.
  * Eval (K11+K12+K15): z = rint(qm-pm)+pm; kl = -ln max(Phi((.5-|z-pm|)/s) - Phi((-.5-|z-pm|)/s), 1e-9),

@@ -66,6 +66,9 @@ struct TcParams {
   float acc_scale;       // 1 / (scale the weight planes carry): 1, or 2^-8 in the fp16 mode -- exact
   // implicit 3x3 conv (stride 1, pad 1) from NHWC planes: an M-tile is a CONV_TH x CONV_TW pixel patch of one image
   int conv, cH, cW, cC, tiles_w, tiles_h;
+  // split-K (weight gradients: K = pixels is the long dimension): tile index t = z * base_tiles + tile, split z owns the
+  // k-blocks [z * kb_per, (z + 1) * kb_per); partial results meet in fp32 atomics on `out` (zeroed by the caller)
+  int base_tiles, kb_per, atomic;
 };
 constexpr int CONV_TW = 16, CONV_TH = 8;       // 128 output pixels per tile
 
@@ -150,13 +153,15 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      for (int tz = blockIdx.x; tz < p.num_tiles; tz += gridDim.x) {
+        const int z = tz / p.base_tiles, t = tz - z * p.base_tiles;
+        const int kb0 = z * p.kb_per, kb1 = min(nkb, kb0 + p.kb_per);
         const int mt = t / p.n_tiles;
         const int m0 = mt * TC_BM, n0 = (t % p.n_tiles) * p.BN;
         // conv mode: tile -> (image, patch row, patch column)
         const int ctx = mt % p.tiles_w, cty = (mt / p.tiles_w) % p.tiles_h, cb = mt / (p.tiles_w * p.tiles_h);
         const int cpt = p.cC / p.BK;                             // k-blocks per filter tap
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(empty_bar + s), ph ^ 1);
           const uint32_t fb = smem_u32(full_bar + s);
           mbar_expect_tx(fb, (uint32_t)stage_bytes);
@@ -181,7 +186,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             // optional: pull the same k-block of this CTA's NEXT tile into L2 (off by default, see TcParams::prefetch)
             if (p.prefetch) {
               const int tn = t + gridDim.x;
-              if (tn < p.num_tiles && (tn / p.n_tiles) != mt) {
+              if (tn < p.base_tiles && (tn / p.n_tiles) != mt) {
                 const int m1 = (tn / p.n_tiles) * TC_BM;
 #pragma unroll
                 for (int pl = 0; pl < NPL; ++pl) tma_prefetch_2d(&maps.a[pl], kb * p.BK, m1);
@@ -200,13 +205,14 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     const uint32_t idesc2n = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 2) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // N = 2 * BN
     int s = 0; uint32_t ph = 0; int it = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+    for (int tz = blockIdx.x; tz < p.num_tiles; tz += gridDim.x, ++it) {
       const int acc = it & 1;
+      const int kb0 = (tz / p.base_tiles) * p.kb_per, kb1 = min(nkb, kb0 + p.kb_per);
       mbar_wait(smem_u32(tempty_bar + acc), (((uint32_t)it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);      // main accumulator
       const uint32_t d_cross = d_tmem + (uint32_t)p.BN;                       // correction terms (NPL >= 2)
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(smem_u32(full_bar + s), ph);
         tc_fence_after();
         if (lane == 0) {
@@ -220,7 +226,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           const int ksteps = p.BK / 16;
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t ko = (uint64_t)(k * 2);           // 16 bf16 = 32 bytes = 2 x 16-byte units along K
-            const uint32_t first = (kb | k) ? 1u : 0u;
+            const uint32_t first = ((kb - kb0) | k) ? 1u : 0u;
             if (NPL >= 2) {
               // one tcgen05.mma costs ~142 cycles whatever its N (scripts/probe/mma_probe.cu), so a0 * b0 (-> main) and
               // a0 * b1 (-> cross) ride in ONE instruction of N = 2 * BN: the B planes 0 and 1 are adjacent in the stage
@@ -237,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             }
           }
           tc_commit(smem_u32(empty_bar + s));               // frees the stage once these MMAs have read it
-          if (kb == nkb - 1) tc_commit(smem_u32(tfull_bar + acc));
+          if (kb == kb1 - 1) tc_commit(smem_u32(tfull_bar + acc));
         }
         __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -251,8 +257,9 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     uint32_t* stg = reinterpret_cast<uint32_t*>(epi_smem) + ew * tc_stage_words(EK);
     const bool f16 = p.f16 != 0;
     int it = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+    for (int tz = blockIdx.x; tz < p.num_tiles; tz += gridDim.x, ++it) {
       const int acc = it & 1;
+      const int t = tz % p.base_tiles;
       const int m0 = (t / p.n_tiles) * TC_BM, n0 = (t % p.n_tiles) * p.BN;
       mbar_wait(smem_u32(tfull_bar + acc), ((uint32_t)it >> 1) & 1);
       tc_fence_after();
@@ -456,7 +463,10 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 #pragma unroll 2
             for (int r = 0; r < 32; ++r) {
               const int m = row0 + r;
-              if (m < p.M) epi_store(p, m, n, epi_value(p, m, n, __uint_as_float(stg[r * 33 + lane])));
+              if (m < p.M) {
+                if (p.atomic) atomicAdd(p.out + (int64_t)m * p.N + n, __uint_as_float(stg[r * 33 + lane]) * p.acc_scale);
+                else epi_store(p, m, n, epi_value(p, m, n, __uint_as_float(stg[r * 33 + lane])));
+              }
             }
           }
           __syncwarp();
@@ -580,7 +590,12 @@ static int pick_bn(int N, int npl) {
   return (bn + 15) & ~15;
 }
 
-int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
+int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stream);
+int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) { return gemm_tc_launch_split(d, 0, stream); }
+
+// split_k != 0: split-K over the persistent grid, partial tiles added atomically into d->out (which the caller zeroed);
+// plain [M,K] x [N,K] only (LVAE_EPI_BIAS without bias)
+int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stream) {
   const int npl = num_planes(d->precision);
   int Ho, Wo, K; int64_t M64;
   tc_geometry(d, &Ho, &Wo, &M64, &K);
@@ -641,7 +656,7 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   // epilogue specialisation
   const bool shuffle = d->epilogue == LVAE_EPI_SHUFFLE_NHWC || d->epilogue == LVAE_EPI_SHUFFLE_NCHW;
   int ek = EK_MISC;
-  if (conv) ek = EK_MISC;                                      // tile rows are pixel patches: its own store loop
+  if (conv || split_k) ek = EK_MISC;                           // tile rows are pixel patches: its own store loop | atomics
   else if (d->epilogue == LVAE_EPI_BIAS_GELU && p.out_pl[0] != nullptr && p.out == nullptr && d->N % 2 == 0) ek = EK_GELU;
   else if (!shuffle && d->N % 4 == 0) ek = EK_ROWS;
   const int fixed = 1024 + tc_epi_stage_bytes(ek) + 256;       // alignment slack + transpose buffers + barriers
@@ -660,6 +675,20 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) {
   if (stages < 2) stages = 2;
   LVAE_CHECK_ARG(stages * stage_bytes <= budget);
   p.stages = stages;
+  p.base_tiles = p.num_tiles; p.kb_per = nkb; p.atomic = 0;
+  if (split_k) {
+    LVAE_CHECK_ARG(!conv && !concat_planes && d->bias == nullptr && d->epilogue == LVAE_EPI_BIAS && d->out != nullptr &&
+                   d->out_planes[0] == nullptr);
+    int dev_sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev); }
+    int splits = (2 * dev_sms + p.base_tiles - 1) / p.base_tiles;
+    if (splits > nkb) splits = nkb;
+    if (splits < 1) splits = 1;
+    p.kb_per = (nkb + splits - 1) / splits;
+    splits = (nkb + p.kb_per - 1) / p.kb_per;                  // every split owns at least one k-block
+    p.num_tiles = p.base_tiles * splits;
+    p.atomic = 1;
+  }
   p.bias = d->bias; p.gamma = d->gamma; p.res = d->res;
   p.epi = d->epilogue; p.r = d->shuffle_r; p.Ho = Ho; p.Wo = Wo;
   { static const char* e = getenv("LVAE_TC_PREFETCH"); p.prefetch = e ? atoi(e) : 0; }

@@ -1,0 +1,70 @@
+// Weight gradients of the dense layers on the tensor cores (training step):
+//   dW[n, k] = sum_p dY[p, n] * X[p, k]        (nn.Linear / 1x1 conv; p runs over the B*H*W pixels)
+// is the GEMM of gemm_tc.cu with the pixel index as the contraction dimension.  Both operands are stored pixel-major
+// ([P, C] rows), so they are first transposed into K-major 2-plane bf16 operands [C, P] (lvae_split_planes_t, one
+// HBM pass each: read 4 B, write 4 B per element); bf16 planes because dY is a gradient (fp32 exponent range, see
+// lvae/training.py), two of them = 16 significand bits.  The contraction is split over the persistent grid (split-K,
+// ~2 work items per SM) and the partial tiles meet in fp32 atomics.
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace lvae {
+
+int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stream);
+
+// x [P, C] fp32 -> hi / lo bf16 planes [C, P];  P even
+__global__ void __launch_bounds__(256) split_planes_t_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ p0,
+                                                             __nv_bfloat16* __restrict__ p1, int64_t P, int C) {
+  __shared__ float tile[64][33];
+  const int64_t pbase = (int64_t)blockIdx.x * 64;
+  const int cbase = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 64; r += 8) {
+    const int64_t pp = pbase + r;
+    const int c = cbase + tx;
+    tile[r][tx] = (pp < P && c < C) ? __ldg(x + pp * C + c) : 0.f;
+  }
+  __syncthreads();
+  const int64_t pp = pbase + 2 * tx;
+  if (pp >= P) return;
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int c = cbase + cc;
+    if (c >= C) break;
+    float2 v = make_float2(tile[2 * tx][cc], tile[2 * tx + 1][cc]);
+    const uint32_t hi = split_next<false>(v);
+    const uint32_t lo = split_next<false>(v);
+    *reinterpret_cast<uint32_t*>(p0 + (int64_t)c * P + pp) = hi;
+    *reinterpret_cast<uint32_t*>(p1 + (int64_t)c * P + pp) = lo;
+  }
+}
+
+}  // namespace lvae
+
+using namespace lvae;
+
+extern "C" int lvae_split_planes_t(const float* x, void* p0, void* p1, int64_t P, int C, void* stream) {
+  LVAE_CHECK_ARG(x && p0 && p1 && P > 0 && C > 0 && P % 2 == 0);
+  const dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 31) / 32));
+  split_planes_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)p0, (__nv_bfloat16*)p1, P, C);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lvae_gemm_wgrad(const void* dyt_p0, const void* dyt_p1, const void* xt_p0, const void* xt_p1,
+                               float* dw, int n_out, int k_in, int64_t P, void* stream) {
+  LVAE_CHECK_ARG(dyt_p0 && dyt_p1 && xt_p0 && xt_p1 && dw && n_out > 0 && k_in > 0);
+  LVAE_CHECK_ARG(P >= 8 && P % 8 == 0 && P < (1ll << 31));
+  cudaStream_t st = (cudaStream_t)stream;
+  LVAE_CUDA_CALL(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)n_out * k_in, st));
+  lvae_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.B = 1; d.H = 1; d.W = n_out; d.C0 = (int)P; d.C1 = 0;
+  d.ksize = 1; d.stride = 1; d.pad = 0;
+  d.N = k_in;
+  d.epilogue = LVAE_EPI_BIAS;
+  d.out = dw;
+  d.precision = LVAE_PREC_BF16X3;
+  d.a_planes[0] = dyt_p0; d.a_planes[1] = dyt_p1;
+  d.w_planes[0] = xt_p0; d.w_planes[1] = xt_p1;
+  return gemm_tc_launch_split(&d, 1, st);
+}

@@ -57,6 +57,8 @@ _PROTOS = {
     'lvae_dwconv': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_dwconv_wgrad': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_ln_mod_bwd': (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'lvae_split_planes_t': (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int, _fp]),
+    'lvae_gemm_wgrad': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int64, _fp]),
     'lvae_latent_num_partials': (C.c_int, [C.c_int, C.c_int]),
     'lvae_latent_eval': (C.c_int, [_fp, _fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp, _fp,
                                    C.c_int, C.c_int, C.c_int, C.c_int, _fp]),

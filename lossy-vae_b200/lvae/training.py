@@ -233,6 +233,7 @@ class TrainPath:
         self.P = None
         # LVAE_TRAIN_NATIVE_BWD=0: every backward through ATen on recomputed sub-graphs (the cross-check of the native pieces)
         self.native_bwd = os.environ.get('LVAE_TRAIN_NATIVE_BWD', '1') != '0'
+        self.native_wgrad = os.environ.get('LVAE_TRAIN_NATIVE_WGRAD', '1') != '0'
         self.force_refresh = False      # GraphedTrainStep: the captured step must always re-pack the weights
 
     # ---- helpers
@@ -273,6 +274,20 @@ class TrainPath:
         """packed operand planes of a transposed (and possibly row-scaled) weight for the data-gradient GEMMs"""
         return self.eng._pack_gemm_weight(w2d.t().contiguous(), None, prec=self.DGRAD_PREC)
 
+    def _t_planes(self, name, x2d):
+        """[P, C] fp32 -> two K-major bf16 planes [C, P] in a scratch buffer (the operand format of lvae_gemm_wgrad)"""
+        P_, C_ = x2d.shape
+        buf = self.P.named(name, 2 * P_ * C_, dtype=torch.bfloat16)
+        p0, p1 = buf[:P_ * C_], buf[P_ * C_:2 * P_ * C_]
+        self.P.op('split_t', self.eng.lib.lvae_split_planes_t, _ptr(x2d), _ptr(p0), _ptr(p1), P_, C_)
+        return p0, p1
+
+    def _wgrad(self, dy_t, x_t, n_out, k_in, P_):
+        dw = torch.empty(n_out, k_in, device=self.eng.device)
+        self.P.op('wgrad', self.eng.lib.lvae_gemm_wgrad, _ptr(dy_t[0]), _ptr(dy_t[1]), _ptr(x_t[0]), _ptr(x_t[1]), _ptr(dw),
+                  n_out, k_in, P_)
+        return dw
+
     def block_backward(self, blk, x, ada, params, gout):
         """Gradients of one ConvNeXt block w.r.t. (x, ada, *params).  The two GEMM data gradients and the recomputation
         of the fc1 pre-activation run on the tcgen05 GEMM; see the module docstring for what is still ATen."""
@@ -295,7 +310,11 @@ class TrainPath:
         g = F.gelu(h)
         go = gout.reshape(M, C_)
         # fc2: out = x + gamma * (g W2^T + b2)
-        dw2_raw = go.t().mm(g)                                  # cuBLAS fp32  [C, hid]
+        tc_wgrad = self.native_wgrad and M % 8 == 0 and M >= 1024
+        if tc_wgrad:                                            # tcgen05, split over the pixels (csrc/wgrad.cu)
+            dw2_raw = self._wgrad(self._t_planes('wg_a', go), self._t_planes('wg_b', g), C_, hid, M)
+        else:
+            dw2_raw = go.t().mm(g)                              # tiny layers: cuBLAS fp32  [C, hid]
         db2_raw = go.sum(0)
         d_w2 = gam[:, None] * dw2_raw
         d_b2 = gam * db2_raw
@@ -309,7 +328,10 @@ class TrainPath:
         a32 = torch.empty(M, C_, device=x.device)
         P.op('dwln', eng.lib.lvae_dwconv_ln_adaln, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']), _ptr(ada), eng.ada_total, off,
              _ptr(wb.get('ln_w')), _ptr(wb.get('ln_b')), _ptr(a32), B, H, W, C_, k)
-        d_w1 = dh.t().mm(a32)
+        if tc_wgrad:
+            d_w1 = self._wgrad(self._t_planes('wg_b', dh), self._t_planes('wg_a', a32), hid, C_, M)
+        else:
+            d_w1 = dh.t().mm(a32)
         d_b1 = dh.sum(0)
         da = torch.empty(M, C_, device=x.device)
         eng._gemm(P, 'fc1.dgrad', dh, (1, 1, M, hid, 1, 1, 0), self._transposed('w1', w1.detach()), da, epi=N.EPI_BIAS, prec=self.DGRAD_PREC)
