@@ -8,15 +8,17 @@ Forward: the SAME liblvae_b200 kernels as the inference plans (dwconv+LN+AdaLN, 
 kernel), launched op by op through `torch.autograd.Function`s that keep only each op's inputs (activation checkpointing
 at op granularity: ConvNeXt block, convolution, VDBlock, latent layer).
 
-Backward -- STATE OF THIS ROUND (DESIGN.md §4.6), per op:
+Backward -- STATE OF THIS ROUND (DESIGN.md 4.6), per op:
   * latent layer: native (`lvae_latent_train_bwd`);
-  * ConvNeXt block: the pre-activation of fc1 is recomputed with the native kernels (dwconv+LN kernel, tcgen05 GEMM),
-    both data gradients (through fc2 and fc1) are native tcgen05 GEMMs on transposed packed weights; the weight
-    gradients are cuBLAS fp32 matmuls (`torch.mm`), GELU' is ATen's elementwise `gelu_backward`, and the
-    dwconv + LayerNorm + AdaLN part is differentiated by ATen on a recomputed sub-graph;
+  * ConvNeXt block: native except two elementwise ops -- the fc1 pre-activation is recomputed with the forward kernels
+    (dwconv+LN kernel, tcgen05 GEMM); both data gradients are tcgen05 GEMMs on transposed packed weights; both weight
+    gradients are tcgen05 GEMMs contracting over the pixels (`lvae_split_planes_t` + split-K `lvae_gemm_wgrad`); the
+    dwconv + LayerNorm + AdaLN / affine part runs on the kernels of csrc/dwln_bwd.cu.  GELU / GELU' are ATen's
+    elementwise kernels and the two bias gradients ATen column sums;
   * convolutions (patch down / up, 1x1 and 3x3 heads) and qres VDBlocks: ATen autograd on a recomputed sub-graph.
 Everything ATen here is a LIBRARY call (cuBLAS / cuDNN), not this repo's product; it is what the native backward
-kernels of the next round replace, one op at a time, each against the gradient tests in tests/test_gpu_train.py.
+kernels of the next round replace, one op at a time, each against the gradient tests in tests/test_gpu_train.py
+(`TrainPath.native_bwd = False` runs every backward through ATen: the cross-check of the native pieces).
 There is no CPU path: every Function launches CUDA kernels of liblvae_b200.so.
 """
 import math
