@@ -228,7 +228,7 @@ def run_train(args):
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
     graphed = world == 1 and not args.no_train_graph
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graphed)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graphed, fused=True)
     im_host = make_input('rand', B, h, w, 1000 + rank).pin_memory()
     im_dev = im_host.to(dev)
     torch.manual_seed(1234 + rank)                      # lambda / noise draws differ per rank
@@ -288,7 +288,7 @@ def run_train(args):
                                                  f'batch {B} per GPU (BASELINE configs[3])'),
                        'batch_per_gpu': B, 'global_batch': B * world,
                        'parallelism': f'data parallel x{world}' + (', NCCL gradient all-reduce (DistributedDataParallel buckets)' if world > 1 else ''),
-                       'weights': 'seeded default init', 'optimizer': 'Adam (torch.optim)',
+                       'weights': 'seeded default init', 'optimizer': 'Adam (torch.optim, fused=True)',
                        'value_path': 'whole step replayed as one CUDA graph (lvae.training.GraphedTrainStep)' if graphed else 'eager step',
                        'e2e_path': 'eager step through model.forward() / loss.backward() / optimizer.step()',
                        'backward': 'latent layers and ConvNeXt blocks native (tcgen05 data + weight gradients in 2-plane bf16, dwconv/LN/'

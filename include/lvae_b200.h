@@ -51,7 +51,9 @@ enum lvae_epilogue {
   LVAE_EPI_SCALE_RES = 2,     /* out = (acc + bias) * gamma[n] + res[m,n] (common.py:157-160) */
   LVAE_EPI_BIAS_RES = 3,      /* out = res[m,n] + (acc + bias)         (qarv/model.py:74) */
   LVAE_EPI_SHUFFLE_NHWC = 4,  /* PixelShuffle(r) into NHWC [B,H*r,W*r,N/r^2]; packed n = (i*r+j)*Co + c */
-  LVAE_EPI_SHUFFLE_NCHW = 5   /* PixelShuffle(r) into NCHW [B,N/r^2,H*r,W*r] (final image)  */
+  LVAE_EPI_SHUFFLE_NCHW = 5,  /* PixelShuffle(r) into NCHW [B,N/r^2,H*r,W*r] (final image)  */
+  LVAE_EPI_GELU_BWD = 6       /* out = (acc + bias) * gelu'(res[m,n]): data gradient through Mlp.act, res = the
+                               * pre-activation (training step; tensor-core modes, plain [M,K] GEMMs, N % 4 == 0) */
 };
 
 enum lvae_precision {
@@ -177,6 +179,10 @@ int lvae_ln_mod_bwd(const float* c, const float* da, const float* ada, int64_t a
  * [P, C] into two K-major bf16 planes [C, P] (hi | lo; P even), lvae_gemm_wgrad contracts two such operands over P
  * (P % 8 == 0) with split-K over the grid and writes dw [n_out, k_in] fp32 (zeroed first, fp32 atomics). */
 int lvae_split_planes_t(const float* x, void* p0, void* p1, int64_t P, int C, void* stream);
+/* the same with act = 1: planes of gelu(x) (the fc2 weight gradient's operand from the recomputed pre-activation), and /
+ * or colsum != NULL: colsum[c] += sum_p x[p, c] (the bias gradient of the layer whose dY is being split; the caller
+ * zeroes it) */
+int lvae_split_planes_t_ex(const float* x, void* p0, void* p1, int64_t P, int C, int act, float* colsum, void* stream);
 int lvae_gemm_wgrad(const void* dyt_p0, const void* dyt_p1, const void* xt_p0, const void* xt_p1,
                     float* dw, int n_out, int k_in, int64_t P, void* stream);
 

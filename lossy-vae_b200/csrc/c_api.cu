@@ -29,7 +29,10 @@ extern "C" int lvae_gemm(const lvae_gemm_desc* d, void* stream) {
                                             d->epilogue != LVAE_EPI_BIAS_GELU && d->N % 4 == 0 && d->ksize == 1));
   LVAE_CHECK_ARG(d->a_act == 0 || (d->a_act == 1 && d->a0 != nullptr && d->a_planes[0] == nullptr));
   LVAE_CHECK_ARG(d->H + 2 * d->pad >= d->ksize && d->W + 2 * d->pad >= d->ksize);
-  LVAE_CHECK_ARG(d->epilogue >= LVAE_EPI_BIAS && d->epilogue <= LVAE_EPI_SHUFFLE_NCHW);
+  LVAE_CHECK_ARG(d->epilogue >= LVAE_EPI_BIAS && d->epilogue <= LVAE_EPI_GELU_BWD);
+  if (d->epilogue == LVAE_EPI_GELU_BWD)
+    LVAE_CHECK_ARG(d->res != nullptr && d->out != nullptr && d->precision != LVAE_PREC_FP32 && d->ksize == 1 && d->N % 4 == 0 &&
+                   d->out_planes[0] == nullptr && d->C0 >= 64);
   if (d->epilogue == LVAE_EPI_SCALE_RES) LVAE_CHECK_ARG(d->gamma && d->res);
   if (d->epilogue == LVAE_EPI_BIAS_RES) LVAE_CHECK_ARG(d->res != nullptr);
   if (d->epilogue == LVAE_EPI_SHUFFLE_NHWC || d->epilogue == LVAE_EPI_SHUFFLE_NCHW)

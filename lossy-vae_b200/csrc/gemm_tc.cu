@@ -74,6 +74,12 @@ constexpr int CONV_TW = 16, CONV_TH = 8;       // 128 output pixels per tile
 
 struct TcMaps { CUtensorMap a[3]; CUtensorMap b[3]; CUtensorMap a1[3]; };   // a1: second K segment (K-concat from planes)
 
+// d/dh gelu(h) = Phi(h) + h phi(h)  (erf form, as F.gelu's autograd)
+__device__ __forceinline__ float gelu_grad(float h) {
+  const float cdf = 0.5f * (1.f + erff(h * 0.70710678118654752f));
+  return fmaf(h * 0.39894228040143268f, __expf(-0.5f * h * h), cdf);
+}
+
 __device__ __forceinline__ float epi_value(const TcParams& p, int m, int n, float acc) {
   float v = acc;
   if (p.bias) v = __fadd_rn(v, __ldg(p.bias + n));
@@ -81,6 +87,7 @@ __device__ __forceinline__ float epi_value(const TcParams& p, int m, int n, floa
     case LVAE_EPI_BIAS_GELU: v = gelu_erf(v); break;
     case LVAE_EPI_SCALE_RES: v = __fadd_rn(__fmul_rn(v, __ldg(p.gamma + n)), p.res[(int64_t)m * p.N + n]); break;
     case LVAE_EPI_BIAS_RES:  v = __fadd_rn(p.res[(int64_t)m * p.N + n], v); break;
+    case LVAE_EPI_GELU_BWD:  v *= gelu_grad(p.res[(int64_t)m * p.N + n]); break;
     default: break;
   }
   return v;
@@ -376,7 +383,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           if (4 * l8 < width && n < p.N) {                   // N % 4 == 0 (host-checked): n + 3 < N
             const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
             const bool scale_res = p.epi == LVAE_EPI_SCALE_RES;
-            const bool has_res = scale_res || p.epi == LVAE_EPI_BIAS_RES;
+            const bool gelu_bwd = p.epi == LVAE_EPI_GELU_BWD;
+            const bool has_res = scale_res || gelu_bwd || p.epi == LVAE_EPI_BIAS_RES;
             const float4 g4 = scale_res ? __ldg(reinterpret_cast<const float4*>(p.gamma + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
             const int64_t o0 = (int64_t)(row0 + sub) * p.N + n;
             const int rows = p.M - row0 - sub;               // valid while 4 * i < rows
@@ -394,6 +402,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
               if (scale_res) {
                 x.x = __fadd_rn(__fmul_rn(x.x, g4.x), rr[i].x); x.y = __fadd_rn(__fmul_rn(x.y, g4.y), rr[i].y);
                 x.z = __fadd_rn(__fmul_rn(x.z, g4.z), rr[i].z); x.w = __fadd_rn(__fmul_rn(x.w, g4.w), rr[i].w);
+              } else if (gelu_bwd) {
+                x.x *= gelu_grad(rr[i].x); x.y *= gelu_grad(rr[i].y); x.z *= gelu_grad(rr[i].z); x.w *= gelu_grad(rr[i].w);
               } else if (has_res) {
                 x.x = __fadd_rn(rr[i].x, x.x); x.y = __fadd_rn(rr[i].y, x.y);
                 x.z = __fadd_rn(rr[i].z, x.z); x.w = __fadd_rn(rr[i].w, x.w);

@@ -12,29 +12,53 @@ namespace lvae {
 
 int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stream);
 
-// x [P, C] fp32 -> hi / lo bf16 planes [C, P];  P even
+// x [P, C] fp32 -> hi / lo bf16 planes [C, P];  P even.  One CTA owns 32 channels x ST_TILES * 64 pixels.
+// ACT: planes of gelu(x).  colsum != NULL: colsum[c] += sum over the CTA's pixels of x[p, c] (one atomic per channel).
+constexpr int ST_TILES = 8;
+template <bool ACT>
 __global__ void __launch_bounds__(256) split_planes_t_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ p0,
-                                                             __nv_bfloat16* __restrict__ p1, int64_t P, int C) {
+                                                             __nv_bfloat16* __restrict__ p1, int64_t P, int C,
+                                                             float* __restrict__ colsum) {
   __shared__ float tile[64][33];
-  const int64_t pbase = (int64_t)blockIdx.x * 64;
+  __shared__ float red[8][32];
   const int cbase = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 64; r += 8) {
-    const int64_t pp = pbase + r;
-    const int c = cbase + tx;
-    tile[r][tx] = (pp < P && c < C) ? __ldg(x + pp * C + c) : 0.f;
+  float csum = 0.f;
+  for (int it = 0; it < ST_TILES; ++it) {
+    const int64_t pbase = ((int64_t)blockIdx.x * ST_TILES + it) * 64;
+    if (pbase >= P) break;
+    __syncthreads();
+    for (int r = ty; r < 64; r += 8) {
+      const int64_t pp = pbase + r;
+      const int c = cbase + tx;
+      float v = (pp < P && c < C) ? __ldg(x + pp * C + c) : 0.f;
+      if (ACT) v = gelu_erf(v);
+      csum += v;
+      tile[r][tx] = v;
+    }
+    __syncthreads();
+    const int64_t pp = pbase + 2 * tx;
+    if (pp < P) {
+      for (int cc = ty; cc < 32; cc += 8) {
+        const int c = cbase + cc;
+        if (c >= C) break;
+        float2 v = make_float2(tile[2 * tx][cc], tile[2 * tx + 1][cc]);
+        const uint32_t hi = split_next<false>(v);
+        const uint32_t lo = split_next<false>(v);
+        *reinterpret_cast<uint32_t*>(p0 + (int64_t)c * P + pp) = hi;
+        *reinterpret_cast<uint32_t*>(p1 + (int64_t)c * P + pp) = lo;
+      }
+    }
   }
-  __syncthreads();
-  const int64_t pp = pbase + 2 * tx;
-  if (pp >= P) return;
-  for (int cc = ty; cc < 32; cc += 8) {
-    const int c = cbase + cc;
-    if (c >= C) break;
-    float2 v = make_float2(tile[2 * tx][cc], tile[2 * tx + 1][cc]);
-    const uint32_t hi = split_next<false>(v);
-    const uint32_t lo = split_next<false>(v);
-    *reinterpret_cast<uint32_t*>(p0 + (int64_t)c * P + pp) = hi;
-    *reinterpret_cast<uint32_t*>(p1 + (int64_t)c * P + pp) = lo;
+  if (colsum != nullptr) {
+    red[ty][tx] = csum;
+    __syncthreads();
+    if (ty == 0 && cbase + tx < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][tx];
+      atomicAdd(colsum + cbase + tx, t);
+    }
   }
 }
 
@@ -42,12 +66,17 @@ __global__ void __launch_bounds__(256) split_planes_t_kernel(const float* __rest
 
 using namespace lvae;
 
-extern "C" int lvae_split_planes_t(const float* x, void* p0, void* p1, int64_t P, int C, void* stream) {
-  LVAE_CHECK_ARG(x && p0 && p1 && P > 0 && C > 0 && P % 2 == 0);
-  const dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 31) / 32));
-  split_planes_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)p0, (__nv_bfloat16*)p1, P, C);
+extern "C" int lvae_split_planes_t_ex(const float* x, void* p0, void* p1, int64_t P, int C, int act, float* colsum, void* stream) {
+  LVAE_CHECK_ARG(x && p0 && p1 && P > 0 && C > 0 && P % 2 == 0 && (act == 0 || act == 1));
+  const dim3 grid((unsigned)((P + 64 * ST_TILES - 1) / (64 * ST_TILES)), (unsigned)((C + 31) / 32));
+  if (act) split_planes_t_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)p0, (__nv_bfloat16*)p1, P, C, colsum);
+  else split_planes_t_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)p0, (__nv_bfloat16*)p1, P, C, colsum);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int lvae_split_planes_t(const float* x, void* p0, void* p1, int64_t P, int C, void* stream) {
+  return lvae_split_planes_t_ex(x, p0, p1, P, C, 0, nullptr, stream);
 }
 
 extern "C" int lvae_gemm_wgrad(const void* dyt_p0, const void* dyt_p1, const void* xt_p0, const void* xt_p1,

@@ -8,7 +8,7 @@ from pathlib import Path
 _LIB_PATH = Path(__file__).resolve().parent.parent / 'lib' / 'liblvae_b200.so'
 _lib = None
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_SCALE_RES, EPI_BIAS_RES, EPI_SHUFFLE_NHWC, EPI_SHUFFLE_NCHW = range(6)
+EPI_BIAS, EPI_BIAS_GELU, EPI_SCALE_RES, EPI_BIAS_RES, EPI_SHUFFLE_NHWC, EPI_SHUFFLE_NCHW, EPI_GELU_BWD = range(7)
 PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_BF16X6, PREC_F16X3 = range(5)
 PRECISIONS = {'fp32': PREC_FP32, 'bf16x3': PREC_BF16X3, 'bf16': PREC_BF16, 'bf16x6': PREC_BF16X6, 'f16x3': PREC_F16X3}
 NUM_PLANES = {PREC_FP32: 0, PREC_BF16: 1, PREC_BF16X3: 2, PREC_BF16X6: 3, PREC_F16X3: 2}
@@ -58,6 +58,7 @@ _PROTOS = {
     'lvae_dwconv_wgrad': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_ln_mod_bwd': (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_split_planes_t': (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int, _fp]),
+    'lvae_split_planes_t_ex': (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, _fp, _fp]),
     'lvae_gemm_wgrad': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int64, _fp]),
     'lvae_latent_num_partials': (C.c_int, [C.c_int, C.c_int]),
     'lvae_latent_eval': (C.c_int, [_fp, _fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp, _fp,

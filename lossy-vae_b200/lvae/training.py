@@ -276,12 +276,13 @@ class TrainPath:
         """packed operand planes of a transposed (and possibly row-scaled) weight for the data-gradient GEMMs"""
         return self.eng._pack_gemm_weight(w2d.t().contiguous(), None, prec=self.DGRAD_PREC)
 
-    def _t_planes(self, name, x2d):
-        """[P, C] fp32 -> two K-major bf16 planes [C, P] in a scratch buffer (the operand format of lvae_gemm_wgrad)"""
+    def _t_planes(self, name, x2d, act=0, colsum=None):
+        """[P, C] fp32 -> two K-major bf16 planes [C, P] in a scratch buffer (the operand format of lvae_gemm_wgrad);
+        act = 1: planes of gelu(x); colsum [C] (zeroed): += column sums of x (the bias gradient when x is a dY)"""
         P_, C_ = x2d.shape
         buf = self.P.named(name, 2 * P_ * C_, dtype=torch.bfloat16)
         p0, p1 = buf[:P_ * C_], buf[P_ * C_:2 * P_ * C_]
-        self.P.op('split_t', self.eng.lib.lvae_split_planes_t, _ptr(x2d), _ptr(p0), _ptr(p1), P_, C_)
+        self.P.op('split_t', self.eng.lib.lvae_split_planes_t_ex, _ptr(x2d), _ptr(p0), _ptr(p1), P_, C_, act, _ptr(colsum))
         return p0, p1
 
     def _wgrad(self, dy_t, x_t, n_out, k_in, P_):
@@ -309,32 +310,33 @@ class TrainPath:
              eng.ada_total, off, _ptr(wb.get('ln_w')), _ptr(wb.get('ln_b')), ap[0], ap[1], ap[2], eng.pfmt, B, H, W, C_, k)
         h = torch.empty(M, hid, device=x.device)
         eng._gemm(P, 'fc1.re', None, (1, 1, M, C_, 1, 1, 0), wb['fc1'], h, epi=N.EPI_BIAS, a_planes=A)
-        g = F.gelu(h)
         go = gout.reshape(M, C_)
-        # fc2: out = x + gamma * (g W2^T + b2)
+        # fc2: out = x + gamma * (g W2^T + b2),  g = gelu(h)
         tc_wgrad = self.native_wgrad and M % 8 == 0 and M >= 1024
         if tc_wgrad:                                            # tcgen05, split over the pixels (csrc/wgrad.cu)
-            dw2_raw = self._wgrad(self._t_planes('wg_a', go), self._t_planes('wg_b', g), C_, hid, M)
-        else:
-            dw2_raw = go.t().mm(g)                              # tiny layers: cuBLAS fp32  [C, hid]
-        db2_raw = go.sum(0)
+            db2_raw = torch.zeros(C_, device=x.device)          # bias gradient rides in the operand split of dout
+            go_t = self._t_planes('wg_a', go, colsum=db2_raw)
+            dw2_raw = self._wgrad(go_t, self._t_planes('wg_b', h, act=1), C_, hid, M)
+        else:                                                   # tiny layers: cuBLAS fp32  [C, hid]
+            dw2_raw = go.t().mm(F.gelu(h))
+            db2_raw = go.sum(0)
         d_w2 = gam[:, None] * dw2_raw
         d_b2 = gam * db2_raw
         d_gamma = ((w2.detach() * dw2_raw).sum(1) + b2.detach() * db2_raw).reshape(gamma.shape)
-        dg = torch.empty(M, hid, device=x.device)
-        eng._gemm(P, 'fc2.dgrad', go, (1, 1, M, C_, 1, 1, 0), self._transposed('w2', gam[:, None] * w2.detach()), dg, epi=N.EPI_BIAS,
-                  prec=self.DGRAD_PREC)
-        dh = torch.ops.aten.gelu_backward(dg, h)
-        del dg, g
+        # dh = ((dout * gamma) W2) * gelu'(h): GELU' applied in the GEMM's epilogue
+        dh = torch.empty(M, hid, device=x.device)
+        eng._gemm(P, 'fc2.dgrad', go, (1, 1, M, C_, 1, 1, 0), self._transposed('w2', gam[:, None] * w2.detach()), dh,
+                  epi=N.EPI_GELU_BWD, res=h, prec=self.DGRAD_PREC)
         # fc1: h = a W1^T + b1;  a is needed for the weight gradient: one more (fp32) dwln launch
         a32 = torch.empty(M, C_, device=x.device)
         P.op('dwln', eng.lib.lvae_dwconv_ln_adaln, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']), _ptr(ada), eng.ada_total, off,
              _ptr(wb.get('ln_w')), _ptr(wb.get('ln_b')), _ptr(a32), B, H, W, C_, k)
         if tc_wgrad:
-            d_w1 = self._wgrad(self._t_planes('wg_b', dh), self._t_planes('wg_a', a32), hid, C_, M)
+            d_b1 = torch.zeros(hid, device=x.device)
+            d_w1 = self._wgrad(self._t_planes('wg_b', dh, colsum=d_b1), self._t_planes('wg_a', a32), hid, C_, M)
         else:
             d_w1 = dh.t().mm(a32)
-        d_b1 = dh.sum(0)
+            d_b1 = dh.sum(0)
         da = torch.empty(M, C_, device=x.device)
         eng._gemm(P, 'fc1.dgrad', dh, (1, 1, M, hid, 1, 1, 0), self._transposed('w1', w1.detach()), da, epi=N.EPI_BIAS, prec=self.DGRAD_PREC)
         del dh, h, a32
