@@ -225,9 +225,9 @@ def run_train(args):
         model.precision = args.precision
     model = model.to(dev).train()
     net = model
-    if world > 1:
+    graphed = not args.no_train_graph
+    if world > 1 and not graphed:     # the eager path: DistributedDataParallel exactly as lvae/trainer.py wraps the model
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
-    graphed = world == 1 and not args.no_train_graph
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graphed, fused=True)
     im_host = make_input('rand', B, h, w, 1000 + rank).pin_memory()
     im_dev = im_host.to(dev)
@@ -248,10 +248,14 @@ def run_train(args):
     resident = step
     if graphed:          # lvae.training.GraphedTrainStep: the whole step as one CUDA graph (device-resident number)
         from lvae.training import GraphedTrainStep
-        resident = GraphedTrainStep(model, opt, tuple(im_dev.shape))
+        resident = GraphedTrainStep(model, opt, tuple(im_dev.shape), process_group=True if world > 1 else None)
+    # end to end: pinned host batch in, loss out, every step -- through the graphed step when there is one (N > 1: its
+    # all-reduce is the only collective on the path), else through model.forward() / loss.backward() / optimizer.step()
+    eager_e2e = not (graphed and world > 1)
     for _ in range(warmup):
         resident(im_dev)
-        step(im_dev)
+        if eager_e2e:
+            step(im_dev)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -268,8 +272,12 @@ def run_train(args):
     launches = N.launch_count - launches0
     e[2].record(st)
     for _ in range(args.steps):
-        out = step(im_host.to(dev, non_blocking=True))
-        loss = out['loss'].item()
+        if eager_e2e:
+            out = step(im_host.to(dev, non_blocking=True))
+            loss = out['loss'].item()
+        else:
+            loss = resident(im_host).item()
+            out = {'bppix': None, 'psnr': None}
     e[3].record(st)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -287,10 +295,12 @@ def run_train(args):
                                     if qres else f'qarv_base train-var-rate step (lambda sampled per image), synthetic {h}x{w} crops, '
                                                  f'batch {B} per GPU (BASELINE configs[3])'),
                        'batch_per_gpu': B, 'global_batch': B * world,
-                       'parallelism': f'data parallel x{world}' + (', NCCL gradient all-reduce (DistributedDataParallel buckets)' if world > 1 else ''),
+                       'parallelism': f'data parallel x{world}' + ((', one NCCL all-reduce of the flat gradient inside the captured step' if graphed
+                                                                    else ', NCCL gradient all-reduce (DistributedDataParallel buckets)') if world > 1 else ''),
                        'weights': 'seeded default init', 'optimizer': 'Adam (torch.optim, fused=True)',
                        'value_path': 'whole step replayed as one CUDA graph (lvae.training.GraphedTrainStep)' if graphed else 'eager step',
-                       'e2e_path': 'eager step through model.forward() / loss.backward() / optimizer.step()',
+                       'e2e_path': ('eager step through model.forward() / loss.backward() / optimizer.step()' if eager_e2e else
+                                    'GraphedTrainStep(batch on pinned host memory) + loss read-back'),
                        'backward': 'latent layers and ConvNeXt blocks native (tcgen05 data + weight gradients in 2-plane bf16, dwconv/LN/'
                                    'modulation kernels of csrc/dwln_bwd.cu; GELU derivative and bias sums ATen elementwise); head convolutions '
                                    'and VDBlocks via ATen autograd on recomputed sub-graphs (lvae/training.py, DESIGN.md 4.6)',
@@ -300,9 +310,15 @@ def run_train(args):
             'gpu_launches': launches, 'launches_per_step': launches // max(1, args.steps),
             'clocks': clocks, 'result': {'loss': loss, 'bppix': out['bppix'], 'psnr': out['psnr']},
             'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30,
-        }))
+        }), flush=True)
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
+        if graphed:
+            # a CUDA graph that recorded NCCL work keeps the communicator busy: destroy_process_group() did not return in
+            # the 2-GPU run of this round (the result line was already out).  Leave without tearing the communicator down.
+            sys.stdout.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 

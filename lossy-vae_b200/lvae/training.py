@@ -486,10 +486,20 @@ class GraphedTrainStep:
         loss = step(batch)            # 0-d device tensor, overwritten by the next call
     """
 
-    def __init__(self, model, optimizer, batch_shape, warmup=3):
+    def __init__(self, model, optimizer, batch_shape, warmup=3, process_group=None):
+        """process_group: a torch.distributed (NCCL) group, or True for the default one -> data parallel: the gradients of
+        all parameters are averaged over the group by ONE all-reduce of a flat buffer, recorded inside the graph between
+        backward and the optimizer update (parameters must start out identical on every rank, as with DDP)."""
         self.model, self.opt = model, optimizer
         self.tp = model.train_path
         self.im = torch.zeros(batch_shape, device=model._device())
+        self.pg, self.world = None, 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.pg = dist.group.WORLD if process_group is True else process_group
+            self.world = dist.get_world_size(self.pg)
+            for p in model.parameters():                         # same starting point on every rank (DDP does the same)
+                dist.broadcast(p.data, src=dist.get_global_rank(self.pg, 0), group=self.pg)
         self.graph, self.loss, self.warmup = None, None, max(1, warmup)   # >= 1: lazy state (packed weights, scratch) exists before capture
 
     def _step(self):
@@ -502,8 +512,18 @@ class GraphedTrainStep:
             self.tp.force_refresh = False
         self.opt.zero_grad(set_to_none=True)
         res['loss'].backward()
+        if self.world > 1:
+            self._allreduce_grads()
         self.opt.step()
         return res['loss'].detach()
+
+    def _allreduce_grads(self):
+        import torch.distributed as dist
+        grads = [p.grad for p in self.model.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, group=self.pg)                     # the step's single collective (NVLink / NVSwitch)
+        flat.mul_(1.0 / self.world)
+        torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
 
     def __call__(self, im):
         assert self.model.training and tuple(im.shape) == tuple(self.im.shape)
