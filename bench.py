@@ -301,9 +301,9 @@ def run_train(args):
                        'value_path': 'whole step replayed as one CUDA graph (lvae.training.GraphedTrainStep)' if graphed else 'eager step',
                        'e2e_path': ('eager step through model.forward() / loss.backward() / optimizer.step()' if eager_e2e else
                                     'GraphedTrainStep(batch on pinned host memory) + loss read-back'),
-                       'backward': 'latent layers and ConvNeXt blocks native (tcgen05 data + weight gradients in 2-plane bf16, dwconv/LN/'
-                                   'modulation kernels of csrc/dwln_bwd.cu; GELU derivative and bias sums ATen elementwise); head convolutions '
-                                   'and VDBlocks via ATen autograd on recomputed sub-graphs (lvae/training.py, DESIGN.md 4.6)',
+                       'backward': 'latent layers and ConvNeXt blocks native (tcgen05 data + weight gradients in 2-plane bf16, GELU derivative in '
+                                   'the GEMM epilogue, dwconv/LN/modulation kernels of csrc/dwln_bwd.cu); head convolutions and VDBlocks via '
+                                   'ATen autograd on recomputed sub-graphs (lvae/training.py, DESIGN.md 4.6)',
                        'l2': 'no flush: per-step working set exceeds the 126 MB L2'},
             'e2e': {'value': n_img / (ms_e2e / 1e3), 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': im_host.numel() * 4, 'd2h_bytes_per_step': 4},

@@ -10,11 +10,12 @@ at op granularity: ConvNeXt block, convolution, VDBlock, latent layer).
 
 Backward -- STATE OF THIS ROUND, per op:
   * latent layer: native (`lvae_latent_train_bwd`);
-  * ConvNeXt block: native except two elementwise ops -- the fc1 pre-activation is recomputed with the forward kernels
-    (dwconv+LN kernel, tcgen05 GEMM); both data gradients are tcgen05 GEMMs on transposed packed weights; both weight
-    gradients are tcgen05 GEMMs contracting over the pixels (`lvae_split_planes_t` + split-K `lvae_gemm_wgrad`); the
-    dwconv + LayerNorm + AdaLN / affine part runs on the kernels of csrc/dwln_bwd.cu.  GELU / GELU' are ATen's
-    elementwise kernels and the two bias gradients ATen column sums;
+  * ConvNeXt block: native -- the fc1 pre-activation is recomputed with the forward kernels (dwconv+LN kernel, tcgen05
+    GEMM); both data gradients are tcgen05 GEMMs on transposed packed weights, GELU' applied in the epilogue of the first;
+    both weight gradients are tcgen05 GEMMs contracting over the pixels (`lvae_split_planes_t_ex` + split-K
+    `lvae_gemm_wgrad`; gelu(h) and the bias gradients ride in the operand splits); the dwconv + LayerNorm + AdaLN /
+    affine part runs on the kernels of csrc/dwln_bwd.cu.  (Layers with fewer than 1024 pixels: `torch.mm` weight
+    gradients; a few [C]-sized elementwise torch ops per block.)
   * convolutions (patch down / up, 1x1 and 3x3 heads) and qres VDBlocks: ATen autograd on a recomputed sub-graph.
 Everything ATen here is a LIBRARY call (cuBLAS / cuDNN), not this repo's product; it is what the native backward
 kernels of the next round replace, one op at a time, each against the gradient tests in tests/test_gpu_train.py
@@ -272,7 +273,7 @@ class TrainPath:
     # reference's convolutions is TF32: 11 bits).
     DGRAD_PREC = N.PREC_BF16X3
 
-    def _transposed(self, key, w2d):
+    def _transposed(self, w2d):
         """packed operand planes of a transposed (and possibly row-scaled) weight for the data-gradient GEMMs"""
         return self.eng._pack_gemm_weight(w2d.t().contiguous(), None, prec=self.DGRAD_PREC)
 
@@ -325,7 +326,7 @@ class TrainPath:
         d_gamma = ((w2.detach() * dw2_raw).sum(1) + b2.detach() * db2_raw).reshape(gamma.shape)
         # dh = ((dout * gamma) W2) * gelu'(h): GELU' applied in the GEMM's epilogue
         dh = torch.empty(M, hid, device=x.device)
-        eng._gemm(P, 'fc2.dgrad', go, (1, 1, M, C_, 1, 1, 0), self._transposed('w2', gam[:, None] * w2.detach()), dh,
+        eng._gemm(P, 'fc2.dgrad', go, (1, 1, M, C_, 1, 1, 0), self._transposed(gam[:, None] * w2.detach()), dh,
                   epi=N.EPI_GELU_BWD, res=h, prec=self.DGRAD_PREC)
         # fc1: h = a W1^T + b1;  a is needed for the weight gradient: one more (fp32) dwln launch
         a32 = torch.empty(M, C_, device=x.device)
@@ -338,7 +339,7 @@ class TrainPath:
             d_w1 = dh.t().mm(a32)
             d_b1 = dh.sum(0)
         da = torch.empty(M, C_, device=x.device)
-        eng._gemm(P, 'fc1.dgrad', dh, (1, 1, M, hid, 1, 1, 0), self._transposed('w1', w1.detach()), da, epi=N.EPI_BIAS, prec=self.DGRAD_PREC)
+        eng._gemm(P, 'fc1.dgrad', dh, (1, 1, M, hid, 1, 1, 0), self._transposed(w1.detach()), da, epi=N.EPI_BIAS, prec=self.DGRAD_PREC)
         del dh, h, a32
         # dwconv + LayerNorm + modulation: recompute the conv output, LayerNorm / modulation backward, filter gradient,
         # data gradient (transposed conv + the residual branch's gradient) -- csrc/dwln_bwd.cu
