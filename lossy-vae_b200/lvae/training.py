@@ -477,6 +477,20 @@ class TrainPath:
         return res
 
 
+def allreduce_flat_gradients(params, group, world):
+    """Average the gradients of `params` over `group` with ONE all-reduce: the gradients are concatenated into a flat
+    buffer, summed over the ranks (NCCL over NVLink / NVSwitch on the GPUs; gloo in the CPU test), scaled by 1 / world and
+    copied back in place.  Parameters without a gradient are skipped -- every rank must skip the same ones."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    flat.mul_(1.0 / world)
+    torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
+
+
 class GraphedTrainStep:
     """One training step -- lambda draw, forward, backward, optimizer update, including the re-packing of the updated
     weights into tensor-core operand planes -- captured once into a CUDA graph and replayed per batch: the training
@@ -519,12 +533,7 @@ class GraphedTrainStep:
         return res['loss'].detach()
 
     def _allreduce_grads(self):
-        import torch.distributed as dist
-        grads = [p.grad for p in self.model.parameters() if p.grad is not None]
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat, group=self.pg)                     # the step's single collective (NVLink / NVSwitch)
-        flat.mul_(1.0 / self.world)
-        torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
+        allreduce_flat_gradients(self.model.parameters(), self.pg, self.world)
 
     def __call__(self, im):
         assert self.model.training and tuple(im.shape) == tuple(self.im.shape)

@@ -62,3 +62,45 @@ def test_shard_range_partitions_exactly():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from lvae.training import allreduce_flat_gradients
+        g = torch.Generator().manual_seed(100 + rank)
+        shapes = [(3, 5), (7,), (2, 1, 3, 3), (1,)]
+        params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
+        for p in params[:-1]:                                   # the last one has no gradient on any rank
+            p.grad = torch.rand(p.shape, generator=g)
+        before = [None if p.grad is None else p.grad.clone() for p in params]
+        ptrs = [None if p.grad is None else p.grad.data_ptr() for p in params]
+        allreduce_flat_gradients(params, dist.group.WORLD, world)
+        in_place = all(p.grad is None or p.grad.data_ptr() == a for p, a in zip(params, ptrs))
+        q.put((rank, before, [None if p.grad is None else p.grad.clone() for p in params], in_place))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_averages_in_place():
+    """The training step's single collective (lvae.training.allreduce_flat_gradients; NCCL on the GPUs) on gloo."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, b0, a0, ip0), (_, b1, a1, ip1) = res
+    assert ip0 and ip1
+    for x0, x1, y0, y1 in zip(b0, b1, a0, a1):
+        if x0 is None:
+            assert y0 is None and y1 is None
+            continue
+        want = (x0 + x1) / 2
+        assert torch.allclose(y0, want, atol=1e-7) and torch.equal(y0, y1)
