@@ -247,3 +247,46 @@ def test_c_rans_encode_streams_equals_single_stream_calls(native_lib, tables):
     for i, n in enumerate(sizes):                     # and every stream decodes back
         rc, dec = _dec(native_lib, want[i], idx[begin[i]:begin[i + 1]], tables)
         assert rc == 0 and np.array_equal(dec, sym[begin[i]:begin[i + 1]])
+
+
+def test_c_rans_all_symbols_out_of_table_grows_the_scratch(native_lib, tables):
+    """Every symbol bypass-coded (40 bits each instead of <= 16): the encoder's scratch, sized for table symbols, must grow;
+    bytes still equal the Python restatement."""
+    rng = np.random.default_rng(11)
+    n = 3000
+    idx = rng.integers(0, 64, size=n).astype(np.int32)
+    sym = (rng.integers(100000, 2000000, size=n) * rng.choice([-1, 1], size=n)).astype(np.int32)
+    data = _enc(native_lib, sym, idx, tables)
+    assert data == O.rans_encode(sym.tolist(), idx.tolist(), *tables)
+    rc, out = _dec(native_lib, data, idx, tables)
+    assert rc == 0 and np.array_equal(out, sym)
+
+
+def test_c_rans_decode_streams_pairs_ragged_and_unaligned(native_lib, tables):
+    """lvae_rans_decode_streams: streams are decoded two at a time in lockstep per worker; ragged sizes (incl. empty and a
+    lone last stream), byte offsets that are not word-aligned, any thread count; a corrupt stream is reported."""
+    rng = np.random.default_rng(5)
+    sizes = [4000, 3, 0, 9001, 257, 1200, 77]
+    idx = rng.integers(0, 64, size=sum(sizes)).astype(np.int32)
+    sym = np.rint(rng.normal(size=sum(sizes)) * (1 + idx * 0.3)).astype(np.int32)
+    sym[::53] *= 30
+    cdf, clen, off = (np.ascontiguousarray(t.numpy()) for t in tables)
+    begin = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    blobs = [_enc(native_lib, sym[begin[i]:begin[i + 1]], idx[begin[i]:begin[i + 1]], tables) for i in range(len(sizes))]
+    for lead in (0, 1, 2):                            # leading pad bytes: misaligned stream starts
+        packed = np.frombuffer(b'\x00' * lead + b''.join(blobs), dtype=np.uint8).copy()
+        in_begin = (np.concatenate([[0], np.cumsum([len(b) for b in blobs])]) + lead).astype(np.int64)
+        for threads in (1, 2, 3, 16):
+            out = np.full(sum(sizes), -12345, dtype=np.int32)
+            rc = native_lib.lvae_rans_decode_streams(packed.ctypes.data, in_begin.ctypes.data, idx.ctypes.data, begin.ctypes.data,
+                                                     len(sizes), cdf.ctypes.data, cdf.shape[1], clen.ctypes.data, off.ctypes.data,
+                                                     cdf.shape[0], out.ctypes.data, threads)
+            assert rc == 0 and np.array_equal(out, sym), (lead, threads)
+    trunc = np.frombuffer(blobs[3][:-8], dtype=np.uint8).copy()       # stream 3 without its last two words: it runs dry
+    one_begin, sym_begin = np.array([0, trunc.size], dtype=np.int64), np.array([0, sizes[3]], dtype=np.int64)
+    idx3 = idx[begin[3]:begin[4]].copy()
+    out = np.zeros(sizes[3], dtype=np.int32)
+    rc = native_lib.lvae_rans_decode_streams(trunc.ctypes.data, one_begin.ctypes.data, idx3.ctypes.data, sym_begin.ctypes.data, 1,
+                                             cdf.ctypes.data, cdf.shape[1], clen.ctypes.data, off.ctypes.data, cdf.shape[0],
+                                             out.ctypes.data, 1)
+    assert rc == -3
