@@ -183,6 +183,36 @@ def main_qres():
                         cdf_length=dg._cdf_length.numpy(), offset=dg._offset.numpy())
 
 
+from gen_golden_cases import GRAD_CASES, grad_probe   # noqa: E402
+
+
+def main_grads():
+    """Training-step gradients of the UNMODIFIED reference (train mode, torch.manual_seed(noise_seed) right before the
+    forward so that its uniform_ draws are reproducible; sensitised weights): loss, and per parameter tensor the gradient's
+    L2 norm and its inner product with grad_probe().  tests/test_oracle_pinned.py checks the oracles' autograd against it."""
+    ref = ref_loader.load_reference()
+    for fam, (nB, H, W, lmbs, seed, nseed) in GRAD_CASES.items():
+        torch.manual_seed(0)
+        if fam == 'qarv':
+            model = ref.get_model('qarv_base')
+            sd = O.sensitised_state_dict(O.qarv_param_shapes(), seed=0)
+        else:
+            model = ref.get_model('qres34m', lmb=QRES_LMB)
+            sd = O.sensitised_state_dict(Q.qres_param_shapes(), seed=0)
+        model.load_state_dict(sd, strict=False)
+        model.train()
+        im = make_input('rand', nB, H, W, seed)
+        torch.manual_seed(nseed)
+        stats = model(im, lmb=torch.tensor(lmbs)) if fam == 'qarv' else model(im)
+        stats['loss'].backward()
+        names = [k for k, _ in model.named_parameters()]
+        norms = np.array([float(p.grad.double().norm()) for _, p in model.named_parameters()])
+        dots = np.array([float((p.grad.double() * grad_probe(k, p.shape).double()).sum()) for k, p in model.named_parameters()])
+        np.savez_compressed(OUT / f'{fam}_train_grads.npz', loss=np.float64(stats['loss'].item()), names=np.array(names),
+                            grad_norm=norms, grad_dot=dots)
+        print(fam, 'train loss', stats['loss'].item(), 'grad norms', norms.min(), norms.max())
+
+
 if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
     if which in ('qarv', 'all'):
@@ -191,3 +221,5 @@ if __name__ == '__main__':
         main_rd()
     if which in ('qres', 'all'):
         main_qres()
+    if which in ('grads', 'all'):
+        main_grads()

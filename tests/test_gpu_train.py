@@ -181,3 +181,36 @@ def test_graphed_train_step_matches_eager_step(native_lib):
     (b0, a0), (b1, a1) = finals
     assert b0 == b1 and a0 < b0 and a1 < b1, finals            # both paths trained the weights the eval plans read
     assert abs(a1 - a0) <= 0.25 * abs(b0 - a0), finals
+
+
+@pytest.mark.parametrize('fam', ['qarv', 'qres'])
+def test_gradients_match_the_unmodified_reference_fixture(native_lib, golden, fam):
+    """Directly against tests/golden/{qarv,qres}_train_grads.npz (loss.backward() of the unmodified reference, generated by
+    oracle/gen_golden.py grads): loss, and per parameter tensor the gradient norm and its inner product with a fixed probe."""
+    import lvae
+    from gen_golden_cases import GRAD_CASES, grad_probe
+    from oracle_inputs import QRES_LMB, make_input
+    from test_oracle_pinned import _qres_noise
+    nB, H, W, lmbs, seed, nseed = GRAD_CASES[fam]
+    g = golden(f'{fam}_train_grads')
+    im = make_input('rand', nB, H, W, seed)
+    if fam == 'qarv':
+        m = lvae.get_model('qarv_base')
+        m.load_state_dict(O.sensitised_state_dict(O.qarv_param_shapes(), seed=0), strict=False)
+        m = m.to(DEV).train()
+        noise = _qres_noise(None, O.qarv_base_arch(), nB, H, W, nseed)
+        st = m._forward_train(im.to(DEV), torch.tensor(lmbs, device=DEV), noise=noise)
+    else:
+        m = lvae.get_model('qres34m', lmb=QRES_LMB)
+        m.load_state_dict(O.sensitised_state_dict(Q.qres_param_shapes(), seed=0), strict=False)
+        m = m.to(DEV).train()
+        noise = _qres_noise(Q, Q.qres34m_arch(), nB, H, W, nseed)
+        st = m(im.to(DEV), noise=noise)
+    st['loss'].backward()
+    assert abs(st['loss'].item() - float(g['loss'])) <= 1e-4 * abs(float(g['loss']))
+    grads = dict(m.named_parameters())
+    for name, norm, dot in zip(g['names'].tolist(), g['grad_norm'], g['grad_dot']):
+        gr = grads[name].grad.detach().cpu().double()
+        assert abs(float(gr.norm()) - norm) <= GRAD_RTOL * norm + 1e-9, name
+        pr = grad_probe(name, gr.shape).double()
+        assert abs(float((gr * pr).sum()) - dot) <= GRAD_RTOL * norm * float(pr.norm()) + 1e-9, name

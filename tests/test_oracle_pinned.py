@@ -217,3 +217,39 @@ def test_qres_oracle_matches_golden(name, golden):
             for b in range(nB):
                 assert obj[li][b] == g[f'bytes{li}_{b}'].tobytes()
         assert torch.equal(Q.qres_decompress(sd, obj), torch.from_numpy(g['dec_im_hat']))
+
+
+# ----------------------------------------------------------------------------- training-step gradients
+def _grad_case(fam):
+    from gen_golden_cases import GRAD_CASES, grad_probe
+    return GRAD_CASES[fam], grad_probe
+
+
+@pytest.mark.parametrize('fam', ['qarv', 'qres'])
+def test_oracle_autograd_matches_reference_gradients(fam, golden):
+    """tests/golden/{qarv,qres}_train_grads.npz hold, from the UNMODIFIED reference's loss.backward() in train mode, every
+    parameter gradient's norm and its inner product with a fixed probe: autograd over the oracle reproduces them, which
+    makes the oracle the gradient reference of tests/test_gpu_train.py."""
+    import qres_oracle as Q
+    (nB, H, W, lmbs, seed, nseed), grad_probe = _grad_case(fam)
+    g = golden(f'{fam}_train_grads')
+    im = make_input('rand', nB, H, W, seed)
+    if fam == 'qarv':
+        sd = O.sensitised_state_dict(O.qarv_param_shapes(), seed=0)
+        noise = _qres_noise(None, O.qarv_base_arch(), nB, H, W, nseed)
+        fwd, args = O.qarv_forward, (im, torch.tensor(lmbs))
+    else:
+        sd = O.sensitised_state_dict(Q.qres_param_shapes(), seed=0)
+        noise = _qres_noise(Q, Q.qres34m_arch(), nB, H, W, nseed)
+        from oracle_inputs import QRES_LMB
+        fwd, args = Q.qres_forward, (im, QRES_LMB)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    with torch.enable_grad():
+        out = fwd.__wrapped__(sd, *args, mode='train', noise=noise)
+        out['loss'].backward()
+    assert abs(float(out['loss']) - float(g['loss'])) <= 1e-6 * abs(float(g['loss']))
+    for name, norm, dot in zip(g['names'].tolist(), g['grad_norm'], g['grad_dot']):
+        gr = sd[name].grad.double()
+        assert abs(float(gr.norm()) - norm) <= 1e-4 * norm + 1e-12, name
+        pr = grad_probe(name, gr.shape).double()
+        assert abs(float((gr * pr).sum()) - dot) <= 1e-4 * norm * float(pr.norm()) + 1e-12, name
