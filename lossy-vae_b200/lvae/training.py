@@ -501,13 +501,18 @@ class GraphedTrainStep:
         loss = step(batch)            # 0-d device tensor, overwritten by the next call
     """
 
-    def __init__(self, model, optimizer, batch_shape, warmup=3, process_group=None):
-        """process_group: a torch.distributed (NCCL) group, or True for the default one -> data parallel: the gradients of
+    def __init__(self, model, optimizer, batch_shape, warmup=3, process_group=None, grad_clip=None, ema=None, ema_decay=0.9999):
+        """grad_clip: max global gradient norm (torch.nn.utils.clip_grad_norm_ on the reduced gradients, as
+        lvae/trainer.py:395 does), recorded in the graph; ema: a module with the model's parameter structure (e.g.
+        timm's ModelEmaV2(model).module or copy.deepcopy(model)) whose parameters follow ema = decay * ema + (1 - decay) * p
+        after every update (trainer.py:374-377), also inside the graph.
+        process_group: a torch.distributed (NCCL) group, or True for the default one -> data parallel: the gradients of
         all parameters are averaged over the group by ONE all-reduce of a flat buffer, recorded inside the graph between
         backward and the optimizer update (parameters must start out identical on every rank, as with DDP)."""
         self.model, self.opt = model, optimizer
         self.tp = model.train_path
         self.im = torch.zeros(batch_shape, device=model._device())
+        self.grad_clip, self.ema, self.ema_decay = grad_clip, ema, float(ema_decay)
         self.pg, self.world = None, 1
         if process_group is not None:
             import torch.distributed as dist
@@ -529,7 +534,12 @@ class GraphedTrainStep:
         res['loss'].backward()
         if self.world > 1:
             self._allreduce_grads()
+        if self.grad_clip is not None:
+            torch.nn.utils.clip_grad_norm_(list(m.parameters()), self.grad_clip, foreach=True)
         self.opt.step()
+        if self.ema is not None:
+            with torch.no_grad():
+                torch._foreach_lerp_(list(self.ema.parameters()), [p.detach() for p in m.parameters()], 1.0 - self.ema_decay)
         return res['loss'].detach()
 
     def _allreduce_grads(self):

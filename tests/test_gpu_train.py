@@ -214,3 +214,26 @@ def test_gradients_match_the_unmodified_reference_fixture(native_lib, golden, fa
         assert abs(float(gr.norm()) - norm) <= GRAD_RTOL * norm + 1e-9, name
         pr = grad_probe(name, gr.shape).double()
         assert abs(float((gr * pr).sum()) - dot) <= GRAD_RTOL * norm * float(pr.norm()) + 1e-9, name
+
+
+def test_graphed_step_with_gradient_clipping_and_ema(native_lib):
+    """The tail of the reference's training step (lvae/trainer.py:374-377,395): global-norm clipping and the EMA copy's
+    update, recorded in the same CUDA graph as the step.  With decay 0 the EMA copy must equal the live weights after every
+    replay (the update ran, after the optimizer); the gradients left in .grad are the clipped ones."""
+    import lvae
+    from lvae.training import GraphedTrainStep
+    torch.manual_seed(0)
+    m = lvae.get_model('qarv_base').to(DEV).train()
+    ema = copy.deepcopy(m).eval()
+    p0 = [p.detach().clone() for p in m.parameters()]
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True)
+    step = GraphedTrainStep(m, opt, (2, 3, 64, 64), warmup=1, grad_clip=0.5, ema=ema, ema_decay=0.0)
+    im = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(8)).to(DEV)
+    for _ in range(3):
+        assert np.isfinite(float(step(im)))
+        assert all(torch.equal(e, p) for e, p in zip(ema.parameters(), m.parameters()))
+    gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in m.parameters()))
+    assert 0 < float(gn) <= 0.5 * 1.001
+    assert sum(int(not torch.equal(a, p)) for a, p in zip(p0, m.parameters())) > 800
+    with torch.no_grad():
+        assert np.isfinite(ema(im, lmb=torch.full((2,), 256.0, device=DEV))['loss'].item())
