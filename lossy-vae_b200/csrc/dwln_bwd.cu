@@ -8,9 +8,11 @@
 //   lvae_dwconv_wgrad    dw[t, c] = sum_p dc[p, c] x[p + t, c],  db[c] = sum_p dc[p, c]
 //
 // All tensors NHWC fp32; the filter is packed [k*k, C] like the forward kernel's.  Tiles: 8 x 8 output pixels x 64
-// channels per CTA (8 warps: warp = output column, lane = channel pair), the (8+k-1)^2 halo staged in shared memory
-// with zero fill = the conv's padding.  Every input row of the halo is read from shared memory once per thread and feeds
-// up to k output rows (k*k*8 packed FFMA2 per (8+k-1)*k LDS.64).
+// channels (8 warps: warp = output column, lane = channel pair).  The two convolution kernels are persistent over the
+// tiles of one 64-channel group; the (8+k-1)^2 halo of a tile is ONE TMA 4-D box load (cp.async.bulk.tensor over the
+// (C, W, H, B) view, out-of-image coordinates zero-filled by the hardware = the conv's padding), double-buffered on two
+// mbarriers so that tile t+1 streams in while tile t is computed.  Every input row of the halo is read from shared
+// memory once per thread and feeds up to k output rows (k*k*8 packed FFMA2 per (8+k-1)*k LDS.64).
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
