@@ -290,3 +290,50 @@ def test_c_rans_decode_streams_pairs_ragged_and_unaligned(native_lib, tables):
                                              cdf.ctypes.data, cdf.shape[1], clen.ctypes.data, off.ctypes.data, cdf.shape[0],
                                              out.ctypes.data, 1)
     assert rc == -3
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_c_rans_arbitrary_tables_equal_python_oracle(native_lib, seed):
+    """Random (non-Gaussian) table sets: rows of length 1 .. 60 symbols with spiky, flat and long-tailed pmfs (many
+    frequency-1 entries inside one decoder LUT bucket, single-symbol rows where everything but one value is bypass-coded),
+    arbitrary offsets.  C encoder bytes == Python restatement, C decoder inverts them."""
+    rng = np.random.default_rng(100 + seed)
+    n_rows, stride = 12, 64
+    cdf = np.zeros((n_rows, stride), dtype=np.int32)
+    clen = np.zeros(n_rows, dtype=np.int32)
+    off = rng.integers(-40, 5, size=n_rows).astype(np.int32)
+    for r in range(n_rows):
+        k = int(rng.integers(1, 61)) if r else 1                    # symbols incl. the escape symbol; row 0: escape only
+        kind = r % 3
+        pmf = (rng.random(k) ** 8 if kind == 0 else (np.ones(k) if kind == 1 else 1.0 / (1 + np.arange(k)) ** 3)).astype(np.float32)
+        pmf = np.maximum(pmf / pmf.sum(), 0).astype(np.float32)
+        out = np.zeros(k + 1, dtype=np.int32)
+        assert native_lib.lvae_pmf_to_quantized_cdf(pmf.ctypes.data, k, 16, out.ctypes.data) == 0
+        cdf[r, :k + 1] = out
+        clen[r] = k + 1
+    tables = (torch.from_numpy(cdf), torch.from_numpy(clen), torch.from_numpy(off))
+    n = 4000
+    idx = rng.integers(0, n_rows, size=n).astype(np.int32)
+    sym = (off[idx] + rng.integers(-3, 66, size=n)).astype(np.int32)       # in-table and out-of-table on both sides
+    sym[::401] = rng.integers(-10 ** 6, 10 ** 6, size=sym[::401].size)
+    data = _enc(native_lib, sym, idx, tables)
+    assert data == O.rans_encode(sym.tolist(), idx.tolist(), *tables)
+    rc, dec = _dec(native_lib, data, idx, tables)
+    assert rc == 0 and np.array_equal(dec, sym)
+    assert O.rans_decode(data, idx.tolist(), *tables) == sym.tolist()
+
+
+def test_c_rans_rejects_malformed_tables(native_lib, tables):
+    cdf, clen, off = (np.ascontiguousarray(t.numpy()).copy() for t in tables)
+    sym, idx = np.zeros(4, dtype=np.int32), np.zeros(4, dtype=np.int32)
+    buf, n = np.empty(1024, dtype=np.uint8), C.c_int64(0)
+    bad = cdf.copy()
+    bad[0, 3] = bad[0, 2]                                           # not strictly increasing
+    rc = native_lib.lvae_rans_encode(sym.ctypes.data, idx.ctypes.data, 4, bad.ctypes.data, bad.shape[1], clen.ctypes.data,
+                                     off.ctypes.data, bad.shape[0], buf.ctypes.data, 1024, C.byref(n))
+    assert rc == -1
+    bad_len = clen.copy()
+    bad_len[1] = cdf.shape[1] + 1                                    # longer than the row stride
+    rc = native_lib.lvae_rans_encode(sym.ctypes.data, idx.ctypes.data, 4, cdf.ctypes.data, cdf.shape[1], bad_len.ctypes.data,
+                                     off.ctypes.data, cdf.shape[0], buf.ctypes.data, 1024, C.byref(n))
+    assert rc == -1
