@@ -499,7 +499,7 @@ def main():
             'data': 'synthetic',
             'config': {'workload': (f'rd_model_base forward (KL + MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 256 (BASELINE configs[4])'
                                     if rd else f'qres34m eval forward (rate + lambda * MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 2048 '
-                                               f'(forward half of BASELINE configs[2]; the backward pass is not built)' if qres else
+                                               f'(forward half of BASELINE configs[2]; forward + backward + Adam: --workload train-qres)' if qres else
                                     f'qarv_base eval forward (rate + MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 2048 '
                                     f'(BASELINE configs[1])'), 'batch_per_gpu': B, 'global_batch': B * world, 'precision': model.precision,
                        'parallelism': f'batch-shard x{world}, no data-path collective', 'weights': 'seeded sensitised init (no checkpoint offline)',
