@@ -4,6 +4,15 @@ Same import surface as the reference package (`/root/reference/lvae/__init__.py:
 `lvae.get_model`, `lvae.known_datasets`; the compute underneath is hand-written sm_100a CUDA in
 `liblvae_b200.so`, reached through the C ABI of `include/lvae_b200.h`.
 """
+import os as _os
+
+# Overlay mode (INTEGRATION.md A): with LVAE_REFERENCE_ROOT=/path/to/lossy-vae, sub-modules this package does not have --
+# the reference's trainer, datasets, logging utilities: callers of the path, not the path -- are loaded, unmodified, from
+# that checkout, while lvae.models / lvae.evaluation / lvae.utils.coding / lvae.paths stay the ones of this package.
+_ref_root = _os.environ.get('LVAE_REFERENCE_ROOT')
+if _ref_root and _os.path.isdir(_os.path.join(_ref_root, 'lvae')):
+    __path__.append(_os.path.join(_ref_root, 'lvae'))
+
 from .paths import known_datasets
 from .models.registry import get_model, register_model
 from . import models

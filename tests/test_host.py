@@ -337,3 +337,32 @@ def test_c_rans_rejects_malformed_tables(native_lib, tables):
     rc = native_lib.lvae_rans_encode(sym.ctypes.data, idx.ctypes.data, 4, cdf.ctypes.data, cdf.shape[1], bad_len.ctypes.data,
                                      off.ctypes.data, cdf.shape[0], buf.ctypes.data, 1024, C.byref(n))
     assert rc == -1
+
+
+def test_overlay_mode_loads_trainer_from_the_reference_checkout():
+    """LVAE_REFERENCE_ROOT: lvae.trainer / lvae.datasets / lvae.utils.general come, unmodified, from the reference checkout
+    (with the timm / wandb they need -- here the test shims), bound to THIS package's models; without the variable nothing
+    changes.  Skipped where the reference tree is absent."""
+    import os
+    import subprocess
+    import sys
+    import ref_loader
+    if not ref_loader.available():
+        pytest.skip('reference tree not present')
+    root = os.path.join(os.path.dirname(__file__), '..')
+    code = (
+        "import sys, lvae, lvae.trainer, lvae.datasets, lvae.utils\n"
+        "import lvae.models.qarv.model as qm\n"
+        "assert lvae.trainer.__file__.startswith('/root/reference'), lvae.trainer.__file__\n"
+        "assert lvae.datasets.__file__.startswith('/root/reference')\n"
+        "assert not qm.__file__.startswith('/root/reference') and not lvae.evaluation.__file__.startswith('/root/reference')\n"
+        "assert lvae.trainer.get_model is lvae.get_model and hasattr(lvae.utils, 'SimpleTable') and hasattr(lvae.utils.coding, 'bd_rate')\n"
+        "assert hasattr(lvae.trainer.BaseTrainingWrapper, 'training_loop') or hasattr(lvae.trainer.BaseTrainingWrapper, 'main')\n"
+        "print('overlay ok')\n")
+    env = dict(os.environ, LVAE_REFERENCE_ROOT='/root/reference',
+               PYTHONPATH=os.pathsep.join([os.path.join(root, 'lossy-vae_b200'), str(ref_loader.SHIMS)]))
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'overlay ok' in r.stdout, r.stderr[-2000:]
+    env.pop('LVAE_REFERENCE_ROOT')
+    r = subprocess.run([sys.executable, '-c', 'import lvae.trainer'], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and 'No module named' in r.stderr
