@@ -366,3 +366,50 @@ def test_overlay_mode_loads_trainer_from_the_reference_checkout():
     env.pop('LVAE_REFERENCE_ROOT')
     r = subprocess.run([sys.executable, '-c', 'import lvae.trainer'], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and 'No module named' in r.stderr
+
+
+def test_training_aten_restatements_equal_the_oracle_ops(native_lib):
+    """lvae/training.py differentiates the head convolutions, VDBlocks and (in the cross-check mode) whole ConvNeXt blocks
+    through ATen restatements on NHWC tensors; on CPU they must equal the oracle's NCHW ops value for value."""
+    import torch.nn.functional as F
+    import qres_oracle as Q
+    from lvae import training as T
+    g = torch.Generator().manual_seed(0)
+    B, H, W, C_, k = 2, 6, 5, 8, 7
+    x = torch.randn(B, C_, H, W, generator=g)
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    # ConvNeXt block with AdaLN (common.py:142-161) and with affine LayerNorm (qresvae/model.py:163-182)
+    sd = {'b.conv_dw.weight': torch.randn(C_, 1, k, k, generator=g) / k, 'b.conv_dw.bias': torch.randn(C_, generator=g),
+          'b.embedding_layer.1.weight': torch.randn(2 * C_, 16, generator=g) / 4, 'b.embedding_layer.1.bias': torch.randn(2 * C_, generator=g),
+          'b.mlp.fc1.weight': torch.randn(2 * C_, C_, generator=g) / 3, 'b.mlp.fc1.bias': torch.randn(2 * C_, generator=g),
+          'b.mlp.fc2.weight': torch.randn(C_, 2 * C_, generator=g) / 4, 'b.mlp.fc2.bias': torch.randn(C_, generator=g),
+          'b.gamma': torch.randn(1, C_, 1, 1, generator=g), 'b.norm.weight': torch.randn(C_, generator=g), 'b.norm.bias': torch.randn(C_, generator=g)}
+    emb = torch.randn(B, 16, generator=g)
+    ada = F.linear(F.gelu(emb), sd['b.embedding_layer.1.weight'], sd['b.embedding_layer.1.bias'])
+    a = T._dwln_aten(nhwc(x), ada, sd['b.conv_dw.weight'], sd['b.conv_dw.bias'], None, None, k)
+    y = F.linear(F.gelu(F.linear(a, sd['b.mlp.fc1.weight'], sd['b.mlp.fc1.bias'])), sd['b.mlp.fc2.weight'], sd['b.mlp.fc2.bias'])
+    got = nhwc(x) + y * sd['b.gamma'].reshape(-1)
+    assert torch.allclose(got, nhwc(O.convnext_block(sd, 'b.', x, emb)), atol=1e-5)
+    sdq = dict(sd, **{'b.gamma': sd['b.gamma'].reshape(-1)})
+    a = T._dwln_aten(nhwc(x), None, sd['b.conv_dw.weight'], sd['b.conv_dw.bias'], sd['b.norm.weight'], sd['b.norm.bias'], k)
+    y = F.linear(F.gelu(F.linear(a, sd['b.mlp.fc1.weight'], sd['b.mlp.fc1.bias'])), sd['b.mlp.fc2.weight'], sd['b.mlp.fc2.bias'])
+    assert torch.allclose(nhwc(x) + y * sdq['b.gamma'], nhwc(Q.convnext_block(sdq, 'b.', x)), atol=1e-5)
+    # VDBlock on a channel concat (qresvae/model.py:143-149,270)
+    x1 = torch.randn(B, 4, H, W, generator=g)
+    vd = {f'v.c{i}.weight': w for i, w in enumerate([torch.randn(6, C_ + 4, 1, 1, generator=g), torch.randn(6, 6, 3, 3, generator=g) / 3,
+                                                     torch.randn(6, 6, 3, 3, generator=g) / 3, torch.randn(5, 6, 1, 1, generator=g)], 1)}
+    vd.update({f'v.c{i}.bias': torch.randn(n, generator=g) for i, n in zip(range(1, 5), (6, 6, 6, 5))})
+    ps = [vd[f'v.c{i}.{t}'] for i in range(1, 5) for t in ('weight', 'bias')]
+    assert torch.allclose(T._vd_aten(nhwc(x), nhwc(x1), *ps), nhwc(Q.vdblock(vd, 'v.', torch.cat([x, x1], 1))), atol=1e-5)
+    # convolutions: 3x3 head, 1x1 + residual, patch down, 1x1 + pixel shuffle (NHWC and the final NCHW form)
+    w3, b3 = torch.randn(5, C_, 3, 3, generator=g) / 3, torch.randn(5, generator=g)
+    assert torch.allclose(T._conv_aten(nhwc(x), None, None, w3, b3, dict(stride=1, pad=1)), nhwc(F.conv2d(x, w3, b3, padding=1)), atol=1e-5)
+    w1, b1 = torch.randn(C_, 4, 1, 1, generator=g), torch.randn(C_, generator=g)
+    assert torch.allclose(T._conv_aten(nhwc(x1), None, nhwc(x), w1, b1, dict(stride=1, pad=0)), nhwc(x + F.conv2d(x1, w1, b1)), atol=1e-5)
+    xe = torch.randn(B, C_, 8, 6, generator=g)
+    wd, bd = torch.randn(12, C_, 2, 2, generator=g), torch.randn(12, generator=g)
+    assert torch.allclose(T._conv_aten(nhwc(xe), None, None, wd, bd, dict(stride=2, pad=0)), nhwc(F.conv2d(xe, wd, bd, stride=2)), atol=1e-5)
+    wu, bu = torch.randn(12, C_, 1, 1, generator=g), torch.randn(12, generator=g)
+    up = F.pixel_shuffle(F.conv2d(x, wu, bu), 2)
+    assert torch.allclose(T._conv_aten(nhwc(x), None, None, wu, bu, dict(stride=1, pad=0, r=2)), nhwc(up), atol=1e-5)
+    assert torch.allclose(T._conv_aten(nhwc(x), None, None, wu, bu, dict(stride=1, pad=0, r=2, nchw_out=1)), up, atol=1e-5)
