@@ -114,6 +114,17 @@ typedef struct lvae_gemm_desc {
 
 int lvae_gemm(const lvae_gemm_desc* d, void* stream);
 int64_t lvae_gemm_workspace_bytes(const lvae_gemm_desc* d);
+/* diagnostics: number of lvae_gemm calls served so far by the CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x BN
+ * tiles; csrc/gemm2_tc.cu).  Opt-in (environment, read per call: LVAE_GEMM2=1; LVAE_G2_MIN_TILES / LVAE_G2_BN override
+ * the eligibility threshold / the tile width): lvae_gemm then uses it for the large plain [M,K] x [N,K]^T contractions of
+ * the 2-plane modes.  Results are bit-identical to the 128-row kernel; on B200 it measured slower, so it is off by
+ * default (profiles/r2_gemm2_pair_kernel.md). */
+long long lvae_gemm2_launch_count(void);
+/* diagnostics: cycle breakdown (clock64) of CTA 0 of the LAST tensor-core GEMM launch -- which = 1: gemm_tc_kernel,
+ * 2: the CTA-pair kernel.  out16[0] MMA-issuing thread total, [1] of it waiting for operand stages (TMA / L2), [2]
+ * waiting for the epilogue to free the accumulator, [3] producer total, [4] producer waiting for a free stage,
+ * [5..7] (pair kernel) one epilogue warp: total, waiting for the accumulator, draining TMEM; [8] tiles.  Synchronises. */
+int lvae_debug_prof(int which, unsigned long long* out16);
 /* split fp32 -> bf16 planes p0 = rn(x), p1 = rn(x - p0), p2 = rn(x - p0 - p1); p1 / p2 may be NULL */
 int lvae_split_bf16(const float* x, void* p0, void* p1, void* p2, int64_t n, void* stream);
 /* the same split of (x * scale) into planes of `plane_format` (enum lvae_plane_format); weights of an

@@ -74,6 +74,15 @@ constexpr int CONV_TW = 16, CONV_TH = 8;       // 128 output pixels per tile
 
 struct TcMaps { CUtensorMap a[3]; CUtensorMap b[3]; CUtensorMap a1[3]; };   // a1: second K segment (K-concat from planes)
 
+// cycle breakdown of CTA 0 (diagnostics, lvae_debug_prof(1, ...)): [0] MMA thread total, [1] waiting for operands (full),
+// [2] waiting for the accumulator (tempty), [3] producer total, [4] producer waiting for a free stage, [8] tiles
+__device__ unsigned long long tc_prof[16];
+int gemm_tc_prof_read(unsigned long long* out16) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out16, tc_prof, sizeof(unsigned long long) * 16);
+  return (int)e;
+}
+
 // d/dh gelu(h) = Phi(h) + h phi(h)  (erf form, as F.gelu's autograd)
 __device__ __forceinline__ float gelu_grad(float h) {
   const float cdf = 0.5f * (1.f + erff(h * 0.70710678118654752f));
@@ -160,6 +169,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
+      long long t_wait = 0; const long long t_begin = clock64();
       for (int tz = blockIdx.x; tz < p.num_tiles; tz += gridDim.x) {
         const int z = tz / p.base_tiles, t = tz - z * p.base_tiles;
         const int kb0 = z * p.kb_per, kb1 = min(nkb, kb0 + p.kb_per);
@@ -169,7 +179,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int ctx = mt % p.tiles_w, cty = (mt / p.tiles_w) % p.tiles_h, cb = mt / (p.tiles_w * p.tiles_h);
         const int cpt = p.cC / p.BK;                             // k-blocks per filter tap
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(smem_u32(empty_bar + s), ph ^ 1);
+          { const long long tw = clock64(); mbar_wait(smem_u32(empty_bar + s), ph ^ 1); t_wait += clock64() - tw; }
           const uint32_t fb = smem_u32(full_bar + s);
           mbar_expect_tx(fb, (uint32_t)stage_bytes);
           const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
@@ -203,6 +213,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
+      if (blockIdx.x == 0) { tc_prof[3] = clock64() - t_begin; tc_prof[4] = t_wait; }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
@@ -212,15 +223,16 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     const uint32_t idesc2n = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 2) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // N = 2 * BN
     int s = 0; uint32_t ph = 0; int it = 0;
+    long long t_full = 0, t_tempty = 0; const long long t_begin = clock64();
     for (int tz = blockIdx.x; tz < p.num_tiles; tz += gridDim.x, ++it) {
       const int acc = it & 1;
       const int kb0 = (tz / p.base_tiles) * p.kb_per, kb1 = min(nkb, kb0 + p.kb_per);
-      mbar_wait(smem_u32(tempty_bar + acc), (((uint32_t)it >> 1) & 1) ^ 1);
+      { const long long tw = clock64(); mbar_wait(smem_u32(tempty_bar + acc), (((uint32_t)it >> 1) & 1) ^ 1); t_tempty += clock64() - tw; }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);      // main accumulator
       const uint32_t d_cross = d_tmem + (uint32_t)p.BN;                       // correction terms (NPL >= 2)
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(smem_u32(full_bar + s), ph);
+        { const long long tw = clock64(); mbar_wait(smem_u32(full_bar + s), ph); t_full += clock64() - tw; }
         tc_fence_after();
         if (lane == 0) {
           const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
@@ -256,6 +268,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
+    if (blockIdx.x == 0 && lane == 0) { tc_prof[0] = clock64() - t_begin; tc_prof[1] = t_full; tc_prof[2] = t_tempty; tc_prof[8] = (unsigned long long)it; }
   } else {
     // ============================ epilogue (warps 2 .. 2+TC_EPI_WARPS) ============================
     const int ew = warp - 2;
@@ -601,6 +614,9 @@ static int pick_bn(int N, int npl) {
 }
 
 int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stream);
+// gemm2_tc.cu: the CTA-pair (cta_group::2) kernel for the large plain GEMMs of the 2-plane modes
+int gemm2_tc_launch(const lvae_gemm_desc* d, const void* const* a_pl, const void* const* a1_pl, int M, int K, int Ka, int C1,
+                    int ek, cudaStream_t stream, int* handled);
 int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) { return gemm_tc_launch_split(d, 0, stream); }
 
 // split_k != 0: split-K over the persistent grid, partial tiles added atomically into d->out (which the caller zeroed);
@@ -669,6 +685,16 @@ int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stre
   if (conv || split_k) ek = EK_MISC;                           // tile rows are pixel patches: its own store loop | atomics
   else if (d->epilogue == LVAE_EPI_BIAS_GELU && p.out_pl[0] != nullptr && p.out == nullptr && d->N % 2 == 0) ek = EK_GELU;
   else if (!shuffle && d->N % 4 == 0) ek = EK_ROWS;
+  if (npl == 2 && !conv && !split_k && (ek == EK_GELU || ek == EK_ROWS)) {
+    // large plain GEMMs: 256 x BN tiles on CTA pairs (half the operand bytes per flop); bit-identical results
+    const void* ap[2] = {a_pl[0], a_pl[1]};
+    const void* a1p[2] = {d->a1_planes[0], d->a1_planes[1]};
+    int handled = 0;
+    const int rc2 = gemm2_tc_launch(d, ap, concat_planes ? a1p : nullptr, M, K, concat_planes ? d->C0 : K, d->C1,
+                                    ek == EK_GELU ? 0 : 1, stream, &handled);
+    if (rc2) return rc2;
+    if (handled) return 0;
+  }
   const int fixed = 1024 + tc_epi_stage_bytes(ek) + 256;       // alignment slack + transpose buffers + barriers
   const int budget = 227 * 1024 - fixed;
   // k-block: a 128-byte swizzle row (64 bf16) whenever two such stages fit (measured: 2 x 64 beats 4 x 32 on every

@@ -21,6 +21,9 @@ SHAPES = [  # (name, M, K, N, epi)
     ('s32 fc1', 3072, 512, 1024, 1), ('s64 fc1', 768, 512, 2048, 1),
     ('s4 dec fc1', 196608, 128, 192, 1), ('s4 dec fc2', 196608, 192, 128, 2),
     ('s8 dec fc1', 49152, 256, 448, 1), ('s8 dec fc2', 49152, 448, 256, 2),
+    ('s8 dec2 fc1', 49152, 256, 512, 1), ('s8 dec2 fc2', 49152, 512, 256, 2),
+    ('s16 dec fc1', 12288, 384, 768, 1), ('s16 dec fc2', 12288, 768, 384, 2),
+    ('s32 fc2', 3072, 1024, 512, 2), ('s32 wide fc1', 3072, 512, 1536, 1), ('s32 wide fc2', 3072, 1536, 512, 2),
     ('n32 probe', 196608, 192, 32, 0), ('n64 probe', 196608, 192, 64, 0), ('n128 probe', 196608, 192, 128, 0),
 ]
 def planes(x, n, prec=3, weight=False):
@@ -65,7 +68,16 @@ for prec in precs:
         ms = e0.elapsed_time(e1) / (reps * nbuf)
         fl = 2.0 * M * K * Nn
         byts = M * K * 2 * NPL.get(prec, 2) + M * Nn * (2 * NPL.get(prec, 2) if epi == 1 else 8) if prec else M * (K + Nn) * 4
-        print(f'prec={prec} {name:12s} M={M:6d} K={K:4d} N={Nn:4d}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s algorithmic '
+        pair = lib.lvae_gemm2_launch_count()
+        print(f'prec={prec} pair={int(pair > globals().get("_pair0", 0))} {name:12s} M={M:6d} K={K:4d} N={Nn:4d}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s algorithmic '
               f'({fl * TERMS[prec] / ms / 1e9:7.1f} issued)  {byts / ms / 1e6:7.0f} GB/s', flush=True)
+        import numpy as _np
+        pr = _np.zeros(16, dtype=_np.uint64)
+        lib.lvae_debug_prof(2 if pair > globals().get("_pair0", 0) else 1, pr.ctypes.data)
+        nt = max(1, int(pr[8]))
+        print(f'    per tile (clk): mma thread {int(pr[0]) // nt} = wait operands {int(pr[1]) // nt} + wait accumulator {int(pr[2]) // nt} + issue '
+              f'{(int(pr[0]) - int(pr[1]) - int(pr[2])) // nt}; producer waits for a free stage {int(pr[4]) // nt} of {int(pr[3]) // nt}; '
+              f'epilogue warp: wait acc {int(pr[6]) // nt}, drain {int(pr[7]) // nt}, total {int(pr[5]) // nt}; tiles {nt}', flush=True)
+        _pair0 = pair
         del bufs
         torch.cuda.empty_cache()
