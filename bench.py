@@ -29,6 +29,11 @@ for p in (ROOT / 'lossy-vae_b200', ROOT / 'oracle'):
     sys.path.insert(0, str(p))
 
 H, W = 512, 768
+# Benched images: seeded image-like content (low-frequency waves + noise, oracle/oracle_inputs.py:synth_image), Kodak shape.
+# (r1 benched iid uniform noise; throughput does not depend on the content, but the parity record does: on iid noise the
+# randomly initialised priors put thousands of latents at likelihoods of a few 2^-25 quanta, where one ulp of the host's
+# erf moves the rate by whole quanta -- tests/test_gpu_model.py:bpp_tol, profiles/r2_parity.md.)
+BENCH_INPUT = 'synth'
 METRIC = '512x768 images/sec (enc+dec)'
 DENSE_GFLOP_PER_IMAGE = 287.61       # qarv_base eval forward, Linear + non-depthwise conv, 2*MAC
 
@@ -88,56 +93,84 @@ class ClockSampler:
                     power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
 
 
-def cpu_reference_images_per_s(n_timed, threads=None):
-    """The oracle's eval forward on the host CPU: B=1, 512x768, seeded sensitised weights.  Returns (img/s, cores, sample)."""
+def _reference_forward():
+    """(forward(im, lmb) -> dict(bppix, psnr, ...), kind, what): the reference's OWN `lvae` package on the host CPU when a copy
+    of it is reachable (/root/reference in the build container, else the staged byte-identical copy oracle/_ref/reference
+    made by oracle/make_ref.py; imported through oracle/ref_loader.py with the timm / compressai stand-ins of
+    oracle/shims) -> kind 'reference'; else the pinned torch-CPU restatement oracle/lvae_oracle.py -> kind 'port'.
+    Only this function (the reference arm / cpu_baseline leg) imports the reference; it runs in its own process."""
     import torch
     import lvae_oracle as O
-    from oracle_inputs import make_input
-    cores = threads or os.cpu_count() or 1
-    torch.set_num_threads(cores)
     sd = O.sensitised_state_dict(O.qarv_param_shapes(), seed=0)
-    im = make_input('rand', 1, H, W, 0)
-    lmb = torch.tensor([2048.0])
-    O.qarv_forward(sd, im, lmb)                         # warm-up (thread pools, oneDNN primitive caches)
-    t0 = time.perf_counter()
-    for _ in range(n_timed):
-        O.qarv_forward(sd, im, lmb)
-    dt = time.perf_counter() - t0
-    return n_timed / dt, cores, f'{n_timed} x (1 image 512x768, eval forward) after 1 warm-up, torch CPU fp32, {cores} threads'
+    try:
+        import ref_loader
+        if not ref_loader.available():
+            raise ImportError('no reference copy')
+        ref = ref_loader.load_reference()
+        torch.manual_seed(0)
+        model = ref.get_model('qarv_base').eval()
+        model.load_state_dict(sd, strict=False)
+
+        def fwd(im, lmb):
+            with torch.no_grad():
+                return model(im, lmb=lmb, return_rec=True)
+        return fwd, 'reference', f"the reference's own lvae package ({ref_loader.REFERENCE_ROOT}, unmodified) on torch CPU fp32"
+    except Exception as e:      # noqa: BLE001 -- any import problem of the third-party-dependent reference -> the port
+        why = f'{type(e).__name__}: {e}'
+        return (lambda im, lmb: O.qarv_forward(sd, im, lmb)), 'port', f'oracle/lvae_oracle.py (torch-CPU restatement; reference not importable: {why})'
 
 
 def run_reference(args):
+    """The reference arm: the reference's CPU implementation of the path on this box's host cores.  One step = one
+    512x768 image through the eval forward (a bounded sample of the batch-8 workload); --steps / --warmup are honoured.
+    Under torchrun only rank 0 works.  With --parity-seed S the line also carries bppix / psnr of image 0 of the batch
+    make_input('rand', B, H, W, S) (what the B200 arm benches on rank 0): the B200 arm's `parity` record compares to it."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    # every "step" is a bounded sample: one 512x768 image through the oracle
     import torch
-    import lvae_oracle as O
     from oracle_inputs import make_input
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = O.sensitised_state_dict(O.qarv_param_shapes(), seed=0)
-    im = make_input('rand', 1, H, W, 0)
+    fwd, kind, what = _reference_forward()
+    B = args.batch
+    im = make_input(BENCH_INPUT, 1, H, W, args.parity_seed if args.parity_seed is not None else 1000)
     lmb = torch.tensor([2048.0])
-    steps, warm = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    steps, warm = max(1, args.steps), max(1, args.warmup)
     for _ in range(warm):
-        O.qarv_forward(sd, im, lmb)
+        out = fwd(im, lmb)
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.qarv_forward(sd, im, lmb)
+        out = fwd(im, lmb)
     dt = time.perf_counter() - t0
     v = steps / dt
-    sample = f'{steps} steps x 1 image 512x768 eval forward (bounded sample of the batch-8 workload), {cores} host threads'
+    sample = (f'{steps} steps x 1 image 512x768 eval forward after {warm} warm-up (bounded sample of the batch-{B} workload), '
+              f'{cores} host threads')
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
         'warmup': warm, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'qarv_base eval forward, synthetic 512x768 RGB, 1 image per step on host CPU '
-                               '(torch-CPU restatement of the reference: oracle/lvae_oracle.py)'},
-        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'config': {'workload': f'qarv_base eval forward (rate + MSE), synthetic 512x768 RGB, lambda 2048, 1 image per step on the host CPU: {what}'},
+        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
+        'result': {'bppix': float(out['bppix']), 'psnr': float(out['psnr']), 'image': f"make_input('{BENCH_INPUT}', 1, {H}, {W}, seed)"},
     }))
+
+
+def cpu_baseline_subprocess(n_timed, batch, seed):
+    """The cpu_baseline leg (N = 1 only): the reference arm in its OWN process, before this one touches CUDA or NCCL --
+    two different `lvae` packages cannot share an interpreter, and a rank spinning in an NCCL barrier next to it would
+    steal its cores (r1's 0.04 images/s record).  Returns the parsed line or None."""
+    cmd = [sys.executable, str(ROOT / 'bench.py'), '--impl', 'reference', '--steps', str(n_timed), '--warmup', '1',
+           '--batch', str(batch), '--parity-seed', str(seed)]
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE')}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:      # noqa: BLE001
+        print(f'cpu_baseline leg failed: {e}', file=sys.stderr)
+        return None
 
 
 def run_codec(args):
@@ -194,6 +227,90 @@ def run_codec(args):
     }))
 
 
+def teardown_process_group(step=None):
+    """destroy_process_group() with the captured NCCL work released first.  r1 left through os._exit(0) because the call
+    did not return while a CUDA graph holding recorded collectives was alive; dropping the graph (GraphedTrainStep.release)
+    is the fix.  A watchdog still guarantees that a rank can never hang the bench."""
+    import torch
+    import torch.distributed as dist
+    if step is not None:
+        step.release()
+    torch.cuda.synchronize()
+    if not dist.is_initialized():
+        return
+    dist.barrier()
+    done = threading.Event()
+
+    def _watch():
+        if not done.wait(60):
+            sys.stdout.flush()
+            print('destroy_process_group() did not return within 60 s: leaving', file=sys.stderr, flush=True)
+            os._exit(0)
+    threading.Thread(target=_watch, daemon=True).start()
+    dist.destroy_process_group()
+    done.set()
+
+
+def train_record(dev, rank, world, steps, precision=None):
+    """The `train` sub-record of the default line: BASELINE configs[3] -- qarv_base train-var-rate step
+    (forward + backward + gradient all-reduce over NCCL + clip + Adam + EMA), 256x256 crops, 16 per GPU -- as ONE CUDA graph
+    replayed `steps` times.  Device-timed with CUDA events, max over ranks.  Returns a dict (rank 0) or None."""
+    import copy
+    import torch
+    import torch.distributed as dist
+    import lvae
+    from lvae import _native as N
+    from lvae.training import GraphedTrainStep
+    from oracle_inputs import make_input
+    B, h, w = 16, 256, 256
+    torch.manual_seed(0)
+    model = lvae.get_model('qarv_base')
+    if precision:
+        model.precision = precision
+    model = model.to(dev).train()
+    ema = copy.deepcopy(model).eval()
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+    im = make_input('rand', B, h, w, 2000 + rank).to(dev)
+    torch.manual_seed(4321 + rank)
+    step = GraphedTrainStep(model, opt, (B, 3, h, w), warmup=1, process_group=True if world > 1 else None, grad_clip=2.0,
+                            ema=ema, ema_decay=0.9999)
+    for _ in range(3):
+        step(im)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    st = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(steps):
+        loss = step(im)
+    e1.record(st)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / steps
+    rec = None
+    if rank == 0:
+        nbytes = step.layout.total * 4
+        rec = {'metric': '256x256 images/sec (training step: forward + backward + all-reduce + clip + Adam + EMA)',
+               'value': B * world / (ms / 1e3), 'unit': 'images/s', 'ms_per_step': ms, 'steps': steps, 'n_gpus': world,
+               'workload': 'qarv_base train-var-rate step, synthetic 256x256 crops, 16 per GPU (BASELINE configs[3] per-GPU shape), '
+                           'lambda sampled per image, grad_clip 2.0, EMA 0.9999, whole step = one CUDA graph',
+               'collective': ('none (1 GPU)' if world == 1 else
+                              f'{len(step.buckets.ranges)} NCCL all-reduces (ReduceOp.AVG) over {nbytes / 1e6:.0f} MB of flat fp32 gradients, issued '
+                              'from post-accumulate hooks while the backward runs'),
+               'optimizer': 'clip + Adam + EMA fused on flat buffers (csrc/optim.cu)' if step.native else 'torch.optim.Adam',
+               'launches_per_step': step.launches_per_replay, 'loss': float(loss),
+               'grad_norm': float(step.grad_norm), 'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30}
+    step.release()
+    del step, model, ema, opt
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_train(args):
     """Training step images/s (BASELINE configs[2]: qres34m 512x768 batch 16 fwd+bwd on one GPU; configs[3]: qarv_base
     train-var-rate step on 256x256 crops, 16 per GPU, gradients all-reduced over NCCL by DistributedDataParallel).
@@ -228,7 +345,7 @@ def run_train(args):
     graphed = not args.no_train_graph
     if world > 1 and not graphed:     # the eager path: DistributedDataParallel exactly as lvae/trainer.py wraps the model
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graphed, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4) if graphed else torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
     im_host = make_input('rand', B, h, w, 1000 + rank).pin_memory()
     im_dev = im_host.to(dev)
     torch.manual_seed(1234 + rank)                      # lambda / noise draws differ per rank
@@ -295,9 +412,9 @@ def run_train(args):
                                     if qres else f'qarv_base train-var-rate step (lambda sampled per image), synthetic {h}x{w} crops, '
                                                  f'batch {B} per GPU (BASELINE configs[3])'),
                        'batch_per_gpu': B, 'global_batch': B * world,
-                       'parallelism': f'data parallel x{world}' + ((', one NCCL all-reduce of the flat gradient inside the captured step' if graphed
+                       'parallelism': f'data parallel x{world}' + ((', bucketed NCCL all-reduce (AVG) of the flat gradient buffer inside the captured step, overlapped with the backward' if graphed
                                                                     else ', NCCL gradient all-reduce (DistributedDataParallel buckets)') if world > 1 else ''),
-                       'weights': 'seeded default init', 'optimizer': 'Adam (torch.optim, fused=True)',
+                       'weights': 'seeded default init', 'optimizer': 'Adam on flat buffers (csrc/optim.cu)' if graphed else 'Adam (torch.optim, fused=True)',
                        'value_path': 'whole step replayed as one CUDA graph (lvae.training.GraphedTrainStep)' if graphed else 'eager step',
                        'e2e_path': ('eager step through model.forward() / loss.backward() / optimizer.step()' if eager_e2e else
                                     'GraphedTrainStep(batch on pinned host memory) + loss read-back'),
@@ -312,14 +429,8 @@ def run_train(args):
             'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30,
         }), flush=True)
     if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-        if graphed:
-            # a CUDA graph that recorded NCCL work keeps the communicator busy: destroy_process_group() did not return in
-            # the 2-GPU run of this round (the result line was already out).  Leave without tearing the communicator down.
-            sys.stdout.flush()
-            os._exit(0)
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        teardown_process_group(resident if graphed else None)
 
 
 def main():
@@ -338,7 +449,9 @@ def main():
                          '512x768 batch 16 forward + backward + Adam')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train-graph', action='store_true', help='--workload train*: time the eager step also for `value`')
-    ap.add_argument('--cpu-samples', type=int, default=5)
+    ap.add_argument('--cpu-samples', type=int, default=8)
+    ap.add_argument('--parity-seed', type=int, default=None, help='--impl reference: seed of the batch whose image 0 is evaluated')
+    ap.add_argument('--no-train-record', action='store_true', help='skip the `train` sub-record (configs[3] step) of the default line')
     ap.add_argument('--codec-batch', type=int, default=1, help='--workload codec: images per compress / decompress call')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -360,6 +473,11 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', 1))
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (there is no CPU path; use --impl reference for the CPU baseline)')
+    # cpu_baseline leg: N = 1 only, in its own process, BEFORE this process touches CUDA (at N > 1 the driver's reference
+    # arm on the same box is the CPU number; a rank spinning in an NCCL barrier would only distort it)
+    cpu_line = None
+    if world == 1 and not args.no_cpu_baseline and args.workload == 'qarv':
+        cpu_line = cpu_baseline_subprocess(args.cpu_samples, args.batch, 1000 + rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
@@ -398,7 +516,8 @@ def main():
     eng = model.engine
 
     # each rank gets its own seeded batch (weak scaling)
-    im_host = make_input('rand', B, H, W, 1000 + rank).pin_memory()
+    # image 0 of every rank's batch is make_input(kind, 1, H, W, 1000 + rank): what the reference arm evaluates for `parity`
+    im_host = torch.cat([make_input(BENCH_INPUT, 1, H, W, 1000 + rank), make_input(BENCH_INPUT, B - 1, H, W, 5000 + rank)]).pin_memory()
     lmb_host = torch.full((B,), 256.0 if rd else 2048.0).pin_memory()
     lmb_dev = lmb_host.to(dev)
 
@@ -467,11 +586,15 @@ def main():
                     launches=gm['n'], share_of_step=gm['ms'] / tot_ms, issued_mma_multiplier=issued,
                     note='achieved = sum over the GEMM launches of 2*M*N*K / sum of their CUDA-event durations')
         roof['frac'] = roof['achieved'] / roof['peak']
-        # DRAM traffic per launch from the committed ncu --set full captures (profiles/r1_final_ncu_summary.md): the class
-        # has 226 launches of ~40 shapes, so the two largest are quoted instead of one number
-        roof['traffic_examples'] = {
-            'fc2 H/4 M=196608 K=384 N=192': {'dram_bytes': 573.1e6, 'algorithmic_bytes': 604.0e6, 'us': 125.6},
-            'fc1 H/4 M=196608 K=192 N=384': {'dram_bytes': 402.1e6, 'algorithmic_bytes': 453.0e6, 'us': 161.6}}
+        # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` captures,
+        # parsed from the raw csv pages by scripts/ncu_traffic.py into profiles/r2_ncu_traffic.json (never typed in by hand);
+        # the GEMM class has ~220 launches of ~40 shapes, so the captured shapes are quoted instead of one number
+        traffic = {}
+        tf = ROOT / 'profiles' / 'r2_ncu_traffic.json'
+        if tf.is_file():
+            traffic = json.loads(tf.read_text())
+        roof['traffic_examples'] = traffic.get('gemm')
+        roof['traffic_source'] = 'profiles/r2_ncu_traffic.json' if traffic else None
         roof['issued_tflops'] = roof['achieved'] * issued          # MMA FLOPs actually issued to the tensor pipe
         roof['issued_frac'] = roof['issued_tflops'] / roof['peak']
         # biggest latent layer alone (the only ones large enough to be bandwidth- rather than latency-bound)
@@ -480,14 +603,25 @@ def main():
                       unit='GB/s', traffic=None, peak_source=pk['src'], elems=big[1]['elems'],
                       all_layers_gbs=lt['bytes'] / lt['ms'] / 1e6, share_of_step=lt['ms'] / tot_ms)
         roof_e['frac'] = roof_e['achieved'] / roof_e['peak']
+        dwt = (traffic.get('dwln') or {})
         roof_d = dict(bound='hbm', kernel='dwln_kernel', achieved=dw['bytes'] / dw['ms'] / 1e6, peak=pk['hbm'], unit='GB/s',
-                      frac=dw['bytes'] / dw['ms'] / 1e6 / pk['hbm'], share_of_step=dw['ms'] / tot_ms, traffic=262.8e6,
-                      traffic_of='H/4 C=192 k=7 launch: 151.1 MB read + 111.6 MB written (ncu), 302 MB algorithmic')
+                      frac=dw['bytes'] / dw['ms'] / 1e6 / pk['hbm'], share_of_step=dw['ms'] / tot_ms,
+                      traffic=dwt.get('dram_bytes'), traffic_of=dwt.get('what'), traffic_source=roof['traffic_source'])
+        lat_t = (traffic.get('latent') or {})
+        roof_e['traffic'] = lat_t.get('dram_bytes'); roof_e['traffic_of'] = lat_t.get('what')
 
-        cpu = None
-        if not args.no_cpu_baseline and not rd and not qres:
-            v, cores, sample = cpu_reference_images_per_s(args.cpu_samples)
-            cpu = dict(value=v, unit='images/s', cores=cores, kind='port', sample=sample)
+        cpu = cpu_line['cpu_baseline'] if cpu_line else None
+        # ---- parity on the benched input (outside the timed region): image 0 of this rank's batch through the public API
+        # against the CPU reference arm's numbers for the same image (north star: |dbpp| <= 1e-4, |dPSNR| <= 0.01 dB)
+        parity = None
+        if cpu_line and cpu_line.get('result') and not rd and not qres:
+            o1 = model(im_host[:1].contiguous(), lmb=lmb_dev[:1])
+            rb, rp = cpu_line['result']['bppix'], cpu_line['result']['psnr']
+            parity = dict(against=cpu_line['cpu_baseline']['kind'], image='image 0 of the benched batch (rank 0)',
+                          bppix=o1['bppix'], bppix_ref=rb, dbpp=abs(o1['bppix'] - rb), psnr=o1['psnr'], psnr_ref=rp,
+                          dpsnr=abs(o1['psnr'] - rp), tol=dict(dbpp=1e-4, dpsnr=0.01),
+                          tail_quantum_bpp=3.4 * 1.4427 / (H * W),      # one likelihood-floor event of the reference's fp32 CDF difference
+                          ok=bool(abs(o1['bppix'] - rb) <= 1e-4 and abs(o1['psnr'] - rp) <= 0.01))
 
         n_img = B * world * args.steps
         line = {
@@ -502,6 +636,7 @@ def main():
                                                f'(forward half of BASELINE configs[2]; forward + backward + Adam: --workload train-qres)' if qres else
                                     f'qarv_base eval forward (rate + MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 2048 '
                                     f'(BASELINE configs[1])'), 'batch_per_gpu': B, 'global_batch': B * world, 'precision': model.precision,
+                       'input': f'{BENCH_INPUT}: seeded image-like RGB (low-frequency waves + noise, oracle/oracle_inputs.py), Kodak shape',
                        'parallelism': f'batch-shard x{world}, no data-path collective', 'weights': 'seeded sensitised init (no checkpoint offline)',
                        'l2': 'no flush: per-step working set (weights 374 MB + activations > 1 GB) exceeds the 126 MB L2',
                        'dense_gflop_per_image': DENSE_GFLOP_PER_IMAGE},
@@ -510,13 +645,24 @@ def main():
             'gpu_launches': launches, 'launches_per_step': launches // max(1, args.steps),
             'clocks': clocks, 'roofline': roof, 'roofline_entropy': roof_e, 'roofline_dwln': roof_d,
             'tensor_frac_of_step': DENSE_GFLOP_PER_IMAGE * B / (ms_dev / args.steps) / pk['tensor_sustained'],
-            'cpu_baseline': cpu,
+            'cpu_baseline': cpu, 'parity': parity,
             'result': {'bppix': float(stats[1]) * 1.4426950408889634 * 3, 'loss': float(stats[0]), 'e2e_bppix': out['bppix'], 'e2e_psnr': out['psnr']},
         }
-        print(json.dumps(line))
+    # ---- `train` sub-record: the configs[3] step with its gradient all-reduce, at this N (every rank takes part)
+    train = None
+    if args.workload == 'qarv' and not args.no_train_record:
+        del P
+        eng._plans.clear()
+        torch.cuda.empty_cache()
+        try:
+            train = train_record(dev, rank, world, max(10, min(args.steps, 20)), args.precision)
+        except Exception as e:      # noqa: BLE001 -- the headline line must survive a failure of the extra record
+            train = {'error': f'{type(e).__name__}: {e}'}
+    if rank == 0:
+        line['train'] = train
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        teardown_process_group()
 
 
 if __name__ == '__main__':

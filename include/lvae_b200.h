@@ -197,6 +197,22 @@ int lvae_split_planes_t_ex(const float* x, void* p0, void* p1, int64_t P, int C,
 int lvae_gemm_wgrad(const void* dyt_p0, const void* dyt_p1, const void* xt_p0, const void* xt_p1,
                     float* dw, int n_out, int k_in, int64_t P, void* stream);
 
+/* ---- training-step tail on flat buffers: global-norm clipping + Adam + EMA (lvae/trainer.py:360-377,394-406) --------
+ * Replaces clip_grad_norm_(params, max_norm) -> torch.optim.Adam.step() (weight_decay 0, no amsgrad) -> ModelEmaV2.update
+ * when parameters, gradients, Adam moments and the EMA copy each live in ONE flat fp32 buffer of n elements (16-byte
+ * aligned; lvae.training.GraphedTrainStep lays them out).  Two launches, 36 bytes per parameter:
+ *   g' = g * min(1, max_norm / (||g||_2 + 1e-6))   (max_norm <= 0: no clipping)
+ *   m += (g' - m)(1 - beta1);  v = beta2 v + (1 - beta2) g'^2;  p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)
+ *   ema = decay * ema + (1 - decay) * p            (timm ModelEmaV2, same roundings; ema == NULL: skipped)
+ * lr, step (= t of this update, >= 1, as a float) and ema_decay (TWO floats: decay and 1 - decay, rounded from the host's
+ * double values) are DEVICE scalars, so that a captured step can be
+ * replayed while the host runs the learning-rate schedule / EMA warm-up.  scratch: lvae_optim_scratch_doubles() doubles
+ * (deterministic two-stage sum of squares).  grad_norm_out (optional, device): ||g||_2 before clipping. */
+int lvae_optim_scratch_doubles(void);
+int lvae_adam_clip_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, double* scratch,
+                       float max_norm, const float* lr, const float* step, const float* ema_decay,
+                       float beta1, float beta2, float eps, float* grad_norm_out, void* stream);
+
 /* ---- fused latent-layer kernels (qarv/model.py:51-53,90-96,104-113; CompressAI GaussianConditional) --
  * prior [M, 2*zdim] (pm | plogv_raw) and qm [M, zdim] are NHWC matrices; hw = h*w positions per image.
  * Eval (K11+K12+K15): z = rint(qm-pm)+pm; kl = -ln max(Phi((.5-|z-pm|)/s) - Phi((-.5-|z-pm|)/s), 1e-9),

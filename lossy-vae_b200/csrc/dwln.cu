@@ -13,9 +13,11 @@
 //     rows, every shared-memory row and every filter row is loaded once and feeds both outputs -- 161 loads per 784
 //     packed FFMA2 instead of 294, which moves the bound from the L1/shared pipe (62 % busy before) to the FMA pipe;
 //   * LayerNorm: per-CTA two-pass statistics in registers (16-value halving warp reduction: 16 shuffles instead of
-//     80), then Chan's parallel-variance combination of the CL partial (sum, M2) pairs read through distributed
-//     shared memory, always in rank order, so every CTA of the cluster -- and every launch -- agrees bit for bit;
-//     one cluster barrier before the exchange, one before exit;
+//     80), then Chan's parallel-variance combination of the CL partial (sum, M2) pairs, always in rank order, so every
+//     CTA of the cluster -- and every launch -- agrees bit for bit.  The partials are PUSHED: every CTA writes its pair
+//     into each peer's shared memory with st.async (complete_tx on the peer's mbarrier) and waits on its own mbarrier
+//     for CL x 512 bytes.  No cluster barrier on the critical path: r1's barrier.cluster release / acquire pair and the
+//     exit barrier were MEMBAR.ALL.GPU + ERRBAR waits, 25 % of the kernel's stall samples (ncu source view);
 //   * modulation (AdaLN or affine) and the split into 16-bit planes for the tensor-core GEMM that consumes them.
 #include "common.cuh"
 #include <cuda_bf16.h>
@@ -57,6 +59,14 @@ __device__ __forceinline__ void dw_tma_load_4d(uint32_t dst, const CUtensorMap* 
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// remote (distributed shared memory) 8-byte store that credits 8 bytes to an mbarrier of the destination CTA
+__device__ __forceinline__ void dw_st_async_v2(uint32_t remote_addr, float a, float b, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(remote_addr), "f"(a), "f"(b), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ uint32_t dw_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
 }
 // packed fp32x2 FMA (sm_100): both lanes are IEEE fma, i.e. bit-identical to two fmaf() at half the issue slots
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -102,14 +112,14 @@ __global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
     const float* __restrict__ ada, int64_t ada_stride, int64_t ada_off,
     const float* __restrict__ ln_w, const float* __restrict__ ln_b,
     float* __restrict__ y, __nv_bfloat16* __restrict__ y0, __nv_bfloat16* __restrict__ y1, __nv_bfloat16* __restrict__ y2,
-    int f16, int H, int W, int tiles_x, int tiles_y) {
+    int f16, int H, int W, int tiles_x, int tiles_y, int nbatch, int l2_ahead) {
   constexpr int C = NJ * DW_CH * CL, NLOC = NJ * DW_CH, PAD = (KS - 1) / 2;
   constexpr int HW_ = DW_TW + KS - 1, HH_ = DW_TH + KS - 1;                  // halo tile width / height
   constexpr int CHUNK_FLOATS = HH_ * HW_ * DW_CH;
   constexpr int NBUF = NJ > 1 ? 2 : 1;
   extern __shared__ __align__(128) float dw_smem[];                          // [NBUF][HH_][HW_][64]
-  __shared__ __align__(8) uint64_t dw_bar[2];
-  __shared__ __align__(16) float ln_pub[2][DW_WARPS * DW_PIX];                      // this CTA's (sum, M2) per tile pixel, read by the cluster
+  __shared__ __align__(8) uint64_t dw_bar[3];                                       // [0], [1]: halo chunks; [2]: LayerNorm partials of the cluster
+  __shared__ __align__(16) float2 ln_recv[CL][DW_WARPS * DW_PIX];                   // (sum, M2) per tile pixel, written by CTA r of the cluster
   __shared__ __align__(16) float ln_loc[DW_WARPS][2][DW_PIX];                       // per warp: broadcast scratch
   const int tid = threadIdx.x, lane = tid & 31, wrow = tid >> 5;
   const int crank = (CL > 1) ? (int)(blockIdx.x % CL) : 0;                   // cluster dims (CL,1,1): rank == blockIdx.x % CL
@@ -122,9 +132,18 @@ __global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
   if (tid == 0) {
     dw_mbar_init(dw_smem_u32(&dw_bar[0]), 1);
     dw_mbar_init(dw_smem_u32(&dw_bar[1]), 1);
+    if (CL > 1) {
+      // armed for the whole exchange right away: every CTA of the cluster (this one included) sends 8 bytes per pixel
+      dw_mbar_init(dw_smem_u32(&dw_bar[2]), 1);
+      dw_mbar_expect_tx(dw_smem_u32(&dw_bar[2]), (uint32_t)(CL * DW_WARPS * DW_PIX * 8));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  // peers may signal dw_bar[2] only once it exists: arrive now, wait before the first remote store.  fence.mbarrier_init
+  // above is what publishes the initialisation, so the arrive can be RELAXED (the release form costs a MEMBAR.ALL.GPU +
+  // ERRBAR: 9 % of the kernel's stall samples when it stood here)
+  if (CL > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   auto load_chunk = [&](int j, int buf) {                                    // one thread
     const uint32_t bar = dw_smem_u32(&dw_bar[buf]);
     dw_mbar_expect_tx(bar, (uint32_t)(CHUNK_FLOATS * 4));
@@ -133,15 +152,34 @@ __global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
 
   // res[j][p]: conv output of pixel p = r * 8 + s (r = 0, 1: rows 2 wrow + r; s: column) for this lane's 2 channels
   float2 res[NJ][DW_PIX];
-  if (tid == 0) load_chunk(0, 0);
+  if (tid == 0) {
+    load_chunk(0, 0);
+    // pull the halo of the tile a later CTA of this SM will want into L2 (one wave of resident CTAs ahead)
+    if (l2_ahead > 0) {
+      int t2 = (int)(blockIdx.x / CL) + l2_ahead;
+      const int tx2 = t2 % tiles_x; t2 /= tiles_x;
+      const int ty2 = t2 % tiles_y; const int b2 = t2 / tiles_y;
+      if (b2 < nbatch)
+        for (int j = 0; j < NJ; ++j)
+          asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+                       ::"l"(&x_map), "r"(cbase + j * DW_CH), "r"(tx2 * DW_TW - PAD), "r"(ty2 * DW_TH - PAD), "r"(b2) : "memory");
+    }
+  }
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     // buffer (j+1)&1 was last read in iteration j-1, which ended with __syncthreads()
     if (NJ > 1 && tid == 0 && j + 1 < NJ) load_chunk(j + 1, (j + 1) & 1);
-    dw_mbar_wait(dw_smem_u32(&dw_bar[j & (NBUF - 1)]), (uint32_t)((j >> 1) & 1));
-    const float* tile = dw_smem + (j & (NBUF - 1)) * CHUNK_FLOATS;
     const int c = cbase + j * DW_CH + lane * 2;
+    // bias and the first filter row are in flight while the halo arrives; row i + 1 is fetched while row i is used
     const float2 bias = __ldg(reinterpret_cast<const float2*>(dw_b + c));
+    float2 wnext[KS];
+#pragma unroll
+    for (int kx = 0; kx < KS; ++kx) wnext[kx] = __ldg(reinterpret_cast<const float2*>(dw_w + kx * C + c));
+    dw_mbar_wait(dw_smem_u32(&dw_bar[j & (NBUF - 1)]), (uint32_t)((j >> 1) & 1));
+    // the peers' matching arrive was the first thing they did (cluster CTAs start together): this returns at once, and
+    // from here on every peer's dw_bar[2] is known to exist
+    if (CL > 1 && j == 0) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const float* tile = dw_smem + (j & (NBUF - 1)) * CHUNK_FLOATS;
 #pragma unroll
     for (int p = 0; p < DW_PIX; ++p) res[j][p] = bias;
     // rolling over the KS + 1 halo rows that feed output rows o1 = 2 wrow (tap row ky = i) and o2 = o1 + 1 (ky = i - 1):
@@ -155,9 +193,11 @@ __global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
 #pragma unroll
       for (int q = 0; q < HW_; ++q) xv[q] = *reinterpret_cast<const float2*>(row + q * DW_CH);
       float2 wcur[KS];
-      if (i < KS) {
 #pragma unroll
-        for (int kx = 0; kx < KS; ++kx) wcur[kx] = __ldg(reinterpret_cast<const float2*>(dw_w + (i * KS + kx) * C + c));
+      for (int kx = 0; kx < KS; ++kx) wcur[kx] = wnext[kx];
+      if (i + 1 < KS) {
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) wnext[kx] = __ldg(reinterpret_cast<const float2*>(dw_w + ((i + 1) * KS + kx) * C + c));
       }
 #pragma unroll
       for (int kx = 0; kx < KS; ++kx) {
@@ -177,6 +217,22 @@ __global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
       for (int kx = 0; kx < KS; ++kx) wprev[kx] = wcur[kx];
     }
     if (NJ > 1) __syncthreads();           // everyone is done with this buffer before chunk j+2 overwrites it
+  }
+
+  // modulation coefficients v * mul + add (mul = (1 + scale) | gamma, add = shift | beta): the loads are issued here so
+  // that their latency hides behind the statistics and the cluster exchange below
+  float2 mod_mul[NJ], mod_add[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int c = cbase + j * DW_CH + lane * 2;
+    if (ln_w != nullptr) {
+      mod_mul[j] = __ldg(reinterpret_cast<const float2*>(ln_w + c));
+      mod_add[j] = __ldg(reinterpret_cast<const float2*>(ln_b + c));
+    } else {
+      const float* e = ada + (int64_t)b * ada_stride + ada_off + c;
+      mod_add[j] = __ldg(reinterpret_cast<const float2*>(e));
+      mod_mul[j] = __ldg(reinterpret_cast<const float2*>(e + C));        // scale; 1 + scale is formed at the use
+    }
   }
 
   // ---- LayerNorm statistics: two-pass over this CTA's channels (registers), Chan's combination across the cluster
@@ -226,18 +282,20 @@ __global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
     }
   } else {
     if ((lane & 1) == 0) {
-      ln_pub[0][wrow * DW_PIX + (lane >> 1)] = tot;
-      ln_pub[1][wrow * DW_PIX + (lane >> 1)] = m2;
+      // push this CTA's (sum, M2) of pixel (lane >> 1) to every CTA of the cluster, itself included
+      const uint32_t slot = dw_smem_u32(&ln_recv[crank][wrow * DW_PIX + (lane >> 1)]);
+      const uint32_t bar = dw_smem_u32(&dw_bar[2]);
+#pragma unroll
+      for (int r = 0; r < CL; ++r) dw_st_async_v2(dw_mapa(slot, (uint32_t)r), tot, m2, dw_mapa(bar, (uint32_t)r));
     }
-    // publish -> read: release / acquire cluster barrier (orders the shared-memory writes above)
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    dw_mbar_wait(dw_smem_u32(&dw_bar[2]), 0);
     if (lane < DW_PIX) {
       // pixel `lane` of this warp: combine the CL partial (sum, M2) pairs in rank order (identical in every CTA)
       float s_r[CL], q_r[CL];
 #pragma unroll
       for (int r = 0; r < CL; ++r) {
-        s_r[r] = *cg::this_cluster().map_shared_rank(&ln_pub[0][wrow * DW_PIX + lane], r);
-        q_r[r] = *cg::this_cluster().map_shared_rank(&ln_pub[1][wrow * DW_PIX + lane], r);
+        const float2 pr = ln_recv[r][wrow * DW_PIX + lane];
+        s_r[r] = pr.x; q_r[r] = pr.y;
       }
       float S = 0.f;
 #pragma unroll
@@ -252,9 +310,6 @@ __global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
       ln_loc[wrow][0][lane] = mu;
       ln_loc[wrow][1][lane] = 1.0f / sqrtf(M2 * (1.0f / C) + 1e-6f);
     }
-    // this warp's remote reads have returned (their values were consumed above): arrive now, without memory ordering,
-    // and wait only before exit -- the output stores below overlap the barrier and no fence has to drain them
-    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     __syncwarp();
 #pragma unroll
     for (int p4 = 0; p4 < DW_PIX; p4 += 4) {
@@ -275,22 +330,13 @@ __global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int c = cbase + j * DW_CH + lane * 2;
-      float2 mul, add;                       // v * mul + add with mul = (1 + scale) | gamma, add = shift | beta
-      if (ln_w != nullptr) {
-        mul = __ldg(reinterpret_cast<const float2*>(ln_w + c));
-        add = __ldg(reinterpret_cast<const float2*>(ln_b + c));
-      } else {
-        const float* e = ada + (int64_t)b * ada_stride + ada_off + c;
-        add = __ldg(reinterpret_cast<const float2*>(e));
-        const float2 sc = __ldg(reinterpret_cast<const float2*>(e + C));
-        mul = make_float2(__fadd_rn(1.0f, sc.x), __fadd_rn(1.0f, sc.y));
-      }
+      const float2 add = mod_add[j];
+      const float2 mul = ln_w != nullptr ? mod_mul[j] : make_float2(__fadd_rn(1.0f, mod_mul[j].x), __fadd_rn(1.0f, mod_mul[j].y));
 #pragma unroll
       for (int p = 0; p < DW_PIX; ++p) {
         if (!INTERIOR && (h0 + 2 * wrow + p / DW_TW >= H || w0 + p % DW_TW >= W)) continue;      // warp-uniform
-        float2 v;
-        v.x = __fadd_rn(__fmul_rn(__fmul_rn(res[j][p].x - mean[p], rstd[p]), mul.x), add.x);
-        v.y = __fadd_rn(__fmul_rn(__fmul_rn(res[j][p].y - mean[p], rstd[p]), mul.y), add.y);
+        // ((x - mean) * rstd) * mul + add, one rounding per operation as before, two channels per instruction
+        float2 v = add2(mul2(mul2(add2(res[j][p], splat2(-mean[p])), splat2(rstd[p])), mul), add);
         const int64_t o = o00 + ((int64_t)(p / DW_TW) * W + p % DW_TW) * C + c;
         if constexpr (MODE == 0) {
           *reinterpret_cast<float2*>(y + o) = v;
@@ -322,7 +368,8 @@ __global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
     else emit(integral_constant<int, 1>{}, interior_c);
   };
   if (interior) emit_mode(std::true_type{}); else emit_mode(std::false_type{});
-  if (CL > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // nobody exits while a peer may still read its shared memory
+  // No exit barrier: the only remote accesses are the peers' st.async into ln_recv, and this CTA passed its own
+  // mbarrier wait only after every one of them had landed.
 }
 
 typedef CUresult (*DwEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -367,9 +414,15 @@ static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, con
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (dwconv input) failed: %d", (int)r); return LVAE_E_BADARG; }
   const int tiles_x = (W + DW_TW - 1) / DW_TW, tiles_y = (H + DW_TH - 1) / DW_TH;
   const int64_t blocks = (int64_t)B * tiles_x * tiles_y;
+  // optional L2 prefetch of the tile a later CTA will want, in waves of resident CTAs (4 per SM: 148 * 4 / CL tiles).
+  // Measured (profiles/r2_dwln.md): no effect at 1 or 2 waves -- the input was just written by the previous kernel and
+  // is largely L2-resident already -- so it is off unless LVAE_DW_L2_AHEAD says otherwise.
+  static int l2_ahead = -1;
+  if (l2_ahead < 0) { const char* e = getenv("LVAE_DW_L2_AHEAD"); l2_ahead = e ? atoi(e) : 0; }
+  const int ahead_tiles = l2_ahead > 0 ? l2_ahead * (148 * 4 / CL) : 0;
   if (CL == 1) {
     dwln_kernel<NJ, KS, CL><<<(unsigned)blocks, 32 * DW_WARPS, smem, stream>>>(
-        map, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, f16, H, W, tiles_x, tiles_y);
+        map, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, f16, H, W, tiles_x, tiles_y, B, ahead_tiles);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(blocks * CL)); cfg.blockDim = dim3(32 * DW_WARPS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -378,7 +431,7 @@ static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, con
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     LVAE_CUDA_CALL(cudaLaunchKernelEx(&cfg, dwln_kernel<NJ, KS, CL>, map, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b,
-                                      y, y0, y1, y2, f16, H, W, tiles_x, tiles_y));
+                                      y, y0, y1, y2, f16, H, W, tiles_x, tiles_y, B, ahead_tiles));
   }
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;

@@ -13,6 +13,14 @@ _ref_root = _os.environ.get('LVAE_REFERENCE_ROOT')
 if _ref_root and _os.path.isdir(_os.path.join(_ref_root, 'lvae')):
     __path__.append(_os.path.join(_ref_root, 'lvae'))
 
+# The reference's harness (lvae/trainer.py:14, lvae/evaluation.py:9, train-var-rate.py:5) imports four helpers from
+# `timm.utils`.  With timm installed, that is what they get; on a box without it (this image), the restatement under
+# ../compat is put on the path so that the reference's scripts run unchanged.
+import importlib.util as _ilu
+import sys as _sys
+if _ilu.find_spec('timm') is None:
+    _sys.path.append(_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), 'compat'))
+
 from .paths import known_datasets
 from .models.registry import get_model, register_model
 from . import models

@@ -98,7 +98,9 @@ class QarvEngine:
         self.lib = N.lib()
         self.device = None
         self._wver = None
-        self._plans = {}
+        self._epoch = 0                # bumped by invalidate()
+        self._plans = {}               # key -> Plan, in least-recently-used order (see _get_plan)
+        self.max_plans = int(__import__('os').environ.get('LVAE_MAX_PLANS', '6'))
         self.use_graphs = True
         # lvae_convnext_mlp for C <= 192 (False / LVAE_FUSE_MLP=0: the unfused GEMM pair, bit-identical)
         self.fuse_mlp = __import__('os').environ.get('LVAE_FUSE_MLP', '1') != '0'
@@ -115,14 +117,29 @@ class QarvEngine:
                 off += 2 * b.dim
         self.ada_total = off
         self.w = {}
+        # load_state_dict() bumps the version counters already; the hook makes the re-pack explicit and also covers
+        # state dicts loaded with assign=True
+        model.register_load_state_dict_post_hook(lambda module, incompatible: self.invalidate())
 
     # ------------------------------------------------------------------ weights
     def _weights_version(self):
+        """What the packed operand planes were made from: device, precision mode, and for EVERY parameter its storage
+        address and autograd version counter (an optimizer step, load_state_dict(), .to(), `p.data = ...` all change one of
+        them).  A write THROUGH `.data` (p.data.copy_(), dist.broadcast(p.data), ...) changes neither: callers that do
+        that must call invalidate() -- lvae's own code paths (GraphedTrainStep, the model's load_state_dict / _apply
+        hooks) do."""
         tables = tuple(b.discrete_gaussian.scale_table.numel() for b in self.model.dec_blocks
                        if hasattr(b, 'discrete_gaussian'))[:1]      # qres: the table appears with compress_mode()
-        return (self.model._dummy.device, self.model.precision,
-                sum(p._version for p in self.model.parameters()),
-                tuple(p.data_ptr() for p in (self.model.bias, self.blocks[0].gamma)), tables)
+        ver = ptr = 0
+        for p in self.model.parameters():
+            ver += p._version
+            ptr = (ptr * 1000003 + p.data_ptr()) & 0xFFFFFFFFFFFFFFFF
+        return (self.model._dummy.device, self.model.precision, ver, ptr, self._epoch, tables)
+
+    def invalidate(self):
+        """Force a re-pack of the weights (and a rebuild of the launch plans, which hold raw weight pointers) at the next
+        use.  Needed after in-place writes through `.data`, which no version counter records."""
+        self._epoch += 1
 
     def _dev_f32(self, t):
         return t.detach().to(self.device, torch.float32).contiguous()
@@ -613,11 +630,19 @@ class QarvEngine:
         return P
 
     def _get_plan(self, key, builder):
-        P = self._plans.get(key)
+        """Launch plans are cached per (batch, height, width, mode): each owns its activation buffers, pinned host mirrors
+        and CUDA graphs, i.e. hundreds of MB at Kodak size.  The cache is an LRU of `max_plans` entries (LVAE_MAX_PLANS,
+        default 6) so that a data set with many resolutions (CLIC, Tecnick through compress_file / self_evaluate) runs in
+        bounded memory, like the reference; an evicted plan's graphs and buffers are freed before the new one is built."""
+        P = self._plans.pop(key, None)
         if P is None:
+            while len(self._plans) >= max(1, self.max_plans):
+                old = self._plans.pop(next(iter(self._plans)))
+                old.graphs = None
+                del old
             with torch.cuda.device(self.device):
                 P = builder()
-            self._plans[key] = P
+        self._plans[key] = P            # most recently used last
         return P
 
     def _launch(self, P, seg=0):

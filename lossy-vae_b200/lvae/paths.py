@@ -1,9 +1,10 @@
 """Dataset roots (mirrors the name -> Path table of the reference, lvae/paths.py:1-33).
-Override the root with the LVAE_DATASETS environment variable."""
+Override the root with the LVAE_DATASETS environment variable.  The default is the reference's: the `datasets` directory
+two levels above the checkout (this package sits one directory deeper than the reference's `lvae/`, hence one more `..`)."""
 import os
 from pathlib import Path
 
-_root = Path(os.environ.get('LVAE_DATASETS', (Path(__file__).parent / '../../../datasets'))).resolve()
+_root = Path(os.environ.get('LVAE_DATASETS', (Path(__file__).parent / '../../../../datasets'))).resolve()
 
 known_datasets = {
     'kodak': _root / 'kodak',

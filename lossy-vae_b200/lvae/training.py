@@ -480,7 +480,9 @@ class TrainPath:
 def allreduce_flat_gradients(params, group, world):
     """Average the gradients of `params` over `group` with ONE all-reduce: the gradients are concatenated into a flat
     buffer, summed over the ranks (NCCL over NVLink / NVSwitch on the GPUs; gloo in the CPU test), scaled by 1 / world and
-    copied back in place.  Parameters without a gradient are skipped -- every rank must skip the same ones."""
+    copied back in place.  Parameters without a gradient are skipped -- every rank must skip the same ones.
+    (Stand-alone helper for eager loops.  GraphedTrainStep does not use it: there the gradients ARE views of one flat
+    buffer, reduced bucket by bucket while the backward is still running -- GradientBuckets.)"""
     import torch.distributed as dist
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
@@ -491,28 +493,129 @@ def allreduce_flat_gradients(params, group, world):
     torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
 
 
-class GraphedTrainStep:
-    """One training step -- lambda draw, forward, backward, optimizer update, including the re-packing of the updated
-    weights into tensor-core operand planes -- captured once into a CUDA graph and replayed per batch: the training
-    counterpart of the inference launch plans (the eager step is bound by ~4000 host-side launches).  The optimizer must be
-    graph-capturable (torch.optim.Adam(..., capturable=True)); batch shape and lambda policy are fixed per instance.
+class FlatLayout:
+    """Offsets of a parameter list inside one flat fp32 buffer; every tensor starts on a 256-byte boundary (TMA maps and
+    128-bit loads of the kernels keep working on the views), padding elements stay zero."""
+    ALIGN = 64      # elements
 
-        step = GraphedTrainStep(model, optimizer, (16, 3, 256, 256))
+    def __init__(self, params):
+        self.params = list(params)
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += -(-p.numel() // self.ALIGN) * self.ALIGN
+        self.total = off
+
+    def new(self, device, like=None):
+        """a zeroed flat buffer; like: list of tensors (same structure as params) whose values are copied in"""
+        flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+        if like is not None:
+            torch._foreach_copy_(self.views(flat), [t.detach() for t in like])
+        return flat
+
+    def views(self, flat):
+        return [flat[o:o + p.numel()].view(p.shape) for o, p in zip(self.offsets, self.params)]
+
+
+class GradientBuckets:
+    """Data-parallel gradient averaging overlapped with the backward pass (the one collective of the training step:
+    reference lvae/trainer.py:63-64 wraps the model in DistributedDataParallel for this).
+
+    The gradients of all parameters are views of ONE flat buffer (FlatLayout), so there is nothing to gather or copy back.
+    The buffer is cut into contiguous buckets; a post-accumulate hook per parameter counts arrivals and, when a bucket is
+    complete, issues its all-reduce asynchronously (NCCL: ReduceOp.AVG on the communicator's own stream, ordered after the
+    kernels that produced the bucket) while autograd keeps running the rest of the backward on the compute stream.
+    finish() reduces whatever never completed (parameters without a gradient in this step: every rank sees the same set)
+    and makes the compute stream wait for all of them.  Works under CUDA-graph capture (the collectives become graph
+    nodes on a forked branch) and on gloo / CPU (SUM + scale), which is how tests/test_sharding_gloo.py covers it."""
+
+    def __init__(self, layout, flat_grad, group, world, bucket_bytes=32 << 20):
+        import torch.distributed as dist
+        self.dist, self.group, self.world, self.flat = dist, group, world, flat_grad
+        self.avg = flat_grad.is_cuda                               # gloo has no AVG
+        self.ranges, self.bucket_of, lo, n = [], {}, 0, 0
+        for p, off in zip(layout.params, layout.offsets):
+            self.bucket_of[id(p)] = len(self.ranges)
+            n += 1
+            end = off + -(-p.numel() // layout.ALIGN) * layout.ALIGN
+            if (end - lo) * 4 >= bucket_bytes:
+                self.ranges.append((lo, end, n))
+                lo, n = end, 0
+        if n:
+            self.ranges.append((lo, layout.total, n))
+        self.active, self.count, self.fired, self.works = False, [], [], []
+        self.hooks = [p.register_post_accumulate_grad_hook(self._hook) for p in layout.params]
+
+    def start(self):
+        self.count = [0] * len(self.ranges)
+        self.fired = [False] * len(self.ranges)
+        self.works, self.active = [], True
+
+    def _hook(self, p):
+        if not self.active:
+            return
+        bi = self.bucket_of[id(p)]
+        self.count[bi] += 1
+        if self.count[bi] == self.ranges[bi][2] and not self.fired[bi]:
+            self._fire(bi)
+
+    def _fire(self, bi):
+        lo, hi, _ = self.ranges[bi]
+        self.fired[bi] = True
+        op = self.dist.ReduceOp.AVG if self.avg else self.dist.ReduceOp.SUM
+        self.works.append(self.dist.all_reduce(self.flat[lo:hi], op=op, group=self.group, async_op=True))
+
+    def finish(self):
+        for bi in range(len(self.ranges)):
+            if not self.fired[bi]:
+                self._fire(bi)
+        for w in self.works:
+            w.wait()
+        if not self.avg:
+            self.flat.mul_(1.0 / self.world)
+        self.active, self.works = False, []
+
+    def remove(self):
+        for h in self.hooks:
+            h.remove()
+        self.hooks = []
+
+
+class GraphedTrainStep:
+    """One training step -- lambda draw, forward, backward, gradient averaging, clipping, optimizer update, EMA, and the
+    re-packing of the updated weights into tensor-core operand planes -- captured once into a CUDA graph and replayed per
+    batch: the training counterpart of the inference launch plans (the eager step is bound by ~4000 host-side launches).
+    Batch shape and lambda policy are fixed per instance.
+
+        step = GraphedTrainStep(model, optimizer, (16, 3, 256, 256), grad_clip=2.0, ema=ema.module)
         loss = step(batch)            # 0-d device tensor, overwritten by the next call
+
+    Memory layout: parameters, gradients, Adam moments and the EMA copy each become views of ONE flat fp32 buffer
+    (FlatLayout; `p.data` / `p.grad` are re-pointed, values preserved), so that
+      * the gradient all-reduce works on the buffer itself, bucket by bucket, overlapped with the backward
+        (GradientBuckets) -- no concatenation, no copy back;
+      * clipping + Adam + EMA are two kernel launches over the flat buffers (csrc/optim.cu, `native_optimizer`), instead
+        of ~10 torch foreach passes over 907 tensors.
+    `optimizer` must be a torch.optim.Adam whose groups share lr / betas / eps with weight_decay 0 (what
+    lvae/trainer.py:176-216 builds) for the native update; anything else (or native_optimizer=False) keeps
+    `optimizer.step()` inside the graph (the optimizer must then be capturable).  The learning rate and the EMA decay are
+    device scalars: set_lr() / set_ema_decay() between replays run the schedule of trainer.py:231-252,373-377.
     """
 
-    def __init__(self, model, optimizer, batch_shape, warmup=3, process_group=None, grad_clip=None, ema=None, ema_decay=0.9999):
-        """grad_clip: max global gradient norm (torch.nn.utils.clip_grad_norm_ on the reduced gradients, as
-        lvae/trainer.py:395 does), recorded in the graph; ema: a module with the model's parameter structure (e.g.
-        timm's ModelEmaV2(model).module or copy.deepcopy(model)) whose parameters follow ema = decay * ema + (1 - decay) * p
-        after every update (trainer.py:374-377), also inside the graph.
-        process_group: a torch.distributed (NCCL) group, or True for the default one -> data parallel: the gradients of
-        all parameters are averaged over the group by ONE all-reduce of a flat buffer, recorded inside the graph between
-        backward and the optimizer update (parameters must start out identical on every rank, as with DDP)."""
+    def __init__(self, model, optimizer, batch_shape, warmup=1, process_group=None, grad_clip=None, ema=None, ema_decay=0.9999,
+                 native_optimizer=None, bucket_bytes=32 << 20):
+        """grad_clip: max global gradient norm (clip_grad_norm_ on the reduced gradients, lvae/trainer.py:395);
+        ema: a module with the model's parameter structure (timm's ModelEmaV2(model).module or copy.deepcopy(model)) whose
+        parameters follow ema += (p - ema)(1 - decay) after every update (trainer.py:374-377).
+        process_group: a torch.distributed group (NCCL), or True for the default one -> data parallel (parameters are
+        broadcast from rank 0 first, as DDP does).
+        warmup: eager steps run before capture (lazy state must exist); parameters, optimizer state and EMA are RESTORED
+        afterwards, so the first replay is the first update -- one update per batch, as in the reference's loop."""
         self.model, self.opt = model, optimizer
         self.tp = model.train_path
-        self.im = torch.zeros(batch_shape, device=model._device())
-        self.grad_clip, self.ema, self.ema_decay = grad_clip, ema, float(ema_decay)
+        dev = model._device()
+        self.im = torch.zeros(batch_shape, device=dev)
+        self.grad_clip, self.ema = grad_clip, ema
         self.pg, self.world = None, 1
         if process_group is not None:
             import torch.distributed as dist
@@ -520,7 +623,58 @@ class GraphedTrainStep:
             self.world = dist.get_world_size(self.pg)
             for p in model.parameters():                         # same starting point on every rank (DDP does the same)
                 dist.broadcast(p.data, src=dist.get_global_rank(self.pg, 0), group=self.pg)
+        # ---- flat storage
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.layout = FlatLayout(self.params)
+        self.flat_p = self.layout.new(dev, like=self.params)
+        self.flat_g = self.layout.new(dev)
+        for p, vp, vg in zip(self.params, self.layout.views(self.flat_p), self.layout.views(self.flat_g)):
+            p.data = vp
+            p.grad = vg
+        model.engine.invalidate()
+        self.flat_e = None
+        if ema is not None:
+            eps_ = [q for q, p in zip(ema.parameters(), model.parameters()) if p.requires_grad]
+            self.flat_e = self.layout.new(dev, like=eps_)
+            for q, ve in zip(eps_, self.layout.views(self.flat_e)):
+                q.data = ve
+        self.native = self._native_ok(optimizer) if native_optimizer is None else bool(native_optimizer)
+        if self.native and not self._native_ok(optimizer):
+            raise ValueError('native_optimizer needs torch.optim.Adam with weight_decay 0, amsgrad False and one (lr, betas, eps) for all groups')
+        g0 = optimizer.param_groups[0]
+        self.lr = torch.tensor(float(g0['lr']), device=dev)
+        self.ema_decay = torch.tensor([float(ema_decay), 1.0 - float(ema_decay)], device=dev)      # (decay, 1 - decay)
+        self.step_t = torch.zeros((), device=dev)
+        self.grad_norm = torch.zeros((), device=dev)             # global gradient norm of the last step (before clipping)
+        if self.native:
+            self.betas, self.eps = tuple(g0['betas']), float(g0['eps'])
+            self.flat_m, self.flat_v = self.layout.new(dev), self.layout.new(dev)
+            self.scratch = torch.zeros(N.lib().lvae_optim_scratch_doubles(), dtype=torch.float64, device=dev)
+        self.buckets = GradientBuckets(self.layout, self.flat_g, self.pg, self.world, bucket_bytes) if self.world > 1 else None
         self.graph, self.loss, self.warmup = None, None, max(1, warmup)   # >= 1: lazy state (packed weights, scratch) exists before capture
+        # the gradient views were created on the current stream, warm-up and capture run on side streams: intended
+        if hasattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch'):
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+
+    @staticmethod
+    def _native_ok(opt):
+        if type(opt) is not torch.optim.Adam:
+            return False
+        gs = opt.param_groups
+        same = all((g['lr'], tuple(g['betas']), g['eps']) == (gs[0]['lr'], tuple(gs[0]['betas']), gs[0]['eps']) for g in gs)
+        return same and all(g['weight_decay'] == 0 and not g['amsgrad'] and not g.get('maximize', False) for g in gs) and not opt.state
+
+    def set_lr(self, lr):
+        self.lr.fill_(float(lr))
+        if not self.native:
+            for g in self.opt.param_groups:
+                if isinstance(g['lr'], torch.Tensor):
+                    g['lr'].fill_(float(lr))
+                else:
+                    g['lr'] = float(lr)      # takes effect at the next capture only
+
+    def set_ema_decay(self, decay):
+        self.ema_decay.copy_(torch.tensor([float(decay), 1.0 - float(decay)]))
 
     def _step(self):
         m, B = self.model, self.im.shape[0]
@@ -530,26 +684,64 @@ class GraphedTrainStep:
             res = self.tp.objective(self.im, lmb, stats=False)
         finally:
             self.tp.force_refresh = False
-        self.opt.zero_grad(set_to_none=True)
+        self.flat_g.zero_()                                       # the gradients are views of it: autograd accumulates in place
+        if self.buckets is not None:
+            self.buckets.start()
         res['loss'].backward()
-        if self.world > 1:
-            self._allreduce_grads()
-        if self.grad_clip is not None:
-            torch.nn.utils.clip_grad_norm_(list(m.parameters()), self.grad_clip, foreach=True)
-        self.opt.step()
-        if self.ema is not None:
-            with torch.no_grad():
-                torch._foreach_lerp_(list(self.ema.parameters()), [p.detach() for p in m.parameters()], 1.0 - self.ema_decay)
+        if self.buckets is not None:
+            self.buckets.finish()
+        if self.native:
+            self.step_t.add_(1.0)
+            N.check(N.lib().lvae_adam_clip_ema(
+                self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
+                0 if self.flat_e is None else self.flat_e.data_ptr(), self.layout.total, self.scratch.data_ptr(),
+                float(self.grad_clip or 0.0), self.lr.data_ptr(), self.step_t.data_ptr(), self.ema_decay.data_ptr(),
+                self.betas[0], self.betas[1], self.eps, self.grad_norm.data_ptr(), self.tp.eng._stream()), 'adam_clip_ema')
+            N.launch_count += 2
+        else:
+            if self.grad_clip is not None:
+                self.grad_norm.copy_(torch.nn.utils.clip_grad_norm_(self.params, self.grad_clip, foreach=True))
+            self.opt.step()
+            if self.flat_e is not None:
+                self.flat_e.mul_(self.ema_decay[0]).add_(self.flat_p * self.ema_decay[1])
         return res['loss'].detach()
 
-    def _allreduce_grads(self):
-        allreduce_flat_gradients(self.model.parameters(), self.pg, self.world)
+    def _snapshot(self):
+        st = dict(p=self.flat_p.clone(), e=None if self.flat_e is None else self.flat_e.clone(), t=self.step_t.clone())
+        if self.native:
+            st['m'], st['v'] = self.flat_m.clone(), self.flat_v.clone()
+        else:
+            import copy
+            st['opt'] = copy.deepcopy(self.opt.state_dict())
+        return st
+
+    def _restore(self, st):
+        self.flat_p.copy_(st['p'])
+        self.step_t.copy_(st['t'])
+        if st['e'] is not None:
+            self.flat_e.copy_(st['e'])
+        if self.native:
+            self.flat_m.copy_(st['m'])
+            self.flat_v.copy_(st['v'])
+        else:
+            # in place: the captured graph must keep pointing at the state tensors the warm-up created
+            cur = self.opt.state_dict()['state']
+            for k, d in st['opt']['state'].items():
+                for name, val in d.items():
+                    if isinstance(val, torch.Tensor):
+                        cur[k][name].copy_(val)
+            if not st['opt']['state']:
+                for d in cur.values():
+                    for val in d.values():
+                        if isinstance(val, torch.Tensor):
+                            val.zero_()
 
     def __call__(self, im):
         assert self.model.training and tuple(im.shape) == tuple(self.im.shape)
         self.im.copy_(im, non_blocking=True)
         if self.graph is None:
             dev = self.im.device
+            snap = self._snapshot()
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
@@ -558,13 +750,24 @@ class GraphedTrainStep:
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
             self.graph = torch.cuda.CUDAGraph()
-            self.opt.zero_grad(set_to_none=True)
             n0 = N.launch_count
             with torch.cuda.graph(self.graph):
                 self.loss = self._step()
             self.launches_per_replay = N.launch_count - n0        # liblvae_b200 launches recorded in the graph
             N.launch_count = n0
+            self._restore(snap)                                   # the warm-up steps leave no trace: one update per batch
+            del snap
         self.graph.replay()
         N.launch_count += self.launches_per_replay
-        self.tp.eng._wver = None        # the replay updated the parameters in place: the next eager / inference use re-packs
+        self.tp.eng.invalidate()        # the replay updated the parameters in place: the next eager / inference use re-packs
         return self.loss
+
+    def release(self):
+        """Drop the captured graph (it holds the recorded NCCL work and every buffer of the step).  Call before
+        torch.distributed.destroy_process_group(): a live graph with collectives in it keeps the communicator busy."""
+        dev = self.im.device
+        torch.cuda.synchronize(dev)
+        self.graph, self.loss = None, None
+        if self.buckets is not None:
+            self.buckets.remove()
+        torch.cuda.synchronize(dev)

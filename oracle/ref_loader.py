@@ -1,17 +1,19 @@
-"""Import the UNMODIFIED reference (`/root/reference/lvae`) in the build container.
+"""Import the UNMODIFIED reference `lvae` package: from `/root/reference` in the build container, else from the
+byte-identical staged copy `oracle/_ref/reference` (made by the committed recipe oracle/make_ref.py; git-ignored, it
+travels to the GPU box).
 
-TEST INFRASTRUCTURE ONLY. Puts `oracle/shims` (timm/compressai stand-ins) and `/root/reference`
+TEST / MEASUREMENT INFRASTRUCTURE ONLY. Puts `oracle/shims` (timm/compressai stand-ins) and the reference root
 on sys.path under a private import so that the reference's own model code is the thing that runs.
-Used by `oracle/gen_golden.py` (fixture generation) and by the `not gpu` tests that pin
-`oracle/lvae_oracle.py` against it. `/root/reference` does not exist on the GPU box, so nothing
-that runs there imports this module.
+Used by `oracle/gen_golden.py` (fixture generation), by the `not gpu` tests that pin `oracle/lvae_oracle.py` against
+it, and by `bench.py --impl reference` / its `cpu_baseline` leg (the reference's CPU path timed on the box's host cores).
 """
 import importlib
 import sys
 from pathlib import Path
 
-REFERENCE_ROOT = Path('/root/reference')
 SHIMS = Path(__file__).resolve().parent / 'shims'
+STAGED = Path(__file__).resolve().parent / '_ref' / 'reference'
+REFERENCE_ROOT = Path('/root/reference') if (Path('/root/reference') / 'lvae' / '__init__.py').is_file() else STAGED
 
 
 def available():

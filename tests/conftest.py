@@ -75,3 +75,15 @@ def gpu_model(native_lib, sensitised_sd):
     model = model.to('cuda:0').eval()
     model.compress_mode()
     return model
+
+
+def parity_log(**record):
+    """Append one parity measurement (case, precision, symbol / index flips, d bpp, d PSNR ...) to
+    gpurun_out/r2_parity_records.jsonl -- the raw material of profiles/r2_parity.md (scripts/parity_report.py).  The
+    directory is what gpurun brings back from the GPU box; without it (plain CPU run) this is a no-op."""
+    import json
+    out = ROOT / 'gpurun_out'
+    if not out.is_dir():
+        return
+    with open(out / 'r2_parity_records.jsonl', 'a') as f:
+        f.write(json.dumps(record) + '\n')

@@ -12,12 +12,18 @@ import pytest
 import torch
 
 import lvae_oracle as O
+from conftest import parity_log
 from oracle_inputs import CASES, make_input
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 PSNR_TOL = 0.01
 QUANTUM_NATS = 3.4     # -ln(2^-25) + ln(1e-9): one tail element whose likelihood lands on the other side of the floor
+
+
+# Rounding-boundary flips MEASURED on B200 per (fixture, precision) -- profiles/r2_parity.md.  Every case not listed here
+# must be bit-exact (0 flips); a listed case may not exceed its recorded count.
+MAX_FLIPS = {('qarv_synth_1x256x256', p): 1 for p in ('f16x3', 'bf16x6', 'fp32')}      # the same element in all three modes
 
 
 def bpp_tol(H, W, B=1):
@@ -98,6 +104,9 @@ def test_forward_matches_reference_fixture(name, model_in_precision, golden, sen
         syms, idxs, [torch.from_numpy(g[f'sym{li}'].astype(np.int32)) for li in range(9)],
         [torch.from_numpy(g[f'idx{li}'].astype(np.int32)) for li in range(9)],
         lambda: O.qarv_forward(sensitised_sd, im_cpu, torch.tensor(lmbs))['records'])
+    parity_log(test='qarv fixture (unmodified reference)', case=name, precision=gpu_model.precision, symbols=sum(s_.numel() for s_ in syms),
+               flips=flips, dbpp=abs(st['bppix'] - float(g['bppix'])), dpsnr=abs(st['psnr'] - float(g['psnr'])), bpp_tol=bpp_tol(H, W))
+    assert flips <= MAX_FLIPS.get((name, gpu_model.precision), 0), (name, gpu_model.precision, flips)
     x_hat, lat = gpu_model.forward_end2end(im, lmb, get_latent=True)
     tol_nats = bpp_tol(H, W) * H * W / 1.4427
     for li, stl in enumerate(lat):
@@ -153,6 +162,8 @@ def test_against_live_oracle_at_baseline_size(gpu_model, sensitised_sd):
     assert sum(s.numel() for s in syms) == 617472
     flips = _check_integer_parity(syms, idxs, [r['sym'] for r in ref['records']], [r['idx'] for r in ref['records']],
                                   lambda: ref['records'])
+    parity_log(test='qarv live oracle, BASELINE configs[1] image size', case='synth 1x512x768 lmb 700', precision=gpu_model.precision,
+               symbols=617472, flips=flips, dbpp=abs(st['bppix'] - ref['bppix']), dpsnr=abs(st['psnr'] - ref['psnr']), bpp_tol=1e-4)
     if flips == 0:
         assert (st['im_hat'].cpu() - ref['im_hat']).abs().max().item() < 1e-5
 
@@ -300,3 +311,53 @@ def test_batched_codec_equals_per_image_codec(gpu_model):
         assert torch.equal(rec[b:b + 1], one)
     with pytest.raises(AssertionError):
         gpu_model.decompress_batch([blobs[0], gpu_model.compress(make_input('synth', 1, 64, 64, 1).to(DEV))])
+
+
+def test_plan_cache_is_bounded_over_many_resolutions(gpu_model):
+    """one launch plan (activation buffers, pinned mirrors, CUDA graphs) used to be kept for EVERY distinct
+    (batch, height, width, mode) -- evaluating a data set with many resolutions grew device and pinned memory without
+    bound.  The cache is now an LRU of engine.max_plans entries: 24 distinct shapes leave at most that many plans and
+    the allocated device memory stops growing once the cache is full."""
+    eng = gpu_model.engine
+    eng._plans.clear()
+    torch.cuda.empty_cache()
+    lmb = torch.tensor([256.0], device=DEV)
+    shapes = [(64 * (1 + i % 4), 64 * (1 + i // 4)) for i in range(24)]
+    mem = []
+    for (h, w) in shapes:
+        im = torch.rand(1, 3, h, w, device=DEV)
+        for _ in range(2):                                   # second call replays the captured graph
+            st = gpu_model(im, lmb=lmb)
+        assert np.isfinite(st['bppix'])
+        assert len(eng._plans) <= eng.max_plans
+        torch.cuda.synchronize()
+        mem.append(torch.cuda.memory_allocated())
+    biggest = max(h * w for h, w in shapes)
+    # the plan of the largest shape bounds every later state of the cache: no monotone growth over the last 12 shapes
+    assert max(mem[12:]) <= max(mem[:12]) * 1.5 + 64e6, mem
+    assert len(eng._plans) == eng.max_plans
+    # an evicted shape is rebuilt on demand and still correct
+    a = gpu_model(torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(1)).to(DEV), lmb=lmb)['bppix']
+    eng._plans.clear()
+    b = gpu_model(torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(1)).to(DEV), lmb=lmb)['bppix']
+    assert a == b
+
+
+def test_stale_weights_are_detected_and_invalidate_covers_data_writes(gpu_model):
+    """the packed operand planes are keyed on every parameter's (storage address, version counter); writes
+    through `.data`, which bump neither, need engine.invalidate()."""
+    import copy
+    m = copy.deepcopy(gpu_model)
+    im = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(2)).to(DEV)
+    lmb = torch.tensor([256.0], device=DEV)
+    base = m(im, lmb=lmb)['loss'].item()
+    w = next(p for n, p in m.named_parameters() if n.endswith('mlp.fc1.weight'))       # first encoder block's fc1
+    with torch.no_grad():
+        w.mul_(1.5)                                           # in-place op on the parameter: version counter moves
+    assert m(im, lmb=lmb)['loss'].item() != base
+    with torch.no_grad():
+        w.div_(1.5)
+    again = m(im, lmb=lmb)['loss'].item()
+    w.data.mul_(1.5)                                          # through .data: invisible to the version counters ...
+    m.engine.invalidate()                                     # ... so the caller says so
+    assert m(im, lmb=lmb)['loss'].item() != again

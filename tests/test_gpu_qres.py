@@ -8,6 +8,7 @@ import torch
 import lvae_oracle as O
 import qres_oracle as Q
 from oracle_inputs import QRES_CASES, QRES_LMB, make_input
+from conftest import parity_log
 from test_gpu_model import PSNR_TOL, bpp_tol, _check_integer_parity
 from test_oracle_pinned import _qres_noise
 
@@ -63,6 +64,8 @@ def test_qres_forward_matches_reference_fixture(name, precision, qres_model, qre
         syms, idxs, [torch.from_numpy(g[f'sym{li}'].astype(np.int32)) for li in range(12)],
         [torch.from_numpy(g[f'idx{li}'].astype(np.int32)) for li in range(12)],
         lambda: Q.qres_forward(qres_sd, im_cpu, QRES_LMB)['records'], scale_table=Q.qres_scale_table())
+    parity_log(test='qres34m fixture (unmodified reference)', case=name, precision=precision, symbols=sum(s_.numel() for s_ in syms),
+               flips=flips, dbpp=abs(st['bppix'] - float(g['bppix'])), dpsnr=abs(st['psnr'] - float(g['psnr'])), bpp_tol=bpp_tol(H, W))
     tol_nats = bpp_tol(H, W) * H * W / 1.4427
     for li, stl in enumerate(lat):
         kl = stl['kl'].sum(dim=(1, 2, 3)).cpu().numpy()
@@ -114,3 +117,39 @@ def test_qres_sampling_with_given_latents_reproduces_decoder(qres_model):
     assert (rec - ref).abs().max().item() < 1e-5
     smp = qres_model.uncond_sample((2, 1, 1), temprature=0.0)
     assert tuple(smp.shape) == (2, 3, 64, 64) and bool(torch.isfinite(smp).all())
+
+
+def test_qres_against_live_oracle_at_config_shape_and_batch16_invariance(qres_model, qres_sd):
+    """BASELINE configs[2] shape: qres34m at 512 x 768 against the oracle run live on the host CPU
+    (north-star tolerances unwidened: bpp 1e-4, PSNR 0.01 dB, symbols / indexes one by one), and the same image inside a
+    batch of 16 -- the benched batch size -- must give bit-identical symbols, indexes and per-image statistics."""
+    H, W = 512, 768
+    im1 = make_input('synth', 1, H, W, 44)
+    ref = Q.qres_forward(qres_sd, im1, QRES_LMB)
+    st = qres_model(im1.to(DEV), return_rec=True)
+    assert bpp_tol(H, W) == 1e-4
+    assert abs(st['bppix'] - ref['bppix']) <= 1e-4, (st['bppix'], ref['bppix'])
+    assert abs(st['psnr'] - ref['psnr']) <= PSNR_TOL
+    qres_model.compress(im1.to(DEV))
+    P = qres_model.engine._plans[(1, H, W, 'compress', False)]
+    torch.cuda.synchronize()
+    syms, idxs = [s.cpu() for s in P.sym], [i.cpu() for i in P.idx]
+    flips = _check_integer_parity(syms, idxs, [r['sym'] for r in ref['records']], [r['idx'] for r in ref['records']],
+                                  lambda: ref['records'], scale_table=Q.qres_scale_table())
+    parity_log(test='qres34m live oracle, BASELINE configs[2] image size', case='synth 1x512x768', precision=qres_model.precision,
+               symbols=sum(s_.numel() for s_ in syms), flips=flips, dbpp=abs(st['bppix'] - ref['bppix']),
+               dpsnr=abs(st['psnr'] - ref['psnr']), bpp_tol=1e-4)
+    if flips == 0:
+        assert (st['im_hat'].cpu() - ref['im_hat']).abs().max().item() < 1e-5
+    # batch 16: image 5 of the batch is the image above
+    im16 = make_input('rand', 16, H, W, 45)
+    im16[5] = im1[0]
+    qres_model.compress(im16.to(DEV))
+    P16 = qres_model.engine._plans[(16, H, W, 'compress', False)]
+    torch.cuda.synchronize()
+    for li in range(len(syms)):
+        assert torch.equal(P16.sym[li][5].cpu(), syms[li][0]) and torch.equal(P16.idx[li][5].cpu(), idxs[li][0]), li
+    lat16 = qres_model.forward_get_latents(im16.to(DEV))
+    lat1 = qres_model.forward_get_latents(im1.to(DEV))
+    for a, b in zip(lat16, lat1):
+        assert torch.equal(a['z'][5], b['z'][0]) and torch.equal(a['kl'][5], b['kl'][0])

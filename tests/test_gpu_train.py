@@ -162,9 +162,11 @@ def test_graphed_train_step_matches_eager_step(native_lib):
         m.train()
         opt = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True)
         if graphed:
-            step = GraphedTrainStep(m, opt, tuple(im.shape), warmup=1)        # 1 eager warm-up update + 2 replays
-            losses = [float(step(im)) for _ in range(2)]
+            step = GraphedTrainStep(m, opt, tuple(im.shape), warmup=1)        # the warm-up step is rolled back: 3 replays = 3 updates
+            assert step.native                                                # clip + Adam (+ EMA) on the flat buffers, csrc/optim.cu
+            losses = [float(step(im)) for _ in range(3)]
             assert step.launches_per_replay > 300
+            assert float(step.step_t) == 3.0
         else:
             losses = []
             for _ in range(3):
@@ -232,8 +234,80 @@ def test_graphed_step_with_gradient_clipping_and_ema(native_lib):
     for _ in range(3):
         assert np.isfinite(float(step(im)))
         assert all(torch.equal(e, p) for e, p in zip(ema.parameters(), m.parameters()))
+    # the clip coefficient is applied inside the fused update (the gradients in .grad stay as reduced); the norm it used:
     gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in m.parameters()))
-    assert 0 < float(gn) <= 0.5 * 1.001
+    assert float(gn) > 0 and abs(float(step.grad_norm) - float(gn)) <= 1e-5 * float(gn)
     assert sum(int(not torch.equal(a, p)) for a, p in zip(p0, m.parameters())) > 800
     with torch.no_grad():
         assert np.isfinite(ema(im, lmb=torch.full((2,), 256.0, device=DEV))['loss'].item())
+
+
+@pytest.mark.parametrize('n,max_norm,with_ema', [(100003, 0.7, True), (4096, 0.0, False), (1 << 20, 1e9, True)])
+def test_fused_clip_adam_ema_matches_torch(native_lib, n, max_norm, with_ema):
+    """lvae_adam_clip_ema (csrc/optim.cu) against clip_grad_norm_ + torch.optim.Adam + lerp_ (lvae/trainer.py:360-377,
+    394-406) over four updates on flat buffers; n % 4 != 0 exercises the scalar tail."""
+    g = torch.Generator().manual_seed(n)
+    p0 = torch.randn(n, generator=g).to(DEV)
+    e0 = torch.randn(n, generator=g).to(DEV)
+    grads = [(torch.randn(n, generator=g) * 10 ** float(torch.randn((), generator=g))).to(DEV) for _ in range(4)]
+    lr, betas, eps, decay = 3e-4, (0.9, 0.999), 1e-8, 0.99
+    # torch
+    pt = torch.nn.Parameter(p0.clone())
+    et = e0.clone()
+    opt = torch.optim.Adam([pt], lr=lr, betas=betas, eps=eps)
+    norms_t = []
+    for gr in grads:
+        pt.grad = gr.clone()
+        if max_norm > 0:
+            norms_t.append(float(torch.nn.utils.clip_grad_norm_([pt], max_norm)))
+        else:
+            norms_t.append(float(gr.norm()))
+        opt.step()
+        et.copy_(decay * et + (1.0 - decay) * pt.detach())          # timm ModelEmaV2._update (lvae/trainer.py:377)
+    # native
+    pn, en = p0.clone(), e0.clone()
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    scratch = torch.zeros(native_lib.lvae_optim_scratch_doubles(), dtype=torch.float64, device=DEV)
+    lr_t, step_t, dec_t = torch.tensor(lr, device=DEV), torch.zeros((), device=DEV), torch.tensor([decay, 1.0 - decay], device=DEV)
+    gn = torch.zeros((), device=DEV)
+    for i, gr in enumerate(grads):
+        step_t.add_(1.0)
+        rc = native_lib.lvae_adam_clip_ema(pn.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), en.data_ptr() if with_ema else 0, n,
+                                           scratch.data_ptr(), max_norm, lr_t.data_ptr(), step_t.data_ptr(), dec_t.data_ptr(),
+                                           betas[0], betas[1], eps, gn.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert abs(float(gn) - norms_t[i]) <= 2e-6 * norms_t[i]
+    assert float((pn - pt.detach()).abs().max()) <= 2e-6 * lr / 3e-4 + 1e-6 * float(pt.detach().abs().max()) * 0 + 5e-7
+    st = opt.state[pt]
+    # moments: relative to the largest entry (an entry can cancel to ~0 while its terms do not)
+    assert torch.allclose(m, st['exp_avg'], rtol=1e-5, atol=3e-7 * float(st['exp_avg'].abs().max()))
+    assert torch.allclose(v, st['exp_avg_sq'], rtol=1e-5, atol=3e-7 * float(st['exp_avg_sq'].abs().max()))
+    if with_ema:
+        assert torch.allclose(en, et, rtol=1e-6, atol=1e-6)
+    else:
+        assert torch.equal(en, e0)
+
+
+def test_train_gradients_on_the_tensor_core_weight_gradient_path(native_lib, sensitised_sd):
+    """every other gradient test uses 64 x 64 images (M <= 512 pixels per layer), where block_backward takes the
+    torch.mm fallback for the weight gradients.  At 128 x 128 with B = 4 the H/4 and H/8 stages have M = 4096 / 1024
+    pixels: lvae_split_planes_t_ex (+ gelu, + column sums) and the split-K lvae_gemm_wgrad are what runs -- the path
+    real training shapes take -- and must agree with autograd over the oracle."""
+    import lvae
+    m = lvae.get_model('qarv_base')
+    m.load_state_dict(sensitised_sd, strict=False)
+    m = m.to(DEV).train()
+    B, H, W = 4, 128, 128
+    im = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(15))
+    lmb = torch.tensor([32.0, 256.0, 1024.0, 2048.0])
+    noise = _noise(m, B, H, W, 29)
+    launches = []
+    orig = m.train_path._wgrad
+    m.train_path._wgrad = lambda *a, **k: (launches.append(1), orig(*a, **k))[1]
+    st = m._forward_train(im.to(DEV), lmb.to(DEV), noise=noise)
+    st['loss'].backward()
+    assert len(launches) >= 40, len(launches)                  # two tensor-core weight gradients per block with M >= 1024
+    ref, grads = _oracle_grads(O.qarv_forward, sensitised_sd, im, lmb, mode='train', noise=noise)
+    worst = _compare(m, grads, st['loss'].item(), ref['loss'].item())
+    print('worst relative gradient error (tensor-core weight gradients)', worst)

@@ -104,3 +104,54 @@ def test_flat_gradient_allreduce_averages_in_place():
             continue
         want = (x0 + x1) / 2
         assert torch.allclose(y0, want, atol=1e-7) and torch.equal(y0, y1)
+
+
+def _bucket_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from lvae.training import FlatLayout, GradientBuckets
+        torch.manual_seed(0)                                   # same weights on every rank
+        net = torch.nn.Sequential(torch.nn.Linear(40, 70), torch.nn.GELU(), torch.nn.Linear(70, 30), torch.nn.GELU(),
+                                  torch.nn.Linear(30, 5))
+        unused = torch.nn.Parameter(torch.ones(13))            # never receives a gradient: its bucket is reduced by finish()
+        params = list(net.parameters()) + [unused]
+        lay = FlatLayout(params)
+        flat = lay.new('cpu')
+        for p, v in zip(params, lay.views(flat)):
+            p.grad = v
+        buckets = GradientBuckets(lay, flat, dist.group.WORLD, world, bucket_bytes=4096)      # several small buckets
+        x = torch.randn(16, 40, generator=torch.Generator().manual_seed(50 + rank))
+        local = torch.autograd.grad(net(x).square().mean(), list(net.parameters()))
+        outs = []
+        for _ in range(2):                                     # two steps: the hook state resets
+            flat.zero_()
+            buckets.start()
+            net(x).square().mean().backward()
+            buckets.finish()
+            outs.append([p.grad.clone() for p in net.parameters()])
+        views_ok = all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, lay.views(flat)))
+        q.put((rank, [g.clone() for g in local], outs, views_ok, len(buckets.ranges), float(unused.grad.abs().max())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_buckets_average_flat_views_during_backward():
+    """lvae.training.GradientBuckets (the data-parallel collective of GraphedTrainStep: gradients are views of one flat
+    buffer, reduced bucket by bucket from post-accumulate hooks while the backward runs) on gloo, world size 2."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, l0, o0, v0, nb0, u0), (_, l1, o1, v1, nb1, u1) = res
+    assert v0 and v1 and nb0 == nb1 and nb0 >= 3 and u0 == 0.0 and u1 == 0.0
+    for step in range(2):
+        for a, b, g0, g1 in zip(l0, l1, o0[step], o1[step]):
+            assert torch.allclose(g0, (a + b) / 2, atol=1e-7) and torch.equal(g0, g1)
