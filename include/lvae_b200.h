@@ -211,7 +211,7 @@ int lvae_gemm_wgrad(const void* dyt_p0, const void* dyt_p1, const void* xt_p0, c
 int lvae_optim_scratch_doubles(void);
 int lvae_adam_clip_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, double* scratch,
                        float max_norm, const float* lr, const float* step, const float* ema_decay,
-                       float beta1, float beta2, float eps, float* grad_norm_out, void* stream);
+                       double beta1, double beta2, double eps, float* grad_norm_out, void* stream);
 
 /* ---- fused latent-layer kernels (qarv/model.py:51-53,90-96,104-113; CompressAI GaussianConditional) --
  * prior [M, 2*zdim] (pm | plogv_raw) and qm [M, zdim] are NHWC matrices; hw = h*w positions per image.

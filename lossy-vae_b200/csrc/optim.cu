@@ -47,12 +47,20 @@ struct AdamArgs {
   const double* partial; int n_partial;          // sum-of-squares partials (NULL: no clipping)
   float max_norm;
   const float* lr; const float* step; const float* ema_decay;      // device scalars; step = t of THIS update (>= 1)
-  float beta1, beta2, eps;
+  double beta1, beta2;                           // as the host's doubles: 1 - beta and beta^t are formed in double, like torch
+  float eps;
   float* grad_norm_out;                          // optional: the global gradient norm before clipping
 };
 
 __global__ void __launch_bounds__(OPT_THREADS) adam_ema_kernel(const AdamArgs a) {
-  __shared__ float s_clip;
+  __shared__ float s_clip, s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 32) {
+    // torch.optim.Adam forms these scalars in Python doubles and rounds once (1 - 0.999f in fp32 is off by 1.3e-5)
+    const double t = (double)__ldg(a.step);
+    const double bc1 = 1.0 - pow(a.beta1, t), bc2 = 1.0 - pow(a.beta2, t);
+    s_step_size = (float)((double)__ldg(a.lr) / bc1);
+    s_bc2_sqrt = (float)sqrt(bc2);
+  }
   if (a.partial != nullptr) {
     // every block sums the same partials in the same order: one clip coefficient, bit-identical everywhere
     __shared__ double red[OPT_THREADS / 32];
@@ -77,17 +85,15 @@ __global__ void __launch_bounds__(OPT_THREADS) adam_ema_kernel(const AdamArgs a)
     __syncthreads();
   }
   const float clip = s_clip;
-  const float lr = __ldg(a.lr), t = __ldg(a.step);
-  const float bc1 = 1.0f - powf(a.beta1, t), bc2 = 1.0f - powf(a.beta2, t);
-  const float step_size = lr / bc1, bc2_sqrt = sqrtf(bc2);
-  const float w1 = 1.0f - a.beta1, w2 = 1.0f - a.beta2;
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float w1 = (float)(1.0 - a.beta1), w2 = (float)(1.0 - a.beta2), b2 = (float)a.beta2;
   // ema_decay[0] = decay, [1] = 1 - decay, both rounded from the host's double values as timm's `decay * e + (1. - decay) * m` does
   const float ed = a.ema != nullptr ? __ldg(a.ema_decay) : 0.f, ew = a.ema != nullptr ? __ldg(a.ema_decay + 1) : 0.f;
   const int64_t n4 = a.n >> 2;
   auto upd = [&](float& p, float g, float& m, float& v, float& e) {
     g *= clip;
     m = fmaf(g - m, w1, m);
-    v = fmaf(w2 * g, g, a.beta2 * v);
+    v = fmaf(w2 * g, g, b2 * v);
     p -= step_size * (m / (sqrtf(v) / bc2_sqrt + a.eps));
     e = __fadd_rn(__fmul_rn(ed, e), __fmul_rn(ew, p));
   };
@@ -119,7 +125,7 @@ extern "C" int lvae_optim_scratch_doubles(void) { return OPT_PARTIALS; }
 
 extern "C" int lvae_adam_clip_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, double* scratch,
                                   float max_norm, const float* lr, const float* step, const float* ema_decay,
-                                  float beta1, float beta2, float eps, float* grad_norm_out, void* stream) {
+                                  double beta1, double beta2, double eps, float* grad_norm_out, void* stream) {
   LVAE_CHECK_ARG(p && g && m && v && n > 0 && lr && step);
   LVAE_CHECK_ARG(ema == nullptr || ema_decay != nullptr);
   LVAE_CHECK_ARG(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)ema) % 16 == 0);
@@ -134,7 +140,7 @@ extern "C" int lvae_adam_clip_ema(float* p, const float* g, float* m, float* v, 
   AdamArgs a;
   a.p = p; a.g = g; a.m = m; a.v = v; a.ema = ema; a.n = n;
   a.partial = clip ? scratch : nullptr; a.n_partial = OPT_PARTIALS; a.max_norm = max_norm;
-  a.lr = lr; a.step = step; a.ema_decay = ema_decay; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+  a.lr = lr; a.step = step; a.ema_decay = ema_decay; a.beta1 = beta1; a.beta2 = beta2; a.eps = (float)eps;
   a.grad_norm_out = grad_norm_out;
   static int n_sm = 0;
   if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }

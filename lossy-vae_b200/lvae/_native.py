@@ -64,7 +64,7 @@ _PROTOS = {
     'lvae_gemm_wgrad': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int64, _fp]),
     'lvae_optim_scratch_doubles': (C.c_int, []),
     'lvae_adam_clip_ema': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, _fp, C.c_float, _fp, _fp, _fp,
-                                     C.c_float, C.c_float, C.c_float, _fp, _fp]),
+                                     C.c_double, C.c_double, C.c_double, _fp, _fp]),
     'lvae_latent_num_partials': (C.c_int, [C.c_int, C.c_int]),
     'lvae_latent_eval': (C.c_int, [_fp, _fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp, _fp,
                                    C.c_int, C.c_int, C.c_int, C.c_int, _fp]),

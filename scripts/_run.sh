@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-rm -f gpurun_out/r2_parity_records.jsonl
-timeout -s KILL 1500 python -m pytest tests -q -m gpu --timeout 300 --timeout-method thread 2>&1 | grep -E "^FAILED|^ERROR|passed|failed|AssertionError" | head -40 > gpurun_out/r2_gputest.log; cat gpurun_out/r2_gputest.log
-timeout -s KILL 900 python bench.py --steps 20 --warmup 5 --no-train-record > gpurun_out/r2_bench_b.json 2> gpurun_out/r2_bench_b.err; python -c "
-import json; d=json.load(open('gpurun_out/r2_bench_b.json')); print(d['value'], d['e2e']['value'], d['parity'])"; tail -3 gpurun_out/r2_bench_b.err
+timeout -s KILL 600 python -m pytest tests/test_gpu_train.py -q -m gpu -k "fused_clip or clipping" --timeout 300 --timeout-method thread 2>&1 | tail -3
+time (timeout -s KILL 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err)
+python -c "
+import json; d=json.loads(open('gpurun_out/r2_bench_n2.json').read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value'], d['n_gpus']); print(d['train'])"; tail -5 gpurun_out/r2_bench_n2.err

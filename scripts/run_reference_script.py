@@ -23,5 +23,6 @@ if __name__ == '__main__':
             os.environ.setdefault('LVAE_REFERENCE_ROOT', str(root))
             break
     sys.path.insert(0, str(Path(__file__).resolve().parent.parent / 'lossy-vae_b200'))
+    import lvae  # noqa: F401,E402 -- first: without timm installed it registers the `timm.utils` restatement (lossy-vae_b200/compat), which train-var-rate.py:5 imports before it imports lvae
     sys.argv = sys.argv[1:]
     runpy.run_path(script, run_name='__main__')

@@ -285,9 +285,12 @@ def test_evaluation_helpers_on_a_synthetic_dataset(gpu_model, tmp_path):
     gpu_model.default_lmb = 256.0
     try:
         res = imcoding_evaluate(gpu_model, str(tmp_path))
+        res_b = imcoding_evaluate(gpu_model, str(tmp_path), batch_size=2)     # the two 128x192 images coded in one call
     finally:
         gpu_model.default_lmb = gpu_model.lmb_range[1]
     assert set(res) == {'bpp', 'mse', 'psnr'} and all(np.isfinite(v) for v in res.values()) and res['bpp'] > 0
+    # batched real-bit-stream evaluation: the same bit streams, hence the same averages
+    assert res_b['bpp'] == res['bpp'] and abs(res_b['psnr'] - res['psnr']) < 1e-6 and abs(res_b['mse'] - res['mse']) < 1e-9
     one = image_self_evaluate(gpu_model, str(tmp_path))
     two = image_self_evaluate(gpu_model, str(tmp_path), batch_size=2)     # same-shape images grouped
     assert set(one) >= {'loss', 'bppix', 'psnr'}
