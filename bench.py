@@ -577,10 +577,11 @@ def main():
         tot_ms = sum(ms for _, _, ms in prof)
         by_kind = {}
         for name, meta, ms in prof:
-            k = by_kind.setdefault(meta.get('kind', 'misc'), dict(ms=0.0, flops=0, bytes=0, n=0))
+            k = by_kind.setdefault(meta.get('kind', 'misc'), dict(ms=0.0, flops=0, bytes=0, n=0, issued=0))
             k['ms'] += ms; k['flops'] += meta.get('flops', 0); k['bytes'] += meta.get('bytes', 0); k['n'] += 1
+            k['issued'] += meta.get('flops', 0) * meta.get('terms', 1)      # MMA FLOPs actually issued (3 per product in f16x3, 1 in the tail)
         gm, lt, dw = by_kind['gemm'], by_kind['latent'], by_kind['dwln']
-        issued = {'fp32': 1, 'bf16': 1, 'bf16x3': 3, 'bf16x6': 6, 'f16x3': 3}[model.precision]
+        issued = gm['issued'] / max(1, gm['flops'])
         roof = dict(bound='tensor', kernel=f'lvae_gemm ({model.precision})', achieved=gm['flops'] / gm['ms'] / 1e9,
                     peak=pk['tensor_sustained'], unit='TFLOP/s', traffic=None, peak_source=pk['src'] + ' (sustained bf16 cuBLAS)',
                     launches=gm['n'], share_of_step=gm['ms'] / tot_ms, issued_mma_multiplier=issued,
@@ -595,7 +596,7 @@ def main():
             traffic = json.loads(tf.read_text())
         roof['traffic_examples'] = traffic.get('gemm')
         roof['traffic_source'] = 'profiles/r2_ncu_traffic.json' if traffic else None
-        roof['issued_tflops'] = roof['achieved'] * issued          # MMA FLOPs actually issued to the tensor pipe
+        roof['issued_tflops'] = gm['issued'] / gm['ms'] / 1e9       # MMA FLOPs actually issued to the tensor pipe
         roof['issued_frac'] = roof['issued_tflops'] / roof['peak']
         # biggest latent layer alone (the only ones large enough to be bandwidth- rather than latency-bound)
         big = max((p for p in prof if p[1].get('kind') == 'latent'), key=lambda p: p[1]['bytes'])
@@ -629,7 +630,10 @@ def main():
             'warmup': warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': {'fp32': 'f32', 'bf16x6': 'f32-class (3 bf16 planes per operand, 6 tcgen05 MMAs per product, f32 accumulate)',
                       'bf16x3': 'bf16x3 (2 bf16 planes, 3 MMAs, f32 accumulate)', 'bf16': 'bf16',
-                      'f16x3': 'f32-class (2 fp16 planes per operand = 22 significand bits, 3 tcgen05 MMAs per product, f32 accumulate)'}[model.precision],
+                      'f16x3': 'f32-class (2 fp16 planes per operand = 22 significand bits, 3 tcgen05 MMAs per product, f32 accumulate)',
+                      'f16x3+tail1': 'f32-class (2 fp16 planes per operand, 3 tcgen05 MMAs per product, f32 accumulate) up to the stop flag -- '
+                                     'everything that determines symbols and rate; 1 fp16 plane / 1 MMA in the 9 blocks + 2 up-samplers after it '
+                                     '(reconstruction only, d PSNR <= 0.01 dB parity-tested)'}[model.precision],
             'data': 'synthetic',
             'config': {'workload': (f'rd_model_base forward (KL + MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 256 (BASELINE configs[4])'
                                     if rd else f'qres34m eval forward (rate + lambda * MSE), synthetic {H}x{W} RGB, batch {B} per GPU, lambda 2048 '

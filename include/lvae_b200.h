@@ -62,12 +62,16 @@ enum lvae_precision {
   LVAE_PREC_BF16 = 2,         /* tcgen05, 1 plane, 1 MMA: ~2^-8 (non-parity fast mode)                        */
   LVAE_PREC_BF16X6 = 3,       /* tcgen05, 3 bf16 planes, 6 MMAs (hh + hm + mh + mm + hl + lh): ~2^-23, the    */
                               /* fp32-class mode in which quantised symbols match the fp32 CPU reference      */
+  LVAE_PREC_F16 = 5,          /* tcgen05 kind::f16, ONE fp16 plane (weights scaled like F16X3), 1 MMA: ~2^-11. */
+                              /* Not a parity mode for the coded part: the engine uses it ONLY for the blocks */
+                              /* after CompresionStopFlag (qarv/zoo.py:78-88) in the 'f16x3+tail1' mode -- they */
+                              /* cannot change a symbol or the rate, only the reconstruction (PSNR budget).   */
   LVAE_PREC_F16X3 = 4         /* tcgen05 kind::f16 on fp16 planes: 2 planes of 11 significand bits each, 3    */
                               /* MMAs (hh + hl + lh): ~2^-22 per product -- fp32-class at half the MMAs of    */
                               /* BF16X6.  Weight planes carry w * LVAE_F16_WEIGHT_SCALE (keeps the low plane  */
                               /* of small weights out of the fp16 subnormal range); the epilogue undoes it.   */
 };
-/* planes per operand for a precision mode: fp32 0, bf16 1, bf16x3 2, bf16x6 3, f16x3 2 */
+/* planes per operand for a precision mode: fp32 0, bf16 1, bf16x3 2, bf16x6 3, f16x3 2, f16 1 */
 #define LVAE_MAX_PLANES 3
 /* element format of operand planes */
 enum lvae_plane_format { LVAE_PLANES_BF16 = 0, LVAE_PLANES_F16 = 1 };

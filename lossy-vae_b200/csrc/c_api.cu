@@ -45,6 +45,7 @@ extern "C" int lvae_gemm(const lvae_gemm_desc* d, void* stream) {
     case LVAE_PREC_BF16X3:
     case LVAE_PREC_BF16:
     case LVAE_PREC_BF16X6:
+    case LVAE_PREC_F16:
     case LVAE_PREC_F16X3: return gemm_tc_launch(d, st);
     default: set_error("unknown precision mode %d", d->precision); return LVAE_E_BADARG;
   }

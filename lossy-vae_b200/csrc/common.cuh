@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <utility>
 #include "lvae_b200.h"
 
 namespace lvae {
@@ -35,6 +36,26 @@ void set_error(const char* fmt, ...);
       return (int)e__;                                                              \
     }                                                                               \
   } while (0)
+
+// ---- programmatic dependent launch (PDL).  A kernel launched through launch_pdl() may start while its predecessor in
+// the stream (or in the captured graph) is still draining: its CTAs become resident as SMs free up and run their
+// prologue (barrier init, TMEM allocation, tensor-map prefetch) early, then block in pdl_wait() until the predecessor
+// has completed and its memory is visible.  RULE: every kernel launched with launch_pdl() calls pdl_wait() before its
+// first global-memory access that could alias the predecessor's reads or writes, and pdl_trigger() as early as possible.
+// Opt-in with LVAE_PDL=1 (environment); without the launch attribute the device calls are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // erf as ATen's CPU GELU kernel evaluates it (the parity oracle is the reference on the CPU): at::vec::Vectorized
 // <float>::erf(), i.e. Abramowitz-Stegun 7.1.26 in fp32 with FMAs (torch/include/ATen/cpu/vec/vec512/

@@ -150,6 +150,9 @@ __global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
     dw_tma_load_4d(dw_smem_u32(dw_smem + buf * CHUNK_FLOATS), &x_map, bar, cbase + j * DW_CH, w0 - PAD, h0 - PAD, b);
   };
 
+  // PDL: barrier set-up and the cluster arrive above overlap the predecessor's tail; the halo load below reads its output
+  pdl_trigger();
+  pdl_wait();
   // res[j][p]: conv output of pixel p = r * 8 + s (r = 0, 1: rows 2 wrow + r; s: column) for this lane's 2 channels
   float2 res[NJ][DW_PIX];
   if (tid == 0) {
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
   const bool interior = (h0 + DW_TH <= H) && (w0 + DW_TW <= W);
   const int64_t o00 = (((int64_t)b * H + h0 + 2 * wrow) * W + w0) * C;        // pixel (row 2 wrow, column 0) of the tile
   auto emit = [&](auto mode_c, auto interior_c) {
-    constexpr int MODE = decltype(mode_c)::value;          // 0: fp32 | 1-3: bf16 planes | 4: two fp16 planes
+    constexpr int MODE = decltype(mode_c)::value;          // 0: fp32 | 1-3: bf16 planes | 4: two fp16 planes | 5: one fp16 plane
     constexpr bool INTERIOR = decltype(interior_c)::value;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
@@ -342,8 +345,8 @@ __global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
           *reinterpret_cast<float2*>(y + o) = v;
         } else {
           // A operand of the tensor-core fc1 GEMM: p0 = rn16(v), p1 = rn16(v - p0), p2 = rn16(v - p0 - p1)
-          constexpr bool F16 = MODE == 4;
-          constexpr int NP = MODE == 4 ? 2 : MODE;
+          constexpr bool F16 = MODE >= 4;
+          constexpr int NP = MODE == 4 ? 2 : (MODE == 5 ? 1 : MODE);
           if constexpr (NP == 1) {
             *reinterpret_cast<uint32_t*>(y0 + o) = pack2<F16>(v.x, v.y);
           } else {
@@ -362,6 +365,7 @@ __global__ void __launch_bounds__(32 * DW_WARPS) dwln_kernel(
   auto emit_mode = [&](auto interior_c) {
     using std::integral_constant;
     if (y != nullptr) emit(integral_constant<int, 0>{}, interior_c);
+    else if (f16 && y1 == nullptr) emit(integral_constant<int, 5>{}, interior_c);
     else if (f16) emit(integral_constant<int, 4>{}, interior_c);
     else if (y2 != nullptr) emit(integral_constant<int, 3>{}, interior_c);
     else if (y1 != nullptr) emit(integral_constant<int, 2>{}, interior_c);
@@ -421,15 +425,17 @@ static int launch_dwln(const float* x, const float* dw_w, const float* dw_b, con
   if (l2_ahead < 0) { const char* e = getenv("LVAE_DW_L2_AHEAD"); l2_ahead = e ? atoi(e) : 0; }
   const int ahead_tiles = l2_ahead > 0 ? l2_ahead * (148 * 4 / CL) : 0;
   if (CL == 1) {
-    dwln_kernel<NJ, KS, CL><<<(unsigned)blocks, 32 * DW_WARPS, smem, stream>>>(
-        map, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, f16, H, W, tiles_x, tiles_y, B, ahead_tiles);
+    LVAE_CUDA_CALL(launch_pdl(dwln_kernel<NJ, KS, CL>, dim3((unsigned)blocks), dim3(32 * DW_WARPS), (size_t)smem, stream,
+        map, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, y, y0, y1, y2, f16, H, W, tiles_x, tiles_y, B, ahead_tiles));
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(blocks * CL)); cfg.blockDim = dim3(32 * DW_WARPS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     LVAE_CUDA_CALL(cudaLaunchKernelEx(&cfg, dwln_kernel<NJ, KS, CL>, map, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b,
                                       y, y0, y1, y2, f16, H, W, tiles_x, tiles_y, B, ahead_tiles));
   }
@@ -489,7 +495,7 @@ extern "C" int lvae_dwconv_ln_adaln_planes(const float* x, const float* dw_w, co
                                            int B, int H, int W, int C, int k, void* stream) {
   LVAE_CHECK_ARG(y0 != nullptr && (y2 == nullptr || y1 != nullptr));
   LVAE_CHECK_ARG(plane_format == LVAE_PLANES_BF16 || plane_format == LVAE_PLANES_F16);
-  LVAE_CHECK_ARG(plane_format != LVAE_PLANES_F16 || (y1 != nullptr && y2 == nullptr));    // fp16 operands travel as 2 planes
+  LVAE_CHECK_ARG(plane_format != LVAE_PLANES_F16 || y2 == nullptr);    // fp16 operands travel as 2 planes (F16X3) or 1 (F16)
   return dwln_dispatch(x, dw_w, dw_b, ada, ada_stride, ada_off, ln_w, ln_b, nullptr, y0, y1, y2,
                        plane_format == LVAE_PLANES_F16, B, H, W, C, k, stream);
 }

@@ -164,6 +164,9 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above overlapped the predecessor's tail; from here on this kernel reads what it wrote
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ============================ TMA producer ============================
@@ -317,6 +320,14 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             for (int j = 16; j < 32; ++j) v[j] = 0u;
           }
           tc_wait_ld();
+          if (p.acc_scale != 1.0f) {                         // single fp16 plane (LVAE_PREC_F16): weights carry 2^8
+            const float2 sc = splat2(p.acc_scale);
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float2 x = mul2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc);
+              v[j] = __float_as_uint(x.x); v[j + 1] = __float_as_uint(x.y);
+            }
+          }
         }
         if (c == last_c) {                                   // this warp has read its share of the accumulator
           tc_fence_before();
@@ -513,6 +524,8 @@ __global__ void __launch_bounds__(256) split_im2col_kernel(
     int C0, int C1, int ks, int stride, int pad, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
     __nv_bfloat16* __restrict__ l2, int64_t total4, int K, int f16, int act) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (i >= total4) return;
   const int K4 = K >> 2;
   const int64_t m = i / K4; const int k = (int)(i - m * K4) * 4;
@@ -640,9 +653,9 @@ int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stre
     __nv_bfloat16* ws = (__nv_bfloat16*)d->workspace;
     __nv_bfloat16* pl[3] = {ws, npl > 1 ? ws + (int64_t)M * K : nullptr, npl > 2 ? ws + 2 * (int64_t)M * K : nullptr};
     const int64_t total4 = (int64_t)M * (K / 4);
-    split_im2col_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, stream>>>(
+    LVAE_CUDA_CALL(launch_pdl(split_im2col_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream,
         d->a0, d->a1, d->B, d->H, d->W, Ho, Wo, d->C0, d->a1 ? d->C1 : 0, d->ksize, d->stride, d->pad,
-        pl[0], pl[1], pl[2], total4, K, d->precision == LVAE_PREC_F16X3, d->a_act);
+        pl[0], pl[1], pl[2], total4, K, (int)(d->precision == LVAE_PREC_F16X3 || d->precision == LVAE_PREC_F16), (int)d->a_act));
     LVAE_CUDA_LAUNCH_CHECK();
     for (int i = 0; i < 3; ++i) a_pl[i] = pl[i];
   } else {
@@ -728,7 +741,7 @@ int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stre
   p.bias = d->bias; p.gamma = d->gamma; p.res = d->res;
   p.epi = d->epilogue; p.r = d->shuffle_r; p.Ho = Ho; p.Wo = Wo;
   { static const char* e = getenv("LVAE_TC_PREFETCH"); p.prefetch = e ? atoi(e) : 0; }
-  p.f16 = d->precision == LVAE_PREC_F16X3 ? 1 : 0;
+  p.f16 = (d->precision == LVAE_PREC_F16X3 || d->precision == LVAE_PREC_F16) ? 1 : 0;
   p.acc_scale = p.f16 ? 1.0f / LVAE_F16_WEIGHT_SCALE : 1.0f;
   LVAE_CHECK_ARG(p.out != nullptr || p.out_pl[0] != nullptr);
 
@@ -755,7 +768,7 @@ int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stre
   }
   const int smem = fixed + stages * stage_bytes;
   const int grid = p.num_tiles < n_sm ? p.num_tiles : n_sm;
-#define LVAE_TC_LAUNCH(npl_, ek_) gemm_tc_kernel<npl_, ek_><<<grid, tc_threads(ek_), smem, stream>>>(maps, p)
+#define LVAE_TC_LAUNCH(npl_, ek_) LVAE_CUDA_CALL(launch_pdl(gemm_tc_kernel<npl_, ek_>, dim3(grid), dim3(tc_threads(ek_)), (size_t)smem, stream, maps, p))
 #define LVAE_TC_LAUNCH_EK(npl_) \
   do { if (ek == EK_GELU) LVAE_TC_LAUNCH(npl_, EK_GELU); else if (ek == EK_ROWS) LVAE_TC_LAUNCH(npl_, EK_ROWS); else LVAE_TC_LAUNCH(npl_, EK_MISC); } while (0)
   if (npl == 3) LVAE_TC_LAUNCH_EK(3);

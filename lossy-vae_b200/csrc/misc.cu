@@ -4,12 +4,22 @@
 #include <cuda_bf16.h>
 #include <stdarg.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace lvae {
 
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  // opt-in: measured on B200 (profiles/r2_bench_notes.md) the whole-step graph replays no faster with programmatic edges
+  // (559 vs 566 images/s) -- a persistent GEMM CTA owns its SM's shared memory, so a dependent CTA cannot become resident
+  // before the last tile anyway -- so plain stream order stays the default
+  if (on < 0) { const char* e = getenv("LVAE_PDL"); on = (e && atoi(e) == 1) ? 1 : 0; }
+  return on != 0;
 }
 
 // common.py:101-107 + qarv/model.py:275-279

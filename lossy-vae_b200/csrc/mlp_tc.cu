@@ -101,6 +101,8 @@ mlp_tc_kernel(const __grid_constant__ MlpMaps maps, const MlpParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();                                           // PDL: the set-up above overlapped the predecessor's tail
   const uint32_t t_acc2 = tmem_base, t_acc2x = tmem_base + (uint32_t)C;
   const uint32_t t_acc1 = tmem_base + (uint32_t)(2 * C);          // buffer b: main at + b * 64, cross at + b * 64 + 32
 
@@ -419,9 +421,9 @@ extern "C" int lvae_convnext_mlp_planes(const void* a_p0, const void* a_p1, cons
     LVAE_CUDA_CALL(cudaFuncSetAttribute(mlp_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   const int grid = p.num_tiles < n_sm ? p.num_tiles : n_sm;
-  if (NKB == 3) mlp_tc_kernel<3><<<grid, ML_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
-  else if (NKB == 2) mlp_tc_kernel<2><<<grid, ML_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
-  else mlp_tc_kernel<1><<<grid, ML_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+  if (NKB == 3) LVAE_CUDA_CALL(launch_pdl(mlp_tc_kernel<3>, dim3(grid), dim3(ML_THREADS), (size_t)smem, (cudaStream_t)stream, maps, p));
+  else if (NKB == 2) LVAE_CUDA_CALL(launch_pdl(mlp_tc_kernel<2>, dim3(grid), dim3(ML_THREADS), (size_t)smem, (cudaStream_t)stream, maps, p));
+  else LVAE_CUDA_CALL(launch_pdl(mlp_tc_kernel<1>, dim3(grid), dim3(ML_THREADS), (size_t)smem, (cudaStream_t)stream, maps, p));
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

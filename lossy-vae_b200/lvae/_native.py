@@ -9,14 +9,14 @@ _LIB_PATH = Path(__file__).resolve().parent.parent / 'lib' / 'liblvae_b200.so'
 _lib = None
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_SCALE_RES, EPI_BIAS_RES, EPI_SHUFFLE_NHWC, EPI_SHUFFLE_NCHW, EPI_GELU_BWD = range(7)
-PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_BF16X6, PREC_F16X3 = range(5)
+PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_BF16X6, PREC_F16X3, PREC_F16 = range(6)
 PRECISIONS = {'fp32': PREC_FP32, 'bf16x3': PREC_BF16X3, 'bf16': PREC_BF16, 'bf16x6': PREC_BF16X6, 'f16x3': PREC_F16X3}
-NUM_PLANES = {PREC_FP32: 0, PREC_BF16: 1, PREC_BF16X3: 2, PREC_BF16X6: 3, PREC_F16X3: 2}
-MMA_TERMS = {PREC_FP32: 1, PREC_BF16: 1, PREC_BF16X3: 3, PREC_BF16X6: 6, PREC_F16X3: 3}
+NUM_PLANES = {PREC_FP32: 0, PREC_BF16: 1, PREC_BF16X3: 2, PREC_BF16X6: 3, PREC_F16X3: 2, PREC_F16: 1}
+MMA_TERMS = {PREC_FP32: 1, PREC_BF16: 1, PREC_BF16X3: 3, PREC_BF16X6: 6, PREC_F16X3: 3, PREC_F16: 1}
 PLANES_BF16, PLANES_F16 = 0, 1
 CDF_NORMAL, CDF_ERFC = 0, 1
 PLANE_FORMAT = {PREC_FP32: PLANES_BF16, PREC_BF16: PLANES_BF16, PREC_BF16X3: PLANES_BF16, PREC_BF16X6: PLANES_BF16,
-                PREC_F16X3: PLANES_F16}
+                PREC_F16X3: PLANES_F16, PREC_F16: PLANES_F16}
 F16_WEIGHT_SCALE = 256.0      # LVAE_F16_WEIGHT_SCALE
 
 _fp = C.c_void_p   # device / host pointers are passed as integers

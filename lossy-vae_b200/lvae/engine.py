@@ -193,10 +193,26 @@ class QarvEngine:
         ver = self._weights_version()
         if not force and ver == self._wver:
             return
-        if self.device != dev or self.__dict__.get('prec') != N.PRECISIONS[m.precision]:
+        base, _, tail = m.precision.partition('+')
+        if base not in N.PRECISIONS or tail not in ('', 'tail1') or (tail and base != 'f16x3'):
+            raise ValueError(f"unknown precision mode {m.precision!r}: one of {sorted(N.PRECISIONS)} or 'f16x3+tail1'")
+        if self.device != dev or self.__dict__.get('prec') != N.PRECISIONS[base] or self.__dict__.get('tail_prec', None) != (N.PREC_F16 if tail else None):
             self._plans.clear()
         self.device = dev
-        self.prec = N.PRECISIONS[m.precision]
+        self.prec = N.PRECISIONS[base]
+        # 'f16x3+tail1': the blocks and up-samplers AFTER CompresionStopFlag (qarv/zoo.py:78-88: 9 blocks + 2 patch
+        # up-samplers, 9.3 % of the dense FLOPs) cannot change a symbol or the rate -- they only render the reconstruction --
+        # so inference plans run them with ONE fp16 operand plane (1 MMA per product instead of 3, half the operand bytes).
+        # Measured d PSNR against the reference stays inside the 0.01 dB budget (tests/test_gpu_model.py, profiles/r2_parity.md).
+        self.tail_prec = N.PREC_F16 if tail else None
+        self.tail_ids = set()
+        if self.tail_prec is not None:
+            after = False
+            for mod in m.dec_blocks:
+                if isinstance(mod, common.CompresionStopFlag):
+                    after = True
+                elif after:
+                    self.tail_ids.add(id(mod))
         self.npl = N.NUM_PLANES[self.prec]        # 16-bit planes per tensor-core operand (0: fp32 CUDA-core path)
         self.pfmt = N.PLANE_FORMAT[self.prec]     # their element format (bf16 | fp16)
         w = {}
@@ -212,6 +228,9 @@ class QarvEngine:
                 )
                 if isinstance(b, common.ConvNeXtBlockLN):       # affine LayerNorm instead of AdaLN
                     w[id(b)]['ln_w'], w[id(b)]['ln_b'] = self._dev_f32(b.norm.weight), self._dev_f32(b.norm.bias)
+                if id(b) in self.tail_ids:                      # single-plane copies for the inference plans' tail
+                    w[id(b)]['fc1_tail'] = self._pack_gemm_weight(w[id(b)]['fc1']['w'], b.mlp.fc1.bias, prec=self.tail_prec)
+                    w[id(b)]['fc2_tail'] = self._pack_gemm_weight(w[id(b)]['fc2']['w'], b.mlp.fc2.bias, prec=self.tail_prec)
             if self.ada_total:
                 ada = [b for b in self.blocks if id(b) in self.ada_off]
                 w['ada_w'] = torch.cat([self._dev_f32(b.embedding_layer[1].weight) for b in ada], 0).contiguous()
@@ -236,6 +255,8 @@ class QarvEngine:
                     # packed row (i*r+j)*Co + c  <-  reference row c*r*r + i*r + j  (PixelShuffle, common.py:33-38)
                     perm = torch.arange(conv.out_channels, device=dev).reshape(co, r * r).t().reshape(-1)
                     w[id(mod)] = self._pack_gemm_weight(wt[perm], self._dev_f32(conv.bias)[perm])
+                    if id(mod) in self.tail_ids:
+                        w[(id(mod), 'tail')] = self._pack_gemm_weight(wt[perm], self._dev_f32(conv.bias)[perm], prec=self.tail_prec)
                 elif getattr(mod, 'is_latent_block', False) and self.family == 'qres':
                     ks0 = mod.z_proj[0].kernel_size[0]
                     zpad = self._z_pad(mod.zdim, ks0)
@@ -287,7 +308,7 @@ class QarvEngine:
                 d.workspace, d.workspace_bytes = _ptr(ws), ws.numel() * 2
         else:
             assert a_planes is None and out_planes is None
-        meta = dict(kind='gemm', flops=2 * Mo * went['N'] * went['K'], M=Mo, N=went['N'], K=went['K'],
+        meta = dict(kind='gemm', flops=2 * Mo * went['N'] * went['K'], M=Mo, N=went['N'], K=went['K'], terms=N.MMA_TERMS[prec],
                     bytes=4 * (B * H * W * (C0 + C1) + went['N'] * went['K'] + Mo * went['N'] * (2 if res is not None else 1)))
         P.op(name, self.lib.lvae_gemm, C.byref(d), keep=(d, a0, a1, went, out, gamma, res, a_planes, out_planes, ws, a1_planes),
              meta=meta)
@@ -303,6 +324,19 @@ class QarvEngine:
         ada_off = self.ada_off.get(id(blk), 0)
         # algorithmic bytes: read x fp32, write the GEMM operand (fp32, or npl bf16 planes)
         dw_meta = dict(kind='dwln', bytes=M * C_ * (4 + (2 * self.npl if self.npl else 4)), flops=2 * M * C_ * k * k)
+        if self._tail(P, blk) and out_planes is None:
+            # after the stop flag (inference plans of the 'f16x3+tail1' mode): one fp16 plane per operand, unfused GEMM pair
+            tp = self.tail_prec
+            A = [P.named('scratch_a0', M * C_, dtype=torch.bfloat16)]
+            Hd = [P.named('scratch_h0', M * hid, dtype=torch.bfloat16)]
+            dw_meta['bytes'] = M * C_ * (4 + 2)
+            P.op('dwln', self.lib.lvae_dwconv_ln_adaln_planes, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']),
+                 _ptr(P.ada), self.ada_total, ada_off, ln_w, ln_b, _ptr(A[0]), 0, 0, N.PLANE_FORMAT[tp], B, Hs, Ws, C_, k,
+                 keep=(x, A), meta=dw_meta)
+            self._gemm(P, 'fc1', None, (1, 1, M, C_, 1, 1, 0), wb['fc1_tail'], None, epi=N.EPI_BIAS_GELU, a_planes=A, out_planes=Hd, prec=tp)
+            self._gemm(P, 'fc2', None, (1, 1, M, hid, 1, 1, 0), wb['fc2_tail'], out, epi=N.EPI_SCALE_RES,
+                       gamma=wb['gamma'], res=x, a_planes=Hd, prec=tp)
+            return out
         if self.npl:
             # tensor-core modes: the A operand of each GEMM travels as bf16 planes written by its producer
             A = [P.named(f'scratch_a{i}', M * C_, dtype=torch.bfloat16) for i in range(self.npl)]
@@ -319,7 +353,7 @@ class QarvEngine:
                 P.op('mlp', self.lib.lvae_convnext_mlp_planes, ap[0], ap[1], _ptr(w1['planes'][0]), _ptr(w1['planes'][1]),
                      _ptr(w1['bias']), _ptr(w2['planes'][0]), _ptr(w2['planes'][1]), _ptr(w2['bias']), _ptr(wb['gamma']),
                      _ptr(x), _ptr(out), op0, op1, planes_act, M, C_, hid, self.prec, keep=(x, out, A, wb, out_planes),
-                     meta=dict(kind='gemm', flops=4 * M * C_ * hid, M=M, N=C_, K=hid, bytes=M * C_ * (4 + 4 + 4)))
+                     meta=dict(kind='gemm', flops=4 * M * C_ * hid, M=M, N=C_, K=hid, bytes=M * C_ * (4 + 4 + 4), terms=N.MMA_TERMS[self.prec]))
                 return out
             self._gemm(P, 'fc1', None, (1, 1, M, C_, 1, 1, 0), wb['fc1'], None, epi=N.EPI_BIAS_GELU, a_planes=A, out_planes=Hd)
             # planes_only: the consumer reads the 16-bit planes, the fp32 result is never written
@@ -335,6 +369,11 @@ class QarvEngine:
         self._gemm(P, 'fc2', Hd, (1, 1, M, hid, 1, 1, 0), wb['fc2'], out, epi=N.EPI_SCALE_RES,
                    gamma=wb['gamma'], res=x)
         return out
+
+    def _tail(self, P, mod):
+        """True when `mod` lies after the stop flag and plan P may run it in the reduced tail precision (never a training
+        plan: gradients and the train-mode loss keep the full operand split)."""
+        return self.__dict__.get('tail_prec') is not None and id(mod) in self.tail_ids and P.mode != 'train'
 
     def _mlp_fused(self, blk):
         return (self.fuse_mlp and self.npl == 2 and blk.dim % 64 == 0 and blk.dim <= 192 and blk.hidden % 32 == 0)
@@ -455,8 +494,9 @@ class QarvEngine:
                 co = mod[0].out_channels // (r * r)
                 last = co == 3
                 out = P.f32(B, 3, Hs * r, Ws * r) if last else P.f32(M * r * r, co)
-                self._gemm(P, 'up', x, (B, Hs, Ws, Cc, 1, 1, 0), self.w[id(mod)], out,
-                           epi=N.EPI_SHUFFLE_NCHW if last else N.EPI_SHUFFLE_NHWC, r=r)
+                tail = self._tail(P, mod)
+                self._gemm(P, 'up', x, (B, Hs, Ws, Cc, 1, 1, 0), self.w[(id(mod), 'tail')] if tail else self.w[id(mod)], out,
+                           epi=N.EPI_SHUFFLE_NCHW if last else N.EPI_SHUFFLE_NHWC, r=r, prec=self.tail_prec if tail else None)
                 x, Cc, Hs, Ws = out, co, Hs * r, Ws * r
             elif isinstance(mod, common.CompresionStopFlag):
                 if stop_at_flag:

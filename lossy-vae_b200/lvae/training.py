@@ -16,7 +16,10 @@ Backward -- STATE OF THIS ROUND, per op:
     `lvae_gemm_wgrad`; gelu(h) and the bias gradients ride in the operand splits); the dwconv + LayerNorm + AdaLN /
     affine part runs on the kernels of csrc/dwln_bwd.cu.  (Layers with fewer than 1024 pixels: `torch.mm` weight
     gradients; a few [C]-sized elementwise torch ops per block.)
-  * convolutions (patch down / up, 1x1 and 3x3 heads) and qres VDBlocks: ATen autograd on a recomputed sub-graph.
+  * convolutions of the qarv path (patch down / up, 1x1 heads with K-concat / residual, the 3x3 posterior head): native --
+    data gradient = tcgen05 GEMM on the transposed packed weight, weight gradient = tcgen05 split-K GEMM over the pixels
+    (tap by tap for the 3x3), bias gradient in the operand split (`TrainPath.conv_backward`); torch only re-arranges data;
+  * qres-specific ops (VDBlocks, the GELU-fused / channel-padded z_proj convs): ATen autograd on a recomputed sub-graph.
 Everything ATen here is a LIBRARY call (cuBLAS / cuDNN), not this repo's product; it is what the native backward
 kernels of the next round replace, one op at a time, each against the gradient tests in tests/test_gpu_train.py
 (`TrainPath.native_bwd = False` runs every backward through ATen: the cross-check of the native pieces).
@@ -169,7 +172,7 @@ class _ConvFn(torch.autograd.Function):
             out = torch.empty(B, Ho, Wo, Nn, device=x.device)
         eng._gemm(P, cfg.get('name', 'conv'), a, geom, went, out, epi=cfg['epi'], a1=x1, C1=0 if x1 is None else x1.shape[-1],
                   res=res, r=r, a_act=cfg.get('a_act', 0))
-        ctx.T, ctx.cfg = T, cfg
+        ctx.T, ctx.cfg, ctx.went = T, cfg, went
         ctx.save_for_backward(x, x1, res, w, b)
         return out
 
@@ -177,6 +180,10 @@ class _ConvFn(torch.autograd.Function):
     def backward(ctx, gout):
         x, x1, res, w, b = ctx.saved_tensors
         cfg, m = ctx.cfg, ctx.T.model
+        T = ctx.T
+        if T.native_bwd and T.eng.npl and not (cfg.get('gelu') or cfg.get('a_act') or cfg.get('pad_c')):
+            g = T.conv_backward(cfg, ctx.went, x, x1, res, w, b, gout.contiguous())
+            return (None, None, None) + tuple(g)
         if cfg.get('nchw_in'):
             xin = x.add(m.im_shift).mul_(m.im_scale)
             g = _grad_of(lambda w_, b_: _conv_aten(xin, None, None, w_, b_, cfg), [w, b], gout)
@@ -357,6 +364,118 @@ class TrainPath:
         if ln:
             return (dx, None, d_dww, d_dwb, d_w1, d_b1, d_w2, d_b2, d_gamma, dmod[0, C_:].clone(), dmod[0, :C_].clone())
         return (dx, self.scatter_ada(ada, off, dmod), d_dww, d_dwb, d_w1, d_b1, d_w2, d_b2, d_gamma)
+
+    # ---- convolutions (patch down / up, 1x1 heads with K-concat and residual, the 3x3 posterior head): native backward
+    def _mm_grad(self, name, g2d, a2d, colsum=None):
+        """g2d^T @ a2d -> [N, K] (weight gradient of a linear map) + optional column sums of g2d (bias gradient): tcgen05
+        split-K GEMM over the pixels when there are enough of them, cuBLAS fp32 for the tiny layers."""
+        M, Nn = g2d.shape
+        K = a2d.shape[1]
+        if self.native_wgrad and M % 8 == 0 and M >= 1024:
+            return self._wgrad(self._t_planes('wg_a', g2d, colsum=colsum), self._t_planes('wg_b', a2d), Nn, K, M)
+        if colsum is not None:
+            colsum.add_(g2d.sum(0))
+        return g2d.t().mm(a2d)
+
+    def _dgrad(self, name, g2d, w2d):
+        """g2d [M, N] @ w2d [N, K] -> [M, K]: the data gradient of a linear map, on the tcgen05 GEMM (2-plane bf16)."""
+        M, Nn = g2d.shape
+        out = torch.empty(M, w2d.shape[1], device=g2d.device)
+        self.eng._gemm(self.P, name, g2d, (1, 1, M, Nn, 1, 1, 0), self._transposed(w2d), out, epi=N.EPI_BIAS, prec=self.DGRAD_PREC)
+        return out
+
+    def conv_backward(self, cfg, went, x, x1, res, w, b, gout):
+        """Gradients (x, x1, res, w, b) of one _ConvFn op without ATen's convolution_backward: every convolution of the
+        qarv path is a linear map on a (re-arranged) pixel matrix, so its data gradient is one tcgen05 GEMM on the
+        transposed packed weight and its weight gradient one tcgen05 GEMM contracting over the pixels; what torch still
+        does here is data movement (patch / pixel-shuffle re-arrangement views, copies, small pads)."""
+        eng, m = self.eng, self.model
+        ks, st, r = cfg['ks'], cfg['stride'], cfg.get('r', 0)
+        Wp = went['w']                                     # packed [N, K] fp32 on the device, K order (ky, kx, c) | segment 1
+        Nn, K = Wp.shape
+        dev = gout.device
+        # ---- G: [M, N] in the packed column order of the forward GEMM
+        if r:
+            Co = Nn // (r * r)
+            if cfg.get('nchw_out'):
+                B, _, Hr, Wr = gout.shape
+                G = gout.view(B, Co, Hr // r, r, Wr // r, r).permute(0, 2, 4, 3, 5, 1)
+            else:
+                B, Hr, Wr, _ = gout.shape
+                G = gout.view(B, Hr // r, r, Wr // r, r, Co).permute(0, 1, 3, 2, 4, 5)
+            G = G.reshape(-1, Nn)
+        else:
+            G = gout.reshape(-1, Nn)
+        M = G.shape[0]
+        db_p = torch.zeros(Nn, device=dev) if b is not None else None
+        dx = dx1 = None
+        if ks == 3:
+            # 3x3, stride 1, pad 1 (posterior head): dgrad = the same convolution of G with the flipped, transposed filter;
+            # wgrad tap by tap: dW[:, :, ky, kx] = shift(G, ky - 1, kx - 1)^T @ X
+            B, H, W_, C0 = x.shape
+            w4 = w.detach()
+            wd = w4.flip(2, 3).permute(1, 2, 3, 0).reshape(C0, 9 * Nn).contiguous()      # [c, (ky, kx, n)] of the flipped filter
+            dxm = torch.empty(M, C0, device=dev)
+            eng._gemm(self.P, 'conv3.dgrad', gout, (B, H, W_, Nn, 3, 1, 1), eng._pack_gemm_weight(wd, None, prec=self.DGRAD_PREC),
+                      dxm, epi=N.EPI_BIAS, prec=self.DGRAD_PREC)
+            dx = dxm.view(B, H, W_, C0)
+            X = x.reshape(M, C0)
+            tc = self.native_wgrad and M % 8 == 0 and M >= 1024
+            x_t = self._t_planes('wg_b', X) if tc else None
+            Gp = F.pad(gout, (0, 0, 1, 1, 1, 1))
+            dw4 = torch.empty(Nn, C0, 3, 3, device=dev)
+            for ky in range(3):
+                for kx in range(3):
+                    Gt = Gp[:, 2 - ky:2 - ky + H, 2 - kx:2 - kx + W_, :].reshape(M, Nn)
+                    if tc:
+                        dw4[:, :, ky, kx] = self._wgrad(self._t_planes('wg_a', Gt.contiguous()), x_t, Nn, C0, M)
+                    else:
+                        dw4[:, :, ky, kx] = Gt.t().mm(X)
+            if db_p is not None:
+                db_p = G.sum(0)
+            return dx, None, None, dw4, db_p
+        # ---- A: the forward operand matrix [M, K] (re-arranged input), and the way back for its gradient
+        if cfg.get('nchw_in'):
+            B, _, H, W_ = x.shape
+            A = torch.empty(M, K, device=dev)
+            self.P.op('im2patch', eng.lib.lvae_image_to_patches, _ptr(x), _ptr(A), B, H, W_, st, float(m.im_shift), float(m.im_scale))
+            dWp = self._mm_grad('down0.wgrad', G, A, db_p)
+        else:
+            B, H, W_, C0 = x.shape
+            if ks > 1:                                     # non-overlapping patches: space-to-depth view
+                Ho, Wo = H // ks, W_ // ks
+                A = x.view(B, Ho, ks, Wo, ks, C0).permute(0, 1, 3, 2, 4, 5).reshape(M, K)
+            else:
+                A = x.reshape(M, C0)
+            dA = self._dgrad('conv.dgrad', G, Wp)          # [M, K]
+            if x1 is not None:
+                C1 = x1.shape[-1]
+                dWp = torch.cat([self._mm_grad('conv.wgrad', G, A, db_p), self._mm_grad('conv.wgrad1', G, x1.reshape(M, C1))], dim=1)
+                dx = dA[:, :C0].reshape(x.shape)
+                dx1 = dA[:, C0:].reshape(x1.shape)
+            else:
+                dWp = self._mm_grad('conv.wgrad', G, A, db_p)
+                if ks > 1:
+                    dx = dA.view(B, Ho, Wo, ks, ks, C0).permute(0, 1, 3, 2, 4, 5).reshape(x.shape)
+                else:
+                    dx = dA.view(x.shape)
+        # ---- packed [N, (ky, kx, c) | c1] -> the conv weight's layout
+        if r:                                              # pixel shuffle: packed row (i r + j) Co + c  <-  reference row c r r + i r + j
+            Co = Nn // (r * r)
+            perm = torch.arange(Nn, device=dev).reshape(Co, r * r).t().reshape(-1)
+            dW_ref = torch.empty_like(dWp)
+            dW_ref[perm] = dWp
+            dWp = dW_ref
+            if db_p is not None:
+                db_ref = torch.empty_like(db_p)
+                db_ref[perm] = db_p
+                db_p = db_ref
+        Cin = w.shape[1]
+        if ks > 1:
+            dw4 = dWp.view(Nn, ks, ks, Cin).permute(0, 3, 1, 2).contiguous()
+        else:
+            dw4 = dWp.reshape(w.shape)
+        return dx, dx1, (gout if res is not None else None), dw4, db_p
 
     # ---- lambda embedding (tiny; ATen both ways): qarv/model.py:280-287, common.py:101-107,150
     def _ada(self, lmb):
