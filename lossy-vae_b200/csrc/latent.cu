@@ -10,8 +10,9 @@
 //   compress branch                 qarv/model.py:106-108: sym = int(rint(qm-pm)), idx = build_indexes(pv)
 //   train branch                    qarv/model.py:91-93 + entropy_coding.py:17-49
 //
-// Layout: qm / z are [M, zdim] (NHWC), prior is [M, 2*zdim] = (pm | plogv_raw) per position, so one
-// thread handles one (position, channel) element with fully coalesced 128 B-per-warp accesses.
+// Layout: qm / z are [M, zdim] (NHWC), prior is [M, 2*zdim] = (pm | plogv_raw) per position; a thread owns four
+// consecutive channels of one position (128-bit loads / stores, 512 B per warp and access), the per-image rate is
+// reduced with warp shuffles + one shared-memory step per block.
 // Algorithmic bytes per element: read qm, pm, plogv (12 B) + write z (4 B) = 16 B with the rate
 // reduced in-kernel (20 B when kl_elem is requested; +8 B for sym/idx).
 // The per-image reduction is deterministic: fixed grid, in-block tree, one partial per block.
@@ -53,8 +54,54 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;   // valid in warp 0
 }
 
-// mode 0: eval, 1: train
+// One latent element: z, kl (and for the coder the integer symbol r and the clamped scale s).  mode 0: eval, 1: train.
 template <int MODE>
+__device__ __forceinline__ void latent_elem(float q, float pm, float plogv_raw, float nz, int cdf_kind,
+                                            float& zz, float& kl, float& r, float& s) {
+  const float pv = prior_scale(plogv_raw);
+  if (MODE == 0) {
+    r = rintf(__fsub_rn(q, pm));                           // torch.round: half to even
+    zz = __fadd_rn(r, pm);
+    const float v = fabsf(__fsub_rn(zz, pm));
+    s = fmaxf(pv, 0.11f);
+    const float tu = __fdiv_rn(__fsub_rn(0.5f, v), s), tl = __fdiv_rn(__fsub_rn(-0.5f, v), s);
+    const float up = cdf_kind ? std_normal_cdf_erfc(tu) : std_normal_cdf(tu);
+    const float lo = cdf_kind ? std_normal_cdf_erfc(tl) : std_normal_cdf(tl);
+    const float P = fmaxf(__fsub_rn(up, lo), 1e-9f);
+    kl = -logf(P);
+  } else {
+    r = 0.f; s = pv;
+    zz = __fadd_rn(q, nz);
+    // td.Normal(pm, pv).cdf(x) = 0.5*(1+erf((x-pm)*(1/pv)/sqrt(2)))
+    const float rcp = __frcp_rn(pv);
+    const float cu = __fmul_rn(0.5f, __fadd_rn(1.0f, erf_torch_cpu(__fdiv_rn(__fmul_rn(__fsub_rn(__fadd_rn(zz, 0.5f), pm), rcp), 1.4142135623730951f))));
+    const float cl = __fmul_rn(0.5f, __fadd_rn(1.0f, erf_torch_cpu(__fdiv_rn(__fmul_rn(__fsub_rn(__fsub_rn(zz, 0.5f), pm), rcp), 1.4142135623730951f))));
+    const float mass = __fsub_rn(cu, cl);
+    float lp;
+    if (mass > 1e-6f) {
+      lp = logf(fmaxf(mass, 1e-8f));
+    } else {
+      // Normal.log_prob: -((x-mu)^2)/(2 var) - log(scale) - log(sqrt(2 pi));  + log(bin_size=1) = 0
+      const float d = __fsub_rn(zz, pm);
+      const float var = __fmul_rn(pv, pv);
+      lp = __fsub_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.0f, var)), logf(pv)), 0.9189385332046727f);
+      lp = __fadd_rn(lp, 0.0f);
+    }
+    kl = -lp;
+  }
+}
+
+__device__ __forceinline__ int scale_index(float s, const float* stab, int n_scales) {
+  int k = n_scales - 1;
+  for (int t = 0; t < n_scales - 1; ++t) k -= (s <= stab[t]) ? 1 : 0;
+  return k;
+}
+
+// VEC = true (zdim % 4 == 0: every registered qarv / rd model): a thread owns 4 consecutive channels of one position --
+// 128-bit loads of qm, pm, plogv and 128-bit stores of z / kl_elem, no per-element div / mod, four independent
+// transcendental chains in flight per thread; a block still owns LT * LE consecutive elements of one image, so the
+// per-block partial sums land where they did.  VEC = false: the scalar layout for odd channel counts (qres z_dims 14, 10).
+template <int MODE, bool VEC>
 __global__ void __launch_bounds__(LT) latent_kernel(
     const float* __restrict__ qm, const float* __restrict__ prior, const float* __restrict__ noise,
     const float* __restrict__ table, int n_scales,
@@ -69,55 +116,52 @@ __global__ void __launch_bounds__(LT) latent_kernel(
   const int b = blockIdx.y;
   const int per_img = hw * zdim;
   float local = 0.f;
-#pragma unroll
-  for (int e = 0; e < LE; ++e) {
-    const int i = (blockIdx.x * LE + e) * LT + threadIdx.x;     // element within the image, (pos, c)
+  if (VEC) {
+    const int i = blockIdx.x * (LT * LE) + threadIdx.x * 4;        // first of 4 consecutive elements (same position)
     if (i < per_img) {
       const int pos = i / zdim, c = i - pos * zdim;
       const int64_t m = (int64_t)b * hw + pos;
-      const float q = qm[m * zdim + c];
-      const float pm = prior[m * 2 * zdim + c];
-      const float pv = prior_scale(prior[m * 2 * zdim + zdim + c]);
-      float kl, zz;
-      if (MODE == 0) {
-        const float r = rintf(__fsub_rn(q, pm));             // torch.round: half to even
-        zz = __fadd_rn(r, pm);
-        const float v = fabsf(__fsub_rn(zz, pm));
-        const float s = fmaxf(pv, 0.11f);
-        const float tu = __fdiv_rn(__fsub_rn(0.5f, v), s), tl = __fdiv_rn(__fsub_rn(-0.5f, v), s);
-        const float up = cdf_kind ? std_normal_cdf_erfc(tu) : std_normal_cdf(tu);
-        const float lo = cdf_kind ? std_normal_cdf_erfc(tl) : std_normal_cdf(tl);
-        const float P = fmaxf(__fsub_rn(up, lo), 1e-9f);
-        kl = -logf(P);
-        if (sym != nullptr) {
+      const float4 q4 = __ldg(reinterpret_cast<const float4*>(qm + m * zdim + c));
+      const float4 pm4 = __ldg(reinterpret_cast<const float4*>(prior + m * 2 * zdim + c));
+      const float4 pl4 = __ldg(reinterpret_cast<const float4*>(prior + m * 2 * zdim + zdim + c));
+      float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == 1) n4 = __ldg(reinterpret_cast<const float4*>(noise + m * zdim + c));
+      const float q[4] = {q4.x, q4.y, q4.z, q4.w}, pm[4] = {pm4.x, pm4.y, pm4.z, pm4.w};
+      const float pl[4] = {pl4.x, pl4.y, pl4.z, pl4.w}, nz[4] = {n4.x, n4.y, n4.z, n4.w};
+      float zz[4], kl[4], r[4], sc[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) latent_elem<MODE>(q[e], pm[e], pl[e], nz[e], cdf_kind, zz[e], kl[e], r[e], sc[e]);
+      *reinterpret_cast<float4*>(z + m * zdim + c) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+      if (kl_elem != nullptr) *reinterpret_cast<float4*>(kl_elem + m * zdim + c) = make_float4(kl[0], kl[1], kl[2], kl[3]);
+      if (MODE == 0 && sym != nullptr) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int64_t o = ((int64_t)b * zdim + c + e) * hw + pos;     // NCHW order for the coder
+          sym[o] = (int32_t)r[e];
+          idx[o] = scale_index(sc[e], stab, n_scales);
+        }
+      }
+      local = ((kl[0] + kl[1]) + kl[2]) + kl[3];
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < LE; ++e) {
+      const int i = (blockIdx.x * LE + e) * LT + threadIdx.x;     // element within the image, (pos, c)
+      if (i < per_img) {
+        const int pos = i / zdim, c = i - pos * zdim;
+        const int64_t m = (int64_t)b * hw + pos;
+        float zz, kl, r, sc;
+        latent_elem<MODE>(qm[m * zdim + c], prior[m * 2 * zdim + c], prior[m * 2 * zdim + zdim + c],
+                          MODE == 1 ? noise[m * zdim + c] : 0.f, cdf_kind, zz, kl, r, sc);
+        if (MODE == 0 && sym != nullptr) {
           const int64_t o = ((int64_t)b * zdim + c) * hw + pos;     // NCHW order for the coder
           sym[o] = (int32_t)r;
-          int k = n_scales - 1;
-          for (int t = 0; t < n_scales - 1; ++t) k -= (s <= stab[t]) ? 1 : 0;
-          idx[o] = k;
+          idx[o] = scale_index(sc, stab, n_scales);
         }
-      } else {
-        zz = __fadd_rn(q, noise[m * zdim + c]);
-        // td.Normal(pm, pv).cdf(x) = 0.5*(1+erf((x-pm)*(1/pv)/sqrt(2)))
-        const float rcp = __frcp_rn(pv);
-        const float cu = __fmul_rn(0.5f, __fadd_rn(1.0f, erf_torch_cpu(__fdiv_rn(__fmul_rn(__fsub_rn(__fadd_rn(zz, 0.5f), pm), rcp), 1.4142135623730951f))));
-        const float cl = __fmul_rn(0.5f, __fadd_rn(1.0f, erf_torch_cpu(__fdiv_rn(__fmul_rn(__fsub_rn(__fsub_rn(zz, 0.5f), pm), rcp), 1.4142135623730951f))));
-        const float mass = __fsub_rn(cu, cl);
-        float lp;
-        if (mass > 1e-6f) {
-          lp = logf(fmaxf(mass, 1e-8f));
-        } else {
-          // Normal.log_prob: -((x-mu)^2)/(2 var) - log(scale) - log(sqrt(2 pi));  + log(bin_size=1) = 0
-          const float d = __fsub_rn(zz, pm);
-          const float var = __fmul_rn(pv, pv);
-          lp = __fsub_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.0f, var)), logf(pv)), 0.9189385332046727f);
-          lp = __fadd_rn(lp, 0.0f);
-        }
-        kl = -lp;
+        z[m * zdim + c] = zz;
+        if (kl_elem != nullptr) kl_elem[m * zdim + c] = kl;
+        local += kl;
       }
-      z[m * zdim + c] = zz;
-      if (kl_elem != nullptr) kl_elem[m * zdim + c] = kl;
-      local += kl;
     }
   }
   const float t = block_sum(local, red);
@@ -286,8 +330,11 @@ extern "C" int lvae_latent_eval(const float* qm, const float* prior, const float
   LVAE_CHECK_ARG(sym == nullptr || (scale_table != nullptr && n_scales >= 1 && n_scales <= 64));
   const int np = lvae_latent_num_partials(hw, zdim);
   LVAE_CHECK_ARG(kl_stride >= np);
-  latent_kernel<0><<<dim3(np, B), LT, 0, (cudaStream_t)stream>>>(qm, prior, nullptr, scale_table, n_scales,
-                                                                  z, kl_partial, kl_elem, sym, idx, hw, zdim, kl_stride, cdf_kind);
+  const bool vec = zdim % 4 == 0 && ((uintptr_t)qm | (uintptr_t)prior | (uintptr_t)z | (uintptr_t)kl_elem) % 16 == 0;
+  if (vec) latent_kernel<0, true><<<dim3(np, B), LT, 0, (cudaStream_t)stream>>>(qm, prior, nullptr, scale_table, n_scales,
+                                                                                 z, kl_partial, kl_elem, sym, idx, hw, zdim, kl_stride, cdf_kind);
+  else latent_kernel<0, false><<<dim3(np, B), LT, 0, (cudaStream_t)stream>>>(qm, prior, nullptr, scale_table, n_scales,
+                                                                              z, kl_partial, kl_elem, sym, idx, hw, zdim, kl_stride, cdf_kind);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -298,8 +345,11 @@ extern "C" int lvae_latent_train(const float* qm, const float* prior, const floa
   LVAE_CHECK_ARG(qm && prior && noise && z && kl_partial && B > 0 && hw > 0 && zdim > 0);
   const int np = lvae_latent_num_partials(hw, zdim);
   LVAE_CHECK_ARG(kl_stride >= np);
-  latent_kernel<1><<<dim3(np, B), LT, 0, (cudaStream_t)stream>>>(qm, prior, noise, nullptr, 0,
-                                                                  z, kl_partial, kl_elem, nullptr, nullptr, hw, zdim, kl_stride, 0);
+  const bool vec = zdim % 4 == 0 && ((uintptr_t)qm | (uintptr_t)prior | (uintptr_t)noise | (uintptr_t)z | (uintptr_t)kl_elem) % 16 == 0;
+  if (vec) latent_kernel<1, true><<<dim3(np, B), LT, 0, (cudaStream_t)stream>>>(qm, prior, noise, nullptr, 0,
+                                                                                 z, kl_partial, kl_elem, nullptr, nullptr, hw, zdim, kl_stride, 0);
+  else latent_kernel<1, false><<<dim3(np, B), LT, 0, (cudaStream_t)stream>>>(qm, prior, noise, nullptr, 0,
+                                                                              z, kl_partial, kl_elem, nullptr, nullptr, hw, zdim, kl_stride, 0);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

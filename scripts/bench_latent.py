@@ -10,7 +10,10 @@ lib = N.lib()
 tab = torch.exp(torch.linspace(torch.log(torch.tensor(0.11)), torch.log(torch.tensor(20.0)), 64)).cuda()
 SHAPES = [('L0  b8', 8, 8 * 12, 32), ('L1  b8', 8, 16 * 24, 32), ('L3  b8', 8, 32 * 48, 96), ('L6  b8', 8, 64 * 96, 8),
           ('L3 b64', 64, 32 * 48, 96), ('L3 b256', 256, 32 * 48, 96)]
+only = sys.argv[1].split(',') if len(sys.argv) > 1 else None
 for name, B, hw, zd in SHAPES:
+    if only and not any(o in name for o in only):
+        continue
     M = B * hw
     elems = M * zd
     nbuf = max(2, int(400e6 // (elems * 16)) + 1)
