@@ -413,3 +413,31 @@ def test_training_aten_restatements_equal_the_oracle_ops(native_lib):
     up = F.pixel_shuffle(F.conv2d(x, wu, bu), 2)
     assert torch.allclose(T._conv_aten(nhwc(x), None, None, wu, bu, dict(stride=1, pad=0, r=2)), nhwc(up), atol=1e-5)
     assert torch.allclose(T._conv_aten(nhwc(x), None, None, wu, bu, dict(stride=1, pad=0, r=2, nchw_out=1)), up, atol=1e-5)
+
+
+def test_gemm_desc_layout_matches_the_header_and_the_integration_stub(tmp_path):
+    """the ctypes mirror of lvae_gemm_desc -- lvae/_native.py:GemmDesc AND the stub a maintainer would
+    paste from INTEGRATION.md -- must have the size and field offsets gcc gives the struct in include/lvae_b200.h."""
+    import ctypes as C
+    import re
+    import subprocess
+    from pathlib import Path
+    from lvae import _native as N
+    ROOT = Path(__file__).resolve().parent.parent
+    names = [f[0] for f in N.GemmDesc._fields_]
+    src = tmp_path / 'layout.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lvae_b200.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(lvae_gemm_desc));\n'
+                   + ''.join(f'  printf("%zu\\n", offsetof(lvae_gemm_desc, {n}));\n' for n in names) + '  return 0;\n}\n')
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-I', str(ROOT / 'include'), str(src), '-o', str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert out[0] == C.sizeof(N.GemmDesc)
+    assert out[1:] == [getattr(N.GemmDesc, n).offset for n in names]
+    # the stub in INTEGRATION.md: same field names in the same order, same size
+    md = (ROOT / 'INTEGRATION.md').read_text()
+    block = md[md.index('class GemmDesc(C.Structure)'):]
+    block = block[:block.index('def _check')]
+    stub_names = re.findall(r"\('(\w+)',", block)
+    assert stub_names == names, (stub_names, names)
+    assert f'C.sizeof(GemmDesc) == {out[0]}' in block
