@@ -200,11 +200,16 @@ class _VDFn(torch.autograd.Function):
         B, H, W, C0 = x.shape
         out = torch.empty(B, H, W, wv['c4']['N'], device=x.device)
         T.eng._vdblock(T.P, 'vd', wv, x, (B, H, W, C0), out, a1=x1, C1=0 if x1 is None else x1.shape[-1])
+        ctx.T, ctx.wv = T, wv
         ctx.save_for_backward(x, x1, *params)
         return out
 
     @staticmethod
     def backward(ctx, gout):
+        T = ctx.T
+        if T.native_bwd and T.native_vd and T.eng.npl:
+            x, x1, *params = ctx.saved_tensors
+            return (None, None) + tuple(T.vd_backward(ctx.wv, x, x1, params, gout.contiguous()))
         g = _grad_of(_vd_aten, list(ctx.saved_tensors), gout)
         return (None, None) + tuple(g)
 
@@ -244,6 +249,11 @@ class TrainPath:
         # LVAE_TRAIN_NATIVE_BWD=0: every backward through ATen on recomputed sub-graphs (the cross-check of the native pieces)
         self.native_bwd = os.environ.get('LVAE_TRAIN_NATIVE_BWD', '1') != '0'
         self.native_wgrad = os.environ.get('LVAE_TRAIN_NATIVE_WGRAD', '1') != '0'
+        # qres VDBlock heads: the native backward (vd_backward) is gradient-exact (tests/test_gpu_train.py) but SLOWER than
+        # cuDNN's at the configs[2] shape (229 against 179 ms per step: the tap-by-tap 3x3 weight gradients are 9 transposing
+        # splits + 9 split-K GEMMs per convolution), so it is opt-in (LVAE_TRAIN_NATIVE_VD=1) until the shifted-operand weight
+        # gradient (one transposed plane set, 9 column offsets) replaces it
+        self.native_vd = os.environ.get('LVAE_TRAIN_NATIVE_VD', '0') == '1'
         self.force_refresh = False      # GraphedTrainStep: the captured step must always re-pack the weights
 
     # ---- helpers
@@ -366,22 +376,103 @@ class TrainPath:
         return (dx, self.scatter_ada(ada, off, dmod), d_dww, d_dwb, d_w1, d_b1, d_w2, d_b2, d_gamma)
 
     # ---- convolutions (patch down / up, 1x1 heads with K-concat and residual, the 3x3 posterior head): native backward
-    def _mm_grad(self, name, g2d, a2d, colsum=None):
-        """g2d^T @ a2d -> [N, K] (weight gradient of a linear map) + optional column sums of g2d (bias gradient): tcgen05
-        split-K GEMM over the pixels when there are enough of them, cuBLAS fp32 for the tiny layers."""
+    def _mm_grad(self, name, g2d, a2d, colsum=None, act=0):
+        """g2d^T @ act(a2d) -> [N, K] (weight gradient of a linear map; act = 1: GELU applied to a2d as it is split) + optional
+        column sums of g2d (bias gradient): tcgen05 split-K GEMM over the pixels when there are enough of them, cuBLAS fp32
+        for the tiny layers."""
         M, Nn = g2d.shape
         K = a2d.shape[1]
         if self.native_wgrad and M % 8 == 0 and M >= 1024:
-            return self._wgrad(self._t_planes('wg_a', g2d, colsum=colsum), self._t_planes('wg_b', a2d), Nn, K, M)
+            return self._wgrad(self._t_planes('wg_a', g2d.contiguous(), colsum=colsum), self._t_planes('wg_b', a2d.contiguous(), act=act), Nn, K, M)
         if colsum is not None:
             colsum.add_(g2d.sum(0))
-        return g2d.t().mm(a2d)
+        return g2d.t().mm(F.gelu(a2d) if act else a2d)
+
+    def _conv3_grads(self, G4, X2, w4, act=0):
+        """3x3 / stride 1 / pad 1 convolution y = conv(act(X), w4) + b with G4 = dL/dy [B, H, W, N], X2 [M, C] (its input
+        BEFORE act), w4 [N, C, 3, 3] -> (d act(X) [M, C], dw4, db).  Data gradient: the same im2col GEMM of G with the
+        flipped, transposed filter; weight gradient tap by tap: dW[:, :, ky, kx] = shift(G, ky - 1, kx - 1)^T @ act(X)."""
+        eng = self.eng
+        B, H, W_, Nn = G4.shape
+        M, C0 = X2.shape
+        dev = G4.device
+        wd = w4.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(C0, 9 * Nn).contiguous()      # [c, (ky, kx, n)], flipped
+        dxm = torch.empty(M, C0, device=dev)
+        eng._gemm(self.P, 'conv3.dgrad', G4, (B, H, W_, Nn, 3, 1, 1), eng._pack_gemm_weight(wd, None, prec=self.DGRAD_PREC),
+                  dxm, epi=N.EPI_BIAS, prec=self.DGRAD_PREC)
+        tc = self.native_wgrad and M % 8 == 0 and M >= 1024
+        x_t = self._t_planes('wg_b', X2.contiguous(), act=act) if tc else None
+        Xa = None if tc else (F.gelu(X2) if act else X2)
+        Gp = F.pad(G4, (0, 0, 1, 1, 1, 1))
+        dw4 = torch.empty(Nn, C0, 3, 3, device=dev)
+        for ky in range(3):
+            for kx in range(3):
+                Gt = Gp[:, 2 - ky:2 - ky + H, 2 - kx:2 - kx + W_, :].reshape(M, Nn)
+                if tc:
+                    dw4[:, :, ky, kx] = self._wgrad(self._t_planes('wg_a', Gt.contiguous()), x_t, Nn, C0, M)
+                else:
+                    dw4[:, :, ky, kx] = Gt.t().mm(Xa)
+        return dxm, dw4, G4.reshape(M, Nn).sum(0)
+
+    def vd_backward(self, wv, x, x1, params, gout):
+        """Gradients (x, x1, c1.w, c1.b, ..., c4.w, c4.b) of a qres VDBlock head (qresvae/model.py:118-149, residual = False):
+        out = c4(gelu(c3(gelu(c2(gelu(c1(gelu(cat(x, x1))))))))).  The pre-activations are recomputed in fp32 with the
+        forward GEMM (GELU applied to the operand as it is read); every data gradient is a tcgen05 GEMM, every weight
+        gradient a tcgen05 split-K GEMM over the pixels; GELU' is ATen's elementwise gelu_backward (no cuDNN anywhere)."""
+        eng, P = self.eng, self.P
+        w1, b1, w2, b2, w3, b3, w4, b4 = params
+        B, H, W_, C0 = x.shape
+        M = B * H * W_
+        C1 = 0 if x1 is None else x1.shape[-1]
+        hid, ks = wv['c1']['N'], wv['c2']['ks']
+        dev = x.device
+        pad = (ks - 1) // 2
+        # ---- recompute the three pre-activations (fp32)
+        h1 = torch.empty(B, H, W_, hid, device=dev)
+        eng._gemm(P, 'vd.c1.re', x, (B, H, W_, C0, 1, 1, 0), wv['c1'], h1, a1=x1, C1=C1, a_act=1)
+        h2 = torch.empty_like(h1)
+        eng._gemm(P, 'vd.c2.re', h1, (B, H, W_, hid, ks, 1, pad), wv['c2'], h2, a_act=1)
+        h3 = torch.empty_like(h1)
+        eng._gemm(P, 'vd.c3.re', h2, (B, H, W_, hid, ks, 1, pad), wv['c3'], h3, a_act=1)
+        gelu_bwd = torch.ops.aten.gelu_backward
+        # ---- c4 (1x1): out = gelu(h3) W4^T + b4
+        G = gout.reshape(M, -1)
+        db4 = torch.zeros(G.shape[1], device=dev)
+        dw4 = self._mm_grad('vd.c4.wgrad', G, h3.view(M, hid), db4, act=1).reshape(w4.shape)
+        dh3 = gelu_bwd(self._dgrad('vd.c4.dgrad', G, wv['c4']['w']), h3.view(M, hid))
+        # ---- c3, c2 (3x3 | 1x1)
+        def mid(dh, h_in, went, w):
+            if ks == 3:
+                dg, dw, db = self._conv3_grads(dh.view(B, H, W_, hid), h_in.view(M, hid), w, act=1)
+            else:
+                db = torch.zeros(hid, device=dev)
+                dw = self._mm_grad('vd.mid.wgrad', dh, h_in.view(M, hid), db, act=1).reshape(w.shape)
+                dg = self._dgrad('vd.mid.dgrad', dh, went['w'])
+            return gelu_bwd(dg, h_in.view(M, hid)), dw, db
+        dh2, dw3, db3 = mid(dh3, h2, wv['c3'], w3)
+        dh1, dw2, db2 = mid(dh2, h1, wv['c2'], w2)
+        # ---- c1 (1x1 on gelu(cat(x, x1)))
+        db1 = torch.zeros(hid, device=dev)
+        x2 = x.reshape(M, C0)
+        dwa = self._mm_grad('vd.c1.wgrad', dh1, x2, db1, act=1)
+        dga = self._dgrad('vd.c1.dgrad', dh1, wv['c1']['w'])          # [M, C0 + C1]
+        if x1 is not None:
+            x12 = x1.reshape(M, C1)
+            dw1 = torch.cat([dwa, self._mm_grad('vd.c1.wgrad1', dh1, x12, act=1)], dim=1).reshape(w1.shape)
+            dx = gelu_bwd(dga[:, :C0].contiguous(), x2).view(x.shape)
+            dx1 = gelu_bwd(dga[:, C0:].contiguous(), x12).view(x1.shape)
+        else:
+            dw1 = dwa.reshape(w1.shape)
+            dx, dx1 = gelu_bwd(dga, x2).view(x.shape), None
+        return dx, dx1, dw1, db1, dw2, db2, dw3, db3, dw4, db4
 
     def _dgrad(self, name, g2d, w2d):
         """g2d [M, N] @ w2d [N, K] -> [M, K]: the data gradient of a linear map, on the tcgen05 GEMM (2-plane bf16)."""
         M, Nn = g2d.shape
+        if Nn % 8:                                          # qres z_dims 14 / 12 / 10: a contraction over < 16 channels
+            return g2d.mm(w2d)
         out = torch.empty(M, w2d.shape[1], device=g2d.device)
-        self.eng._gemm(self.P, name, g2d, (1, 1, M, Nn, 1, 1, 0), self._transposed(w2d), out, epi=N.EPI_BIAS, prec=self.DGRAD_PREC)
+        self.eng._gemm(self.P, name, g2d.contiguous(), (1, 1, M, Nn, 1, 1, 0), self._transposed(w2d), out, epi=N.EPI_BIAS, prec=self.DGRAD_PREC)
         return out
 
     def conv_backward(self, cfg, went, x, x1, res, w, b, gout):
@@ -410,30 +501,10 @@ class TrainPath:
         db_p = torch.zeros(Nn, device=dev) if b is not None else None
         dx = dx1 = None
         if ks == 3:
-            # 3x3, stride 1, pad 1 (posterior head): dgrad = the same convolution of G with the flipped, transposed filter;
-            # wgrad tap by tap: dW[:, :, ky, kx] = shift(G, ky - 1, kx - 1)^T @ X
+            # 3x3, stride 1, pad 1 (posterior head)
             B, H, W_, C0 = x.shape
-            w4 = w.detach()
-            wd = w4.flip(2, 3).permute(1, 2, 3, 0).reshape(C0, 9 * Nn).contiguous()      # [c, (ky, kx, n)] of the flipped filter
-            dxm = torch.empty(M, C0, device=dev)
-            eng._gemm(self.P, 'conv3.dgrad', gout, (B, H, W_, Nn, 3, 1, 1), eng._pack_gemm_weight(wd, None, prec=self.DGRAD_PREC),
-                      dxm, epi=N.EPI_BIAS, prec=self.DGRAD_PREC)
-            dx = dxm.view(B, H, W_, C0)
-            X = x.reshape(M, C0)
-            tc = self.native_wgrad and M % 8 == 0 and M >= 1024
-            x_t = self._t_planes('wg_b', X) if tc else None
-            Gp = F.pad(gout, (0, 0, 1, 1, 1, 1))
-            dw4 = torch.empty(Nn, C0, 3, 3, device=dev)
-            for ky in range(3):
-                for kx in range(3):
-                    Gt = Gp[:, 2 - ky:2 - ky + H, 2 - kx:2 - kx + W_, :].reshape(M, Nn)
-                    if tc:
-                        dw4[:, :, ky, kx] = self._wgrad(self._t_planes('wg_a', Gt.contiguous()), x_t, Nn, C0, M)
-                    else:
-                        dw4[:, :, ky, kx] = Gt.t().mm(X)
-            if db_p is not None:
-                db_p = G.sum(0)
-            return dx, None, None, dw4, db_p
+            dxm, dw4, db = self._conv3_grads(gout, x.reshape(M, C0), w)
+            return dxm.view(B, H, W_, C0), None, None, dw4, (db if b is not None else None)
         # ---- A: the forward operand matrix [M, K] (re-arranged input), and the way back for its gradient
         if cfg.get('nchw_in'):
             B, _, H, W_ = x.shape

@@ -128,14 +128,16 @@ def test_qarv_forward_routes_to_training_path_and_adam_reduces_the_loss(native_l
     assert np.isfinite(ev['loss'].item())
 
 
-@pytest.mark.parametrize('native_bwd', [True, False])
+@pytest.mark.parametrize('native_bwd', [True, False, 'vd'])
 def test_qres_train_step_gradients_match_oracle_autograd(native_lib, native_bwd):
+    """native_bwd 'vd': additionally the VDBlock heads through TrainPath.vd_backward (opt-in: correct but slower than cuDNN)"""
     import lvae
     sd = O.sensitised_state_dict(Q.qres_param_shapes(), seed=0)
     m = lvae.get_model('qres34m', lmb=2048)
     m.load_state_dict(sd, strict=False)
     m = m.to(DEV).train()
-    m.train_path.native_bwd = native_bwd
+    m.train_path.native_bwd = bool(native_bwd)
+    m.train_path.native_vd = native_bwd == 'vd'
     B, H, W = 1, 64, 64
     im = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(9))
     noise = _noise(m, B, H, W, 23)
