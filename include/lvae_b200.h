@@ -217,6 +217,25 @@ int lvae_adam_clip_ema(float* p, const float* g, float* m, float* v, float* ema,
                        float max_norm, const float* lr, const float* step, const float* ema_decay,
                        double beta1, double beta2, double eps, float* grad_norm_out, void* stream);
 
+/* ---- GaussianNLLOutputNet of qres34m_lossless (qresvae/model.py:16-94): the arithmetic after the two patch_upsample
+ * heads (which are lvae_gemm launches with LVAE_EPI_SHUFFLE_NCHW).  All tensors NCHW [B,3,H,W] fp32, chw = 3*H*W.
+ * lvae_nll_output: nll_partial[b * np + blk] += -gaussian_log_prob_mass(p_mean, exp(softplus(p_logscale + 16) - 16),
+ *   (im - .5) * 2, bin = 1/127.5, prob_clamp = 1e-6) summed per block, np = lvae_image_num_partials(chw) (model.py:24-40).
+ * lvae_outnet_codec: pm = (round(p_mean*127.5+127.5)/127.5 - 1)/bin, idx = table index of max(exp(p_logscale - ln bin),
+ *   0.11) on scale_table (n_scales <= 128) and, with im != NULL, sym = round((im - .5)*2/bin - pm) (model.py:68-86).
+ * lvae_outnet_decode: im_hat = clamp((sym + pm) * bin, -1, 1) * .5 + .5 (model.py:88-94 + process_output). */
+int lvae_nll_output(const float* p_mean, const float* p_logscale, const float* im, float* nll_partial,
+                    int B, int chw, void* stream);
+int lvae_outnet_codec(const float* p_mean, const float* p_logscale, const float* im, const float* scale_table,
+                      int n_scales, float* pm, int32_t* idx, int32_t* sym, int64_t total, void* stream);
+int lvae_outnet_decode(const int32_t* sym, const float* pm, float* im_hat, int64_t total, void* stream);
+
+/* GPU-side input pipeline of the training step: RandomCrop(crop) + RandomHorizontalFlip + ToTensor
+ * (lvae/datasets/image.py:45-56) on a device batch of decoded uint8 images src [B,3,Hs,Ws]; y0 / x0 [B] int32 crop
+ * origins (y0 + crop <= Hs, x0 + crop <= Ws), flip [B] uint8 -> out [B,3,crop,crop] fp32 = x / 255. */
+int lvae_crop_flip_u8(const void* src, const int32_t* y0, const int32_t* x0, const void* flip, float* out,
+                      int B, int Hs, int Ws, int crop, void* stream);
+
 /* ---- fused latent-layer kernels (qarv/model.py:51-53,90-96,104-113; CompressAI GaussianConditional) --
  * prior [M, 2*zdim] (pm | plogv_raw) and qm [M, zdim] are NHWC matrices; hw = h*w positions per image.
  * Eval (K11+K12+K15): z = rint(qm-pm)+pm; kl = -ln max(Phi((.5-|z-pm|)/s) - Phi((-.5-|z-pm|)/s), 1e-9),

@@ -255,6 +255,35 @@ extern "C" int lvae_image_to_patches(const float* im, float* a, int B, int H, in
   return 0;
 }
 
+// GPU-side input pipeline of the training step: RandomCrop + RandomHorizontalFlip + ToTensor of
+// lvae/datasets/image.py:45-56 on a batch of decoded uint8 images that is already on the device.  src [B, 3, Hs, Ws]
+// uint8 (NCHW), per-image crop origin (y0, x0) and flip flag -> out [B, 3, crop, crop] fp32 in [0, 1] (x / 255, the value
+// torchvision's to_tensor produces).  Pure data movement: 1 byte read + 4 bytes written per element.
+namespace lvae {
+__global__ void __launch_bounds__(256) crop_flip_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ y0,
+                                                        const int32_t* __restrict__ x0, const uint8_t* __restrict__ flip,
+                                                        float* __restrict__ out, int B, int Hs, int Ws, int crop) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * 3 * crop * crop;
+  if (i >= total) return;
+  const int x = (int)(i % crop); int64_t t = i / crop;
+  const int y = (int)(t % crop); t /= crop;
+  const int c = (int)(t % 3); const int b = (int)(t / 3);
+  const int sx = x0[b] + (flip[b] ? crop - 1 - x : x), sy = y0[b] + y;
+  out[i] = __fdiv_rn((float)src[(((int64_t)b * 3 + c) * Hs + sy) * Ws + sx], 255.0f);
+}
+}  // namespace lvae
+
+extern "C" int lvae_crop_flip_u8(const void* src, const int32_t* y0, const int32_t* x0, const void* flip, float* out,
+                                 int B, int Hs, int Ws, int crop, void* stream) {
+  LVAE_CHECK_ARG(src && y0 && x0 && flip && out && B > 0 && crop > 0 && crop <= Hs && crop <= Ws);
+  const int64_t total = (int64_t)B * 3 * crop * crop;
+  lvae::crop_flip_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint8_t*)src, y0, x0, (const uint8_t*)flip, out, B, Hs, Ws, crop);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int lvae_image_num_partials(int chw) { return (chw + DT * DE - 1) / (DT * DE); }
 
 extern "C" int lvae_image_distortion(const float* x_hat, const float* im, float* im_hat,

@@ -62,6 +62,10 @@ _PROTOS = {
     'lvae_split_planes_t': (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int, _fp]),
     'lvae_split_planes_t_ex': (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, _fp, _fp]),
     'lvae_gemm_wgrad': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int64, _fp]),
+    'lvae_nll_output': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp]),
+    'lvae_outnet_codec': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, _fp, _fp, _fp, C.c_int64, _fp]),
+    'lvae_outnet_decode': (C.c_int, [_fp, _fp, _fp, C.c_int64, _fp]),
+    'lvae_crop_flip_u8': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_optim_scratch_doubles': (C.c_int, []),
     'lvae_adam_clip_ema': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, _fp, C.c_float, _fp, _fp, _fp,
                                      C.c_double, C.c_double, C.c_double, _fp, _fp]),

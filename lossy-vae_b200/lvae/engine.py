@@ -173,6 +173,17 @@ class QarvEngine:
     def _vd_weights(self, vd):
         return {k: self._conv_weight(getattr(vd, k)) for k in ('c1', 'c2', 'c3', 'c4')}
 
+    def _pack_up(self, w, mod, dev):
+        """patch_upsample = 1x1 conv + PixelShuffle(r): the packed weight is row-permuted so that the shuffle is a pure
+        store pattern -- packed row (i*r+j)*Co + c  <-  reference row c*r*r + i*r + j  (common.py:33-38)"""
+        conv, r = mod[0], mod.rate
+        wt = self._dev_f32(conv.weight).reshape(conv.out_channels, conv.in_channels)
+        co = conv.out_channels // (r * r)
+        perm = torch.arange(conv.out_channels, device=dev).reshape(co, r * r).t().reshape(-1)
+        w[id(mod)] = self._pack_gemm_weight(wt[perm], self._dev_f32(conv.bias)[perm])
+        if id(mod) in self.tail_ids:
+            w[(id(mod), 'tail')] = self._pack_gemm_weight(wt[perm], self._dev_f32(conv.bias)[perm], prec=self.tail_prec)
+
     @staticmethod
     def _z_pad(zdim, ks):
         """channels lvae_pad_channels appends to z before the z_proj conv: the GEMM needs C % 4 == 0 and K % 8 == 0"""
@@ -249,14 +260,7 @@ class QarvEngine:
                 if kind == 'down':
                     w[id(mod)] = self._conv_weight(mod)
                 elif kind == 'up':
-                    conv, r = mod[0], mod.rate
-                    wt = self._dev_f32(conv.weight).reshape(conv.out_channels, conv.in_channels)
-                    co = conv.out_channels // (r * r)
-                    # packed row (i*r+j)*Co + c  <-  reference row c*r*r + i*r + j  (PixelShuffle, common.py:33-38)
-                    perm = torch.arange(conv.out_channels, device=dev).reshape(co, r * r).t().reshape(-1)
-                    w[id(mod)] = self._pack_gemm_weight(wt[perm], self._dev_f32(conv.bias)[perm])
-                    if id(mod) in self.tail_ids:
-                        w[(id(mod), 'tail')] = self._pack_gemm_weight(wt[perm], self._dev_f32(conv.bias)[perm], prec=self.tail_prec)
+                    self._pack_up(w, mod, dev)
                 elif getattr(mod, 'is_latent_block', False) and self.family == 'qres':
                     ks0 = mod.z_proj[0].kernel_size[0]
                     zpad = self._z_pad(mod.zdim, ks0)
@@ -272,6 +276,13 @@ class QarvEngine:
                                       prior=self._conv_weight(mod.prior))
                     if self.family == 'qarv':
                         w[id(mod)]['table'] = mod.discrete_gaussian.scale_table.detach().to(dev, torch.float32).contiguous()
+            on = getattr(m, 'out_net', None)
+            if on is not None and hasattr(on, 'conv_mean'):        # GaussianNLLOutputNet (qres34m_lossless): two shuffle heads
+                self._pack_up(w, on.conv_mean, dev)
+                self._pack_up(w, on.conv_scale, dev)
+                dg = getattr(on, 'discrete_gaussian', None)       # appears with compress_mode()
+                w['out_table'] = (dg.scale_table.detach().to(dev, torch.float32).contiguous()
+                                  if dg is not None and dg.scale_table.numel() else None)
         self.w = w
         self._wver = ver
         # plans hold raw weight pointers -> rebuild them
@@ -655,19 +666,47 @@ class QarvEngine:
             return z
 
         x_hat = self._top_down(P, feats, nH, nW, latent_fn, stop_at_flag=(mode == 'compress'))
+        lossless = getattr(m, 'lossless', False)
+        chw = 3 * H * W
+        if lossless:                # GaussianNLLOutputNet: x_hat is the H/4 feature -> mean / log-scale images (NCHW)
+            x_hat, P.out_ls = self._out_heads(P, x_hat, B, H, W)
         if mode != 'compress':
             P.x_hat = x_hat
-            chw = 3 * H * W
             npi = self.lib.lvae_image_num_partials(chw)
             P.im_hat = P.f32(B, 3, H, W)
             pt, pi = P.f32(B, npi), P.f32(B, npi)
             P.stats = P.f32(4 + 3 * B)
             P.op('distortion', self.lib.lvae_image_distortion, _ptr(x_hat), _ptr(P.im), _ptr(P.im_hat), _ptr(pt), _ptr(pi),
                  B, chw, keep=(pt, pi))
+            if lossless:            # the out-net loss is the NLL, not lambda * MSE: its per-image sums replace `pt` (lmb = 1)
+                pt = P.f32(B, npi)
+                P.op('nll', self.lib.lvae_nll_output, _ptr(x_hat), _ptr(P.out_ls), _ptr(P.im), _ptr(pt), B, chw, keep=(pt,))
             P.op('finalize', self.lib.lvae_rd_finalize, _ptr(P.kl_partial), kl_cols, kl_cols, _ptr(pt), _ptr(pi), npi,
                  _ptr(P.lmb), B, chw, _ptr(P.stats))
             P.stats_host = torch.empty(4 + 3 * B, dtype=torch.float32, pin_memory=True)
+        elif lossless:              # the image's own residual stream (qresvae/model.py:81-86)
+            tab = self.w['out_table']
+            if tab is None:
+                raise ValueError('Uninitialized CDFs. Run update() first')
+            P.on_pm, P.on_idx, P.on_sym = P.f32(B * chw), P.i32(B * chw), P.i32(B * chw)
+            P.on_idx_host = torch.empty(B * chw, dtype=torch.int32, pin_memory=True)
+            P.on_sym_host = torch.empty(B * chw, dtype=torch.int32, pin_memory=True)
+            P.op('outnet_codec', self.lib.lvae_outnet_codec, _ptr(x_hat), _ptr(P.out_ls), _ptr(P.im), _ptr(tab), tab.numel(),
+                 _ptr(P.on_pm), _ptr(P.on_idx), _ptr(P.on_sym), B * chw, keep=(x_hat, tab))
         return P
+
+    def _out_heads(self, P, feat, B, H, W):
+        """GaussianNLLOutputNet's conv_mean / conv_scale (patch_upsample(C, 3, rate)) on the decoder's last feature
+        [B*h*w, C] -> (p_mean, p_logscale), each NCHW [B, 3, H, W]"""
+        on = self.model.out_net
+        r = on.conv_mean.rate
+        Hs, Ws, Cc = H // r, W // r, on.conv_mean[0].in_channels
+        outs = []
+        for head in (on.conv_mean, on.conv_scale):
+            out = P.f32(B, 3, H, W)
+            self._gemm(P, 'up', feat, (B, Hs, Ws, Cc, 1, 1, 0), self.w[id(head)], out, epi=N.EPI_SHUFFLE_NCHW, r=r)
+            outs.append(out)
+        return outs[0], outs[1]
 
     def _get_plan(self, key, builder):
         """Launch plans are cached per (batch, height, width, mode): each owns its activation buffers, pinned host mirrors
@@ -765,7 +804,10 @@ class QarvEngine:
             if mode == 'compress':
                 strings = self._encode_strings(P)
                 self._assert_range(rng)
-                return dict(strings=strings)
+                res = dict(strings=strings)
+                if getattr(self.model, 'lossless', False):
+                    res['out_strings'] = self._encode_outnet(P)
+                return res
             P.stats_host.copy_(P.stats, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
             self._assert_range(rng)
@@ -839,6 +881,29 @@ class QarvEngine:
         self.host_coder_s += time.perf_counter() - t0
         return out
 
+    def _encode_outnet(self, P):
+        """The lossless model's last stream: per image the 3*H*W residual symbols of the image itself against the out-net's
+        128-scale tables (one rANS stream per image, coded in parallel)."""
+        B = P.B
+        P.on_sym_host.copy_(P.on_sym, non_blocking=True)
+        P.on_idx_host.copy_(P.on_idx, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        t0 = time.perf_counter()
+        cdf, clen, coff = self.model.out_net.discrete_gaussian.host_tables()
+        per = P.on_sym_host.numel() // B
+        cap = int(self.lib.lvae_rans_bound(per))
+        out = np.empty(B * cap, dtype=np.uint8)
+        begin = np.arange(B + 1, dtype=np.int64) * per
+        out_begin = np.arange(B + 1, dtype=np.int64) * cap
+        out_len = np.zeros(B, dtype=np.int64)
+        sym_np, idx_np = P.on_sym_host.numpy(), P.on_idx_host.numpy()
+        N.check(self.lib.lvae_rans_encode_streams(sym_np.ctypes.data, idx_np.ctypes.data, begin.ctypes.data, B,
+                                                  cdf.ctypes.data, cdf.shape[1], clen.ctypes.data, coff.ctypes.data,
+                                                  cdf.shape[0], out.ctypes.data, out_begin.ctypes.data,
+                                                  out_len.ctypes.data, self.coder_threads), 'rans_encode_streams')
+        self.host_coder_s += time.perf_counter() - t0
+        return [out[out_begin[b]:out_begin[b] + out_len[b]].tobytes() for b in range(B)]
+
     def _build_decode_plan(self, B, nH, nW, sampling=False):
         m = self.model
         H, W = nH * m.max_stride, nW * m.max_stride
@@ -873,10 +938,25 @@ class QarvEngine:
 
         x_hat = self._top_down(P, None, nH, nW, latent_fn)
         P.x_hat = x_hat
+        if getattr(m, 'lossless', False):
+            chw = 3 * H * W
+            P.x_hat, P.out_ls = self._out_heads(P, x_hat, B, H, W)
+            if not sampling:
+                tab = self.w['out_table']
+                if tab is None:
+                    raise ValueError('Uninitialized CDFs. Run update() first')
+                P.on_pm, P.on_idx, P.on_sym = P.f32(B * chw), P.i32(B * chw), P.i32(B * chw)
+                P.on_idx_host = torch.empty(B * chw, dtype=torch.int32, pin_memory=True)
+                P.on_sym_host = torch.empty(B * chw, dtype=torch.int32, pin_memory=True)
+                P.on_im_hat = P.f32(B, 3, H, W)
+                P.op('outnet_codec', self.lib.lvae_outnet_codec, _ptr(P.x_hat), _ptr(P.out_ls), 0, _ptr(tab), tab.numel(),
+                     _ptr(P.on_pm), _ptr(P.on_idx), 0, B * chw, keep=(tab,))
+                P.cut()              # host: D2H indexes -> rANS decode of the image residual -> H2D symbols
+                P.op('outnet_decode', self.lib.lvae_outnet_decode, _ptr(P.on_sym), _ptr(P.on_pm), _ptr(P.on_im_hat), B * chw)
         return P
 
     @torch.no_grad()
-    def decompress(self, lmb, strings, bhw):
+    def decompress(self, lmb, strings, bhw, out_strings=None):
         """strings[li]: the byte string of latent layer li, or a list of B of them (one per image).  The B streams of a
         layer are decoded on a thread pool (lvae_rans_decode_streams); layers stay sequential, because the prior of
         layer i + 1 needs z_i (qarv/model.py:546-554)."""
@@ -908,6 +988,26 @@ class QarvEngine:
                 self.host_coder_s += time.perf_counter() - t0
                 P.sym[li].copy_(P.sym_host[li].view_as(P.sym[li]), non_blocking=True)
             self._launch(P, len(blocks))
+            if getattr(self.model, 'lossless', False):
+                # qresvae/model.py:88-94: indexes from the out-net's scale head, the image residual from its own stream
+                assert out_strings is not None and len(out_strings) == B
+                P.on_idx_host.copy_(P.on_idx, non_blocking=True)
+                stream.synchronize()
+                cdf, clen, coff = self.model.out_net.discrete_gaussian.host_tables()
+                idx_np, sym_np = P.on_idx_host.numpy(), P.on_sym_host.numpy()
+                per = idx_np.size // B
+                t0 = time.perf_counter()
+                data = np.frombuffer(b''.join(out_strings), dtype=np.uint8)
+                in_begin = np.concatenate([[0], np.cumsum([len(s_) for s_ in out_strings])]).astype(np.int64)
+                begin = np.arange(B + 1, dtype=np.int64) * per
+                N.check(self.lib.lvae_rans_decode_streams(data.ctypes.data, in_begin.ctypes.data, idx_np.ctypes.data,
+                                                          begin.ctypes.data, B, cdf.ctypes.data, cdf.shape[1],
+                                                          clen.ctypes.data, coff.ctypes.data, cdf.shape[0],
+                                                          sym_np.ctypes.data, self.coder_threads), 'rans_decode_streams')
+                self.host_coder_s += time.perf_counter() - t0
+                P.on_sym.copy_(P.on_sym_host, non_blocking=True)
+                self._launch(P, len(blocks) + 1)
+                return P.on_im_hat.clone()
             return P.x_hat.clone().clamp_(min=-1.0, max=1.0).mul_(0.5).add_(0.5)
 
     @torch.no_grad()
@@ -934,4 +1034,8 @@ class QarvEngine:
                     assert tuple(latents[li].shape) == (B, zd, Hs, Ws)
                     P.z[li].view(B, Hs, Ws, zd).copy_(latents[li].to(self.device).permute(0, 2, 3, 1))
             self._launch(P, len(P.z))
+            if getattr(self.model, 'lossless', False):
+                # GaussianNLLOutputNet.sample (qresvae/model.py:46-56): mean + scale * t * N(0,1); not a hot path
+                x = P.x_hat + torch.exp(P.out_ls) * (1.0 if t is None else t) * torch.randn_like(P.x_hat)
+                return x.clamp_(min=-1.0, max=1.0).mul_(0.5).add_(0.5)
             return P.x_hat.clone().clamp_(min=-1.0, max=1.0).mul_(0.5).add_(0.5)

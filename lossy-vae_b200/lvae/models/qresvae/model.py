@@ -36,6 +36,30 @@ class MSEOutputNet(nn.Module):
     sample = mean
 
 
+class GaussianNLLOutputNet(nn.Module):
+    """Output net of `qres34m_lossless` (reference model.py:16-94): two patch_upsample heads turn the decoder's last feature
+    into the mean and log-scale of a per-pixel discretised Gaussian over the 8-bit image (bin 1/127.5); the training /
+    eval loss is its negative log-likelihood, `compress` codes the image's own residual round(x / bin - mean) with rANS
+    against a 128-scale table, which makes the codec lossless.  Parameter container (state-dict keys `conv_mean.0.*`,
+    `conv_scale.0.*` as in the reference); the arithmetic is lvae_gemm (heads) + csrc/outnet.cu, sequenced by the engine."""
+    def __init__(self, conv_mean, conv_scale, bin_size=1 / 127.5):
+        super().__init__()
+        self.conv_mean = conv_mean
+        self.conv_scale = conv_scale
+        assert abs(bin_size - 1 / 127.5) < 1e-12, 'the kernels are built for 8-bit images (bin 1/127.5)'
+        self.bin_size = bin_size
+        self.loss_name = 'nll'
+        self.mse_lmb = 1.0          # the engine's loss assembly is kl + lmb * (per-image out-net loss): lmb = 1 here
+
+    def update(self):
+        """128 scales from the 0.11 scale bound to 20 and their CDF tables (reference model.py:58-66)."""
+        self.discrete_gaussian = entropy_coding.GaussianConditional(None, scale_bound=0.11)
+        self.discrete_gaussian = self.discrete_gaussian.to(device=next(self.parameters()).device)
+        scale_table = torch.exp(torch.linspace(math.log(0.11), math.log(20), steps=128))
+        self.discrete_gaussian.update_scale_table(scale_table)
+        self.discrete_gaussian.update()
+
+
 class VDBlock(nn.Module):
     """c1 1x1 -> c2 -> c3 (3x3 or 1x1) -> c4 1x1, GELU before every conv (reference model.py:120-149): container."""
     def __init__(self, in_ch, hidden_ch=None, out_ch=None, residual=True, use_3x3=True, zero_last=False):
@@ -204,7 +228,7 @@ class HierarchicalVAE(nn.Module):
         stats = OrderedDict()
         stats['loss'] = res['stats'][0]
         stats['kl'] = float(host[1])
-        stats[self.out_net.loss_name] = float(host[2]) * self.out_net.mse_lmb
+        stats[self.out_net.loss_name] = float(host[2]) * self.out_net.mse_lmb      # lambda * MSE | the NLL (lmb = 1)
         stats['bppix'] = float(host[1]) * self.log2_e * imC
         stats['psnr'] = -10 * math.log10(float(host[3]))
         if return_rec:
@@ -267,9 +291,16 @@ class HierarchicalVAE(nn.Module):
         return self.engine.sample(self._lmb(nB), list(latents), (nB, nH, nW), float(temprature))
 
     # ------------------------------------------------------------------ real entropy coding
+    @property
+    def lossless(self):
+        return isinstance(self.out_net, GaussianNLLOutputNet)
+
     def compress_mode(self, mode=True):
         if mode:
             self.decoder.update()
+            if self.lossless:
+                self.out_net.update()
+                self.engine.invalidate()        # the engine keeps a device copy of the out-net's scale table
         self.compressing = mode
 
     @torch.no_grad()
@@ -283,15 +314,20 @@ class HierarchicalVAE(nn.Module):
         out = list(res['strings'])
         width = self.decoder.dec_blocks[0].in_channels
         out.append((nB, width, imH // self.max_stride, imW // self.max_stride))
+        if self.lossless:                       # the image's own residual stream, one string per image (model.py:664-667)
+            out.append(res['out_strings'])
         return out
 
     @torch.no_grad()
     def decompress(self, compressed_object):
         """Inverse of compress -> [B,3,H,W] in [0,1] (reference model.py:670-687)."""
+        out_strings = None
+        if self.lossless:
+            compressed_object, out_strings = compressed_object[:-1], compressed_object[-1]
         nB, _, nH, nW = compressed_object[-1]
         strings = compressed_object[:-1]
         assert len(strings) == self.num_latents, f'decoded={len(strings)}, len={len(compressed_object)}'
-        return self.engine.decompress(self._lmb(nB), strings, (nB, nH, nW))
+        return self.engine.decompress(self._lmb(nB), strings, (nB, nH, nW), out_strings=out_strings)
 
     @torch.no_grad()
     def compress_file(self, img_path, output_path):

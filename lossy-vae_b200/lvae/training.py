@@ -653,7 +653,20 @@ class TrainPath:
         kl = sum(k.reshape(B, -1).sum(1) for k in res['kl']) / ndims
         x_hat = res['x_hat']
         target = im.sub(0.5).mul_(2.0)
-        distortion = (x_hat - target).square().mean(dim=(1, 2, 3))
+        if getattr(self.model, 'lossless', False):
+            # GaussianNLLOutputNet.forward_loss (qresvae/model.py:24-40): the two shuffle heads run on the tcgen05 GEMM (native
+            # backward, conv_backward); the per-pixel likelihood is a handful of ATen elementwise ops on [B,3,H,W]
+            on, eng = self.model.out_net, self.eng
+            heads = [self._conv(h[0], eng.w[id(h)], x_hat, r=h.rate, nchw_out=True, name='up', epi=N.EPI_SHUFFLE_NCHW)
+                     for h in (on.conv_mean, on.conv_scale)]
+            x_hat = heads[0]
+            scale = torch.exp(F.softplus(heads[1] + 16) - 16)
+            dist = torch.distributions.Normal(x_hat, scale)
+            mass = dist.cdf(target + 0.5 * on.bin_size) - dist.cdf(target - 0.5 * on.bin_size)
+            log_prob = torch.where(mass > 1e-6, torch.log(mass.clamp(min=1e-8)), dist.log_prob(target) + math.log(on.bin_size))
+            distortion = -log_prob.mean(dim=(1, 2, 3))
+        else:
+            distortion = (x_hat - target).square().mean(dim=(1, 2, 3))
         loss = (kl + lmb * distortion).mean(0)
         res['loss'] = loss
         if not stats:
@@ -665,6 +678,26 @@ class TrainPath:
         res.update(loss=loss, kl_mean=float(host[0]), mse=float(host[1]), im_mse=float(host[2]),
                    lmb_mse=float(host[3]), im_hat=im_hat, kl_img=kl.detach())
         return res
+
+
+def gpu_random_crop_flip(src_u8, crop, hflip=True, generator=None, out=None):
+    """The reference's training transform -- RandomCrop(crop) + RandomHorizontalFlip(0.5) + ToTensor
+    (lvae/datasets/image.py:45-56, 'crop=256,hflip=True' of train-var-rate.py) -- on the GPU: src_u8 [B,3,Hs,Ws] uint8 on
+    the device (decoded images, e.g. a pinned-host batch copied once) -> [B,3,crop,crop] fp32 in [0,1].  Crop origins and
+    flip flags are drawn on the device (torch.randint with `generator`), one launch does the rest: no per-sample PIL work,
+    no float32 H2D copy (1 byte per element crosses PCIe instead of 4)."""
+    assert src_u8.is_cuda and src_u8.dtype == torch.uint8 and src_u8.dim() == 4 and src_u8.shape[1] == 3
+    src_u8 = src_u8.contiguous()
+    B, _, Hs, Ws = src_u8.shape
+    dev = src_u8.device
+    y0 = torch.randint(0, Hs - crop + 1, (B,), device=dev, generator=generator, dtype=torch.int32)
+    x0 = torch.randint(0, Ws - crop + 1, (B,), device=dev, generator=generator, dtype=torch.int32)
+    flip = (torch.rand(B, device=dev, generator=generator) < 0.5).to(torch.uint8) if hflip else torch.zeros(B, device=dev, dtype=torch.uint8)
+    out = torch.empty(B, 3, crop, crop, device=dev) if out is None else out
+    N.check(N.lib().lvae_crop_flip_u8(src_u8.data_ptr(), y0.data_ptr(), x0.data_ptr(), flip.data_ptr(), out.data_ptr(),
+                                      B, Hs, Ws, crop, torch.cuda.current_stream(dev).cuda_stream), 'crop_flip')
+    N.launch_count += 1
+    return out, (y0, x0, flip)
 
 
 def allreduce_flat_gradients(params, group, world):

@@ -183,6 +183,47 @@ def main_qres():
                         cdf_length=dg._cdf_length.numpy(), offset=dg._offset.numpy())
 
 
+def main_lossless():
+    """qres34m_lossless fixtures (GaussianNLLOutputNet, qresvae/model.py:16-94, zoo.py:63-114): the unmodified reference's
+    eval forward (loss = kl + nll), train forward with torch.manual_seed(noise_seed), compress (latent layers + the image's
+    own residual stream) and decompress on 8-bit images."""
+    from oracle_inputs import LOSSLESS_CASES, make_input_8bit
+    ref = ref_loader.load_reference()
+    torch.manual_seed(0)
+    model = ref.get_model('qres34m_lossless').eval()
+    sd = O.sensitised_state_dict(Q.qres_param_shapes(Q.qres34m_lossless_arch()), seed=0)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all('discrete_gaussian' in k for k in missing)
+    model.compress_mode()
+    for name, (kind, nB, H, W, seed, nseed) in LOSSLESS_CASES.items():
+        im = make_input_8bit(kind, nB, H, W, seed)
+        with torch.no_grad():
+            stats = model(im, return_rec=True)
+            lat = model.forward_get_latents(im)
+            obj = model.compress(im)
+            dec = model.decompress(obj)
+            model.train()
+            torch.manual_seed(nseed)
+            tstats = model(im)
+            model.eval()
+        rec = dict(loss=np.float32(stats['loss'].item()), kl=np.float64(stats['kl']), nll=np.float64(stats['nll']),
+                   bppix=np.float64(stats['bppix']), psnr=np.float64(stats['psnr']), im_hat=stats['im_hat'].numpy(),
+                   dec_im_hat=dec.numpy(), shape=np.array(obj[-2]),
+                   kl_per_image=np.stack([st['kl'].sum(dim=(1, 2, 3)).numpy() for st in lat]),
+                   train_loss=np.float32(tstats['loss'].item()), train_nll=np.float64(tstats['nll']))
+        for li in range(len(obj) - 2):
+            for b in range(nB):
+                rec[f'bytes{li}_{b}'] = np.frombuffer(obj[li][b], dtype=np.uint8)
+        for b in range(nB):
+            rec[f'final_bytes_{b}'] = np.frombuffer(obj[-1][b], dtype=np.uint8)
+        np.savez_compressed(OUT / f'{name}.npz', **rec)
+        print(name, 'loss', float(rec['loss']), 'nll', float(rec['nll']), 'bppix', float(rec['bppix']),
+              'lossless', bool(torch.equal((dec * 255).round(), (im * 255).round())), 'final bytes', [len(s) for s in obj[-1]])
+    dg = model.out_net.discrete_gaussian
+    np.savez_compressed(OUT / 'qresll_tables.npz', scale_table=dg.scale_table.numpy(), cdf=dg._quantized_cdf.numpy(),
+                        cdf_length=dg._cdf_length.numpy(), offset=dg._offset.numpy())
+
+
 from gen_golden_cases import GRAD_CASES, grad_probe   # noqa: E402
 
 
@@ -223,3 +264,5 @@ if __name__ == '__main__':
         main_qres()
     if which in ('grads', 'all'):
         main_grads()
+    if which in ('lossless', 'all'):
+        main_lossless()

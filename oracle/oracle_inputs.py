@@ -48,3 +48,12 @@ QRES_CASES = {
     'qres_rand_2x64x128': ('rand', 2, 64, 128, 3, 21),
     'qres_synth_1x192x256': ('synth', 1, 192, 256, 12, 22),
 }
+
+# qres34m_lossless fixtures: name -> (kind, nB, H, W, image seed, train-noise seed); images are rounded to 8 bits
+LOSSLESS_CASES = {
+    'qresll_synth_2x64x128': ('synth', 2, 64, 128, 9, 31),
+}
+
+
+def make_input_8bit(kind, nB, H, W, seed):
+    return (make_input(kind, nB, H, W, seed) * 255).round() / 255

@@ -38,6 +38,25 @@ def qres34m_arch():
     return dict(enc=enc, dec=dec, im_shift=-0.4546259594901961, im_scale=3.67572653978347, max_stride=64)
 
 
+def qres34m_lossless_arch():
+    """`qres34m_lossless` (qresvae/zoo.py:63-114): qres34m without the final patch up-sampler; the decoder's H/4 feature
+    feeds GaussianNLLOutputNet's two patch_upsample(192, 3, rate=4) heads (qresvae/model.py:16-94)."""
+    a = qres34m_arch()
+    assert a['dec'][-1] == ('up', 192, 3, 4)
+    a['dec'] = a['dec'][:-1]
+    a['out'] = 'nll'
+    return a
+
+
+def lossless_scale_table():
+    """GaussianNLLOutputNet.update (qresvae/model.py:58-66): 128 scales from the 0.11 scale bound to 20."""
+    t = torch.exp(torch.linspace(math.log(0.11), math.log(20), steps=128))
+    return torch.Tensor(tuple(float(s) for s in t))
+
+
+BIN = 1 / 127.5
+
+
 def qres_param_shapes(arch=None):
     arch = arch or qres34m_arch()
     out = []
@@ -85,6 +104,10 @@ def qres_param_shapes(arch=None):
             kz = 3 if k3 else 1
             out += [(p + 'z_proj.0.weight', (hid // 2, zd, kz, kz)), (p + 'z_proj.0.bias', (hid // 2,)),
                     (p + 'z_proj.2.weight', (W, hid // 2, 1, 1)), (p + 'z_proj.2.bias', (W,))]
+    if arch.get('out') == 'nll':
+        W = arch['dec'][-1][1]
+        for head in ('conv_mean', 'conv_scale'):
+            out += [(f'out_net.{head}.0.weight', (3 * 16, W, 1, 1)), (f'out_net.{head}.0.bias', (3 * 16,))]
     return out
 
 
@@ -178,9 +201,18 @@ def qres_forward(sd, im, lmb, arch=None, mode='eval', noise=None):
             li += 1
             feature = feature + z_proj(sd, p, z)
             feature = convnext_block(sd, p + 'resnet_end.', feature)
-    x_hat = feature
-    mse = F.mse_loss(x_hat, x_target, reduction='none').mean(dim=(1, 2, 3))
-    out_loss = mse * float(lmb)
+    if arch.get('out') == 'nll':
+        # GaussianNLLOutputNet.forward_loss (qresvae/model.py:24-40)
+        p_mean = F.pixel_shuffle(F.conv2d(feature, sd['out_net.conv_mean.0.weight'], sd['out_net.conv_mean.0.bias']), 4)
+        p_ls = F.pixel_shuffle(F.conv2d(feature, sd['out_net.conv_scale.0.weight'], sd['out_net.conv_scale.0.bias']), 4)
+        p_ls = F.softplus(p_ls + 16) - 16
+        log_prob = O.gaussian_log_prob_mass(p_mean, torch.exp(p_ls), x=x_target, bin_size=BIN, prob_clamp=1e-6)
+        out_loss = -log_prob.mean(dim=(1, 2, 3))
+        x_hat = p_mean
+    else:
+        x_hat = feature
+        mse = F.mse_loss(x_hat, x_target, reduction='none').mean(dim=(1, 2, 3))
+        out_loss = mse * float(lmb)
     kls = [r['kl'].sum(dim=(1, 2, 3)) for r in records]
     ndims = imC * imH * imW
     kl = sum(kls) / ndims
@@ -189,7 +221,53 @@ def qres_forward(sd, im, lmb, arch=None, mode='eval', noise=None):
     im_hat = x_hat.clone().clamp_(min=-1.0, max=1.0).mul_(0.5).add_(0.5)
     im_mse = F.mse_loss(im_hat, im, reduction='mean')
     return dict(loss=loss, kl=nats_per_dim, mse=out_loss.mean(0).item(), bppix=nats_per_dim * O.LOG2_E * imC,
-                psnr=-10 * math.log10(im_mse.item()), kl_per_image=kl, x_hat=x_hat, im_hat=im_hat, records=records)
+                psnr=-10 * math.log10(im_mse.item()), kl_per_image=kl, x_hat=x_hat, im_hat=im_hat, records=records,
+                feature=feature, out_loss=out_loss)
+
+
+def lossless_tables():
+    return O.build_cdf_tables(lossless_scale_table(), cdf=O.std_normal_cdf_erfc)
+
+
+def _prepare_codec(sd, feature, x=None):
+    """GaussianNLLOutputNet._preapre_codec (qresvae/model.py:68-79)."""
+    pm = F.pixel_shuffle(F.conv2d(feature, sd['out_net.conv_mean.0.weight'], sd['out_net.conv_mean.0.bias']), 4)
+    pm = torch.round(pm * 127.5 + 127.5) / 127.5 - 1
+    plogv = F.pixel_shuffle(F.conv2d(feature, sd['out_net.conv_scale.0.weight'], sd['out_net.conv_scale.0.bias']), 4)
+    pm = pm / BIN
+    plogv = plogv - math.log(BIN)
+    if x is not None:
+        x = x / BIN
+    return pm, plogv, x
+
+
+@torch.no_grad()
+def lossless_compress(sd, im, arch=None, tables=None, out_tables=None):
+    """HierarchicalVAE.compress with a GaussianNLLOutputNet (qresvae/model.py:649-668,81-86): latent strings, feature
+    shape, then the image's own residual symbols round(x / bin - pm) coded against the out-net's 128-scale tables."""
+    arch = arch or qres34m_lossless_arch()
+    out_tables = out_tables or lossless_tables()
+    fw = qres_forward(sd, im, 0.0, arch)
+    obj = qres_compress(sd, im, arch, tables)
+    pm, plogv, x = _prepare_codec(sd, fw['feature'], (im - 0.5) * 2.0)
+    idx = O.build_indexes(torch.exp(plogv), scale_table=lossless_scale_table())
+    sym = torch.round(x - pm).to(torch.int32)
+    obj.append([O.rans_encode(sym[b].reshape(-1).tolist(), idx[b].reshape(-1).tolist(), *out_tables) for b in range(im.shape[0])])
+    return obj, dict(sym=sym, idx=idx, pm=pm)
+
+
+@torch.no_grad()
+def lossless_decompress(sd, obj, arch=None, tables=None, out_tables=None):
+    """HierarchicalVAE.decompress, lossless branch (qresvae/model.py:670-687,88-94) -> image in [0, 1]."""
+    arch = arch or qres34m_lossless_arch()
+    out_tables = out_tables or lossless_tables()
+    feature = qres_decompress(sd, obj[:-1], arch, tables, return_feature=True)
+    pm, plogv, _ = _prepare_codec(sd, feature)
+    idx = O.build_indexes(torch.exp(plogv), scale_table=lossless_scale_table())
+    nB = pm.shape[0]
+    vals = [O.rans_decode(obj[-1][b], idx[b].reshape(-1).tolist(), *out_tables) for b in range(nB)]
+    x_hat = (torch.tensor(vals, dtype=torch.int32).reshape(pm.shape).type_as(pm) + pm) * BIN
+    return x_hat.clone().clamp_(min=-1.0, max=1.0).mul_(0.5).add_(0.5)
 
 
 def qres_tables():
@@ -212,7 +290,7 @@ def qres_compress(sd, im, arch=None, tables=None):
 
 
 @torch.no_grad()
-def qres_decompress(sd, obj, arch=None, tables=None):
+def qres_decompress(sd, obj, arch=None, tables=None, return_feature=False):
     """HierarchicalVAE.decompress (qresvae/model.py:670-687)."""
     arch = arch or qres34m_arch()
     tables = tables or qres_tables()
@@ -233,4 +311,6 @@ def qres_decompress(sd, obj, arch=None, tables=None):
             z = torch.tensor(vals, dtype=torch.int32).reshape(pm.shape).type_as(pm) + pm
             feature = feature + z_proj(sd, p, z)
             feature = convnext_block(sd, p + 'resnet_end.', feature)
+    if return_feature:
+        return feature
     return feature.clone().clamp_(min=-1.0, max=1.0).mul_(0.5).add_(0.5)

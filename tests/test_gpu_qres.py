@@ -153,3 +153,99 @@ def test_qres_against_live_oracle_at_config_shape_and_batch16_invariance(qres_mo
     lat1 = qres_model.forward_get_latents(im1.to(DEV))
     for a, b in zip(lat16, lat1):
         assert torch.equal(a['z'][5], b['z'][0]) and torch.equal(a['kl'][5], b['kl'][0])
+
+
+# ----------------------------------------------------------------------------- qres34m_lossless
+@pytest.fixture(scope='module')
+def lossless_model(native_lib):
+    import lvae
+    torch.manual_seed(0)
+    model = lvae.get_model('qres34m_lossless')
+    sd = O.sensitised_state_dict(Q.qres_param_shapes(Q.qres34m_lossless_arch()), seed=0)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all('discrete_gaussian' in k for k in missing), (missing, unexpected)
+    model = model.to(DEV).eval()
+    model.compress_mode()
+    return model, sd
+
+
+def test_lossless_forward_and_codec_match_reference_fixture(lossless_model, golden):
+    """GaussianNLLOutputNet path (reference qresvae/model.py:16-94): loss = kl + nll against the fixture of the unmodified
+    reference, the compressed object (12 latent layers + feature shape + the image's own residual stream) byte for byte,
+    and decompress(compress(x)) == x exactly on 8-bit images."""
+    from oracle_inputs import LOSSLESS_CASES, make_input_8bit
+    model, sd = lossless_model
+    name = 'qresll_synth_2x64x128'
+    g = golden(name)
+    kind, nB, H, W, seed, nseed = LOSSLESS_CASES[name]
+    im_cpu = make_input_8bit(kind, nB, H, W, seed)
+    im = im_cpu.to(DEV)
+    st = model(im, return_rec=True)
+    assert abs(st['loss'].item() - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
+    assert abs(st['nll'] - float(g['nll'])) <= 1e-5 * float(g['nll'])
+    assert abs(st['bppix'] - float(g['bppix'])) <= bpp_tol(H, W) and abs(st['psnr'] - float(g['psnr'])) <= PSNR_TOL
+    assert (st['im_hat'].cpu() - torch.from_numpy(g['im_hat'])).abs().max().item() < 1e-5
+    obj = model.compress(im)
+    assert len(obj) == 14 and tuple(obj[-2]) == tuple(g['shape']) and len(obj[-1]) == nB
+    same = all(obj[li][b] == g[f'bytes{li}_{b}'].tobytes() for li in range(12) for b in range(nB))
+    rec = model.decompress(obj)
+    assert torch.equal((rec.cpu() * 255).round(), (im_cpu * 255).round())           # lossless, whatever the latents did
+    # the residual stream: its means round(p_mean * 127.5 + 127.5) and scale-table indexes come out of two GEMMs, so -- like
+    # the latents' symbols -- they can differ from the CPU reference at rounding boundaries.  Compare them element by
+    # element with the oracle's; when none differs the stream must be the reference's byte for byte.
+    fw = Q.qres_forward(sd, im_cpu, 0.0, Q.qres34m_lossless_arch())
+    pm_o, plogv_o, x_o = Q._prepare_codec(sd, fw['feature'], (im_cpu - 0.5) * 2.0)
+    idx_o = O.build_indexes(torch.exp(plogv_o), scale_table=Q.lossless_scale_table())
+    P = model.engine._plans[(nB, H, W, 'compress', False)]
+    torch.cuda.synchronize()
+    d_pm = (P.on_pm.cpu().view_as(pm_o) != pm_o)
+    d_idx = (P.on_idx.cpu().view_as(idx_o) != idx_o)
+    n_diff = int(d_pm.sum()) + int(d_idx.sum())
+    assert n_diff <= 1e-3 * pm_o.numel(), (int(d_pm.sum()), int(d_idx.sum()))
+    if d_pm.any():      # only where p_mean * 127.5 + 127.5 sits on a .5 boundary (the two sides differ by exactly one bin)
+        assert float((P.on_pm.cpu().view_as(pm_o) - pm_o)[d_pm].abs().max()) == 1.0
+    if same and n_diff == 0:
+        for b in range(nB):
+            assert obj[-1][b] == g[f'final_bytes_{b}'].tobytes(), b
+        assert (rec.cpu() - torch.from_numpy(g['dec_im_hat'])).abs().max().item() < 1e-6
+    print(f'lossless residual stream: {int(d_pm.sum())} mean and {int(d_idx.sum())} index differences of {pm_o.numel()}')
+    parity_log(test='qres34m_lossless fixture (unmodified reference)', case=name, precision=model.precision,
+               symbols=nB * 3 * H * W, flips=n_diff, dbpp=abs(st['bppix'] - float(g['bppix'])),
+               dpsnr=abs(st['psnr'] - float(g['psnr'])), bpp_tol=bpp_tol(H, W))
+    # training branch with the reference's noise (launch-plan forward, no autograd) and with autograd recording
+    model.train()
+    try:
+        noise = _qres_noise(Q, Q.qres34m_lossless_arch(), nB, H, W, nseed)
+        with torch.no_grad():
+            tr = model(im, noise=noise)
+        assert abs(tr['loss'].item() - float(g['train_loss'])) <= 2e-5 * abs(float(g['train_loss']))
+        tg = model(im, noise=noise)
+        assert tg['loss'].requires_grad and abs(tg['loss'].item() - float(g['train_loss'])) <= 2e-5 * abs(float(g['train_loss']))
+        tg['loss'].backward()
+        gmean = model.out_net.conv_mean[0].weight.grad
+        assert gmean is not None and bool(torch.isfinite(gmean).all()) and float(gmean.abs().max()) > 0
+    finally:
+        model.eval()
+        model.zero_grad(set_to_none=True)
+
+
+def test_lossless_file_roundtrip_and_live_oracle_on_a_photo_shaped_image(lossless_model, tmp_path):
+    """compress_file / decompress_file on a non-aligned 8-bit PNG (pad + crop, pickle container) reproduce the file exactly;
+    a 192 x 256 forward agrees with the oracle run live on the host."""
+    from PIL import Image
+    from oracle_inputs import make_input_8bit
+    model, sd = lossless_model
+    arr = (make_input('synth', 1, 100, 150, 8)[0].permute(1, 2, 0).numpy() * 255).round().astype(np.uint8)
+    src, bits = tmp_path / 'x.png', tmp_path / 'x.bits'
+    Image.fromarray(arr).save(src)
+    model.compress_file(src, bits)
+    out = model.decompress_file(bits)
+    assert tuple(out.shape) == (1, 3, 100, 150)
+    assert np.array_equal((out.cpu()[0].permute(1, 2, 0).numpy() * 255).round().astype(np.uint8), arr)
+    im = make_input_8bit('synth', 1, 192, 256, 13)
+    ref = Q.qres_forward(sd, im, 0.0, Q.qres34m_lossless_arch())
+    st = model(im.to(DEV))
+    assert abs(st['loss'].item() - ref['loss'].item()) <= 1e-5 * abs(ref['loss'].item())
+    assert abs(st['nll'] - ref['mse']) <= 1e-5 * ref['mse'] and abs(st['bppix'] - ref['bppix']) <= bpp_tol(192, 256)
+    smp = model.uncond_sample((1, 1, 1), temprature=0.5)
+    assert tuple(smp.shape) == (1, 3, 64, 64) and bool(torch.isfinite(smp).all())

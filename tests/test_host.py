@@ -441,3 +441,36 @@ def test_gemm_desc_layout_matches_the_header_and_the_integration_stub(tmp_path):
     stub_names = re.findall(r"\('(\w+)',", block)
     assert stub_names == names, (stub_names, names)
     assert f'C.sizeof(GemmDesc) == {out[0]}' in block
+
+
+def test_lossless_model_surface_state_dict_and_tables(native_lib, golden):
+    """qres34m_lossless (reference qresvae/zoo.py:63-114, model.py:16-94): parameter names / shapes of the
+    reference (incl. out_net.conv_mean / conv_scale), the seeded default init equal to the live reference's when it is
+    present, and the 128-scale table set GaussianNLLOutputNet.update() builds."""
+    import lvae
+    import qres_oracle as Q
+    import ref_loader
+    torch.manual_seed(0)
+    m = lvae.get_model('qres34m_lossless')
+    want = dict(Q.qres_param_shapes(Q.qres34m_lossless_arch()))
+    assert sorted(k for k, _ in m.named_parameters()) == sorted(want)
+    for k, p in m.named_parameters():
+        assert tuple(p.shape) == tuple(want[k]), k
+    assert m.lossless and m.out_net.loss_name == 'nll' and m.num_latents == 12
+    mine = {k: v.clone() for k, v in m.state_dict().items()}
+    m.compress_mode()
+    t = golden('qresll_tables')
+    dg = m.out_net.discrete_gaussian
+    assert np.array_equal(dg.scale_table.numpy(), t['scale_table'])
+    cdf, clen, off = dg.host_tables()
+    assert np.array_equal(cdf, t['cdf']) and np.array_equal(clen, t['cdf_length']) and np.array_equal(off, t['offset'])
+    if ref_loader.available():
+        ref = ref_loader.load_reference()
+        try:
+            torch.manual_seed(0)
+            r = ref.get_model('qres34m_lossless')
+            for k, v in r.state_dict().items():
+                if 'discrete_gaussian' not in k:
+                    assert torch.equal(v, mine[k]), k
+        finally:
+            ref_loader.unload_reference()

@@ -253,3 +253,58 @@ def test_oracle_autograd_matches_reference_gradients(fam, golden):
         assert abs(float(gr.norm()) - norm) <= 1e-4 * norm + 1e-12, name
         pr = grad_probe(name, gr.shape).double()
         assert abs(float((gr * pr).sum()) - dot) <= 1e-4 * norm * float(pr.norm()) + 1e-12, name
+
+
+# ----------------------------------------------------------------------------- qres34m_lossless (GaussianNLLOutputNet)
+def test_lossless_oracle_matches_golden(golden):
+    """oracle/qres_oracle.py's lossless variant (qresvae/model.py:16-94, zoo.py:63-114) against the fixture
+    the unmodified reference produced: loss = kl + nll, train loss with the reference's noise, every bit stream incl. the
+    image's own residual stream, the decoded image, and the round trip being lossless on 8-bit input."""
+    import qres_oracle as Q
+    from oracle_inputs import LOSSLESS_CASES, make_input_8bit
+    name = 'qresll_synth_2x64x128'
+    g = golden(name)
+    kind, nB, H, W, seed, nseed = LOSSLESS_CASES[name]
+    arch = Q.qres34m_lossless_arch()
+    sd = O.sensitised_state_dict(Q.qres_param_shapes(arch), seed=0)
+    im = make_input_8bit(kind, nB, H, W, seed)
+    out = Q.qres_forward(sd, im, 0.0, arch)
+    assert np.float32(out['loss'].item()) == g['loss'] and out['mse'] == float(g['nll'])
+    assert out['bppix'] == float(g['bppix']) and out['psnr'] == float(g['psnr'])
+    assert torch.equal(out['im_hat'], torch.from_numpy(g['im_hat']))
+    tr = Q.qres_forward(sd, im, 0.0, arch, mode='train', noise=_qres_noise(Q, arch, nB, H, W, nseed))
+    assert np.float32(tr['loss'].item()) == g['train_loss'] and tr['mse'] == float(g['train_nll'])
+    t = golden('qresll_tables')
+    assert np.array_equal(Q.lossless_scale_table().numpy(), t['scale_table'])
+    cdf, length, offset = Q.lossless_tables()
+    assert np.array_equal(cdf.numpy(), t['cdf']) and np.array_equal(length.numpy(), t['cdf_length'])
+    obj, _ = Q.lossless_compress(sd, im[:1], arch)          # one image: the pure-python coder is slow
+    for li in range(12):
+        assert obj[li][0] == g[f'bytes{li}_0'].tobytes()
+    assert obj[-1][0] == g['final_bytes_0'].tobytes()
+    dec = Q.lossless_decompress(sd, obj, arch)
+    assert torch.equal(dec, torch.from_numpy(g['dec_im_hat'][:1]))
+    assert torch.equal((dec * 255).round(), (im[:1] * 255).round())          # lossless
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_lossless_oracle_equals_live_reference():
+    import qres_oracle as Q
+    from oracle_inputs import make_input_8bit
+    arch = Q.qres34m_lossless_arch()
+    shapes = Q.qres_param_shapes(arch)
+    sd = O.sensitised_state_dict(shapes, seed=0)
+    ref = ref_loader.load_reference()
+    try:
+        torch.manual_seed(0)
+        model = ref.get_model('qres34m_lossless').eval()
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not unexpected and all('discrete_gaussian' in k for k in missing)
+        assert sorted(k for k, _ in model.named_parameters()) == sorted(k for k, _ in shapes)
+        im = make_input_8bit('rand', 1, 64, 64, 5)
+        with torch.no_grad():
+            st = model(im)
+        out = Q.qres_forward(sd, im, 0.0, arch)
+        assert st['loss'].item() == out['loss'].item() and st['nll'] == out['mse'] and st['bppix'] == out['bppix']
+    finally:
+        ref_loader.unload_reference()
