@@ -9,8 +9,9 @@ per-layer quantise + likelihood, loss assembly) on N B200s, next to the referenc
 One JSON line on stdout (rank 0).  A "step" is one eval `forward()` of BASELINE.json configs[1]:
 qarv_base, synthetic 512x768 RGB, batch 8 per GPU (weak scaling: every rank runs its own batch, no
 data-path collective -- SURVEY 8(e)).  `value` = images/s with the batch resident in HBM (CUDA-graph
-replay of the launch plan), `e2e` = images/s through `model.forward(batch_on_pinned_host, lmb)` with the
-H2D image copy and the D2H stats read inside the timed region.  `roofline` is the dominant kernel
+replay of the launch plan), `e2e` = images/s through the public streaming call `model.forward_stream(batches on pinned
+host memory, lmb)` with every step's H2D image copy and D2H stats read inside the timed region (the copy of step i+1 overlaps
+the kernels of step i); `e2e.sync_value` = the same through the blocking, reference-shaped `model.forward(batch, lmb)`.  `roofline` is the dominant kernel
 class (the dense contractions) measured per launch with CUDA events; `roofline_entropy` the fused
 latent kernel against HBM bandwidth; `cpu_baseline` the oracle (torch-CPU restatement of the
 reference, oracle/lvae_oracle.py) timed on this box's host cores on a bounded sample.
@@ -567,13 +568,32 @@ def main():
         out = call()
     e3.record(st)
     barrier()
-    ms_e2e = e2.elapsed_time(e3)
+    ms_e2e_sync = e2.elapsed_time(e3)
+    # the same work through the pipelined public call (model.forward_stream): every step still copies its own batch from
+    # pinned host memory and reads its own results back, but step i+1's H2D copy overlaps step i's kernels
+    def feed(n):
+        for _ in range(n):
+            yield im_host
+    stream = (lambda n: model.forward_stream(feed(n))) if qres else (lambda n: model.forward_stream(feed(n), lmb=lmb_dev))
+    for out_s in stream(warmup):
+        pass
+    barrier()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e4.record(st)
+    n_out = 0
+    for out_s in stream(args.steps):
+        n_out += 1
+    e5.record(st)
+    barrier()
+    assert n_out == args.steps
+    ms_e2e = e4.elapsed_time(e5)
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_dev, ms_e2e, ms_e2e_sync], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = t.tolist()
+    ms_dev, ms_e2e, ms_e2e_sync = t.tolist()
 
     if rank == 0:
         pk = peaks()
@@ -650,7 +670,13 @@ def main():
                        'l2': 'no flush: per-step working set (weights 374 MB + activations > 1 GB) exceeds the 126 MB L2',
                        'dense_gflop_per_image': DENSE_GFLOP_PER_IMAGE},
             'e2e': {'value': n_img / (ms_e2e / 1e3), 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,
-                    'h2d_bytes_per_step': im_host.numel() * 4, 'd2h_bytes_per_step': P.stats_host.numel() * 4 + 8},
+                    'h2d_bytes_per_step': im_host.numel() * 4, 'd2h_bytes_per_step': P.stats_host.numel() * 4 + 8,
+                    'call': 'model.forward_stream(batches on pinned host memory): one H2D copy of the batch and one D2H read of '
+                            'its results per step, step i+1 copied in on a second stream while step i runs',
+                    'sync_value': n_img / (ms_e2e_sync / 1e3), 'sync_ms_per_step': ms_e2e_sync / args.steps,
+                    'sync_call': 'model.forward(batch on pinned host memory): the reference-shaped blocking call, copy -> '
+                                 'kernels -> read-back in series',
+                    'stream_bppix': out_s['bppix'], 'stream_psnr': out_s['psnr']},
             'gpu_launches': launches, 'launches_per_step': launches // max(1, args.steps),
             'clocks': clocks, 'roofline': roof, 'roofline_entropy': roof_e, 'roofline_dwln': roof_d,
             'tensor_frac_of_step': DENSE_GFLOP_PER_IMAGE * B / (ms_dev / args.steps) / pk['tensor_sustained'],

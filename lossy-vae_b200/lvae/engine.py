@@ -822,6 +822,88 @@ class QarvEngine:
                 res['z'] = [self._nchw(z, B, l) for z, l in zip(P.z, P.layout)]
             return res
 
+    def _stream_slots(self, P, depth):
+        """Per-plan staging for run_stream: `depth` device copies of the input batch, pinned result slots and events."""
+        S = getattr(P, 'stream_slots', None)
+        if S is None or len(S['stage']) != depth:
+            n_lay = len(P.layout)
+            S = dict(stage=[torch.empty_like(P.im) for _ in range(depth)],
+                     dev=[torch.zeros(2 + n_lay, dtype=torch.float32, device=self.device) for _ in range(depth)],
+                     host=[torch.empty(P.stats.numel(), dtype=torch.float32, pin_memory=True) for _ in range(depth)],
+                     host_x=[torch.empty(2 + n_lay, dtype=torch.float32, pin_memory=True) for _ in range(depth)],
+                     ready=[torch.cuda.Event() for _ in range(depth)], free=[torch.cuda.Event() for _ in range(depth)],
+                     done=[torch.cuda.Event() for _ in range(depth)], n=0)
+            P.stream_slots = S
+        return S
+
+    @torch.no_grad()
+    def run_stream(self, items, mode='eval', depth=2, check_range=True):
+        """Pipelined form of run(): `items` yields (im [B,3,H,W] fp32 in [0,1], lmb [B]); one dict(stats_host[, kl_layers_host])
+        per item comes back, in order, `depth - 1` items late.  The host->device copy of item i+1 runs on a copy stream
+        into a staging slot while the launch plan of item i executes; the results of item i travel to a pinned slot
+        behind its plan, so every item still pays its own H2D and D2H copy but neither sits on the critical path.
+        Same kernels, same plan, same numbers as run() (tests/test_gpu_model.py::test_forward_stream_equals_forward)."""
+        assert mode in ('eval', 'train') and depth >= 1
+        self.refresh_weights()
+        from collections import deque
+        inflight, cur_key = deque(), None
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            if getattr(self, '_copy_stream', None) is None:
+                self._copy_stream = torch.cuda.Stream(self.device)
+            cs = self._copy_stream
+            for im, lmb in items:
+                B, _, H, W = im.shape
+                key = (B, H, W, mode, False)
+                while inflight and (key != cur_key or len(inflight) >= depth):     # a new shape drains the pipeline first:
+                    yield self._collect(*inflight.popleft(), check_range)          # its plan may evict the one in flight
+                cur_key = key
+                P = self._get_plan(key, lambda: self._build_forward_plan(B, H, W, mode, False))
+                S = self._stream_slots(P, depth)
+                k = S['n'] % depth
+                S['n'] += 1
+                if im.device.type == 'cpu':                  # H2D on the copy stream, into this item's staging slot
+                    cs.wait_event(S['free'][k])
+                    with torch.cuda.stream(cs):
+                        S['stage'][k].copy_(im, non_blocking=True)
+                        S['ready'][k].record(cs)
+                    cur.wait_event(S['ready'][k])
+                    P.im.copy_(S['stage'][k], non_blocking=True)
+                    S['free'][k].record(cur)
+                else:
+                    P.im.copy_(im, non_blocking=True)
+                P.lmb.copy_(lmb.to(torch.float32), non_blocking=True)
+                dv = S['dev'][k]
+                if check_range:
+                    lo, hi = torch.aminmax(P.im)
+                    dv[0].copy_(lo); dv[1].copy_(hi)
+                for nz in P.noise:
+                    if self.family == 'rd':
+                        nz.normal_()
+                    else:
+                        nz.uniform_(-0.5, 0.5)
+                self._launch(P)
+                S['host'][k].copy_(P.stats, non_blocking=True)
+                if self.family == 'qres':
+                    for li, (_, _, np_, off, _, _) in enumerate(P.layout):
+                        dv[2 + li].copy_(P.kl_partial[:, off:off + np_].sum(dim=1).mean(0))
+                S['host_x'][k].copy_(dv, non_blocking=True)
+                S['done'][k].record(cur)
+                inflight.append((P, k))
+            while inflight:
+                yield self._collect(*inflight.popleft(), check_range)
+
+    def _collect(self, P, k, check_range):
+        S = P.stream_slots
+        S['done'][k].synchronize()
+        x = S['host_x'][k].numpy().copy()
+        if check_range:
+            self._assert_range((x[0], x[1]))
+        res = dict(stats_host=S['host'][k].numpy().copy())
+        if self.family == 'qres':
+            res['kl_layers_mean_host'] = x[2:]
+        return res
+
     @staticmethod
     def _assert_range(rng):
         # reference: assert 0 <= im.min() <= im.max() <= 1 (lvae/models/qarv/model.py:220)

@@ -196,6 +196,29 @@ class VariableRateLossyVAE(nn.Module):
             stats['im_hat'] = res['im_hat']
         return stats
 
+    @torch.no_grad()
+    def forward_stream(self, batches, lmb=None, depth=2):
+        """Throughput form of forward() for evaluation loops (an extension: the reference has one synchronous call per
+        batch).  `batches` yields image batches ([B,3,H,W] fp32 in [0,1]; pinned host memory for asynchronous copies --
+        or (im, label) pairs); one OrderedDict(loss, bppix, mse, psnr -- all Python floats) per batch comes back, in
+        order.  Batch i+1 is copied to the device while batch i runs (lvae.engine.run_stream); values equal forward()'s.
+        lmb: None (sampled per batch), a float, or a [B] tensor used for every batch."""
+        assert not (self.training and torch.is_grad_enabled()), 'forward_stream is an inference path'
+        shapes = []
+
+        def items():
+            for batch in batches:
+                im = batch[0] if isinstance(batch, (tuple, list)) else batch
+                self._check_image(im)
+                nB = im.shape[0]
+                l = self.sample_lmb(n=nB) if lmb is None else self.expand_to_tensor(lmb, n=nB)
+                shapes.append(im.shape[1])
+                yield im, l.to(self._device(), torch.float32)
+        for i, res in enumerate(self.engine.run_stream(items(), mode='train' if self.training else 'eval', depth=depth)):
+            host, imC = res['stats_host'], shapes[i]
+            yield OrderedDict([('loss', float(host[0])), ('bppix', float(host[1]) * self.log2_e * imC),
+                               (self.distortion_name, float(host[2])), ('psnr', -10 * math.log10(float(host[3])))])
+
     @property
     def train_path(self):
         if self.__dict__.get('_train_path') is None:

@@ -235,6 +235,30 @@ class HierarchicalVAE(nn.Module):
             stats['im_hat'] = res['im_hat']
         return stats
 
+    @torch.no_grad()
+    def forward_stream(self, batches, depth=2):
+        """Throughput form of forward() for evaluation loops (an extension; see
+        lvae.models.qarv.model.VariableRateLossyVAE.forward_stream): one OrderedDict(loss, kl, mse | nll, bppix, psnr -- Python
+        floats) per batch, batch i+1 copied to the device while batch i runs; `_stats_log` holds the last batch's rates."""
+        assert not (self.training and torch.is_grad_enabled()), 'forward_stream is an inference path'
+        mode = 'train' if self.training else 'eval'
+        shapes = []
+
+        def items():
+            for im in batches:
+                im = im[0] if isinstance(im, (tuple, list)) else im
+                self._check_image(im)
+                shapes.append(tuple(im.shape))
+                yield im, self._lmb(im.shape[0])
+        for i, res in enumerate(self.engine.run_stream(items(), mode=mode, depth=depth)):
+            host, (nB, imC, imH, imW) = res['stats_host'], shapes[i]
+            bpdim = [float(k) / (imC * imH * imW) * self.log2_e for k in res['kl_layers_mean_host']]
+            self._stats_log[f'{mode}_bpdim'] = bpdim
+            self._stats_log[f'{mode}_bppix'] = [b * imC for b in bpdim]
+            yield OrderedDict([('loss', float(host[0])), ('kl', float(host[1])),
+                               (self.out_net.loss_name, float(host[2]) * self.out_net.mse_lmb),
+                               ('bppix', float(host[1]) * self.log2_e * imC), ('psnr', -10 * math.log10(float(host[3])))])
+
     @property
     def train_path(self):
         if self.__dict__.get('_train_path') is None:

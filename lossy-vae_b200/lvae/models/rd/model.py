@@ -162,6 +162,25 @@ class VariableRateLossyVAE(nn.Module):
             stats['im_hat'] = res['im_hat']
         return stats
 
+    @torch.no_grad()
+    def forward_stream(self, batches, lmb=None, depth=2):
+        """Throughput form of forward() (an extension; see lvae.models.qarv.model.VariableRateLossyVAE.forward_stream):
+        one OrderedDict of Python floats per batch, batch i+1 copied in while batch i runs."""
+        shapes = []
+
+        def items():
+            for batch in batches:
+                im = batch[0] if isinstance(batch, (tuple, list)) else batch
+                self._check_image(im)
+                nB = im.shape[0]
+                l = self.sample_lmb(n=nB) if lmb is None else self.expand_to_tensor(lmb, n=nB)
+                shapes.append(im.shape[1])
+                yield im, l.to(self._device(), torch.float32)
+        for i, res in enumerate(self.engine.run_stream(items(), mode='eval', depth=depth)):
+            host, imC = res['stats_host'], shapes[i]
+            yield OrderedDict([('loss', float(host[0])), ('bppix', float(host[1]) * self.log2_e * imC),
+                               (self.distortion_name, float(host[2])), ('psnr', -10 * math.log10(float(host[3])))])
+
     def conditional_sample(self, lmb, latents, emb=None, bhw_repeat=None, t=1.0):
         """rd/model.py:447-486"""
         if latents is None:

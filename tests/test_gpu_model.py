@@ -316,6 +316,30 @@ def test_batched_codec_equals_per_image_codec(gpu_model):
         gpu_model.decompress_batch([blobs[0], gpu_model.compress(make_input('synth', 1, 64, 64, 1).to(DEV))])
 
 
+def test_forward_stream_equals_forward(gpu_model):
+    """model.forward_stream (pipelined H2D copy / launch plan / D2H read-back, lvae.engine.run_stream) returns, batch by
+    batch and in order, exactly what the blocking forward() returns -- host batches (pinned and pageable), device batches,
+    a shape change in the middle of the stream, depth 1 / 2 / 3 -- and raises the reference's range assertion."""
+    lmb = torch.tensor([64.0, 2048.0], device=DEV)
+    shapes = [(128, 192)] * 4 + [(64, 128)] * 2 + [(128, 192)] * 2
+    ims = [make_input('synth', 2, h, w, 300 + i) for i, (h, w) in enumerate(shapes)]
+    want = [gpu_model(im.to(DEV), lmb=lmb) for im in ims]
+    feeds = {'pinned': [im.pin_memory() for im in ims], 'pageable': ims, 'device': [im.to(DEV) for im in ims]}
+    for depth in (1, 2, 3):
+        for kind, feed in feeds.items():
+            got = list(gpu_model.forward_stream(iter(feed), lmb=lmb, depth=depth))
+            assert len(got) == len(want)
+            for g, w_ in zip(got, want):
+                assert g['loss'] == w_['loss'].item() and g['bppix'] == w_['bppix'] and g['psnr'] == w_['psnr'] \
+                    and g['mse'] == w_['mse'], (depth, kind, g, w_)
+    # a lambda per call, sampled when omitted, floats accepted
+    one = list(gpu_model.forward_stream([ims[0]], lmb=2048.0))[0]
+    assert one['bppix'] == gpu_model(ims[0].to(DEV), lmb=torch.full((2,), 2048.0, device=DEV))['bppix']
+    assert np.isfinite(list(gpu_model.forward_stream([ims[0]]))[0]['loss'])
+    with pytest.raises(AssertionError):
+        list(gpu_model.forward_stream([ims[0], ims[1] * 1.5], lmb=lmb))
+
+
 def test_plan_cache_is_bounded_over_many_resolutions(gpu_model):
     """one launch plan (activation buffers, pinned mirrors, CUDA graphs) used to be kept for EVERY distinct
     (batch, height, width, mode) -- evaluating a data set with many resolutions grew device and pinned memory without

@@ -109,6 +109,22 @@ def test_qres_batched_container_roundtrip_and_errors(qres_model, tmp_path):
         qres_model(torch.rand(1, 3, 64, 64, device=DEV) * 2)
 
 
+def test_qres_forward_stream_equals_forward(qres_model):
+    """HierarchicalVAE.forward_stream: same numbers as forward(), per-layer rate log included."""
+    ims = [make_input('synth', 2, 64, 128, 400 + i) for i in range(3)]
+    want, logs = [], []
+    for im in ims:
+        want.append(qres_model(im.to(DEV)))
+        logs.append(list(qres_model._stats_log['eval_bppix']))
+    got = []
+    for i, g in enumerate(qres_model.forward_stream([im.pin_memory() for im in ims])):
+        got.append(g)
+        np.testing.assert_allclose(qres_model._stats_log['eval_bppix'], logs[i], rtol=1e-6)
+    for g, w_ in zip(got, want):
+        assert g['loss'] == w_['loss'].item() and g['bppix'] == w_['bppix'] and g['psnr'] == w_['psnr'] and g['kl'] == w_['kl']
+        assert g['mse'] == w_['mse']
+
+
 def test_qres_sampling_with_given_latents_reproduces_decoder(qres_model):
     im = make_input('rand', 1, 64, 64, 31).to(DEV)
     lat = qres_model.forward_get_latents(im)
