@@ -129,6 +129,10 @@ long long lvae_gemm2_launch_count(void);
  * waiting for the epilogue to free the accumulator, [3] producer total, [4] producer waiting for a free stage,
  * [5..7] (pair kernel) one epilogue warp: total, waiting for the accumulator, draining TMEM; [8] tiles.  Synchronises. */
 int lvae_debug_prof(int which, unsigned long long* out16);
+/* Tuning knobs of the tensor-core GEMM (diagnostics / A-B measurements; results never depend on them): which 0 = force the
+ * N-tile width BN (multiple of 16, 0 = automatic; env LVAE_TC_BN), 1 = unused,
+ * 2 = narrower N-tiles for GEMMs that do not fill the SMs (default 1; LVAE_TC_AUTOBN). */
+int lvae_set_tuning(int which, int value);
 /* split fp32 -> bf16 planes p0 = rn(x), p1 = rn(x - p0), p2 = rn(x - p0 - p1); p1 / p2 may be NULL */
 int lvae_split_bf16(const float* x, void* p0, void* p1, void* p2, int64_t n, void* stream);
 /* the same split of (x * scale) into planes of `plane_format` (enum lvae_plane_format); weights of an

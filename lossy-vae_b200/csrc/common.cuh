@@ -61,27 +61,36 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // <float>::erf(), i.e. Abramowitz-Stegun 7.1.26 in fp32 with FMAs (torch/include/ATen/cpu/vec/vec512/
 // vec512_float.h:269-299; |error| <= 1.5e-7 -- larger than an fp32 ulp, so matching the formula, not the true
 // erf, is what keeps hidden activations within rounding noise of the oracle).
-__device__ __forceinline__ float erf_aten_vec(float x) {
-  const float a = fabsf(x);
-  // t = 1 / (1 + p|x|): the argument is a normal number >= 1, so the correctly rounded reciprocal is the
-  // MUFU approximation plus one Newton step -- the fast path of __frcp_rn without its range checks
-  // (== _mm512_div_ps(1, .) on the host)
-  const float d = fmaf(0.3275911f, a, 1.0f);
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(d));
-  t = fmaf(t, -fmaf(d, t, -1.0f), t);
-  float r = fmaf(1.061405429f, t, -1.453152027f);
-  r = fmaf(r, t, 1.421413741f);
-  r = fmaf(r, t, -0.284496736f);
-  r = fmaf(r, t, 0.254829592f);
-  const float e = expf(-__fmul_rn(x, x));
-  const float res = fmaf(__fmul_rn(-e, t), r, 1.0f);
-  return copysignf(res, x);
-}
-
-// torch.nn.GELU() (erf form) on CPU: x * 0.5 * (1 + erf(x * M_SQRT1_2))  (ATen native/cpu/Activation.cpp GeluKernelImpl)
+// Carries -t instead of t (every sign flip is exact) and takes e^{-x^2} from an inlined range reduction + ex2.approx
+// (<= 2 ulp, like expf) so that the packed form below can mirror it instruction by instruction.
+//
+// torch.nn.GELU() (erf form) on CPU: x * 0.5 * (1 + erf(x * M_SQRT1_2))  (ATen native/cpu/Activation.cpp GeluKernelImpl).
+// gelu_erf() and gelu_erf2() return the SAME BITS for every input (tests/test_gpu_kernels.py::
+// test_gelu_scalar_and_packed_forms_agree_bitwise): which of the two an element goes through depends on where it falls in a
+// tile (full 32-column chunks are packed, edge chunks scalar), and the tile shape may depend on the batch size.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return __fmul_rn(__fmul_rn(x, 0.5f), __fadd_rn(1.0f, erf_aten_vec(__fmul_rn(x, 0.70710678118654752440f))));
+  const float xk = __fmul_rn(x, 0.70710678118654752440f);
+  const float a = fabsf(xk);
+  // t = 1 / (1 + p|x|): the argument is a normal number >= 1, so the correctly rounded reciprocal is the MUFU
+  // approximation plus one Newton step (== _mm512_div_ps(1, .) on the host)
+  const float d = fmaf(0.3275911f, a, 1.0f);
+  float tn;                                                                    // -1/d
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tn) : "f"(-d));
+  tn = fmaf(tn, fmaf(d, tn, 1.0f), tn);
+  float r = fmaf(1.061405429f, tn, 1.453152027f);                              // -(p5 t + p4)
+  r = fmaf(r, tn, 1.421413741f);
+  r = fmaf(r, tn, 0.284496736f);
+  r = fmaf(r, tn, 0.254829592f);
+  float y = fmaxf(__fmul_rn(xk, -xk), -87.0f);
+  const float z = fmaf(y, 1.4426950408889634f, 12583039.0f);                   // low mantissa bits: n + 127
+  const float nf = __fadd_rn(z, -12583039.0f);
+  float u = fmaf(y, 1.4426950216293335f, -nf);
+  u = fmaf(y, 1.925963033500011e-08f, u);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u));
+  e = __fmul_rn(e, __uint_as_float(__float_as_uint(z) << 23));
+  const float res = fmaf(__fmul_rn(e, tn), r, 1.0f);                           // 1 - e t r
+  return __fmul_rn(__fmul_rn(x, 0.5f), __fadd_rn(1.0f, copysignf(res, xk)));
 }
 
 // ---- packed fp32x2 arithmetic (sm_100): each lane is an IEEE op, i.e. bit-identical to the scalar instruction, at
@@ -102,9 +111,7 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
-// gelu_erf on two values: the same formula and the same roundings as gelu_erf(), except that e^{-x^2} comes from
-// an inlined range reduction + ex2.approx (<= 2 ulp, like expf) so that everything around the two MUFU ops packs.
-// Carries -t instead of t: every sign flip below is exact, so the polynomial matches erf_aten_vec bit for bit.
+// gelu_erf on two values: the same instructions in their packed fp32x2 forms around the two MUFU ops -- the same bits.
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   const float2 xk = mul2(x, splat2(0.70710678118654752440f));
   const float2 a = make_float2(fabsf(xk.x), fabsf(xk.y));

@@ -443,7 +443,8 @@ int gemm2_tc_launch(const lvae_gemm_desc* d, const void* const* a_pl, const void
 
 extern "C" long long lvae_gemm2_launch_count(void) { return lvae::g2_launches; }
 
-namespace lvae { int gemm_tc_prof_read(unsigned long long* out16); }
+namespace lvae { int gemm_tc_prof_read(unsigned long long* out16); int gemm_tc_set_tuning(int which, int value); }
+extern "C" int lvae_set_tuning(int which, int value) { return lvae::gemm_tc_set_tuning(which, value); }
 extern "C" int lvae_debug_prof(int which, unsigned long long* out16) {
   if (which == 2) {
     LVAE_CUDA_CALL(cudaDeviceSynchronize());

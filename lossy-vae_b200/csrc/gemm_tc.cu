@@ -619,6 +619,44 @@ int64_t gemm_tc_workspace_bytes(const lvae_gemm_desc* d) {
   return M * K * 2 * num_planes(d->precision);
 }
 
+// tuning knobs (lvae_set_tuning; initial values from the environment): [0] force BN (0 = automatic), [1] unused (was: fc1 planes stored
+// straight from the row-owner registers -- 32 half-filled sectors per store instruction, 96 -> 137 us at H/8: dropped),
+// [2] narrower N-tiles for GEMMs that do not fill the SMs
+static int tc_tuning[4] = {-1, -1, -1, -1};
+static int tc_tuning_get(int which) {
+  if (tc_tuning[which] < 0) {
+    static const char* names[4] = {"LVAE_TC_BN", "LVAE_TC_DIRECT", "LVAE_TC_AUTOBN", "LVAE_TC_RESERVED"};
+    static const int defaults[4] = {0, 1, 1, 0};
+    const char* e = getenv(names[which]);
+    tc_tuning[which] = e ? atoi(e) : defaults[which];
+  }
+  return tc_tuning[which];
+}
+int gemm_tc_set_tuning(int which, int value) {
+  if (which < 0 || which >= 4 || value < 0) return LVAE_E_BADARG;
+  tc_tuning[which] = value;
+  return 0;
+}
+
+// N-tile width of the 2-plane kernel when the default tiling leaves SMs idle or half a wave over: per 16-deep k-step an SM
+// moves A (2 planes, TMA write + MMA read: 16 KB) plus 5 BN / 32 KB of B through its 128 B/clk shared-memory port
+// (profiles/r2_mma_probe.md section 2), so a narrower tile is cheaper per step and there are more of them.  The result
+// does not depend on BN: every output element is the same fixed-order sum over K (tests/test_gpu_kernels.py::
+// test_gemm_tile_width_does_not_change_bits), so batch invariance holds although the choice looks at M.
+static int pick_bn_fill(int M, int N, int K, int bn0, int n_sm) {
+  const int mt = (M + TC_BM - 1) / TC_BM;
+  int best_bn = bn0;
+  double best = 1e30;
+  for (int nt = (N + 127) / 128; nt <= (N + 31) / 32; ++nt) {
+    int bn = (((N + nt - 1) / nt) + 15) & ~15;
+    if (bn < 32 || bn > 128 || (N + bn - 1) / bn != nt) continue;
+    const int waves = (mt * nt + n_sm - 1) / n_sm;
+    const double cost = (double)waves * (K / 16.0) * (128.0 + 1.25 * bn) + 24.0 * bn;
+    if (cost < best * 0.97) { best = cost; best_bn = bn; }     // ties and near-ties keep the wider tile
+  }
+  return best_bn;
+}
+
 static int pick_bn(int N, int npl) {
   const int maxbn = npl >= 2 ? 128 : 256;                      // split accumulators need 2 x BN columns per buffer
   const int nt = (N + maxbn - 1) / maxbn;
@@ -680,6 +718,14 @@ int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stre
   p.k_split = concat_planes ? d->C0 : K;
   p.pl_act = d->out_planes_act;
   p.BN = pick_bn(d->N, npl);
+  {
+    static int sms = 0;
+    if (sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int mt0 = (M + TC_BM - 1) / TC_BM, nt0 = (d->N + p.BN - 1) / p.BN;
+    if (npl == 2 && !conv && !split_k && d->N >= 64 && mt0 * nt0 <= 2 * sms && tc_tuning_get(2)) p.BN = pick_bn_fill(M, d->N, K, p.BN, sms);
+    const int forced = tc_tuning_get(0);
+    if (forced >= 16 && forced % 16 == 0 && forced <= (npl >= 2 ? 128 : 256)) p.BN = forced;
+  }
   p.n_tiles = (d->N + p.BN - 1) / p.BN;
   p.conv = conv ? 1 : 0; p.cH = d->H; p.cW = d->W; p.cC = d->C0;
   p.tiles_w = conv ? (d->W + CONV_TW - 1) / CONV_TW : 1;

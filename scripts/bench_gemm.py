@@ -24,6 +24,7 @@ SHAPES = [  # (name, M, K, N, epi)
     ('s8 dec2 fc1', 49152, 256, 512, 1), ('s8 dec2 fc2', 49152, 512, 256, 2),
     ('s16 dec fc1', 12288, 384, 768, 1), ('s16 dec fc2', 12288, 768, 384, 2),
     ('s32 fc2', 3072, 1024, 512, 2), ('s32 wide fc1', 3072, 512, 1536, 1), ('s32 wide fc2', 3072, 1536, 512, 2),
+    ('s64 fc2', 768, 1024, 512, 2), ('s64 wide fc2', 768, 2048, 512, 2),
     ('n32 probe', 196608, 192, 32, 0), ('n64 probe', 196608, 192, 64, 0), ('n128 probe', 196608, 192, 128, 0),
 ]
 def planes(x, n, prec=3, weight=False):
