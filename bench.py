@@ -369,10 +369,11 @@ def run_train(args):
         resident = GraphedTrainStep(model, opt, tuple(im_dev.shape), process_group=True if world > 1 else None)
     # end to end: pinned host batch in, loss out, every step -- through the graphed step when there is one (N > 1: its
     # all-reduce is the only collective on the path), else through model.forward() / loss.backward() / optimizer.step()
-    eager_e2e = not (graphed and world > 1)
+    eager_e2e = not graphed
+    eager_too = graphed and world == 1               # also time the reference-shaped eager loop (reported beside e2e)
     for _ in range(warmup):
         resident(im_dev)
-        if eager_e2e:
+        if eager_e2e or eager_too:
             step(im_dev)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -398,6 +399,16 @@ def run_train(args):
             out = {'bppix': None, 'psnr': None}
     e[3].record(st)
     barrier()
+    ms_eager = None
+    if eager_too:
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record(st)
+        for _ in range(args.steps):
+            out = step(im_host.to(dev, non_blocking=True))
+            out['loss'].item()
+        e5.record(st)
+        barrier()
+        ms_eager = e4.elapsed_time(e5)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])], device=dev, dtype=torch.float64)
     if world > 1:
@@ -419,12 +430,16 @@ def run_train(args):
                        'value_path': 'whole step replayed as one CUDA graph (lvae.training.GraphedTrainStep)' if graphed else 'eager step',
                        'e2e_path': ('eager step through model.forward() / loss.backward() / optimizer.step()' if eager_e2e else
                                     'GraphedTrainStep(batch on pinned host memory) + loss read-back'),
-                       'backward': 'latent layers and ConvNeXt blocks native (tcgen05 data + weight gradients in 2-plane bf16, GELU derivative in '
-                                   'the GEMM epilogue, dwconv/LN/modulation kernels of csrc/dwln_bwd.cu); head convolutions and VDBlocks via '
-                                   'ATen autograd on recomputed sub-graphs (lvae/training.py, DESIGN.md 4.6)',
+                       'backward': 'latent layers, ConvNeXt blocks and the convolutions of the qarv path native (tcgen05 data + weight gradients '
+                                   'in 2-plane bf16, GELU derivative in the GEMM epilogue, dwconv/LN/modulation kernels of csrc/dwln_bwd.cu; weight '
+                                   'gradients on a second stream); qres VDBlocks and GELU-fused z_proj convs via ATen autograd on recomputed '
+                                   'sub-graphs (native VDBlock backward: LVAE_TRAIN_NATIVE_VD=1, slower) (lvae/training.py, DESIGN.md 4.6)',
                        'l2': 'no flush: per-step working set exceeds the 126 MB L2'},
             'e2e': {'value': n_img / (ms_e2e / 1e3), 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,
-                    'h2d_bytes_per_step': im_host.numel() * 4, 'd2h_bytes_per_step': 4},
+                    'h2d_bytes_per_step': im_host.numel() * 4, 'd2h_bytes_per_step': 4,
+                    'eager_value': None if ms_eager is None else n_img / (ms_eager / 1e3),
+                    'eager_call': None if ms_eager is None else 'model(batch)["loss"].backward(); optimizer.step() as lvae/trainer.py '
+                                                                'runs it (torch.optim.Adam, one launch at a time: host-bound)'},
             'gpu_launches': launches, 'launches_per_step': launches // max(1, args.steps),
             'clocks': clocks, 'result': {'loss': loss, 'bppix': out['bppix'], 'psnr': out['psnr']},
             'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30,

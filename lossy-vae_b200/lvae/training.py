@@ -25,6 +25,7 @@ kernels of the next round replace, one op at a time, each against the gradient t
 (`TrainPath.native_bwd = False` runs every backward through ATen: the cross-check of the native pieces).
 There is no CPU path: every Function launches CUDA kernels of liblvae_b200.so.
 """
+import contextlib
 import math
 import os
 
@@ -255,8 +256,45 @@ class TrainPath:
         # gradient (one transposed plane set, 9 column offsets) replaces it
         self.native_vd = os.environ.get('LVAE_TRAIN_NATIVE_VD', '0') == '1'
         self.force_refresh = False      # GraphedTrainStep: the captured step must always re-pack the weights
+        # weight gradients (operand splits + split-K GEMMs + their [C]-sized follow-ups) run on a second stream, forked from
+        # and joined back into the stream of the backward inside every op's backward(): they depend only on the op's dY and
+        # saved input, not on each other, and the layers behind the first two stages launch grids far smaller than the GPU
+        # (LVAE_TRAIN_SIDE_STREAM=0: everything on one stream).  Fork / join are events, so a CUDA-graph capture of the step
+        # records them as parallel branches.
+        self.side_enabled = os.environ.get('LVAE_TRAIN_SIDE_STREAM', '1') != '0'
+        self.side_stream = None         # created on first use
+        self._side_used = False
+        self._side_keep = []
 
     # ---- helpers
+    @contextlib.contextmanager
+    def _side(self, *keep):
+        """Run the enclosed launches on the side stream, ordered after everything the current stream has been given so far.
+        `keep`: tensors of the current stream that the side work reads -- held until _join() so that the caching allocator
+        cannot hand their memory to a later allocation of the main stream while the side stream still reads it."""
+        if not self.side_enabled:
+            yield
+            return
+        if self.side_stream is None:
+            self.side_stream = torch.cuda.Stream(self.eng.device)
+        main = torch.cuda.current_stream(self.eng.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side_stream.wait_event(ev)
+        self._side_used = True
+        self._side_keep.extend(keep)
+        with torch.cuda.stream(self.side_stream):
+            yield
+
+    def _join(self):
+        """The current stream waits for the side stream (end of every backward())."""
+        if self._side_used:
+            ev = torch.cuda.Event()
+            ev.record(self.side_stream)
+            torch.cuda.current_stream(self.eng.device).wait_event(ev)
+            self._side_used = False
+        self._side_keep.clear()
+
     def scatter_ada(self, ada, off, g):
         if ada is None or g is None:
             return None
@@ -331,46 +369,58 @@ class TrainPath:
         go = gout.reshape(M, C_)
         # fc2: out = x + gamma * (g W2^T + b2),  g = gelu(h)
         tc_wgrad = self.native_wgrad and M % 8 == 0 and M >= 1024
-        if tc_wgrad:                                            # tcgen05, split over the pixels (csrc/wgrad.cu)
-            db2_raw = torch.zeros(C_, device=x.device)          # bias gradient rides in the operand split of dout
-            go_t = self._t_planes('wg_a', go, colsum=db2_raw)
-            dw2_raw = self._wgrad(go_t, self._t_planes('wg_b', h, act=1), C_, hid, M)
-        else:                                                   # tiny layers: cuBLAS fp32  [C, hid]
-            dw2_raw = go.t().mm(F.gelu(h))
-            db2_raw = go.sum(0)
-        d_w2 = gam[:, None] * dw2_raw
-        d_b2 = gam * db2_raw
-        d_gamma = ((w2.detach() * dw2_raw).sum(1) + b2.detach() * db2_raw).reshape(gamma.shape)
+        lib = eng.lib
+        c = torch.empty(M, C_, device=x.device)
+        c_ready = None
+        with self._side(go, h, gam, c, x):
+            if self.side_enabled:       # the conv output that the LayerNorm backward (last part, main stream) needs: first thing here
+                P.op('dwconv', lib.lvae_dwconv, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']), 0, _ptr(c), B, H, W, C_, k, 0)
+                c_ready = torch.cuda.Event()
+                c_ready.record(self.side_stream)
+            if tc_wgrad:                                            # tcgen05, split over the pixels (csrc/wgrad.cu)
+                db2_raw = torch.zeros(C_, device=x.device)          # bias gradient rides in the operand split of dout
+                go_t = self._t_planes('wg_a', go, colsum=db2_raw)
+                dw2_raw = self._wgrad(go_t, self._t_planes('wg_b', h, act=1), C_, hid, M)
+            else:                                                   # tiny layers: cuBLAS fp32  [C, hid]
+                dw2_raw = go.t().mm(F.gelu(h))
+                db2_raw = go.sum(0)
+            d_w2 = gam[:, None] * dw2_raw
+            d_b2 = gam * db2_raw
+            d_gamma = ((w2.detach() * dw2_raw).sum(1) + b2.detach() * db2_raw).reshape(gamma.shape)
         # dh = ((dout * gamma) W2) * gelu'(h): GELU' applied in the GEMM's epilogue
         dh = torch.empty(M, hid, device=x.device)
         eng._gemm(P, 'fc2.dgrad', go, (1, 1, M, C_, 1, 1, 0), self._transposed(gam[:, None] * w2.detach()), dh,
                   epi=N.EPI_GELU_BWD, res=h, prec=self.DGRAD_PREC)
-        # fc1: h = a W1^T + b1;  a is needed for the weight gradient: one more (fp32) dwln launch
+        # fc1: h = a W1^T + b1;  a is needed for the weight gradient only: one more (fp32) dwln launch, on the side stream
         a32 = torch.empty(M, C_, device=x.device)
-        P.op('dwln', eng.lib.lvae_dwconv_ln_adaln, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']), _ptr(ada), eng.ada_total, off,
-             _ptr(wb.get('ln_w')), _ptr(wb.get('ln_b')), _ptr(a32), B, H, W, C_, k)
-        if tc_wgrad:
-            d_b1 = torch.zeros(hid, device=x.device)
-            d_w1 = self._wgrad(self._t_planes('wg_b', dh, colsum=d_b1), self._t_planes('wg_a', a32), hid, C_, M)
-        else:
-            d_w1 = dh.t().mm(a32)
-            d_b1 = dh.sum(0)
+        with self._side(dh, a32, x, ada):
+            P.op('dwln', eng.lib.lvae_dwconv_ln_adaln, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']), _ptr(ada), eng.ada_total, off,
+                 _ptr(wb.get('ln_w')), _ptr(wb.get('ln_b')), _ptr(a32), B, H, W, C_, k)
+            if tc_wgrad:
+                d_b1 = torch.zeros(hid, device=x.device)
+                d_w1 = self._wgrad(self._t_planes('wg_b', dh, colsum=d_b1), self._t_planes('wg_a', a32), hid, C_, M)
+            else:
+                d_w1 = dh.t().mm(a32)
+                d_b1 = dh.sum(0)
         da = torch.empty(M, C_, device=x.device)
         eng._gemm(P, 'fc1.dgrad', dh, (1, 1, M, hid, 1, 1, 0), self._transposed(w1.detach()), da, epi=N.EPI_BIAS, prec=self.DGRAD_PREC)
         del dh, h, a32
         # dwconv + LayerNorm + modulation: recompute the conv output, LayerNorm / modulation backward, filter gradient,
         # data gradient (transposed conv + the residual branch's gradient) -- csrc/dwln_bwd.cu
-        lib = eng.lib
-        c = torch.empty(M, C_, device=x.device)
-        P.op('dwconv', lib.lvae_dwconv, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']), 0, _ptr(c), B, H, W, C_, k, 0)
+        if c_ready is None:
+            P.op('dwconv', lib.lvae_dwconv, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']), 0, _ptr(c), B, H, W, C_, k, 0)
+        else:
+            torch.cuda.current_stream(x.device).wait_event(c_ready)
         dmod, dc = torch.empty(1 if ln else B, 2 * C_, device=x.device), torch.empty(M, C_, device=x.device)
         P.op('ln_mod_bwd', lib.lvae_ln_mod_bwd, _ptr(c), _ptr(da), _ptr(ada), eng.ada_total, off, _ptr(wb.get('ln_w')),
              _ptr(dc), _ptr(dmod), B, H * W, C_)
-        dwp, d_dwb = torch.empty(k * k, C_, device=x.device), torch.empty(C_, device=x.device)
-        P.op('dwconv_wgrad', lib.lvae_dwconv_wgrad, _ptr(dc), _ptr(x), _ptr(dwp), _ptr(d_dwb), B, H, W, C_, k)
+        with self._side(dc):
+            dwp, d_dwb = torch.empty(k * k, C_, device=x.device), torch.empty(C_, device=x.device)
+            P.op('dwconv_wgrad', lib.lvae_dwconv_wgrad, _ptr(dc), _ptr(x), _ptr(dwp), _ptr(d_dwb), B, H, W, C_, k)
+            d_dww = dwp.t().reshape(C_, 1, k, k)
         dx = torch.empty_like(x)
         P.op('dwconv_dgrad', lib.lvae_dwconv, _ptr(dc), _ptr(wb['dw_w']), 0, _ptr(gout), _ptr(dx), B, H, W, C_, k, 1)
-        d_dww = dwp.t().reshape(C_, 1, k, k)
+        self._join()
         if ln:
             return (dx, None, d_dww, d_dwb, d_w1, d_b1, d_w2, d_b2, d_gamma, dmod[0, C_:].clone(), dmod[0, :C_].clone())
         return (dx, self.scatter_ada(ada, off, dmod), d_dww, d_dwb, d_w1, d_b1, d_w2, d_b2, d_gamma)
@@ -401,18 +451,20 @@ class TrainPath:
         eng._gemm(self.P, 'conv3.dgrad', G4, (B, H, W_, Nn, 3, 1, 1), eng._pack_gemm_weight(wd, None, prec=self.DGRAD_PREC),
                   dxm, epi=N.EPI_BIAS, prec=self.DGRAD_PREC)
         tc = self.native_wgrad and M % 8 == 0 and M >= 1024
-        x_t = self._t_planes('wg_b', X2.contiguous(), act=act) if tc else None
-        Xa = None if tc else (F.gelu(X2) if act else X2)
-        Gp = F.pad(G4, (0, 0, 1, 1, 1, 1))
-        dw4 = torch.empty(Nn, C0, 3, 3, device=dev)
-        for ky in range(3):
-            for kx in range(3):
-                Gt = Gp[:, 2 - ky:2 - ky + H, 2 - kx:2 - kx + W_, :].reshape(M, Nn)
-                if tc:
-                    dw4[:, :, ky, kx] = self._wgrad(self._t_planes('wg_a', Gt.contiguous()), x_t, Nn, C0, M)
-                else:
-                    dw4[:, :, ky, kx] = Gt.t().mm(Xa)
-        return dxm, dw4, G4.reshape(M, Nn).sum(0)
+        with self._side(G4, X2):
+            x_t = self._t_planes('wg_b', X2.contiguous(), act=act) if tc else None
+            Xa = None if tc else (F.gelu(X2) if act else X2)
+            Gp = F.pad(G4, (0, 0, 1, 1, 1, 1))
+            dw4 = torch.empty(Nn, C0, 3, 3, device=dev)
+            for ky in range(3):
+                for kx in range(3):
+                    Gt = Gp[:, 2 - ky:2 - ky + H, 2 - kx:2 - kx + W_, :].reshape(M, Nn)
+                    if tc:
+                        dw4[:, :, ky, kx] = self._wgrad(self._t_planes('wg_a', Gt.contiguous()), x_t, Nn, C0, M)
+                    else:
+                        dw4[:, :, ky, kx] = Gt.t().mm(Xa)
+            db = G4.reshape(M, Nn).sum(0)
+        return dxm, dw4, db
 
     def vd_backward(self, wv, x, x1, params, gout):
         """Gradients (x, x1, c1.w, c1.b, ..., c4.w, c4.b) of a qres VDBlock head (qresvae/model.py:118-149, residual = False):
@@ -438,7 +490,8 @@ class TrainPath:
         # ---- c4 (1x1): out = gelu(h3) W4^T + b4
         G = gout.reshape(M, -1)
         db4 = torch.zeros(G.shape[1], device=dev)
-        dw4 = self._mm_grad('vd.c4.wgrad', G, h3.view(M, hid), db4, act=1).reshape(w4.shape)
+        with self._side(G, h3, db4):
+            dw4 = self._mm_grad('vd.c4.wgrad', G, h3.view(M, hid), db4, act=1).reshape(w4.shape)
         dh3 = gelu_bwd(self._dgrad('vd.c4.dgrad', G, wv['c4']['w']), h3.view(M, hid))
         # ---- c3, c2 (3x3 | 1x1)
         def mid(dh, h_in, went, w):
@@ -446,7 +499,8 @@ class TrainPath:
                 dg, dw, db = self._conv3_grads(dh.view(B, H, W_, hid), h_in.view(M, hid), w, act=1)
             else:
                 db = torch.zeros(hid, device=dev)
-                dw = self._mm_grad('vd.mid.wgrad', dh, h_in.view(M, hid), db, act=1).reshape(w.shape)
+                with self._side(dh, h_in, db):
+                    dw = self._mm_grad('vd.mid.wgrad', dh, h_in.view(M, hid), db, act=1).reshape(w.shape)
                 dg = self._dgrad('vd.mid.dgrad', dh, went['w'])
             return gelu_bwd(dg, h_in.view(M, hid)), dw, db
         dh2, dw3, db3 = mid(dh3, h2, wv['c3'], w3)
@@ -454,16 +508,20 @@ class TrainPath:
         # ---- c1 (1x1 on gelu(cat(x, x1)))
         db1 = torch.zeros(hid, device=dev)
         x2 = x.reshape(M, C0)
-        dwa = self._mm_grad('vd.c1.wgrad', dh1, x2, db1, act=1)
+        x12 = None if x1 is None else x1.reshape(M, C1)
+        with self._side(dh1, x2, x12, db1):
+            dwa = self._mm_grad('vd.c1.wgrad', dh1, x2, db1, act=1)
+            if x1 is not None:
+                dw1 = torch.cat([dwa, self._mm_grad('vd.c1.wgrad1', dh1, x12, act=1)], dim=1).reshape(w1.shape)
+            else:
+                dw1 = dwa.reshape(w1.shape)
         dga = self._dgrad('vd.c1.dgrad', dh1, wv['c1']['w'])          # [M, C0 + C1]
         if x1 is not None:
-            x12 = x1.reshape(M, C1)
-            dw1 = torch.cat([dwa, self._mm_grad('vd.c1.wgrad1', dh1, x12, act=1)], dim=1).reshape(w1.shape)
             dx = gelu_bwd(dga[:, :C0].contiguous(), x2).view(x.shape)
             dx1 = gelu_bwd(dga[:, C0:].contiguous(), x12).view(x1.shape)
         else:
-            dw1 = dwa.reshape(w1.shape)
             dx, dx1 = gelu_bwd(dga, x2).view(x.shape), None
+        self._join()
         return dx, dx1, dw1, db1, dw2, db2, dw3, db3, dw4, db4
 
     def _dgrad(self, name, g2d, w2d):
@@ -504,13 +562,15 @@ class TrainPath:
             # 3x3, stride 1, pad 1 (posterior head)
             B, H, W_, C0 = x.shape
             dxm, dw4, db = self._conv3_grads(gout, x.reshape(M, C0), w)
+            self._join()
             return dxm.view(B, H, W_, C0), None, None, dw4, (db if b is not None else None)
         # ---- A: the forward operand matrix [M, K] (re-arranged input), and the way back for its gradient
         if cfg.get('nchw_in'):
             B, _, H, W_ = x.shape
             A = torch.empty(M, K, device=dev)
             self.P.op('im2patch', eng.lib.lvae_image_to_patches, _ptr(x), _ptr(A), B, H, W_, st, float(m.im_shift), float(m.im_scale))
-            dWp = self._mm_grad('down0.wgrad', G, A, db_p)
+            with self._side(G, A, db_p):
+                dWp = self._mm_grad('down0.wgrad', G, A, db_p)
         else:
             B, H, W_, C0 = x.shape
             if ks > 1:                                     # non-overlapping patches: space-to-depth view
@@ -518,34 +578,39 @@ class TrainPath:
                 A = x.view(B, Ho, ks, Wo, ks, C0).permute(0, 1, 3, 2, 4, 5).reshape(M, K)
             else:
                 A = x.reshape(M, C0)
+            with self._side(G, A, db_p, x1):
+                if x1 is not None:
+                    C1 = x1.shape[-1]
+                    dWp = torch.cat([self._mm_grad('conv.wgrad', G, A, db_p), self._mm_grad('conv.wgrad1', G, x1.reshape(M, C1))], dim=1)
+                else:
+                    dWp = self._mm_grad('conv.wgrad', G, A, db_p)
             dA = self._dgrad('conv.dgrad', G, Wp)          # [M, K]
             if x1 is not None:
-                C1 = x1.shape[-1]
-                dWp = torch.cat([self._mm_grad('conv.wgrad', G, A, db_p), self._mm_grad('conv.wgrad1', G, x1.reshape(M, C1))], dim=1)
                 dx = dA[:, :C0].reshape(x.shape)
                 dx1 = dA[:, C0:].reshape(x1.shape)
             else:
-                dWp = self._mm_grad('conv.wgrad', G, A, db_p)
                 if ks > 1:
                     dx = dA.view(B, Ho, Wo, ks, ks, C0).permute(0, 1, 3, 2, 4, 5).reshape(x.shape)
                 else:
                     dx = dA.view(x.shape)
         # ---- packed [N, (ky, kx, c) | c1] -> the conv weight's layout
-        if r:                                              # pixel shuffle: packed row (i r + j) Co + c  <-  reference row c r r + i r + j
-            Co = Nn // (r * r)
-            perm = torch.arange(Nn, device=dev).reshape(Co, r * r).t().reshape(-1)
-            dW_ref = torch.empty_like(dWp)
-            dW_ref[perm] = dWp
-            dWp = dW_ref
-            if db_p is not None:
-                db_ref = torch.empty_like(db_p)
-                db_ref[perm] = db_p
-                db_p = db_ref
-        Cin = w.shape[1]
-        if ks > 1:
-            dw4 = dWp.view(Nn, ks, ks, Cin).permute(0, 3, 1, 2).contiguous()
-        else:
-            dw4 = dWp.reshape(w.shape)
+        with self._side():
+            if r:                                          # pixel shuffle: packed row (i r + j) Co + c  <-  reference row c r r + i r + j
+                Co = Nn // (r * r)
+                perm = torch.arange(Nn, device=dev).reshape(Co, r * r).t().reshape(-1)
+                dW_ref = torch.empty_like(dWp)
+                dW_ref[perm] = dWp
+                dWp = dW_ref
+                if db_p is not None:
+                    db_ref = torch.empty_like(db_p)
+                    db_ref[perm] = db_p
+                    db_p = db_ref
+            Cin = w.shape[1]
+            if ks > 1:
+                dw4 = dWp.view(Nn, ks, ks, Cin).permute(0, 3, 1, 2).contiguous()
+            else:
+                dw4 = dWp.reshape(w.shape)
+        self._join()
         return dx, dx1, (gout if res is not None else None), dw4, db_p
 
     # ---- lambda embedding (tiny; ATen both ways): qarv/model.py:280-287, common.py:101-107,150
