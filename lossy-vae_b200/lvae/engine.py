@@ -108,6 +108,11 @@ class QarvEngine:
         self.plane_chain = __import__('os').environ.get('LVAE_PLANE_CHAIN', '1') != '0'
         self.host_coder_s = 0.0        # seconds spent in the host rANS coder (bench.py --workload codec reads it)
         self.coder_threads = min(16, __import__('os').cpu_count() or 1)
+        # batched decode in two half-batches, host rANS of one half under the GPU segment of the other.  Opt-in
+        # (LVAE_DECODE_PINGPONG=1): at 8 images per call it is SLOWER (decompress 17.8 -> 23.4 ms) -- a layer's host time is the
+        # latency of its longest single rANS stream, not a throughput: 8 streams on 16 threads take as long as 4, so two
+        # half-batch calls double the host time (5 -> 8.5 ms) and the host, not the GPU, is what a layer waits for
+        self.decode_pingpong = __import__('os').environ.get('LVAE_DECODE_PINGPONG', '0') == '1'
         self.blocks = [m for m in model.modules() if isinstance(m, (common.ConvNeXtBlockAdaLN, common.ConvNeXtBlockLN))]
         self.ada_off = {}
         off = 0
@@ -1045,6 +1050,8 @@ class QarvEngine:
         self.refresh_weights()
         B, nH, nW = bhw
         blocks = [b for b in self.model.dec_blocks if getattr(b, 'is_latent_block', False)]
+        if self.decode_pingpong and B >= 4 and B % 2 == 0 and not getattr(self.model, 'lossless', False):
+            return self._decompress_pingpong(lmb, strings, bhw, blocks)
         with torch.cuda.device(self.device):
             P = self._get_plan(('dec', B, nH, nW), lambda: self._build_decode_plan(B, nH, nW))
             P.lmb.copy_(lmb.to(torch.float32), non_blocking=True)
@@ -1053,21 +1060,8 @@ class QarvEngine:
                 self._launch(P, li)
                 P.idx_host[li].copy_(P.idx[li].view(-1), non_blocking=True)
                 stream.synchronize()
-                cdf, clen, coff = self._tables(blk)
-                idx_np = P.idx_host[li].numpy().reshape(-1)
-                sym_np = P.sym_host[li].numpy().reshape(-1)
                 per_layer = strings[li] if isinstance(strings[li], (list, tuple)) else [strings[li]]
-                assert len(per_layer) == B
-                t0 = time.perf_counter()
-                per = idx_np.size // B
-                data = np.frombuffer(b''.join(per_layer), dtype=np.uint8)
-                in_begin = np.concatenate([[0], np.cumsum([len(s_) for s_ in per_layer])]).astype(np.int64)
-                begin = (np.arange(B + 1, dtype=np.int64) * per)
-                N.check(self.lib.lvae_rans_decode_streams(data.ctypes.data, in_begin.ctypes.data, idx_np.ctypes.data,
-                                                          begin.ctypes.data, B, cdf.ctypes.data, cdf.shape[1],
-                                                          clen.ctypes.data, coff.ctypes.data, cdf.shape[0],
-                                                          sym_np.ctypes.data, self.coder_threads), 'rans_decode_streams')
-                self.host_coder_s += time.perf_counter() - t0
+                self._decode_layer_host(P, li, blk, per_layer)
                 P.sym[li].copy_(P.sym_host[li].view_as(P.sym[li]), non_blocking=True)
             self._launch(P, len(blocks))
             if getattr(self.model, 'lossless', False):
@@ -1091,6 +1085,59 @@ class QarvEngine:
                 self._launch(P, len(blocks) + 1)
                 return P.on_im_hat.clone()
             return P.x_hat.clone().clamp_(min=-1.0, max=1.0).mul_(0.5).add_(0.5)
+
+    def _decode_layer_host(self, P, li, blk, per_layer):
+        """rANS-decode latent layer li of plan P's images on the host thread pool: P.idx_host[li] (table indexes, already on
+        the host) + the images' byte strings -> P.sym_host[li]."""
+        cdf, clen, coff = self._tables(blk)
+        idx_np = P.idx_host[li].numpy().reshape(-1)
+        sym_np = P.sym_host[li].numpy().reshape(-1)
+        nB = P.B
+        assert len(per_layer) == nB
+        t0 = time.perf_counter()
+        per = idx_np.size // nB
+        data = np.frombuffer(b''.join(per_layer), dtype=np.uint8)
+        in_begin = np.concatenate([[0], np.cumsum([len(s_) for s_ in per_layer])]).astype(np.int64)
+        begin = (np.arange(nB + 1, dtype=np.int64) * per)
+        N.check(self.lib.lvae_rans_decode_streams(data.ctypes.data, in_begin.ctypes.data, idx_np.ctypes.data,
+                                                  begin.ctypes.data, nB, cdf.ctypes.data, cdf.shape[1],
+                                                  clen.ctypes.data, coff.ctypes.data, cdf.shape[0],
+                                                  sym_np.ctypes.data, self.coder_threads), 'rans_decode_streams')
+        self.host_coder_s += time.perf_counter() - t0
+
+    def _decompress_pingpong(self, lmb, strings, bhw, blocks):
+        """Batched decode with the coder off the GPU's critical path: the batch is cut into two halves with a
+        decode plan each; while the host decodes layer i of one half, the GPU runs the other half's segment, and the other way
+        round -- layers stay sequential per image (the prior of layer i + 1 needs z_i, qarv/model.py:546-554).  One stream,
+        one event per half: the host waits for `its` half only.  Kernels are batch-invariant, so the images come out bit-equal
+        to the one-plan decode and to per-image decompress() (tests/test_gpu_model.py::test_pingpong_decode_...)."""
+        B, nH, nW = bhw
+        hb = B // 2
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            halves, evs = [], []
+            for h in range(2):
+                P = self._get_plan(('dec', hb, nH, nW, h), lambda: self._build_decode_plan(hb, nH, nW))
+                P.lmb.copy_(lmb[h * hb:(h + 1) * hb].to(torch.float32), non_blocking=True)
+                halves.append(P)
+                evs.append(torch.cuda.Event())
+            for h, P in enumerate(halves):
+                self._launch(P, 0)
+                P.idx_host[0].copy_(P.idx[0].view(-1), non_blocking=True)
+                evs[h].record(stream)
+            for li, blk in enumerate(blocks):
+                per_layer = strings[li]
+                assert isinstance(per_layer, (list, tuple)) and len(per_layer) == B
+                for h, P in enumerate(halves):
+                    evs[h].synchronize()                     # this half's indexes are on the host; the other half's segment runs on
+                    self._decode_layer_host(P, li, blk, per_layer[h * hb:(h + 1) * hb])
+                    P.sym[li].copy_(P.sym_host[li].view_as(P.sym[li]), non_blocking=True)
+                    self._launch(P, li + 1)
+                    if li + 1 < len(blocks):
+                        P.idx_host[li + 1].copy_(P.idx[li + 1].view(-1), non_blocking=True)
+                        evs[h].record(stream)
+            x = torch.cat([P.x_hat for P in halves], dim=0)
+            return x.clamp_(min=-1.0, max=1.0).mul_(0.5).add_(0.5)
 
     @torch.no_grad()
     def sample(self, lmb, latents, bhw, t):

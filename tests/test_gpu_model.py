@@ -316,6 +316,27 @@ def test_batched_codec_equals_per_image_codec(gpu_model):
         gpu_model.decompress_batch([blobs[0], gpu_model.compress(make_input('synth', 1, 64, 64, 1).to(DEV))])
 
 
+def test_pingpong_decode_equals_one_plan_decode_and_per_image_decode(gpu_model):
+    """With engine.decode_pingpong, decompress_batch of an even batch >= 4 runs as two half-batch plans, the host decoding one
+    half's layer while the GPU runs the other half's segment (engine._decompress_pingpong): images bit-equal to the single-plan decode and to
+    decompress() of every blob alone."""
+    im = make_input('synth', 6, 128, 192, 60).to(DEV)
+    lmb = torch.tensor([16.0, 64.0, 200.0, 500.0, 1024.0, 2048.0], device=DEV)
+    blobs = gpu_model.compress_batch(im, lmb=lmb)
+    eng = gpu_model.engine
+    one = gpu_model.decompress_batch(blobs)
+    eng.decode_pingpong = True                                             # opt-in: slower at 8 images per call (engine.py)
+    try:
+        rec = gpu_model.decompress_batch(blobs)
+        assert any(k[0] == 'dec' and len(k) == 5 for k in eng._plans)      # the half-batch plans were really used
+        again = gpu_model.decompress_batch(blobs)                          # replays the captured segments
+    finally:
+        eng.decode_pingpong = False
+    assert torch.equal(rec, one) and torch.equal(again, rec)
+    for b in range(6):
+        assert torch.equal(rec[b:b + 1], gpu_model.decompress(blobs[b]))
+
+
 def test_forward_stream_equals_forward(gpu_model):
     """model.forward_stream (pipelined H2D copy / launch plan / D2H read-back, lvae.engine.run_stream) returns, batch by
     batch and in order, exactly what the blocking forward() returns -- host batches (pinned and pageable), device batches,
