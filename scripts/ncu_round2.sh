@@ -8,6 +8,7 @@ timeout -s KILL 1500 python -m pytest tests -q -m gpu --timeout 300 --timeout-me
 python scripts/bench_latent.py > $O/r2_bench_latent.log 2>&1; cat $O/r2_bench_latent.log
 python scripts/bench_dwln.py > $O/r2_bench_dwln.log 2>&1
 python scripts/bench_gemm.py 4 > $O/r2_bench_gemm.log 2>&1
+python scripts/profile_plan.py f16x3+tail1 8 > $O/r2_profile_plan.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2400 --csv --log-file $O/r2_launches_f16x3_tail1.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-train-record > $O/r2_launches_bench.log 2>&1
 NCU="ncu --set full --clock-control none --import-source on"
 $NCU -k regex:gemm_tc_kernel -s 3 -c 1 -o $O/r2_ncu_fc1_s8 -f python scripts/bench_gemm.py 4 "s8 enc fc1" > /dev/null 2>&1
