@@ -16,7 +16,7 @@ python scripts/ncu_extract.py \
   "mlp_tc_kernel<3> fused MLP H/4: M=196608 C=192 hidden=384::$O/r2_ncu_mlp_s4.ncu-rep" \
   "dwln_kernel<1,7,3> H/4 C=192 k=7::$O/r2_ncu_dwln_s4.ncu-rep" \
   "latent_kernel<eval, vec4> B=64 L3 shape::$O/r2_ncu_latent_L3b64.ncu-rep" \
-  > $P/r2_ncu_sections.md
+  > $P/r2_ncu_sections.md   # appended by hand below the analysis header of r2_ncu_summary.md
 python scripts/summarize_launches.py $O/r2_launches_f16x3_tail1.csv > $P/r2_launches_f16x3_tail1.md
 cp $O/r2_launches_f16x3_tail1.csv $P/
 python scripts/parity_report.py $O/r2_parity_records.jsonl $P/r2_parity.md
