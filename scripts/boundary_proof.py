@@ -77,7 +77,7 @@ def run(name, cmd, cwd, env, out, timeout):
         except subprocess.TimeoutExpired:
             rc = 'timeout'
     txt = log.read_text()
-    return dict(script=name, rc=rc, seconds=round(time.time() - t0, 1), log=str(log.relative_to(ROOT)), tail=txt[-1500:])
+    return dict(script=name, rc=rc, seconds=round(time.time() - t0, 1), log=str(log.relative_to(ROOT) if log.is_relative_to(ROOT) else log), tail=txt[-1500:])
 
 
 def main():
@@ -86,7 +86,7 @@ def main():
     ap.add_argument('--work', default='/tmp/lvae_boundary')
     ap.add_argument('--iterations', type=int, default=20)
     args = ap.parse_args()
-    out, work = Path(args.out), Path(args.work)
+    out, work = Path(args.out).resolve(), Path(args.work)
     out.mkdir(parents=True, exist_ok=True)
     work.mkdir(parents=True, exist_ok=True)
     ref, how = reference_root()
