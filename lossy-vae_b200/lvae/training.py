@@ -107,7 +107,8 @@ def _vd_aten(x, x1, *p):
 
 # ------------------------------------------------------------------------------------------ op Functions
 class _BlockFn(torch.autograd.Function):
-    """ConvNeXt block (AdaLN | affine LN).  x [B,H,W,C]; ada: the [B, ada_total] matrix of all blocks' (shift | scale)
+    """ConvNeXt block (AdaLN | affine LN).  x [B,H,W,C]; ada: THIS block's [B, 2C] column slice -- a view, with the row stride
+    ada_total, of the [B, ada_total] matrix of all blocks' (shift | scale)
     rows (AdaLN) or None; params = conv_dw.weight, conv_dw.bias, fc1.weight, fc1.bias, fc2.weight, fc2.bias, gamma
     [, norm.weight, norm.bias]."""
 
@@ -115,7 +116,7 @@ class _BlockFn(torch.autograd.Function):
     def forward(ctx, T, blk, x, ada, *params):
         B, H, W, C_ = x.shape
         out = torch.empty_like(x)
-        T.P.ada = ada
+        T.P.ada = T.ada_full                       # the kernels address the full matrix (pointer, row stride, column offset)
         T.eng._block(T.P, blk, x, B, H, W, out=out)
         ctx.T, ctx.blk = T, blk
         ctx.save_for_backward(x, ada, *params)
@@ -128,16 +129,15 @@ class _BlockFn(torch.autograd.Function):
         gout = gout.contiguous()
         if T.native_bwd and T.eng.npl:
             return (None, None) + T.block_backward(blk, x, ada, params, gout)
-        off = T.eng.ada_off.get(id(blk), 0)
         C_, k = blk.dim, blk.kernel_size
-        ada_s = None if ada is None else ada[:, off:off + 2 * C_]
+        ada_s = ada
 
         def fn(x_, ada_, dw_w, dw_b, w1, b1, w2, b2, gamma, ln_w=None, ln_b=None):
             y = _dwln_aten(x_, ada_, dw_w, dw_b, ln_w, ln_b, k)
             y = F.linear(F.gelu(F.linear(y, w1, b1)), w2, b2)
             return x_ + y * gamma.reshape(-1)
         g = _grad_of(fn, [x, ada_s] + list(params), gout)
-        return (None, None, g[0], T.scatter_ada(ada, off, g[1])) + tuple(g[2:])
+        return (None, None, g[0], g[1]) + tuple(g[2:])
 
 
 class _ConvFn(torch.autograd.Function):
@@ -295,14 +295,20 @@ class TrainPath:
             self._side_used = False
         self._side_keep.clear()
 
-    def scatter_ada(self, ada, off, g):
-        if ada is None or g is None:
-            return None
-        full = torch.zeros_like(ada)
-        full[:, off:off + g.shape[1]] = g
-        return full
+    def split_ada(self, ada):
+        """[B, ada_total] -> {id(block): its [B, 2C] column slice}.  torch.split, so that autograd concatenates the blocks'
+        modulation gradients ONCE (SplitWithSizesBackward) -- slicing per block made every block's backward allocate a zero
+        [B, ada_total] matrix, fill one slice, and autograd add 90 of them up."""
+        self.ada_full = ada
+        if ada is None:
+            return {}
+        blocks = sorted((b for b in self.eng.blocks if id(b) in self.eng.ada_off), key=lambda b: self.eng.ada_off[id(b)])
+        sizes = [2 * b.dim for b in blocks]
+        assert sum(sizes) == ada.shape[1] and all(self.eng.ada_off[id(b)] == sum(sizes[:i]) for i, b in enumerate(blocks))
+        return {id(b): part for b, part in zip(blocks, ada.split(sizes, dim=1))}
 
     def _block(self, blk, x, ada):
+        ada = ada.get(id(blk)) if isinstance(ada, dict) else ada
         ps = [blk.conv_dw.weight, blk.conv_dw.bias, blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight,
               blk.mlp.fc2.bias, blk.gamma]
         if isinstance(blk, common.ConvNeXtBlockLN):
@@ -356,7 +362,7 @@ class TrainPath:
         B, H, W, C_ = x.shape
         M, hid, k = B * H * W, blk.hidden, blk.kernel_size
         wb = eng.w[id(blk)]
-        off = eng.ada_off.get(id(blk), 0)
+        off = 0                                     # `ada` is this block's slice: its data pointer already carries the offset
         gam = gamma.detach().reshape(-1)
         # recompute: a = AdaLN(LN(dwconv(x))) as operand planes, h = a W1^T + b1 (pre-activation)
         P.ada = ada
@@ -423,7 +429,7 @@ class TrainPath:
         self._join()
         if ln:
             return (dx, None, d_dww, d_dwb, d_w1, d_b1, d_w2, d_b2, d_gamma, dmod[0, C_:].clone(), dmod[0, :C_].clone())
-        return (dx, self.scatter_ada(ada, off, dmod), d_dww, d_dwb, d_w1, d_b1, d_w2, d_b2, d_gamma)
+        return (dx, dmod, d_dww, d_dwb, d_w1, d_b1, d_w2, d_b2, d_gamma)
 
     # ---- convolutions (patch down / up, 1x1 heads with K-concat and residual, the 3x3 posterior head): native backward
     def _mm_grad(self, name, g2d, a2d, colsum=None, act=0):
@@ -640,7 +646,7 @@ class TrainPath:
             self.P = _EagerPlan(eng, B)
         qres = self.family == 'qres'
         with torch.cuda.device(eng.device), torch.autocast('cuda', enabled=False):
-            ada = self._ada(lmb)
+            ada = self.split_ada(self._ada(lmb))
             # ---------------- bottom-up
             feats, x, s, first = {}, im, 1, True
             for mod in m.encoder.enc_blocks:
