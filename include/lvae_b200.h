@@ -117,6 +117,25 @@ typedef struct lvae_gemm_desc {
 } lvae_gemm_desc;
 
 int lvae_gemm(const lvae_gemm_desc* d, void* stream);
+
+/* The posterior head and the latent arithmetic of one layer in ONE launch (eval / compress branch of VRLVBlockBase.forward,
+ * lvae/models/qarv/model.py:66-74 + 95-96 + 106-108): `d` describes the implicit 3x3 posterior convolution (pre-split A planes,
+ * stride 1, pad 1, LVAE_EPI_BIAS, N = zdim <= 128, fp32 output); its result qm never reaches memory -- the epilogue reads the
+ * prior parameters (pm | plogv_raw) [M, 2 zdim], and writes z = rint(qm - pm) + pm to d->out, the per-image sums of -ln P to
+ * kl_partial[image * kl_stride + slot] (lvae_gemm_latent_num_partials(H, W, N) slots per image, one per (pixel tile, 32-column
+ * chunk, row quarter): a fixed layout, so the sums are deterministic and batch-invariant; slots a launch does not own are left
+ * untouched), optionally -ln P per element, and for the coder int32 symbols and scale-table indexes in NCHW order.  Same
+ * arithmetic, bit for bit, as lvae_latent_eval (csrc/latent_math.cuh).  cdf_kind: LVAE_CDF_*. */
+typedef struct lvae_latent_epilogue {
+  const float* prior;        /* [M, 2 N]: pm | plogv_raw */
+  const float* scale_table;  /* [n_scales] (needed with sym / idx) */
+  int32_t n_scales, cdf_kind;
+  float* kl_partial; int64_t kl_stride;
+  float* kl_elem;            /* [M, N] or NULL */
+  int32_t* sym; int32_t* idx;   /* [B, N, H, W] or both NULL */
+} lvae_latent_epilogue;
+int lvae_gemm_latent(const lvae_gemm_desc* d, const lvae_latent_epilogue* e, void* stream);
+int lvae_gemm_latent_num_partials(int H, int W, int N);
 int64_t lvae_gemm_workspace_bytes(const lvae_gemm_desc* d);
 /* diagnostics: number of lvae_gemm calls served so far by the CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x BN
  * tiles; csrc/gemm2_tc.cu).  Opt-in (environment, read per call: LVAE_GEMM2=1; LVAE_G2_MIN_TILES / LVAE_G2_BN override

@@ -5,6 +5,8 @@
 namespace lvae {
 int gemm_f32_launch(const lvae_gemm_desc* d, cudaStream_t stream);
 int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream);
+int gemm_tc_launch_latent(const lvae_gemm_desc* d, const lvae_latent_epilogue* lat, cudaStream_t stream);
+int gemm_tc_latent_num_partials(int H, int W, int N);
 bool gemm_smallk_applicable(const lvae_gemm_desc* d);
 int gemm_smallk_launch(const lvae_gemm_desc* d, cudaStream_t stream);
 int64_t gemm_tc_workspace_bytes(const lvae_gemm_desc* d);
@@ -13,6 +15,17 @@ int64_t gemm_tc_workspace_bytes(const lvae_gemm_desc* d);
 extern "C" int64_t lvae_gemm_workspace_bytes(const lvae_gemm_desc* d) {
   if (!d || d->precision == LVAE_PREC_FP32) return 0;
   return lvae::gemm_tc_workspace_bytes(d);
+}
+
+extern "C" int lvae_gemm_latent_num_partials(int H, int W, int N) { return lvae::gemm_tc_latent_num_partials(H, W, N); }
+
+extern "C" int lvae_gemm_latent(const lvae_gemm_desc* d, const lvae_latent_epilogue* e, void* stream) {
+  using namespace lvae;
+  LVAE_CHECK_ARG(d != nullptr && e != nullptr && d->w != nullptr && d->a_planes[0] != nullptr && d->out != nullptr);
+  LVAE_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->N > 0 && d->C0 > 0);
+  LVAE_CHECK_ARG(d->ksize == 3 && d->stride == 1 && d->pad == 1 && d->a1 == nullptr && d->a1_planes[0] == nullptr);
+  LVAE_CHECK_ARG(d->precision != LVAE_PREC_FP32);
+  return gemm_tc_launch_latent(d, e, (cudaStream_t)stream);
 }
 
 extern "C" int lvae_gemm(const lvae_gemm_desc* d, void* stream) {

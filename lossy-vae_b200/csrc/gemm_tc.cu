@@ -27,6 +27,7 @@
 // let the epilogue of tile i overlap the MMAs of tile i+1.  K order is fixed, there is no split-K and BN depends on N only, so results are bit-reproducible
 // and do not depend on the batch an image travels in.
 #include "tc_common.cuh"
+#include "latent_math.cuh"
 #include <cuda_bf16.h>
 #include <mutex>
 #include <stdlib.h>
@@ -66,6 +67,12 @@ struct TcParams {
   float acc_scale;       // 1 / (scale the weight planes carry): 1, or 2^-8 in the fp16 mode -- exact
   // implicit 3x3 conv (stride 1, pad 1) from NHWC planes: an M-tile is a CONV_TH x CONV_TW pixel patch of one image
   int conv, cH, cW, cC, tiles_w, tiles_h;
+  // latent epilogue of the implicit 3x3 posterior convolution (lvae_gemm_latent): the tile's result is qm; with the prior
+  // parameters read from lat_prior [M, 2 N] the epilogue quantises, evaluates the likelihood and writes z (p.out), the per-image
+  // rate partials (one slot per (pixel tile, 32-column chunk, row quarter): lat_kl[image * lat_kl_stride + slot]) and -- for the
+  // coder -- symbols and table indexes in NCHW order.  nullptr: plain epilogue.
+  const float* lat_prior; float* lat_kl; long long lat_kl_stride; float* lat_kl_elem;
+  int32_t* lat_sym; int32_t* lat_idx; const float* lat_table; int lat_nscales, lat_cdf;
   // split-K (weight gradients: K = pixels is the long dimension): tile index t = z * base_tiles + tile, split z owns the
   // k-blocks [z * kb_per, (z + 1) * kb_per); partial results meet in fp32 atomics on `out` (zeroed by the caller)
   int base_tiles, kb_per, atomic;
@@ -457,7 +464,43 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           __syncwarp();
           const int n = nb + lane;
           const bool n_ok = (lane < width) && (n < p.N);
-          if (n_ok && p.conv) {
+          if (p.conv && p.lat_prior != nullptr) {
+            // ---- latent epilogue: qm -> (z, -ln P, symbol, table index), arithmetic of latent_math.cuh (= latent_kernel<eval>)
+            const int mt = t / p.n_tiles;
+            const int ctx = mt % p.tiles_w, cty = (mt / p.tiles_w) % p.tiles_h, cb = mt / (p.tiles_w * p.tiles_h);
+            const int hw_img = p.cH * p.cW;
+            // the chunk holds 32 pixels x wv valid columns (wv = zdim = 8 on the largest layers): element i = lane + 32 k is
+            // pixel i / wv, column i % wv, so that every lane works whatever the width (lane = column would leave 24 of 32 idle)
+            int wv = p.N - nb; wv = wv > width ? width : wv; wv = wv < 0 ? 0 : wv;
+            float kl_sum = 0.f;
+            for (int i = lane; i < 32 * wv; i += 32) {
+              const int r = i / wv, cn = i - r * wv;
+              const int row = q * 32 + r;
+              const int hh = cty * CONV_TH + row / CONV_TW, ww = ctx * CONV_TW + row % CONV_TW;
+              if (hh < p.cH && ww < p.cW) {
+                const int nn = nb + cn;
+                const float qv = __fadd_rn(__uint_as_float(stg[r * 33 + cn]), p.bias ? __ldg(p.bias + nn) : 0.f);
+                const int64_t m = ((int64_t)cb * p.cH + hh) * p.cW + ww;
+                const float pm = __ldg(p.lat_prior + m * 2 * p.N + nn), pl = __ldg(p.lat_prior + m * 2 * p.N + p.N + nn);
+                float zz, kl, rr, sc;
+                latent_elem<0>(qv, pm, pl, 0.f, p.lat_cdf, zz, kl, rr, sc);
+                p.out[m * p.N + nn] = zz;
+                if (p.lat_kl_elem != nullptr) p.lat_kl_elem[m * p.N + nn] = kl;
+                if (p.lat_sym != nullptr) {
+                  const int64_t o = ((int64_t)cb * p.N + nn) * hw_img + (int64_t)hh * p.cW + ww;     // NCHW order for the coder
+                  p.lat_sym[o] = (int32_t)rr;
+                  p.lat_idx[o] = scale_index(sc, p.lat_table, p.lat_nscales);
+                }
+                kl_sum += kl;
+              }
+            }
+            kl_sum = warp_sum(kl_sum);
+            if (lane == 0) {
+              const int nch = (p.N + 31) / 32;
+              const int slot = (((cty * p.tiles_w + ctx) * nch + (nb >> 5)) << 2) + q;
+              p.lat_kl[(int64_t)cb * p.lat_kl_stride + slot] = kl_sum;
+            }
+          } else if (n_ok && p.conv) {
             // rows of the tile are the pixels of a CONV_TH x CONV_TW patch: row -> (h, w) -> m; N is small here
             const int mt = t / p.n_tiles;
             const int ctx = mt % p.tiles_w, cty = (mt / p.tiles_w) % p.tiles_h, cb = mt / (p.tiles_w * p.tiles_h);
@@ -665,6 +708,7 @@ static int pick_bn(int N, int npl) {
 }
 
 int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stream);
+static int gemm_tc_launch_impl(const lvae_gemm_desc* d, int split_k, const lvae_latent_epilogue* lat, cudaStream_t stream);
 // gemm2_tc.cu: the CTA-pair (cta_group::2) kernel for the large plain GEMMs of the 2-plane modes
 int gemm2_tc_launch(const lvae_gemm_desc* d, const void* const* a_pl, const void* const* a1_pl, int M, int K, int Ka, int C1,
                     int ek, cudaStream_t stream, int* handled);
@@ -672,7 +716,16 @@ int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream) { return gemm_t
 
 // split_k != 0: split-K over the persistent grid, partial tiles added atomically into d->out (which the caller zeroed);
 // plain [M,K] x [N,K] only (LVAE_EPI_BIAS without bias)
-int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stream) {
+int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stream) { return gemm_tc_launch_impl(d, split_k, nullptr, stream); }
+// lvae_gemm_latent: the implicit 3x3 convolution with the latent epilogue
+int gemm_tc_launch_latent(const lvae_gemm_desc* d, const lvae_latent_epilogue* lat, cudaStream_t stream) {
+  return gemm_tc_launch_impl(d, 0, lat, stream);
+}
+int gemm_tc_latent_num_partials(int H, int W, int N) {
+  return ((H + CONV_TH - 1) / CONV_TH) * ((W + CONV_TW - 1) / CONV_TW) * ((N + 31) / 32) * 4;
+}
+
+static int gemm_tc_launch_impl(const lvae_gemm_desc* d, int split_k, const lvae_latent_epilogue* lat, cudaStream_t stream) {
   const int npl = num_planes(d->precision);
   int Ho, Wo, K; int64_t M64;
   tc_geometry(d, &Ho, &Wo, &M64, &K);
@@ -783,6 +836,20 @@ int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stre
     splits = (nkb + p.kb_per - 1) / p.kb_per;                  // every split owns at least one k-block
     p.num_tiles = p.base_tiles * splits;
     p.atomic = 1;
+  }
+  p.lat_prior = nullptr; p.lat_kl = nullptr; p.lat_kl_stride = 0; p.lat_kl_elem = nullptr; p.lat_sym = nullptr; p.lat_idx = nullptr;
+  p.lat_table = nullptr; p.lat_nscales = 0; p.lat_cdf = 0;
+  if (lat != nullptr) {
+    if (!conv || ek != EK_MISC || p.n_tiles != 1 || d->epilogue != LVAE_EPI_BIAS || d->out == nullptr || d->out_planes[0] != nullptr) {
+      set_error("lvae_gemm_latent needs the implicit 3x3 convolution (pre-split A planes, stride 1, pad 1, C %% 16 == 0), N <= 128, "
+                "LVAE_EPI_BIAS and an fp32 output");
+      return LVAE_E_UNSUPPORTED;
+    }
+    LVAE_CHECK_ARG(lat->prior != nullptr && lat->kl_partial != nullptr && lat->kl_stride >= gemm_tc_latent_num_partials(d->H, d->W, d->N));
+    LVAE_CHECK_ARG((lat->sym == nullptr) == (lat->idx == nullptr));
+    LVAE_CHECK_ARG(lat->sym == nullptr || (lat->scale_table != nullptr && lat->n_scales >= 1));
+    p.lat_prior = lat->prior; p.lat_kl = lat->kl_partial; p.lat_kl_stride = lat->kl_stride; p.lat_kl_elem = lat->kl_elem;
+    p.lat_sym = lat->sym; p.lat_idx = lat->idx; p.lat_table = lat->scale_table; p.lat_nscales = lat->n_scales; p.lat_cdf = lat->cdf_kind;
   }
   p.bias = d->bias; p.gamma = d->gamma; p.res = d->res;
   p.epi = d->epilogue; p.r = d->shuffle_r; p.Ho = Ho; p.Wo = Wo;

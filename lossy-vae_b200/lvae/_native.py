@@ -39,11 +39,24 @@ class GemmDesc(C.Structure):
     ]
 
 
+class LatentEpilogue(C.Structure):
+    """lvae_latent_epilogue (include/lvae_b200.h): the latent arithmetic as the epilogue of the posterior convolution"""
+    _fields_ = [
+        ('prior', _fp), ('scale_table', _fp),
+        ('n_scales', C.c_int32), ('cdf_kind', C.c_int32),
+        ('kl_partial', _fp), ('kl_stride', C.c_int64),
+        ('kl_elem', _fp),
+        ('sym', _fp), ('idx', _fp),
+    ]
+
+
 _PROTOS = {
     'lvae_version': (C.c_int, []),
     'lvae_last_error': (C.c_char_p, []),
     'lvae_gemm': (C.c_int, [C.POINTER(GemmDesc), _fp]),
     'lvae_gemm_workspace_bytes': (C.c_int64, [C.POINTER(GemmDesc)]),
+    'lvae_gemm_latent': (C.c_int, [C.POINTER(GemmDesc), C.POINTER(LatentEpilogue), _fp]),
+    'lvae_gemm_latent_num_partials': (C.c_int, [C.c_int, C.c_int, C.c_int]),
     'lvae_gemm2_launch_count': (C.c_longlong, []),
     'lvae_debug_prof': (C.c_int, [C.c_int, _fp]),
     'lvae_set_tuning': (C.c_int, [C.c_int, C.c_int]),

@@ -113,6 +113,12 @@ class QarvEngine:
         # latency of its longest single rANS stream, not a throughput: 8 streams on 16 threads take as long as 4, so two
         # half-batch calls double the host time (5 -> 8.5 ms) and the host, not the GPU, is what a layer waits for
         self.decode_pingpong = __import__('os').environ.get('LVAE_DECODE_PINGPONG', '0') == '1'
+        # eval / compress plans of the qarv family: latent arithmetic as the epilogue of the posterior convolution (lvae_gemm_latent;
+        # qm never reaches HBM, 9 launches fewer).  Opt-in (LVAE_FUSE_LATENT=1): same symbols, same rate, but SLOWER at batch 8 --
+        # the posterior GEMMs are sub-wave launches (96 tiles at H/16: one tile per CTA, nothing to overlap the epilogue with) and a
+        # tile has 8 epilogue warps for 128 x zdim elements of 336 instructions each: H/16 head 43.5 -> 117.5 us, where the
+        # stand-alone kernel spreads the same arithmetic over every SM at full occupancy (13 us).  562 -> 556 images/s.
+        self.fuse_latent = __import__('os').environ.get('LVAE_FUSE_LATENT', '0') == '1'
         self.blocks = [m for m in model.modules() if isinstance(m, (common.ConvNeXtBlockAdaLN, common.ConvNeXtBlockLN))]
         self.ada_off = {}
         off = 0
@@ -295,7 +301,7 @@ class QarvEngine:
 
     # ------------------------------------------------------------------ plan construction helpers
     def _gemm(self, P, name, a0, geom, went, out, epi=N.EPI_BIAS, a1=None, C1=0, gamma=None, res=None, r=0,
-              a_planes=None, out_planes=None, a_act=0, a1_planes=None, out_planes_act=0, prec=None):
+              a_planes=None, out_planes=None, a_act=0, a1_planes=None, out_planes_act=0, prec=None, latent=None):
         """geom = (B, H, W, C0, ksize, stride, pad) of the NHWC input a0.  In a tensor-core mode the A operand is
         either `a_planes` (bf16 planes written by the producing kernel) or a0/a1, which the library im2col-splits
         into the plan's workspace first."""
@@ -326,6 +332,11 @@ class QarvEngine:
             assert a_planes is None and out_planes is None
         meta = dict(kind='gemm', flops=2 * Mo * went['N'] * went['K'], M=Mo, N=went['N'], K=went['K'], terms=N.MMA_TERMS[prec],
                     bytes=4 * (B * H * W * (C0 + C1) + went['N'] * went['K'] + Mo * went['N'] * (2 if res is not None else 1)))
+        if latent is not None:      # the implicit 3x3 posterior convolution with the latent arithmetic as its epilogue
+            meta['latent_elems'] = Mo * went['N']
+            P.op(name, self.lib.lvae_gemm_latent, C.byref(d), C.byref(latent),
+                 keep=(d, latent, went, out, a_planes), meta=meta)
+            return
         P.op(name, self.lib.lvae_gemm, C.byref(d), keep=(d, a0, a1, went, out, gamma, res, a_planes, out_planes, ws, a1_planes),
              meta=meta)
 
@@ -548,8 +559,10 @@ class QarvEngine:
         self._gemm(P, name + '.c3', h2, (B, Hs, Ws, hid, ks, 1, (ks - 1) // 2), wv['c3'], h1, epi=N.EPI_BIAS_GELU)
         self._gemm(P, name + '.c4', h1, (B, Hs, Ws, hid, 1, 1, 0), wv['c4'], out)
 
-    def _posterior(self, P, blk, x, enc_feat, geom):
-        """transform_posterior (qarv/model.py:56-70) -> qm [M, zdim]"""
+    def _posterior(self, P, blk, x, enc_feat, geom, fuse=None):
+        """transform_posterior (qarv/model.py:56-70) -> qm [M, zdim].  fuse = dict(lat=LatentEpilogue, z=buffer): when the head
+        runs as the implicit tensor-core convolution, the latent arithmetic becomes its epilogue (lvae_gemm_latent): z is
+        written instead of qm, fuse['done'] is set and None comes back."""
         B, Hs, Ws, Cc = geom
         M = B * Hs * Ws
         wl = self.w[id(blk)]
@@ -589,6 +602,10 @@ class QarvEngine:
             # head convolves implicitly (shifted TMA boxes) -- no im2col workspace
             mp = [P.named(f'post_m_pl{i}', M * Cc, dtype=torch.bfloat16)[:M * Cc] for i in range(self.npl)]
             mg = self._block(P, blk.posterior2, mg, B, Hs, Ws, out_planes=mp)
+            if fuse is not None and wl['posterior']['N'] <= 128:
+                self._gemm(P, 'posterior', None, (B, Hs, Ws, Cc, 3, 1, 1), wl['posterior'], fuse['z'], a_planes=mp, latent=fuse['lat'])
+                fuse['done'] = True
+                return None
             self._gemm(P, 'posterior', None, (B, Hs, Ws, Cc, 3, 1, 1), wl['posterior'], qm, a_planes=mp)
         else:
             mg = self._block(P, blk.posterior2, mg, B, Hs, Ws)
@@ -604,6 +621,8 @@ class QarvEngine:
             if getattr(mod, 'is_latent_block', False):
                 hw = Hs * Ws
                 np_ = self.lib.lvae_latent_num_partials(hw, mod.zdim)
+                if self.family == 'qarv':       # the latent epilogue of the posterior convolution has its own slot layout
+                    np_ = max(np_, self.lib.lvae_gemm_latent_num_partials(Hs, Ws, mod.zdim))
                 lay.append((hw, mod.zdim, np_, off, Hs, Ws))
                 off += np_
             elif getattr(mod, 'op_kind', None) == 'up':
@@ -632,12 +651,36 @@ class QarvEngine:
 
         def latent_fn(P, blk, li, x, prior, geom):
             hw, zd, np_, off, Hs, Ws = lay[li]
-            qm = self._posterior(P, blk, x, feats[blk.enc_key] if self.family == 'qarv' else feats[Hs], geom)
             z = P.f32(B * hw, zd)
             kle = P.f32(B * hw, zd) if want_elem else None
+            klp = P.kl_partial[:, off:]
+            fuse = None
+            if self.family == 'qarv' and mode in ('eval', 'compress') and self.npl and self.fuse_latent:
+                # eval / compress: quantise + likelihood (+ symbols, indexes) as the epilogue of the posterior convolution
+                sym = idx = None
+                if mode == 'compress':
+                    n_el = B * zd * Hs * Ws
+                    sym = P.sym_all[P.sym_used:P.sym_used + n_el].view(B, zd, Hs, Ws)
+                    idx = P.idx_all[P.sym_used:P.sym_used + n_el].view(B, zd, Hs, Ws)
+                tab = self.w[id(blk)]['table']
+                if tab is None and mode == 'compress':
+                    raise ValueError('Uninitialized CDFs. Run update() first')      # CompressAI's message
+                lat = N.LatentEpilogue()
+                lat.prior, lat.scale_table, lat.n_scales = _ptr(prior), _ptr(tab), 0 if tab is None else tab.numel()
+                lat.cdf_kind = N.CDF_ERFC if blk.discrete_gaussian.cdf_kind == 'erfc' else N.CDF_NORMAL
+                lat.kl_partial, lat.kl_stride, lat.kl_elem = klp.data_ptr(), kl_cols, _ptr(kle)
+                lat.sym, lat.idx = _ptr(sym), _ptr(idx)
+                fuse = dict(lat=lat, z=z, keep=(prior, tab, kle, sym, idx))
+            qm = self._posterior(P, blk, x, feats[blk.enc_key] if self.family == 'qarv' else feats[Hs], geom, fuse=fuse)
             P.z.append(z)
             P.kl_elem.append(kle)
-            klp = P.kl_partial[:, off:]
+            if fuse is not None and fuse.get('done'):
+                P.keepalive = getattr(P, 'keepalive', []) + [fuse]
+                if mode == 'compress':
+                    P.sym_used += B * zd * Hs * Ws
+                    P.sym.append(fuse['keep'][3])
+                    P.idx.append(fuse['keep'][4])
+                return z
             if self.family == 'rd':
                 # continuous posterior: z = qm + qv * eps with eps ~ N(0,1) also in eval (rd/model.py:206-213)
                 noise = P.f32(B * hw, zd)

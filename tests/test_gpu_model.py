@@ -337,6 +337,39 @@ def test_pingpong_decode_equals_one_plan_decode_and_per_image_decode(gpu_model):
         assert torch.equal(rec[b:b + 1], gpu_model.decompress(blobs[b]))
 
 
+def test_latent_epilogue_of_the_posterior_convolution_equals_the_latent_kernel(gpu_model):
+    """lvae_gemm_latent (engine.fuse_latent, opt-in): quantise + likelihood + symbols / indexes as the epilogue of the implicit
+    3x3 posterior convolution use the arithmetic of csrc/latent_math.cuh, like the stand-alone kernel: identical latents,
+    identical bit streams, rate equal up to the order of the per-image partial sums."""
+    eng = gpu_model.engine
+    im = make_input('synth', 3, 128, 192, 70).to(DEV)
+    lmb = torch.tensor([32.0, 500.0, 2048.0], device=DEV)
+
+    def run():
+        eng._plans.clear()
+        x_hat, stats = gpu_model.forward_end2end(im, lmb, get_latent=True)
+        out = gpu_model(im, lmb=lmb)
+        return x_hat.clone(), [s_['z'].clone() for s_ in stats], [s_['kl'].clone() for s_ in stats], out, gpu_model.compress_batch(im, lmb=lmb)
+
+    assert not eng.fuse_latent
+    base = run()
+    eng.fuse_latent = True
+    try:
+        fused = run()
+        assert any(o.meta.get('latent_elems') for P in eng._plans.values() for seg in P.segments for o in seg)   # really fused
+    finally:
+        eng.fuse_latent = False
+        eng._plans.clear()
+    assert torch.equal(base[0], fused[0])
+    for a, b in zip(base[1], fused[1]):
+        assert torch.equal(a, b)
+    for a, b in zip(base[2], fused[2]):
+        assert torch.equal(a, b)                                   # -ln P per element: the same bits
+    assert base[4] == fused[4]                                     # compressed bytes
+    assert abs(base[3]['bppix'] - fused[3]['bppix']) <= 1e-6 * base[3]['bppix']
+    assert base[3]['psnr'] == fused[3]['psnr']
+
+
 def test_forward_stream_equals_forward(gpu_model):
     """model.forward_stream (pipelined H2D copy / launch plan / D2H read-back, lvae.engine.run_stream) returns, batch by
     batch and in order, exactly what the blocking forward() returns -- host batches (pinned and pageable), device batches,
