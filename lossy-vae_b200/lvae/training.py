@@ -263,12 +263,15 @@ class TrainPath:
         # records them as parallel branches.
         self.side_enabled = os.environ.get('LVAE_TRAIN_SIDE_STREAM', '1') != '0'
         self.side_stream = None         # created on first use
+        # ConvNeXt block backward: the fc2 weight gradient, the fc1 weight gradient (+ its fp32 dwln recompute) and the depthwise filter
+        # gradient each on a stream of their own (1 lane: 356, 2: 377, 3: 381-385 images/s at qarv 16 x 256^2)
+        self.side_lanes = int(os.environ.get('LVAE_TRAIN_SIDE_LANES', '3'))
         self._side_used = False
         self._side_keep = []
 
     # ---- helpers
     @contextlib.contextmanager
-    def _side(self, *keep):
+    def _side(self, *keep, lane=0):
         """Run the enclosed launches on the side stream, ordered after everything the current stream has been given so far.
         `keep`: tensors of the current stream that the side work reads -- held until _join() so that the caching allocator
         cannot hand their memory to a later allocation of the main stream while the side stream still reads it."""
@@ -277,21 +280,24 @@ class TrainPath:
             return
         if self.side_stream is None:
             self.side_stream = torch.cuda.Stream(self.eng.device)
+            self.side_streams = [self.side_stream] + [torch.cuda.Stream(self.eng.device) for _ in range(3)]
+        st = self.side_streams[lane % max(1, min(self.side_lanes, len(self.side_streams)))]
         main = torch.cuda.current_stream(self.eng.device)
         ev = torch.cuda.Event()
         ev.record(main)
-        self.side_stream.wait_event(ev)
-        self._side_used = True
+        st.wait_event(ev)
+        self._side_used = (self._side_used or set()) | {st}
         self._side_keep.extend(keep)
-        with torch.cuda.stream(self.side_stream):
+        with torch.cuda.stream(st):
             yield
 
     def _join(self):
         """The current stream waits for the side stream (end of every backward())."""
         if self._side_used:
-            ev = torch.cuda.Event()
-            ev.record(self.side_stream)
-            torch.cuda.current_stream(self.eng.device).wait_event(ev)
+            for st in self._side_used:               # only the streams this backward() forked onto
+                ev = torch.cuda.Event()
+                ev.record(st)
+                torch.cuda.current_stream(self.eng.device).wait_event(ev)
             self._side_used = False
         self._side_keep.clear()
 
@@ -399,12 +405,12 @@ class TrainPath:
                   epi=N.EPI_GELU_BWD, res=h, prec=self.DGRAD_PREC)
         # fc1: h = a W1^T + b1;  a is needed for the weight gradient only: one more (fp32) dwln launch, on the side stream
         a32 = torch.empty(M, C_, device=x.device)
-        with self._side(dh, a32, x, ada):
+        with self._side(dh, a32, x, ada, lane=1):
             P.op('dwln', eng.lib.lvae_dwconv_ln_adaln, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']), _ptr(ada), eng.ada_total, off,
                  _ptr(wb.get('ln_w')), _ptr(wb.get('ln_b')), _ptr(a32), B, H, W, C_, k)
             if tc_wgrad:
                 d_b1 = torch.zeros(hid, device=x.device)
-                d_w1 = self._wgrad(self._t_planes('wg_b', dh, colsum=d_b1), self._t_planes('wg_a', a32), hid, C_, M)
+                d_w1 = self._wgrad(self._t_planes('wg_d', dh, colsum=d_b1), self._t_planes('wg_c', a32), hid, C_, M)
             else:
                 d_w1 = dh.t().mm(a32)
                 d_b1 = dh.sum(0)
@@ -420,7 +426,7 @@ class TrainPath:
         dmod, dc = torch.empty(1 if ln else B, 2 * C_, device=x.device), torch.empty(M, C_, device=x.device)
         P.op('ln_mod_bwd', lib.lvae_ln_mod_bwd, _ptr(c), _ptr(da), _ptr(ada), eng.ada_total, off, _ptr(wb.get('ln_w')),
              _ptr(dc), _ptr(dmod), B, H * W, C_)
-        with self._side(dc):
+        with self._side(dc, lane=2):
             dwp, d_dwb = torch.empty(k * k, C_, device=x.device), torch.empty(C_, device=x.device)
             P.op('dwconv_wgrad', lib.lvae_dwconv_wgrad, _ptr(dc), _ptr(x), _ptr(dwp), _ptr(d_dwb), B, H, W, C_, k)
             d_dww = dwp.t().reshape(C_, 1, k, k)
