@@ -468,14 +468,23 @@ class TrainPath:
             Xa = None if tc else (F.gelu(X2) if act else X2)
             Gp = F.pad(G4, (0, 0, 1, 1, 1, 1))
             dw4 = torch.empty(Nn, C0, 3, 3, device=dev)
-            for ky in range(3):
-                for kx in range(3):
-                    Gt = Gp[:, 2 - ky:2 - ky + H, 2 - kx:2 - kx + W_, :].reshape(M, Nn)
-                    if tc:
-                        dw4[:, :, ky, kx] = self._wgrad(self._t_planes('wg_a', Gt.contiguous()), x_t, Nn, C0, M)
-                    else:
-                        dw4[:, :, ky, kx] = Gt.t().mm(Xa)
             db = G4.reshape(M, Nn).sum(0)
+            ready = None
+            if self.side_enabled:
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream(dev))
+        # the nine taps are independent: round-robin over the side lanes, each lane with its own scratch planes for shift(G)
+        lanes = max(1, self.side_lanes) if self.side_enabled else 1
+        for tap in range(9):
+            ky, kx = divmod(tap, 3)
+            with self._side(Gp, x_t, Xa, dw4, lane=tap % lanes):
+                if ready is not None:
+                    torch.cuda.current_stream(dev).wait_event(ready)
+                Gt = Gp[:, 2 - ky:2 - ky + H, 2 - kx:2 - kx + W_, :].reshape(M, Nn)
+                if tc:
+                    dw4[:, :, ky, kx] = self._wgrad(self._t_planes(f'wg_a{tap % lanes}', Gt.contiguous()), x_t, Nn, C0, M)
+                else:
+                    dw4[:, :, ky, kx] = Gt.t().mm(Xa)
         return dxm, dw4, db
 
     def vd_backward(self, wv, x, x1, params, gout):
