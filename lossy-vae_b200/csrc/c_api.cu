@@ -45,7 +45,7 @@ extern "C" int lvae_gemm(const lvae_gemm_desc* d, void* stream) {
   LVAE_CHECK_ARG(d->epilogue >= LVAE_EPI_BIAS && d->epilogue <= LVAE_EPI_GELU_BWD);
   if (d->epilogue == LVAE_EPI_GELU_BWD)
     LVAE_CHECK_ARG(d->res != nullptr && d->out != nullptr && d->precision != LVAE_PREC_FP32 && d->ksize == 1 && d->N % 4 == 0 &&
-                   d->out_planes[0] == nullptr && d->C0 >= 64);
+                   d->C0 >= 64);        // out_planes: operand planes of the result as well (the next data-gradient GEMM's A)
   if (d->epilogue == LVAE_EPI_SCALE_RES) LVAE_CHECK_ARG(d->gamma && d->res);
   if (d->epilogue == LVAE_EPI_BIAS_RES) LVAE_CHECK_ARG(d->res != nullptr);
   if (d->epilogue == LVAE_EPI_SHUFFLE_NHWC || d->epilogue == LVAE_EPI_SHUFFLE_NCHW)

@@ -401,8 +401,11 @@ class TrainPath:
             d_gamma = ((w2.detach() * dw2_raw).sum(1) + b2.detach() * db2_raw).reshape(gamma.shape)
         # dh = ((dout * gamma) W2) * gelu'(h): GELU' applied in the GEMM's epilogue
         dh = torch.empty(M, hid, device=x.device)
+        # dh leaves the epilogue twice: fp32 (for the transposing split of the fc1 weight gradient) and as the two bf16 operand
+        # planes that the fc1 data-gradient GEMM reads -- no split pass over [M, hid] in between
+        dh_pl = [P.named(f'dh_pl{i}', M * hid, dtype=torch.bfloat16)[:M * hid] for i in range(2)] if hid % 8 == 0 else None
         eng._gemm(P, 'fc2.dgrad', go, (1, 1, M, C_, 1, 1, 0), self._transposed(gam[:, None] * w2.detach()), dh,
-                  epi=N.EPI_GELU_BWD, res=h, prec=self.DGRAD_PREC)
+                  epi=N.EPI_GELU_BWD, res=h, prec=self.DGRAD_PREC, out_planes=dh_pl)
         # fc1: h = a W1^T + b1;  a is needed for the weight gradient only: one more (fp32) dwln launch, on the side stream
         a32 = torch.empty(M, C_, device=x.device)
         with self._side(dh, a32, x, ada, lane=1):
@@ -415,7 +418,8 @@ class TrainPath:
                 d_w1 = dh.t().mm(a32)
                 d_b1 = dh.sum(0)
         da = torch.empty(M, C_, device=x.device)
-        eng._gemm(P, 'fc1.dgrad', dh, (1, 1, M, hid, 1, 1, 0), self._transposed(w1.detach()), da, epi=N.EPI_BIAS, prec=self.DGRAD_PREC)
+        eng._gemm(P, 'fc1.dgrad', None if dh_pl else dh, (1, 1, M, hid, 1, 1, 0), self._transposed(w1.detach()), da, epi=N.EPI_BIAS,
+                  prec=self.DGRAD_PREC, a_planes=dh_pl)
         del dh, h, a32
         # dwconv + LayerNorm + modulation: recompute the conv output, LayerNorm / modulation backward, filter gradient,
         # data gradient (transposed conv + the residual branch's gradient) -- csrc/dwln_bwd.cu
