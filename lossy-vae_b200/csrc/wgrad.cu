@@ -28,13 +28,17 @@ __global__ void __launch_bounds__(256) split_planes_t_kernel(const float* __rest
     const int64_t pbase = ((int64_t)blockIdx.x * ST_TILES + it) * 64;
     if (pbase >= P) break;
     __syncthreads();
-    for (int r = ty; r < 64; r += 8) {
-      const int64_t pp = pbase + r;
+    // two rows per step: with ACT the GELU runs in its packed fp32x2 form (same bits as the scalar one, half the issue slots --
+    // this kernel is bound by the erf arithmetic, not by memory, when ACT is set)
+    for (int r = ty; r < 64; r += 16) {
+      const int64_t pa = pbase + r, pb = pbase + r + 8;
       const int c = cbase + tx;
-      float v = (pp < P && c < C) ? __ldg(x + pp * C + c) : 0.f;
-      if (ACT) v = gelu_erf(v);
-      csum += v;
-      tile[r][tx] = v;
+      float2 v = make_float2((pa < P && c < C) ? __ldg(x + pa * C + c) : 0.f, (pb < P && c < C) ? __ldg(x + pb * C + c) : 0.f);
+      if (ACT) v = gelu_erf2(v);
+      csum += v.x;
+      csum += v.y;
+      tile[r][tx] = v.x;
+      tile[r + 8][tx] = v.y;
     }
     __syncthreads();
     const int64_t pp = pbase + 2 * tx;
