@@ -399,7 +399,7 @@ def run_train(args):
             out = {'bppix': None, 'psnr': None}
     e[3].record(st)
     barrier()
-    ms_eager = None
+    ms_eager = ms_autograph = None
     if eager_too:
         e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e4.record(st)
@@ -409,6 +409,19 @@ def run_train(args):
         e5.record(st)
         barrier()
         ms_eager = e4.elapsed_time(e5)
+        # the same unmodified loop with the model's forward + backward replayed as two CUDA graphs (AutoGraphedTrain, opt-in)
+        model.train_path.autograph_enabled = True
+        for _ in range(3):
+            step(im_dev)
+        e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e6.record(st)
+        for _ in range(args.steps):
+            out = step(im_host.to(dev, non_blocking=True))
+            out['loss'].item()
+        e7.record(st)
+        barrier()
+        ms_autograph = e6.elapsed_time(e7)
+        model.train_path.autograph_enabled = False
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])], device=dev, dtype=torch.float64)
     if world > 1:
@@ -438,6 +451,8 @@ def run_train(args):
             'e2e': {'value': n_img / (ms_e2e / 1e3), 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': im_host.numel() * 4, 'd2h_bytes_per_step': 4,
                     'eager_value': None if ms_eager is None else n_img / (ms_eager / 1e3),
+                    'eager_autograph_value': None if ms_autograph is None else n_img / (ms_autograph / 1e3),
+                    'eager_autograph_call': None if ms_autograph is None else 'the same loop with LVAE_TRAIN_AUTOGRAPH=1: model(batch) and loss.backward() replay two captured graphs (lvae.training.AutoGraphedTrain); torch.optim.Adam stays eager',
                     'eager_call': None if ms_eager is None else 'model(batch)["loss"].backward(); optimizer.step() as lvae/trainer.py '
                                                                 'runs it (torch.optim.Adam, one launch at a time: host-bound)'},
             'gpu_launches': launches, 'launches_per_step': launches // max(1, args.steps),

@@ -271,7 +271,23 @@ class HierarchicalVAE(nn.Module):
         `loss.backward()` of lvae/trainer.py:262-270 differentiates (reference model.py:517-569)."""
         assert 0 <= float(im.min()) <= float(im.max()) <= 1, 'image values must lie in [0, 1]'
         nB, imC, imH, imW = im.shape
-        res = self.train_path.objective(im, self._lmb(nB), noise=noise)
+        T = self.train_path
+        if T.autograph_enabled and noise is None and not return_rec and T.autograph.usable(im, None):
+            # forward + backward of this shape as two CUDA-graph replays (lvae.training.AutoGraphedTrain)
+            loss, sv, klv = T.autograph(im, self._lmb(nB))
+            host, klh = sv.cpu(), klv.cpu()
+            ndims = imC * imH * imW
+            bpdim = [float(k) / ndims * self.log2_e for k in klh]
+            self._stats_log['train_bpdim'] = bpdim
+            self._stats_log['train_bppix'] = [b * imC for b in bpdim]
+            stats = OrderedDict()
+            stats['loss'] = loss
+            stats['kl'] = float(host[0])
+            stats[self.out_net.loss_name] = float(host[3])
+            stats['bppix'] = float(host[0]) * self.log2_e * imC
+            stats['psnr'] = -10 * math.log10(float(host[2]))
+            return stats
+        res = T.objective(im, self._lmb(nB), noise=noise)
         ndims = imC * imH * imW
         kls = torch.stack([k.detach().reshape(nB, -1).sum(1).mean(0) / ndims for k in res['kl']])
         bpdim = kls * self.log2_e

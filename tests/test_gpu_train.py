@@ -10,6 +10,7 @@ import torch
 
 import lvae_oracle as O
 import qres_oracle as Q
+from oracle_inputs import make_input
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
@@ -331,3 +332,65 @@ def test_gpu_crop_flip_matches_indexing(native_lib):
         if int(flip[b]):
             ref = ref.flip(-1)
         assert torch.equal(out[b].cpu(), ref)
+
+
+def test_autographed_forward_backward_equals_the_eager_step(native_lib):
+    """lvae.training.AutoGraphedTrain (opt-in): `model(batch)['loss'].backward()` as two CUDA-graph replays gives the loss and
+    the gradients of the eager step -- same seed, same noise draws, every parameter -- on the first call (capture) and on later
+    replays with other batches and updated weights; another shape falls back to the eager path."""
+    import lvae
+    torch.manual_seed(0)
+    m = lvae.get_model('qarv_base').to(DEV).train()
+    ims = [make_input('synth', 2, 64, 64, 500 + i).to(DEV) for i in range(3)]
+    lmb = torch.tensor([64.0, 1024.0], device=DEV)
+    params = [p for p in m.parameters() if p.requires_grad]
+
+    def step(im, seed):
+        torch.manual_seed(seed)
+        for p in params:
+            p.grad = None
+        out = m(im, lmb=lmb)
+        out['loss'].backward()
+        return out['loss'].item(), out['bppix'], out['psnr'], [None if p.grad is None else p.grad.clone() for p in params]
+
+    eager = [step(im, 10 + i) for i, im in enumerate(ims)]
+    m.train_path.autograph_enabled = True
+    try:
+        for rnd in range(2):                                      # round 0 captures on ims[0]; round 1 only replays
+            for i, im in enumerate(ims):
+                got = step(im, 10 + i)
+                assert m.train_path.autograph.core is not None
+                same_noise = got[0] == eager[i][0]
+                assert abs(got[0] - eager[i][0]) <= (1e-6 if same_noise else 5e-2) * abs(eager[i][0]), (rnd, i, got[0], eager[i][0])
+                if same_noise:
+                    assert got[1] == eager[i][1] and got[2] == eager[i][2]
+                    for g, e in zip(got[3], eager[i][3]):
+                        assert (g is None) == (e is None)
+                        if g is not None:
+                            assert torch.allclose(g, e, rtol=1e-5, atol=1e-7 * float(e.abs().max()) + 1e-12), float((g - e).abs().max())
+        # p.grad never aliases the graphs' static gradient buffers (AccumulateGrad copies): the next replay cannot overwrite it,
+        # and accumulating two backward passes adds up
+        ag = m.train_path.autograph
+        static = {g.data_ptr() for g in ag.s_grads if g is not None}
+        assert all(p.grad is None or p.grad.data_ptr() not in static for p in params)
+        one = [None if p.grad is None else p.grad.clone() for p in params]
+        torch.manual_seed(10 + len(ims) - 1)
+        m(ims[-1], lmb=lmb)['loss'].backward()                      # second backward into the same .grad: the sum
+        for p, g1 in zip(params, one):
+            if g1 is not None:
+                assert torch.allclose(p.grad, 2 * g1, rtol=1e-5, atol=1e-7 * float(g1.abs().max()) + 1e-12)
+        # weights move -> the captured forward re-packs them: the loss changes like the eager one does
+        with torch.no_grad():
+            for p in params:
+                p.mul_(1.01)
+        g2 = step(ims[0], 10)
+        m.train_path.autograph_enabled = False
+        e2 = step(ims[0], 10)
+        assert abs(g2[0] - e2[0]) <= 5e-2 * abs(e2[0]) and g2[0] != eager[0][0]
+        m.train_path.autograph_enabled = True
+        other = make_input('synth', 1, 64, 128, 9).to(DEV)         # another shape: eager path, no new capture
+        out = m(other, lmb=lmb[:1])
+        out['loss'].backward()
+        assert m.train_path.autograph.shape == (2, 3, 64, 64)
+    finally:
+        m.train_path.autograph_enabled = False
