@@ -401,6 +401,8 @@ def run_train(args):
     barrier()
     ms_eager = ms_autograph = None
     if eager_too:
+        model.train_path.autograph_enabled = False           # plain eager first: one Python-issued launch at a time
+        step(im_dev)
         e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e4.record(st)
         for _ in range(args.steps):
@@ -452,9 +454,9 @@ def run_train(args):
                     'h2d_bytes_per_step': im_host.numel() * 4, 'd2h_bytes_per_step': 4,
                     'eager_value': None if ms_eager is None else n_img / (ms_eager / 1e3),
                     'eager_autograph_value': None if ms_autograph is None else n_img / (ms_autograph / 1e3),
-                    'eager_autograph_call': None if ms_autograph is None else 'the same loop with LVAE_TRAIN_AUTOGRAPH=1: model(batch) and loss.backward() replay two captured graphs (lvae.training.AutoGraphedTrain); torch.optim.Adam stays eager',
+                    'eager_autograph_call': None if ms_autograph is None else 'the same loop as a user gets it by default: model(batch) and loss.backward() replay two captured graphs (lvae.training.AutoGraphedTrain); torch.optim.Adam stays eager',
                     'eager_call': None if ms_eager is None else 'model(batch)["loss"].backward(); optimizer.step() as lvae/trainer.py '
-                                                                'runs it (torch.optim.Adam, one launch at a time: host-bound)'},
+                                                                'runs it, with LVAE_TRAIN_AUTOGRAPH=0 (torch.optim.Adam, one launch at a time: host-bound)'},
             'gpu_launches': launches, 'launches_per_step': launches // max(1, args.steps),
             'clocks': clocks, 'result': {'loss': loss, 'bppix': out['bppix'], 'psnr': out['psnr']},
             'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30,
