@@ -14,6 +14,35 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _run_ranks(target, extra=(), world=2, attempts=2):
+    """Spawn `world` ranks of `target(rank, world, port, *extra, q)` and return what they put on the queue.  A rendezvous
+    that fails for reasons outside the code under test (the free port taken in between, a slow first `import torch` in a
+    fresh container) is retried once on a new port; the numeric assertions stay with the caller, outside the retry."""
+    last = None
+    for _ in range(attempts):
+        ctx = mp.get_context('spawn')
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=target, args=(r, world, port) + tuple(extra) + (q,)) for r in range(world)]
+        for p in procs:
+            p.start()
+        ok = True
+        try:
+            res = [q.get(timeout=240) for _ in procs]
+        except Exception as e:              # noqa: BLE001 -- queue.Empty: a rank died or never got through the rendezvous
+            last, ok, res = e, False, None
+        for p in procs:
+            p.join(timeout=120)
+            if p.is_alive():
+                p.kill()
+                p.join()
+            ok = ok and p.exitcode == 0
+            last = last or (None if p.exitcode == 0 else f'rank exited with {p.exitcode}')
+        if ok:
+            return res
+    raise AssertionError(f'the ranks failed {attempts} times: {last!r}')
+
+
 def _worker(rank, world, port, n_total, q):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -35,16 +64,7 @@ def _worker(rank, world, port, n_total, q):
 
 @pytest.mark.parametrize('n_total', [8, 7, 1])
 def test_two_rank_shard_gather_equals_single_rank(n_total):
-    ctx = mp.get_context('spawn')
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=120) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _run_ranks(_worker, (n_total,))
     g = torch.Generator().manual_seed(0)
     full = torch.rand(n_total, 2, generator=g)
     lmb = torch.rand(n_total, generator=g) * 2000 + 16
@@ -86,16 +106,7 @@ def _grad_worker(rank, world, port, q):
 
 def test_flat_gradient_allreduce_averages_in_place():
     """The training step's single collective (lvae.training.allreduce_flat_gradients; NCCL on the GPUs) on gloo."""
-    ctx = mp.get_context('spawn')
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = sorted(_run_ranks(_grad_worker), key=lambda t: t[0])
     (_, b0, a0, ip0), (_, b1, a1, ip1) = res
     assert ip0 and ip1
     for x0, x1, y0, y1 in zip(b0, b1, a0, a1):
@@ -140,16 +151,7 @@ def _bucket_worker(rank, world, port, q):
 def test_gradient_buckets_average_flat_views_during_backward():
     """lvae.training.GradientBuckets (the data-parallel collective of GraphedTrainStep: gradients are views of one flat
     buffer, reduced bucket by bucket from post-accumulate hooks while the backward runs) on gloo, world size 2."""
-    ctx = mp.get_context('spawn')
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = sorted(_run_ranks(_bucket_worker), key=lambda t: t[0])
     (_, l0, o0, v0, nb0, u0), (_, l1, o1, v1, nb1, u1) = res
     assert v0 and v1 and nb0 == nb1 and nb0 >= 3 and u0 == 0.0 and u1 == 0.0
     for step in range(2):
