@@ -14,18 +14,20 @@ int gemm_tc_launch_split(const lvae_gemm_desc* d, int split_k, cudaStream_t stre
 
 // x [P, C] fp32 -> hi / lo bf16 planes [C, P];  P even.  One CTA owns 32 channels x ST_TILES * 64 pixels.
 // ACT: planes of gelu(x).  colsum != NULL: colsum[c] += sum over the CTA's pixels of x[p, c] (one atomic per channel).
+// tiles: 64-pixel tiles per CTA (<= ST_TILES; fewer when the matrix is small, so that the grid still covers the SMs -- at the
+// H/16 ... H/64 stages of a 256 x 256 crop a fixed 8 left 32 CTAs looping 8 times: 15-28 us for a few hundred KB).
 constexpr int ST_TILES = 8;
 template <bool ACT>
 __global__ void __launch_bounds__(256) split_planes_t_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ p0,
                                                              __nv_bfloat16* __restrict__ p1, int64_t P, int C,
-                                                             float* __restrict__ colsum) {
+                                                             float* __restrict__ colsum, int tiles) {
   __shared__ float tile[64][33];
   __shared__ float red[8][32];
   const int cbase = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   float csum = 0.f;
-  for (int it = 0; it < ST_TILES; ++it) {
-    const int64_t pbase = ((int64_t)blockIdx.x * ST_TILES + it) * 64;
+  for (int it = 0; it < tiles; ++it) {
+    const int64_t pbase = ((int64_t)blockIdx.x * tiles + it) * 64;
     if (pbase >= P) break;
     __syncthreads();
     // two rows per step: with ACT the GELU runs in its packed fp32x2 form (same bits as the scalar one, half the issue slots --
@@ -72,9 +74,12 @@ using namespace lvae;
 
 extern "C" int lvae_split_planes_t_ex(const float* x, void* p0, void* p1, int64_t P, int C, int act, float* colsum, void* stream) {
   LVAE_CHECK_ARG(x && p0 && p1 && P > 0 && C > 0 && P % 2 == 0 && (act == 0 || act == 1));
-  const dim3 grid((unsigned)((P + 64 * ST_TILES - 1) / (64 * ST_TILES)), (unsigned)((C + 31) / 32));
-  if (act) split_planes_t_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)p0, (__nv_bfloat16*)p1, P, C, colsum);
-  else split_planes_t_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)p0, (__nv_bfloat16*)p1, P, C, colsum);
+  int tiles = ST_TILES;
+  const int64_t cy = (C + 31) / 32;
+  while (tiles > 1 && ((P + 64 * tiles - 1) / (64 * tiles)) * cy < 4 * 148) tiles >>= 1;      // at least ~4 CTAs per SM
+  const dim3 grid((unsigned)((P + 64 * tiles - 1) / (64 * tiles)), (unsigned)cy);
+  if (act) split_planes_t_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)p0, (__nv_bfloat16*)p1, P, C, colsum, tiles);
+  else split_planes_t_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)p0, (__nv_bfloat16*)p1, P, C, colsum, tiles);
   LVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
