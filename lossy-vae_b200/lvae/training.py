@@ -790,13 +790,18 @@ class _GraphedStepFn(torch.autograd.Function):
         ag.s_im.copy_(im, non_blocking=True)
         ag.s_lmb.copy_(lmb, non_blocking=True)
         ag.fwd.replay()
-        ctx.ag = ag
+        ag.generation += 1                 # the backward graph differentiates the LAST replayed forward
+        ctx.ag, ctx.generation = ag, ag.generation
         ctx.mark_non_differentiable(ag.s_stats, ag.s_kl_layers)
         return ag.s_loss.detach().clone(), ag.s_stats, ag.s_kl_layers
 
     @staticmethod
     def backward(ctx, g_loss, *_):
         ag = ctx.ag
+        if ctx.generation != ag.generation or ag.bwd is None:
+            raise RuntimeError('this loss belongs to an earlier forward: the graph-replayed training path keeps the activations of the '
+                               'latest model(batch) call only (one forward, then its backward).  Set LVAE_TRAIN_AUTOGRAPH=0 or '
+                               'model.train_path.autograph_enabled = False for loops that interleave several forward passes.')
         ag.s_gloss.copy_(g_loss)
         ag.bwd.replay()
         return (None, None, None) + tuple(ag.s_grads)
@@ -819,6 +824,8 @@ class AutoGraphedTrain:
         self.shape = None
         self.core = None
         self.plan = None            # keeps the scratch buffers the graphs point into alive
+        self.generation = 0
+        self.fwd = self.bwd = None
 
     def _signature(self):
         """What the captured graphs depend on besides the batch: the precision mode and every trainable parameter's storage

@@ -379,6 +379,24 @@ def test_autographed_forward_backward_equals_the_eager_step(native_lib):
         for p, g1 in zip(params, one):
             if g1 is not None:
                 assert torch.allclose(p.grad, 2 * g1, rtol=1e-5, atol=1e-7 * float(g1.abs().max()) + 1e-12)
+        # an evaluation pass in between (eval plans, their own weight packing) leaves the captured step intact
+        for p in params:
+            p.grad = None
+        m.eval()
+        with torch.no_grad():
+            ev = m(ims[1], lmb=lmb)
+        assert np.isfinite(ev['bppix'])
+        m.train()
+        again = step(ims[0], 10)
+        assert abs(again[0] - eager[0][0]) <= (1e-6 if again[0] == eager[0][0] else 5e-2) * abs(eager[0][0])
+        # a loss whose forward is no longer the latest one cannot be differentiated through the graphs: loud error
+        torch.manual_seed(1)
+        first = m(ims[0], lmb=lmb)['loss']
+        m(ims[1], lmb=lmb)
+        with pytest.raises(RuntimeError, match='earlier forward'):
+            first.backward()
+        for p in params:
+            p.grad = None
         # weights move -> the captured forward re-packs them: the loss changes like the eager one does
         with torch.no_grad():
             for p in params:
