@@ -342,8 +342,19 @@ class TrainPath:
     # reference's convolutions is TF32: 11 bits).
     DGRAD_PREC = N.PREC_BF16X3
 
-    def _transposed(self, w2d):
-        """packed operand planes of a transposed (and possibly row-scaled) weight for the data-gradient GEMMs"""
+    def _transposed(self, w2d, row_scale=None):
+        """packed operand planes of a transposed (and possibly row-scaled) weight for the data-gradient GEMMs.  With at
+        least 64 rows (never the exact-fp32 small-K path, which reads the fp32 matrix) the planes of w2d^T come straight from
+        the transposing split (lvae_split_planes_t: same bf16 hi / lo roundings as lvae_split_planes) -- one launch instead of a
+        transposed copy + a split; row_scale [N]: rows of w2d scaled first (the layer scale folded into fc2's data gradient)."""
+        if row_scale is not None:
+            w2d = row_scale[:, None] * w2d
+        Nr, Kc = w2d.shape
+        if Nr >= 64 and Nr % 2 == 0 and self.DGRAD_PREC == N.PREC_BF16X3:
+            w2d = w2d.contiguous()
+            pl = [torch.empty(Kc * Nr, dtype=torch.bfloat16, device=w2d.device) for _ in range(2)]
+            self.P.op('split_t', self.eng.lib.lvae_split_planes_t_ex, _ptr(w2d), _ptr(pl[0]), _ptr(pl[1]), Nr, Kc, 0, 0)
+            return dict(w=w2d, bias=None, N=Kc, K=Nr, planes=pl)       # `w` only keeps the descriptor's pointer non-null
         return self.eng._pack_gemm_weight(w2d.t().contiguous(), None, prec=self.DGRAD_PREC)
 
     def _t_planes(self, name, x2d, act=0, colsum=None):
@@ -406,7 +417,7 @@ class TrainPath:
         # dh leaves the epilogue twice: fp32 (for the transposing split of the fc1 weight gradient) and as the two bf16 operand
         # planes that the fc1 data-gradient GEMM reads -- no split pass over [M, hid] in between
         dh_pl = [P.named(f'dh_pl{i}', M * hid, dtype=torch.bfloat16)[:M * hid] for i in range(2)] if hid % 8 == 0 else None
-        eng._gemm(P, 'fc2.dgrad', go, (1, 1, M, C_, 1, 1, 0), self._transposed(gam[:, None] * w2.detach()), dh,
+        eng._gemm(P, 'fc2.dgrad', go, (1, 1, M, C_, 1, 1, 0), self._transposed(w2.detach(), row_scale=gam), dh,
                   epi=N.EPI_GELU_BWD, res=h, prec=self.DGRAD_PREC, out_planes=dh_pl)
         # fc1: h = a W1^T + b1;  a is needed for the weight gradient only: one more (fp32) dwln launch, on the side stream
         a32 = torch.empty(M, C_, device=x.device)
