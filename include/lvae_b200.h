@@ -152,6 +152,10 @@ int lvae_debug_prof(int which, unsigned long long* out16);
  * N-tile width BN (multiple of 16, 0 = automatic; env LVAE_TC_BN), 1 = unused,
  * 2 = narrower N-tiles for GEMMs that do not fill the SMs (default 1; LVAE_TC_AUTOBN). */
 int lvae_set_tuning(int which, int value);
+/* Host-only query (no device needed): the N-tile width BN a plain [M, K] x [N, K] tensor-core GEMM of this precision mode is
+ * launched with on a device of n_sm SMs -- the widest tile that divides N evenly, or, for a 2-plane GEMM that would fill at most
+ * two waves, the width that minimises waves x (K / 16) x (128 + 1.25 BN) cycles.  Results never depend on it. */
+int lvae_gemm_tile_width(int M, int N, int K, int precision, int n_sm);
 /* split fp32 -> bf16 planes p0 = rn(x), p1 = rn(x - p0), p2 = rn(x - p0 - p1); p1 / p2 may be NULL */
 int lvae_split_bf16(const float* x, void* p0, void* p1, void* p2, int64_t n, void* stream);
 /* the same split of (x * scale) into planes of `plane_format` (enum lvae_plane_format); weights of an

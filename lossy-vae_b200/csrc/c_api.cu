@@ -7,6 +7,7 @@ int gemm_f32_launch(const lvae_gemm_desc* d, cudaStream_t stream);
 int gemm_tc_launch(const lvae_gemm_desc* d, cudaStream_t stream);
 int gemm_tc_launch_latent(const lvae_gemm_desc* d, const lvae_latent_epilogue* lat, cudaStream_t stream);
 int gemm_tc_latent_num_partials(int H, int W, int N);
+int gemm_tc_tile_width(int M, int N, int K, int precision, int n_sm);
 bool gemm_smallk_applicable(const lvae_gemm_desc* d);
 int gemm_smallk_launch(const lvae_gemm_desc* d, cudaStream_t stream);
 int64_t gemm_tc_workspace_bytes(const lvae_gemm_desc* d);
@@ -15,6 +16,11 @@ int64_t gemm_tc_workspace_bytes(const lvae_gemm_desc* d);
 extern "C" int64_t lvae_gemm_workspace_bytes(const lvae_gemm_desc* d) {
   if (!d || d->precision == LVAE_PREC_FP32) return 0;
   return lvae::gemm_tc_workspace_bytes(d);
+}
+
+extern "C" int lvae_gemm_tile_width(int M, int N, int K, int precision, int n_sm) {
+  if (M <= 0 || N <= 0 || K <= 0 || n_sm <= 0 || precision == LVAE_PREC_FP32) return LVAE_E_BADARG;
+  return lvae::gemm_tc_tile_width(M, N, K, precision, n_sm);
 }
 
 extern "C" int lvae_gemm_latent_num_partials(int H, int W, int N) { return lvae::gemm_tc_latent_num_partials(H, W, N); }

@@ -725,6 +725,16 @@ int gemm_tc_latent_num_partials(int H, int W, int N) {
   return ((H + CONV_TH - 1) / CONV_TH) * ((W + CONV_TW - 1) / CONV_TW) * ((N + 31) / 32) * 4;
 }
 
+// host-only: the N-tile width a plain [M, K] x [N, K] GEMM of this precision would be launched with on a device of n_sm SMs
+// (lvae_gemm_tile_width; the launch itself asks the device for n_sm)
+int gemm_tc_tile_width(int M, int N, int K, int precision, int n_sm) {
+  const int npl = num_planes(precision);
+  int bn = pick_bn(N, npl);
+  const int mt0 = (M + TC_BM - 1) / TC_BM, nt0 = (N + bn - 1) / bn;
+  if (npl == 2 && N >= 64 && mt0 * nt0 <= 2 * n_sm && tc_tuning_get(2)) bn = pick_bn_fill(M, N, K, bn, n_sm);
+  return bn;
+}
+
 static int gemm_tc_launch_impl(const lvae_gemm_desc* d, int split_k, const lvae_latent_epilogue* lat, cudaStream_t stream) {
   const int npl = num_planes(d->precision);
   int Ho, Wo, K; int64_t M64;

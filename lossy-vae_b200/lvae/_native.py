@@ -60,6 +60,7 @@ _PROTOS = {
     'lvae_gemm2_launch_count': (C.c_longlong, []),
     'lvae_debug_prof': (C.c_int, [C.c_int, _fp]),
     'lvae_set_tuning': (C.c_int, [C.c_int, C.c_int]),
+    'lvae_gemm_tile_width': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     'lvae_convnext_mlp': (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_convnext_mlp_planes': (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int,
                                            C.c_int64, C.c_int, C.c_int, C.c_int, _fp]),

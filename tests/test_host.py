@@ -474,3 +474,24 @@ def test_lossless_model_surface_state_dict_and_tables(native_lib, golden):
                     assert torch.equal(v, mine[k]), k
         finally:
             ref_loader.unload_reference()
+
+
+def test_gemm_tile_width_selection_is_a_pure_function_of_the_shape(native_lib):
+    """lvae_gemm_tile_width (host-only): the N-tile width of the tensor-core GEMM.  Large GEMMs keep the widest tile that divides N
+    (<= 128 with two operand planes, <= 256 with one); a 2-plane GEMM that would fill at most two waves of a 148-SM device gets
+    the width that minimises waves x (K / 16) x (128 + 1.25 BN) -- narrower, so that more SMs work.  The GPU test
+    test_gemm_tile_width_does_not_change_bits is what makes this choice free of consequences for the results."""
+    from lvae import _native as NV
+    tw = native_lib.lvae_gemm_tile_width
+    f16x3, bf16 = NV.PREC_F16X3, NV.PREC_BF16
+    for M, Nn, K in [(49152, 384, 768), (49152, 768, 384), (12288, 1024, 512), (196608, 384, 192)]:      # many waves: unchanged
+        assert tw(M, Nn, K, f16x3, 148) == 128
+    assert tw(196608, 192, 128, f16x3, 148) == 96 and tw(49152, 448, 256, f16x3, 148) == 112               # N / 2, N / 4
+    assert tw(768, 512, 1024, f16x3, 148) == 32 and tw(768, 1024, 512, f16x3, 148) == 48                    # H/64 at batch 8
+    assert tw(3072, 1024, 512, f16x3, 148) == 96 and tw(3072, 512, 1024, f16x3, 148) == 96                  # H/32
+    assert tw(768, 512, 1024, bf16, 148) == 256 and tw(49152, 384, 768, bf16, 148) == 192                   # one plane: N only
+    for M in (768, 1536, 3072, 6144):           # monotone: more rows never make the tile narrower
+        assert tw(M, 512, 1024, f16x3, 148) <= tw(2 * M, 512, 1024, f16x3, 148)
+    for bn in (tw(M, Nn, 512, f16x3, 148) for M in (128, 768, 5000) for Nn in (64, 200, 448, 1024)):
+        assert bn % 16 == 0 and 16 <= bn <= 128
+    assert tw(0, 512, 512, f16x3, 148) < 0 and tw(768, 512, 512, NV.PREC_FP32, 148) < 0
