@@ -225,6 +225,9 @@ int lvae_split_planes_t(const float* x, void* p0, void* p1, int64_t P, int C, vo
  * or colsum != NULL: colsum[c] += sum_p x[p, c] (the bias gradient of the layer whose dY is being split; the caller
  * zeroes it) */
 int lvae_split_planes_t_ex(const float* x, void* p0, void* p1, int64_t P, int C, int act, float* colsum, void* stream);
+/* The same K-major bf16 planes [C, P] from an operand that already exists as two 16-bit planes [P, C] (plane_format: LVAE_PLANES_*):
+ * value = hi + lo, re-split.  Lets the fc1 weight gradient reuse the recomputed forward operand instead of an fp32 recomputation. */
+int lvae_planes_transpose(const void* a0, const void* a1, int plane_format, void* p0, void* p1, int64_t P, int C, void* stream);
 int lvae_gemm_wgrad(const void* dyt_p0, const void* dyt_p1, const void* xt_p0, const void* xt_p1,
                     float* dw, int n_out, int k_in, int64_t P, void* stream);
 

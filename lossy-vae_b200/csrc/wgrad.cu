@@ -7,6 +7,7 @@
 // ~2 work items per SM) and the partial tiles meet in fp32 atomics.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace lvae {
 
@@ -68,9 +69,65 @@ __global__ void __launch_bounds__(256) split_planes_t_kernel(const float* __rest
   }
 }
 
+// The same transposition for an operand that already exists as two 16-bit planes [P, C] (fp16 or bf16: the A operand of the
+// forward GEMM, recomputed at the start of a block's backward): value = hi + lo (exact in fp32), re-split into K-major bf16
+// planes [C, P].  Saves the fp32 recomputation of the operand that the fc1 weight gradient would otherwise need.
+template <bool F16IN>
+__global__ void __launch_bounds__(256) planes_t_kernel(const uint16_t* __restrict__ a0, const uint16_t* __restrict__ a1,
+                                                       __nv_bfloat16* __restrict__ p0, __nv_bfloat16* __restrict__ p1,
+                                                       int64_t P, int C, int tiles) {
+  __shared__ float tile[64][33];
+  const int cbase = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  auto cvt = [](uint16_t h) -> float {
+    if (F16IN) return __half2float(__ushort_as_half(h));
+    return __uint_as_float((uint32_t)h << 16);
+  };
+  for (int it = 0; it < tiles; ++it) {
+    const int64_t pbase = ((int64_t)blockIdx.x * tiles + it) * 64;
+    if (pbase >= P) break;
+    __syncthreads();
+    for (int r = ty; r < 64; r += 8) {
+      const int64_t pp = pbase + r;
+      const int c = cbase + tx;
+      float v = 0.f;
+      if (pp < P && c < C) v = __fadd_rn(cvt(__ldg(a0 + pp * C + c)), cvt(__ldg(a1 + pp * C + c)));
+      tile[r][tx] = v;
+    }
+    __syncthreads();
+    const int64_t pp = pbase + 2 * tx;
+    if (pp < P) {
+      for (int cc = ty; cc < 32; cc += 8) {
+        const int c = cbase + cc;
+        if (c >= C) break;
+        float2 v = make_float2(tile[2 * tx][cc], tile[2 * tx + 1][cc]);
+        const uint32_t hi = split_next<false>(v);
+        const uint32_t lo = split_next<false>(v);
+        *reinterpret_cast<uint32_t*>(p0 + (int64_t)c * P + pp) = hi;
+        *reinterpret_cast<uint32_t*>(p1 + (int64_t)c * P + pp) = lo;
+      }
+    }
+  }
+}
+
 }  // namespace lvae
 
 using namespace lvae;
+
+extern "C" int lvae_planes_transpose(const void* a0, const void* a1, int plane_format, void* p0, void* p1, int64_t P, int C, void* stream) {
+  LVAE_CHECK_ARG(a0 && a1 && p0 && p1 && P > 0 && C > 0 && P % 2 == 0);
+  LVAE_CHECK_ARG(plane_format == LVAE_PLANES_BF16 || plane_format == LVAE_PLANES_F16);
+  int tiles = ST_TILES;
+  const int64_t cy = (C + 31) / 32;
+  while (tiles > 1 && ((P + 64 * tiles - 1) / (64 * tiles)) * cy < 4 * 148) tiles >>= 1;
+  const dim3 grid((unsigned)((P + 64 * tiles - 1) / (64 * tiles)), (unsigned)cy);
+  if (plane_format == LVAE_PLANES_F16)
+    planes_t_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)a0, (const uint16_t*)a1, (__nv_bfloat16*)p0, (__nv_bfloat16*)p1, P, C, tiles);
+  else
+    planes_t_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)a0, (const uint16_t*)a1, (__nv_bfloat16*)p0, (__nv_bfloat16*)p1, P, C, tiles);
+  LVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int lvae_split_planes_t_ex(const float* x, void* p0, void* p1, int64_t P, int C, int act, float* colsum, void* stream) {
   LVAE_CHECK_ARG(x && p0 && p1 && P > 0 && C > 0 && P % 2 == 0 && (act == 0 || act == 1));

@@ -76,6 +76,7 @@ _PROTOS = {
     'lvae_ln_mod_bwd': (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     'lvae_split_planes_t': (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int, _fp]),
     'lvae_split_planes_t_ex': (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, _fp, _fp]),
+    'lvae_planes_transpose': (C.c_int, [_fp, _fp, C.c_int, _fp, _fp, C.c_int64, C.c_int, _fp]),
     'lvae_gemm_wgrad': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int64, _fp]),
     'lvae_nll_output': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp]),
     'lvae_outnet_codec': (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, _fp, _fp, _fp, C.c_int64, _fp]),

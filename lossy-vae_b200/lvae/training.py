@@ -268,6 +268,8 @@ class TrainPath:
         # ConvNeXt block backward: the fc2 weight gradient, the fc1 weight gradient (+ its fp32 dwln recompute) and the depthwise filter
         # gradient each on a stream of their own (1 lane: 356, 2: 377, 3: 381-385 images/s at qarv 16 x 256^2)
         self.side_lanes = int(os.environ.get('LVAE_TRAIN_SIDE_LANES', '3'))
+        # fc1 weight gradient: the A operand from the recomputed forward planes (lvae_planes_transpose) instead of an fp32 dwln recompute
+        self.a_from_planes = os.environ.get('LVAE_TRAIN_A_FROM_PLANES', '1') != '0'
         self._side_used = False
         self._side_keep = []
 
@@ -420,13 +422,21 @@ class TrainPath:
         eng._gemm(P, 'fc2.dgrad', go, (1, 1, M, C_, 1, 1, 0), self._transposed(w2.detach(), row_scale=gam), dh,
                   epi=N.EPI_GELU_BWD, res=h, prec=self.DGRAD_PREC, out_planes=dh_pl)
         # fc1: h = a W1^T + b1;  a is needed for the weight gradient only: one more (fp32) dwln launch, on the side stream
-        a32 = torch.empty(M, C_, device=x.device)
-        with self._side(dh, a32, x, ada, lane=1):
-            P.op('dwln', eng.lib.lvae_dwconv_ln_adaln, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']), _ptr(ada), eng.ada_total, off,
-                 _ptr(wb.get('ln_w')), _ptr(wb.get('ln_b')), _ptr(a32), B, H, W, C_, k)
+        from_planes = tc_wgrad and eng.npl == 2 and self.a_from_planes
+        a32 = None if from_planes else torch.empty(M, C_, device=x.device)
+        with self._side(dh, a32, x, ada, A, lane=1):
+            if from_planes:
+                # the operand planes recomputed at the top (value = hi + lo, 22 significand bits) re-split into K-major bf16 planes:
+                # no second dwln launch; the planes stay valid until the next block's backward (which starts after the join)
+                buf = P.named('wg_c', 2 * M * C_, dtype=torch.bfloat16)
+                a_t = (buf[:M * C_], buf[M * C_:2 * M * C_])
+                P.op('planes_t', eng.lib.lvae_planes_transpose, _ptr(A[0]), _ptr(A[1]), eng.pfmt, _ptr(a_t[0]), _ptr(a_t[1]), M, C_)
+            else:
+                P.op('dwln', eng.lib.lvae_dwconv_ln_adaln, _ptr(x), _ptr(wb['dw_w']), _ptr(wb['dw_b']), _ptr(ada), eng.ada_total, off,
+                     _ptr(wb.get('ln_w')), _ptr(wb.get('ln_b')), _ptr(a32), B, H, W, C_, k)
             if tc_wgrad:
                 d_b1 = torch.zeros(hid, device=x.device)
-                d_w1 = self._wgrad(self._t_planes('wg_d', dh, colsum=d_b1), self._t_planes('wg_c', a32), hid, C_, M)
+                d_w1 = self._wgrad(self._t_planes('wg_d', dh, colsum=d_b1), a_t if from_planes else self._t_planes('wg_c', a32), hid, C_, M)
             else:
                 d_w1 = dh.t().mm(a32)
                 d_b1 = dh.sum(0)
