@@ -1,6 +1,6 @@
 """Per-kernel counts of the SASS mnemonics that show tcgen05 / TMEM / TMA / mbarrier / cluster use (B200_PROFILING.md:
 the PTX names never appear in SASS), from `cuobjdump -sass` of the built library.  CPU only.
-usage: python scripts/sass_evidence.py > profiles/r1_sass_evidence.md"""
+usage: python scripts/sass_evidence.py > profiles/r2_sass_evidence.md"""
 import collections
 import re
 import subprocess
